@@ -1,0 +1,209 @@
+/*
+ * zaru_b200.h — C ABI of libzaru_b200.so: the B200 (sm_100a) implementation of Zaru's
+ * per-frame perception hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference (placrosse/Zaru) has NO FFI for this path: its seams are Rust types
+ * (SURVEY.md §8b).  Each entry point below names the Rust item it stands in for; a Rust
+ * `zaru-b200-sys` crate binds these 1:1 (INTEGRATION.md shows the bindings and the
+ * adapter that re-creates `Session::Cuda`, `Detector`, `Estimator` on top).
+ *
+ * Conventions
+ *  - every function returns zb_status (0 = ok, negative = error); the message for the
+ *    last error on the calling thread is available from zb_last_error();
+ *  - the library never frees caller memory and never aborts/exits;
+ *  - zb_ctx: one per GPU.  zb_net: immutable after load, safe for concurrent use.
+ *    zb_detector / zb_estimator / zb_face_pipeline own their workspace, run on their
+ *    context's stream and are single-threaded (mirrors `&mut self` of Detector::detect /
+ *    Estimator::estimate); use one zb_ctx per host thread for concurrent streams;
+ *  - "host_or_device" pointers may be either: the library asks the driver
+ *    (cudaPointerGetAttributes) and copies when needed;
+ *  - all image coordinates, rects and angles are f32 exactly as in the reference.
+ */
+#ifndef ZARU_B200_H
+#define ZARU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t zb_status;
+enum {
+    ZB_OK = 0,
+    ZB_ERR_INVALID_ARGUMENT = -1,
+    ZB_ERR_CUDA = -2,              /* CUDA runtime error (message has the cudaError string)      */
+    ZB_ERR_BAD_MODEL = -3,         /* malformed ONNX bytes                                        */
+    ZB_ERR_UNSUPPORTED_OP = -4,    /* graph uses an operator/shape this path does not implement   */
+    ZB_ERR_BAD_SHAPE = -5,         /* tensor / network shape does not match the wrapper           */
+    ZB_ERR_CAPACITY = -6,          /* caller buffer too small (detections were truncated)         */
+    ZB_ERR_NO_DEVICE = -7          /* no CUDA device: there is NO CPU fallback                     */
+};
+
+typedef struct zb_ctx zb_ctx;
+typedef struct zb_net zb_net;
+typedef struct zb_frames zb_frames;
+typedef struct zb_detector zb_detector;
+typedef struct zb_estimator zb_estimator;
+typedef struct zb_face_pipeline zb_face_pipeline;
+
+/* RotatedRect in the ROOT image's coordinate system = `ViewData::rect`
+ * (crates/zaru/src/image/mod.rs:187-210) of the view to sample, plus the frame it refers to. */
+typedef struct zb_view {
+    int32_t frame;      /* index into the zb_frames batch                                       */
+    float cx, cy;       /* Rect centre                (crates/zaru-image/src/rect.rs:15-18)     */
+    float w, h;         /* Rect size                                                             */
+    float radians;      /* clockwise rotation         (rect.rs:269-273)                          */
+} zb_view;
+
+#define ZB_MAX_KEYPOINTS 7
+/* `zaru::detection::Detection` (crates/zaru/src/detection.rs:282-291), image coordinates.     */
+typedef struct zb_detection {
+    float confidence;
+    float angle;                         /* radians, clockwise                                    */
+    float cx, cy, w, h;                  /* bounding Rect                                         */
+    float keypoints[2 * ZB_MAX_KEYPOINTS];
+    int32_t num_keypoints;
+    int32_t anchor;                      /* seed anchor index of the NMS cluster (provenance)     */
+} zb_detection;
+
+typedef enum zb_detector_kind {
+    ZB_DET_FACE_SHORT_RANGE = 0,  /* face/detection.rs:31-59: 16 params, anchors (2,16,16),(6,8,8)   */
+    ZB_DET_PALM = 1               /* hand/detection.rs:49-179: 18 params, anchors (2,24,24),(6,12,12) */
+} zb_detector_kind;
+
+typedef enum zb_estimator_kind {
+    ZB_EST_FACE_MESH_V1 = 0,      /* face/landmark/mediapipe.rs:44-71: 468 pts + sigmoid(face_flag)   */
+    ZB_EST_EYE = 1,               /* face/eye.rs:30-65: 5 iris pts then 71 contour pts                 */
+    ZB_EST_HAND = 2               /* hand/landmark.rs:298-322: 21 pts, presence, raw handedness        */
+} zb_estimator_kind;
+
+typedef enum zb_nms_mode {        /* detection/nms.rs:153-161 */
+    ZB_NMS_REMOVE = 0,
+    ZB_NMS_AVERAGE = 1
+} zb_nms_mode;
+
+typedef enum zb_tensor_layout {   /* nn/mod.rs:175-181 `CnnInputShape` */
+    ZB_NCHW = 0,
+    ZB_NHWC = 1
+} zb_tensor_layout;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Message of the last failing call on this thread ("" if none). Never NULL. */
+const char *zb_last_error(void);
+/* Library + kernel build description, e.g. "zaru_b200 0.1 sm_100a". */
+const char *zb_version(void);
+zb_status zb_ctx_create(int32_t device_ordinal, zb_ctx **out);
+void zb_ctx_destroy(zb_ctx *ctx);
+zb_status zb_sync(zb_ctx *ctx);
+/* Number of kernels this library has launched on `ctx` since creation (bench.py gpu_launches). */
+int64_t zb_launch_count(zb_ctx *ctx);
+
+/* ---- zaru::nn::NeuralNetwork (crates/zaru/src/nn/mod.rs:365-540) --------------------------- */
+/* `NeuralNetwork::from_onnx(bytes).load()` (:411, :259-363): parse, lower, upload weights once. */
+zb_status zb_net_load(zb_ctx *ctx, const void *onnx_bytes, size_t len, zb_net **out);
+void zb_net_destroy(zb_net *net);
+/* `num_inputs` / `num_outputs` / `inputs()` / `outputs()` (:417-447). shape has up to 8 dims. */
+int32_t zb_net_num_inputs(const zb_net *net);
+int32_t zb_net_num_outputs(const zb_net *net);
+zb_status zb_net_input_info(const zb_net *net, int32_t index, const char **name, int32_t *rank, int64_t shape[8]);
+zb_status zb_net_output_info(const zb_net *net, int32_t index, const char **name, int32_t *rank, int64_t shape[8]);
+/* `NeuralNetwork::estimate(&Inputs) -> Outputs` (:450), extended with a leading batch `n`
+ * (the reference is batch 1): input = f32 [n,3,h,w] NCHW; outputs[i] receives
+ * n * prod(shape_i[1:]) floats in GRAPH OUTPUT ORDER.  Pointers: host_or_device.            */
+zb_status zb_net_estimate(zb_net *net, const float *input_nchw, int32_t n, float *const *outputs);
+/* Sub-batch size used inside forward passes so inter-layer activations stay L2-resident. */
+zb_status zb_net_set_chunk(zb_net *net, int32_t images_per_chunk);
+
+/* ---- zaru::image::Image batches (crates/zaru/src/image/mod.rs:45-180) ---------------------- */
+/* `Image::from_rgba8` for n frames of identical size: copies RGBA8 interleaved pixels
+ * (stride_bytes >= 4*width between rows, frames contiguous) into HBM.                         */
+zb_status zb_frames_upload(zb_ctx *ctx, const uint8_t *rgba_host, int32_t width, int32_t height,
+                           int64_t row_stride_bytes, int32_t n, zb_frames **out);
+/* Same, without a copy: `rgba_device` must stay valid while the handle lives.                 */
+zb_status zb_frames_alias(zb_ctx *ctx, const uint8_t *rgba_device, int32_t width, int32_t height,
+                          int64_t row_stride_bytes, int32_t n, zb_frames **out);
+/* Re-fill an uploaded batch from host memory (steady-state ingest; async on the ctx stream). */
+zb_status zb_frames_update(zb_frames *frames, const uint8_t *rgba_host, int32_t first, int32_t count);
+void zb_frames_destroy(zb_frames *frames);
+
+/* ---- Cnn image->tensor (crates/zaru/src/nn/mod.rs:46-126, :146-167) ------------------------ */
+/* The `image_map` closure + `sample` + `ColorMapper::linear(lo..=hi)` for n views:
+ * out = f32 [n,3,out_h,out_w] (ZB_NCHW) or [n,out_h,out_w,3] (ZB_NHWC); host_or_device.
+ * Nearest-neighbour point sampling, bit-exact with the reference.            */
+zb_status zb_preprocess(zb_ctx *ctx, const zb_frames *frames, const zb_view *views, int32_t n,
+                        int32_t out_w, int32_t out_h, float lo, float hi, zb_tensor_layout layout,
+                        float *out);
+
+/* ---- zaru::detection::Detector (crates/zaru/src/detection.rs:152-276) ---------------------- */
+/* `Detector::new(network)`: `lo..hi` is the network's ColorMapper range.                      */
+zb_status zb_detector_create(zb_ctx *ctx, zb_net *net, zb_detector_kind kind, float lo, float hi,
+                             zb_detector **out);
+void zb_detector_destroy(zb_detector *det);
+zb_status zb_detector_set_threshold(zb_detector *det, float thresh);              /* :188-191 */
+zb_status zb_detector_set_nms(zb_detector *det, float iou_thresh, zb_nms_mode m); /* :197-200 */
+zb_status zb_detector_input_resolution(const zb_detector *det, int32_t *w, int32_t *h);
+/* `Detector::detect(&image)` for n views at once (views == NULL: every whole frame):
+ * aspect-fit view -> tensor -> CNN -> sigmoid/threshold/decode -> NMS -> map back to the
+ * coordinate system of each given view (detection.rs:216-270).
+ * out_dets: host_or_device [n][cap]; out_counts: [n] (true count, may exceed cap ->
+ * ZB_ERR_CAPACITY after filling the first cap).  raw_boxes/raw_scores (optional, may be
+ * NULL): the network's head tensors [n,A,P] / [n,A,1] for inspection.                        */
+zb_status zb_detector_detect(zb_detector *det, const zb_frames *frames, const zb_view *views,
+                             int32_t n, zb_detection *out_dets, int32_t *out_counts, int32_t cap,
+                             float *raw_boxes, float *raw_scores);
+
+/* ---- zaru::landmark::Estimator (crates/zaru/src/landmark.rs:256-349) ----------------------- */
+zb_status zb_estimator_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, float lo, float hi,
+                              zb_estimator **out);
+void zb_estimator_destroy(zb_estimator *est);
+int32_t zb_estimator_num_landmarks(const zb_estimator *est);
+zb_status zb_estimator_input_resolution(const zb_estimator *est, int32_t *w, int32_t *h);
+/* `Estimator::estimate(&view)` for n views: landmarks [n][L][3] in the coordinate system of
+ * each given view (x,y,z scaled; x,y offset: landmark.rs:336-345); scalars [n][2]:
+ *   face: {sigmoid(face_flag), 0}; eye: {0,0}; hand: {presence, raw_handedness}.
+ * flip_x (optional, [n] of 0/1): mirror the sampled tensor left-right and un-mirror x in
+ * network coordinates (right-eye rule, face/eye.rs:24-28, :121-125).      */
+zb_status zb_estimator_estimate(zb_estimator *est, const zb_frames *frames, const zb_view *views,
+                                const uint8_t *flip_x, int32_t n, float *out_landmarks,
+                                float *out_scalars);
+
+/* ---- fused face pipeline (examples/facemesh.rs:36-55 + landmark.rs:456-501) ---------------- */
+/* detect on each whole frame -> highest-confidence detection -> RoI = bounding_rect
+ * (tracker.set_roi) -> LandmarkTracker::track on the same frame: view_rect =
+ * roi.grow_to_fit_aspect(1:1), Estimator::estimate(view), landmarks mapped through
+ * view_rect.transform_out into frame coordinates.  Everything stays on the device; one
+ * device->host copy of the results at the end.                                                */
+zb_status zb_face_pipeline_create(zb_ctx *ctx, zb_net *detector_net, zb_net *landmark_net,
+                                  zb_face_pipeline **out);
+void zb_face_pipeline_destroy(zb_face_pipeline *p);
+zb_status zb_face_pipeline_set_threshold(zb_face_pipeline *p, float det_thresh, float iou_thresh,
+                                         zb_nms_mode mode);
+/* out_dets [n][cap], out_counts [n], out_landmarks [n][468][3], out_flags [n] (sigmoid
+ * face_flag; -1 when the frame had no detection), out_rois [n] (the view_rect used).
+ * Any output pointer may be NULL to skip that copy.  Pointers: host_or_device.               */
+zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int32_t n,
+                               zb_detection *out_dets, int32_t *out_counts, int32_t cap,
+                               float *out_landmarks, float *out_flags, zb_view *out_rois);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+/* JSON description of the lowered plan (fused op list, tensor layouts) of a loaded network and a
+ * pointer to its packed host-side weight blob; tests replay the plan on the CPU to validate the
+ * ONNX reader + lowering independently of the kernels.  `needed` includes the trailing NUL.   */
+zb_status zb_net_plan_json(const zb_net *net, char *buf, size_t cap, size_t *needed);
+zb_status zb_net_weights(const zb_net *net, const float **host_blob, size_t *count);
+/* Parse + lower only (no CUDA device required; nothing is executed).                          */
+zb_status zb_plan_from_onnx(const void *onnx_bytes, size_t len, int32_t fuse_dwpw, char *json,
+                            size_t cap, size_t *needed, float *weights, size_t weights_cap,
+                            size_t *weights_needed);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------- */
+/* Device time (ms, CUDA events on the handle's own stream) of the last *_run/_detect/_estimate
+ * call, excluding host<->device result copies.                                                */
+float zb_last_device_ms(zb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZARU_B200_H */

@@ -113,9 +113,9 @@ class ViewData:
         fy = round_half_away(oy - f32(0.5))
         with np.errstate(invalid="ignore"):
             bad = (fx < 0) | (fy < 0) | (np.ceil(fx) >= U32_MAX_F32) | (np.ceil(fy) >= U32_MAX_F32)
-            bad |= np.isnan(fx) | np.isnan(fy)
-        fx = np.where(bad, f32(0.0), fx)
-        fy = np.where(bad, f32(0.0), fy)
+        # NaN coordinates pass every comparison above (all false) and `NaN as u32` is 0 in Rust
+        fx = np.nan_to_num(np.where(bad, f32(0.0), fx), nan=0.0)
+        fy = np.nan_to_num(np.where(bad, f32(0.0), fy), nan=0.0)
         ix = round_half_away(fx).astype(np.int64)
         iy = round_half_away(fy).astype(np.int64)
         valid = ~bad & (ix < img_w) & (iy < img_h)

@@ -1,0 +1,56 @@
+"""zaru_b200 — host-side mirror of Zaru's perception API over libzaru_b200.so (CUDA, sm_100a).
+
+Module layout follows the reference crate (`zaru::image`, `zaru::rect`, `zaru::nn`,
+`zaru::detection`, `zaru::landmark`, `zaru::face`, `zaru::hand`).  Everything that computes runs in
+the CUDA library; importing this package never falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _ffi
+from ._ffi import ZaruError, load_library  # noqa: F401
+
+_ctx = None
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def context(device: int | None = None):
+    """The process-wide `zb_ctx` (one per GPU; LOCAL_RANK picks the device under torchrun)."""
+    global _ctx
+    if _ctx is None:
+        if device is None:
+            device = int(os.environ.get("ZARU_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_ctx_create(device, C.byref(h)))
+        _ctx = h
+    return _ctx
+
+
+def model_dir() -> str:
+    """Where the MediaPipe `.onnx` blobs live (the reference embeds them with include_blob!,
+    crates/zaru/src/face/detection.rs:38).  build() stages them under assets/_ref/onnx."""
+    env = os.environ.get("ZARU_B200_MODEL_DIR")
+    if env:
+        return env
+    staged = os.path.join(_ROOT, "assets", "_ref", "onnx")
+    if os.path.isdir(staged):
+        return staged
+    return "/root/reference/3rdparty/onnx"
+
+
+def model_path(name: str) -> str:
+    return os.path.join(model_dir(), name)
+
+
+def launch_count() -> int:
+    return int(_ffi.lib().zb_launch_count(context()))
+
+
+def last_device_ms() -> float:
+    return float(_ffi.lib().zb_last_device_ms(context()))
+
+
+def sync():
+    _ffi.check(_ffi.lib().zb_sync(context()))

@@ -1,0 +1,1008 @@
+// C ABI of libzaru_b200.so (see include/zaru_b200.h).  Host glue only: handle management, the
+// reference's per-call view fitting (restated with geom.h), H<->D staging and kernel sequencing.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+// exported C ABI: everything else in the library has hidden visibility
+#pragma GCC visibility push(default)
+#include "../../include/zaru_b200.h"
+#pragma GCC visibility pop
+#include "geom.h"
+#include "kernels.h"
+#include "onnx_reader.h"
+#include "plan.h"
+
+using namespace zb;
+
+static_assert(sizeof(zb_detection) == sizeof(DetDev), "zb_detection layout");
+static_assert(sizeof(zb_view) == sizeof(ViewHost), "zb_view layout");
+
+namespace {
+
+thread_local std::string t_last_error;
+
+zb_status fail(zb_status code, const std::string &msg) {
+    t_last_error = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                  \
+    } while (0)
+
+template <class F>
+zb_status guarded(F &&f) {
+    try {
+        t_last_error.clear();
+        return f();
+    } catch (const CudaError &e) {
+        return fail(ZB_ERR_CUDA, e.what());
+    } catch (const std::runtime_error &e) {
+        std::string m = e.what();
+        if (m.rfind("unsupported op", 0) == 0) return fail(ZB_ERR_UNSUPPORTED_OP, m);
+        if (m.rfind("onnx:", 0) == 0) return fail(ZB_ERR_BAD_MODEL, m);
+        return fail(ZB_ERR_INVALID_ARGUMENT, m);
+    } catch (const std::exception &e) {
+        return fail(ZB_ERR_INVALID_ARGUMENT, e.what());
+    }
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// growable device / pinned-host buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CU(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        CU(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    template <class T>
+    T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CU(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        CU(cudaMallocHost(&p, bytes));
+        cap = bytes;
+    }
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    template <class T>
+    T *as() { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct zb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int default_chunk = 64;
+};
+
+struct zb_net {
+    zb_ctx *ctx = nullptr;
+    Plan plan;
+    float *d_weights = nullptr;
+    int chunk = 0;
+    std::vector<std::string> in_names, out_names;
+    std::mutex mu;                       // guards the cached workspace used by zb_net_estimate
+    struct Workspace *estimate_ws = nullptr;
+};
+
+struct Workspace {
+    DevBuf arena;
+    int cap = 0;                         // images per chunk the arena can hold
+    std::vector<DevBuf> outs;            // graph outputs for the whole batch
+    int out_images = 0;
+    void ensure(const zb_net *net, int chunk, int n) {
+        if (chunk > cap) {
+            arena.reserve((size_t)net->plan.arena_per_image * chunk * sizeof(float));
+            cap = chunk;
+        }
+        if (outs.size() != net->plan.outputs.size()) outs.resize(net->plan.outputs.size());
+        if (n > out_images) {
+            for (size_t k = 0; k < outs.size(); k++)
+                outs[k].reserve((size_t)net->plan.outputs[k].per_image * n * sizeof(float));
+            out_images = n;
+        }
+    }
+};
+
+struct zb_frames {
+    zb_ctx *ctx = nullptr;
+    FramesDev f{};
+    uint8_t *owned = nullptr;
+};
+
+namespace {
+
+int net_chunk(const zb_net *net) { return net->chunk > 0 ? net->chunk : net->ctx->default_chunk; }
+
+ActDev act_dev(const ActSpec &a, const float *weights) {
+    ActDev d;
+    d.kind = a.kind;
+    d.lo = a.lo;
+    d.hi = a.hi;
+    d.slope = a.slope_off >= 0 ? weights + a.slope_off : nullptr;
+    return d;
+}
+
+// Pointer of tensor `t` for the chunk starting at image c0 (arena slot or graph-output row).
+float *tensor_ptr(const zb_net *net, Workspace &ws, int t, int c0) {
+    const TensorInfo &ti = net->plan.tensors[t];
+    if (ti.buffer < 0) return ws.arena.as<float>() + (size_t)ti.offset * ws.cap;
+    return ws.outs[ti.buffer].as<float>() + (size_t)c0 * net->plan.outputs[ti.buffer].per_image + ti.offset;
+}
+
+// Runs the plan's ops for `nc` images whose NHWC4 input already sits in the arena input slot.
+void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, cudaStream_t s) {
+    const Plan &pl = net->plan;
+    const float *W = net->d_weights;
+    for (const Op &op : pl.ops) {
+        const TensorInfo &ti = pl.tensors[op.in];
+        const TensorInfo &to = pl.tensors[op.out];
+        const float *in = tensor_ptr(net, ws, op.in, c0);
+        float *out = tensor_ptr(net, ws, op.out, c0);
+        EpiDev e{};
+        e.bias = op.b_off >= 0 ? W + op.b_off : nullptr;
+        e.act1 = act_dev(op.act1, W);
+        e.act2 = act_dev(op.act2, W);
+        if (op.res >= 0) {
+            const TensorInfo &tr = pl.tensors[op.res];
+            e.res = tensor_ptr(net, ws, op.res, c0);
+            e.res_img_stride = tr.img_stride;
+            e.res_H = tr.H;
+            e.res_W = tr.W;
+            e.res_Cs = tr.Cs;
+            e.res_pool = op.res_pool;
+        }
+        const int out_pix = to.Cs;
+        switch (op.kind) {
+            case OP_CONV:
+            case OP_DW:
+            case OP_DWPW: {
+                ConvDev p{};
+                p.in = in;
+                p.in_img_stride = ti.img_stride;
+                p.H = ti.H;
+                p.W = ti.W;
+                p.Cs_in = ti.Cs;
+                p.out = out;
+                p.out_img_stride = to.img_stride;
+                p.Ho = to.H;
+                p.Wo = to.W;
+                p.out_pix_stride = out_pix;
+                p.K = op.K;
+                p.Ns = op.Ns;
+                p.Nstore = op.Nstore;
+                p.kh = op.kh, p.kw = op.kw, p.sh = op.sh, p.sw = op.sw, p.pt = op.pt, p.pl = op.pl;
+                p.M = nc * to.H * to.W;
+                p.epi = e;
+                if (op.kind == OP_CONV) {
+                    p.w = W + op.w_off;
+                    const bool pw = op.kh == 1 && op.kw == 1 && op.sh == 1 && op.sw == 1 && op.pt == 0 && op.pl == 0;
+                    launch_conv(p, pw ? CONV_PW : CONV_GATHER, s);
+                } else if (op.kind == OP_DW) {
+                    p.w = W + op.w_off;
+                    launch_dw(p, s);
+                } else {
+                    p.w = W + op.w2_off;
+                    p.epi.bias = W + op.b2_off;
+                    p.dw_w = W + op.w_off;
+                    p.dw_b = W + op.b_off;
+                    p.act_mid = act_dev(op.act_mid, W);
+                    launch_conv(p, CONV_DWPW, s);
+                }
+                break;
+            }
+            case OP_MAXPOOL: launch_maxpool2(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); break;
+            case OP_RESIZE: launch_resize2x(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); break;
+            case OP_GAP: launch_gap(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); break;
+            case OP_ADD:
+            case OP_ACT:
+                launch_eltwise(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, out_pix, op.Nstore, e, nc, s);
+                break;
+            default: throw std::runtime_error("internal: unknown op kind");
+        }
+    }
+    CU(cudaGetLastError());
+}
+
+RRectF rrect_from_view(const zb_view &v) {
+    RRectF r;
+    r.r.cx = v.cx, r.r.cy = v.cy, r.r.w = v.w, r.r.h = v.h;
+    r.rad = v.radians;
+    r.c = cosf(v.radians);   // f32::cos / f32::sin -> glibc cosf / sinf, like the reference's Mat2::rotation_*
+    r.s = sinf(v.radians);
+    return r;
+}
+
+ViewDev view_dev(const RRectF &r, int frame, int flip) {
+    ViewDev d;
+    d.frame = frame;
+    d.cx = r.r.cx, d.cy = r.r.cy, d.w = r.r.w, d.h = r.r.h;
+    d.cosr = r.c, d.sinr = r.s;
+    d.flip_x = flip;
+    d.valid = 1;
+    return d;
+}
+
+// Detector::detect_impl / Estimator::estimate_impl front (detection.rs:224-227, landmark.rs:320-323):
+//   rect = image.rect().grow_to_fit_aspect(aspect); view = image.view(rect)
+// plus the numbers the tail needs: scale = rect.width()/input_w and rect.top_left().
+void fit_view(const RRectF &base, int net_w, int net_h, RRectF &sampled, float fit[4]) {
+    const float aspect = aspect_as_f32((unsigned)net_w, (unsigned)net_h);
+    const RectF r0 = rect_from_top_left(0.0f, 0.0f, base.r.w, base.r.h);   // ImageView::rect()
+    const RectF rect = grow_to_fit_aspect(r0, aspect);
+    const float rad = base.rad + 0.0f;
+    sampled = view_compose(base, rect, 0.0f, cosf(rad), sinf(rad));
+    fit[0] = rect.w / (float)net_w;
+    fit[1] = rect_x(rect);
+    fit[2] = rect_y(rect);
+    fit[3] = 0.f;
+}
+
+void check_frames(const zb_frames *frames, const zb_view *views, int n) {
+    if (!frames) throw std::runtime_error("frames is NULL");
+    if (n < 0) throw std::runtime_error("negative batch size");
+    if (!views && n > frames->f.n) throw std::runtime_error("n exceeds the number of frames in the batch");
+    if (views)
+        for (int i = 0; i < n; i++)
+            if (views[i].frame < 0 || views[i].frame >= frames->f.n)
+                throw std::runtime_error("view " + std::to_string(i) + " refers to frame " +
+                                         std::to_string(views[i].frame) + " outside the batch");
+}
+
+// copy results to the caller (host or device pointer)
+void copy_out(void *dst, const void *src_dev, size_t bytes, cudaStream_t s) {
+    if (!dst || !bytes) return;
+    CU(cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+}
+
+struct Timer {
+    zb_ctx *ctx;
+    cudaStream_t s;
+    Timer(zb_ctx *c, cudaStream_t st) : ctx(c), s(st) { CU(cudaEventRecord(ctx->ev0, s)); }
+    void stop() { CU(cudaEventRecord(ctx->ev1, s)); }
+    void finish() {
+        CU(cudaEventSynchronize(ctx->ev1));
+        CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    }
+};
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *zb_last_error(void) { return t_last_error.c_str(); }
+
+const char *zb_version(void) { return "zaru_b200 0.1 (sm_100a, f32 SIMT conv-gemm + fused dw/pw blocks)"; }
+
+zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
+    return guarded([&]() -> zb_status {
+        if (!out) return fail(ZB_ERR_INVALID_ARGUMENT, "out is NULL");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            return fail(ZB_ERR_NO_DEVICE, std::string("no CUDA device available (") +
+                                              (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+                                              "); zaru_b200 has no CPU fallback");
+        }
+        if (device < 0 || device >= count) return fail(ZB_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+        CU(cudaSetDevice(device));
+        auto ctx = std::make_unique<zb_ctx>();
+        ctx->device = device;
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ctx->ev0));
+        CU(cudaEventCreate(&ctx->ev1));
+        if (const char *c = getenv("ZB_CHUNK")) {
+            int v = atoi(c);
+            if (v > 0) ctx->default_chunk = v;
+        }
+        *out = ctx.release();
+        return ZB_OK;
+    });
+}
+
+void zb_ctx_destroy(zb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream), cudaStreamDestroy(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+zb_status zb_sync(zb_ctx *ctx) {
+    return guarded([&]() -> zb_status {
+        if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return ZB_OK;
+    });
+}
+
+int64_t zb_launch_count(zb_ctx *) { return g_launch_count; }
+
+float zb_last_device_ms(zb_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+
+// ---- networks ------------------------------------------------------------------------------------
+zb_status zb_net_load(zb_ctx *ctx, const void *onnx, size_t len, zb_net **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/out is NULL");
+        if (!onnx || len == 0) return fail(ZB_ERR_BAD_MODEL, "onnx: empty model");
+        CU(cudaSetDevice(ctx->device));
+        OnnxGraph g = parse_onnx(onnx, len);
+        LowerOptions opt;
+        if (const char *f = getenv("ZB_NO_FUSE_DWPW")) opt.fuse_dwpw = atoi(f) == 0;
+        auto net = std::make_unique<zb_net>();
+        net->ctx = ctx;
+        net->plan = lower_graph(g, opt);
+        for (auto &i : g.inputs) net->in_names.push_back(i.name);
+        for (auto &o : net->plan.outputs) net->out_names.push_back(o.name);
+        CU(cudaMalloc(&net->d_weights, std::max<size_t>(net->plan.weights.size(), 4) * sizeof(float)));
+        CU(cudaMemcpy(net->d_weights, net->plan.weights.data(), net->plan.weights.size() * sizeof(float),
+                      cudaMemcpyHostToDevice));
+        *out = net.release();
+        return ZB_OK;
+    });
+}
+
+void zb_net_destroy(zb_net *net) {
+    if (!net) return;
+    cudaSetDevice(net->ctx->device);
+    delete net->estimate_ws;
+    if (net->d_weights) cudaFree(net->d_weights);
+    delete net;
+}
+
+int32_t zb_net_num_inputs(const zb_net *net) { return net ? 1 : 0; }
+int32_t zb_net_num_outputs(const zb_net *net) { return net ? (int32_t)net->plan.outputs.size() : 0; }
+
+zb_status zb_net_input_info(const zb_net *net, int32_t index, const char **name, int32_t *rank, int64_t shape[8]) {
+    if (!net || index != 0) return fail(ZB_ERR_INVALID_ARGUMENT, "bad input index");
+    if (name) *name = net->in_names[0].c_str();
+    if (rank) *rank = 4;
+    if (shape) shape[0] = 1, shape[1] = 3, shape[2] = net->plan.in_h, shape[3] = net->plan.in_w;
+    return ZB_OK;
+}
+
+zb_status zb_net_output_info(const zb_net *net, int32_t index, const char **name, int32_t *rank, int64_t shape[8]) {
+    if (!net || index < 0 || index >= (int32_t)net->plan.outputs.size())
+        return fail(ZB_ERR_INVALID_ARGUMENT, "bad output index");
+    const OutputInfo &o = net->plan.outputs[index];
+    if (name) *name = net->out_names[index].c_str();
+    if (rank) *rank = (int32_t)std::min<size_t>(o.shape.size(), 8);
+    if (shape)
+        for (size_t i = 0; i < o.shape.size() && i < 8; i++) shape[i] = o.shape[i];
+    return ZB_OK;
+}
+
+zb_status zb_net_set_chunk(zb_net *net, int32_t chunk) {
+    if (!net || chunk < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "bad chunk");
+    net->chunk = chunk;
+    return ZB_OK;
+}
+
+// introspection (tests emulate the lowered plan on the CPU to validate the lowering itself)
+zb_status zb_net_plan_json(const zb_net *net, char *buf, size_t cap, size_t *needed) {
+    if (!net) return fail(ZB_ERR_INVALID_ARGUMENT, "net is NULL");
+    std::string s = net->plan.to_json();
+    if (needed) *needed = s.size() + 1;
+    if (buf && cap > 0) {
+        size_t n = std::min(cap - 1, s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return ZB_OK;
+}
+
+zb_status zb_net_weights(const zb_net *net, const float **host_blob, size_t *count) {
+    if (!net) return fail(ZB_ERR_INVALID_ARGUMENT, "net is NULL");
+    if (host_blob) *host_blob = net->plan.weights.data();
+    if (count) *count = net->plan.weights.size();
+    return ZB_OK;
+}
+
+// Lowering only (no device needed): used by CPU-side tests of the ONNX reader + plan builder.
+zb_status zb_plan_from_onnx(const void *onnx, size_t len, int32_t fuse_dwpw, char *json, size_t cap, size_t *needed,
+                            float *weights, size_t weights_cap, size_t *weights_needed) {
+    return guarded([&]() -> zb_status {
+        OnnxGraph g = parse_onnx(onnx, len);
+        LowerOptions opt;
+        opt.fuse_dwpw = fuse_dwpw != 0;
+        Plan p = lower_graph(g, opt);
+        std::string s = p.to_json();
+        if (needed) *needed = s.size() + 1;
+        if (json && cap > 0) {
+            size_t n = std::min(cap - 1, s.size());
+            memcpy(json, s.data(), n);
+            json[n] = 0;
+        }
+        if (weights_needed) *weights_needed = p.weights.size();
+        if (weights && weights_cap >= p.weights.size()) memcpy(weights, p.weights.data(), p.weights.size() * 4);
+        return ZB_OK;
+    });
+}
+
+zb_status zb_net_estimate(zb_net *net, const float *input, int32_t n, float *const *outputs) {
+    return guarded([&]() -> zb_status {
+        if (!net || !input || !outputs || n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = net->ctx;
+        CU(cudaSetDevice(ctx->device));
+        std::lock_guard<std::mutex> lock(net->mu);
+        if (!net->estimate_ws) net->estimate_ws = new Workspace();
+        Workspace &ws = *net->estimate_ws;
+        const int chunk = std::min(net_chunk(net), n);
+        ws.ensure(net, chunk, n);
+        cudaStream_t s = ctx->stream;
+        const Plan &pl = net->plan;
+        const size_t in_elems = (size_t)3 * pl.in_h * pl.in_w;
+        DevBuf staging;
+        const float *d_in = input;
+        if (!is_device_ptr(input)) {
+            staging.reserve(in_elems * n * sizeof(float));
+            CU(cudaMemcpyAsync(staging.p, input, in_elems * n * sizeof(float), cudaMemcpyHostToDevice, s));
+            d_in = staging.as<float>();
+        }
+        Timer tm(ctx, s);
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int nc = std::min(chunk, n - c0);
+            launch_nchw_to_nhwc4(d_in + in_elems * c0, nc, pl.in_h, pl.in_w, tensor_ptr(net, ws, pl.input, c0),
+                                 pl.tensors[pl.input].img_stride, s);
+            run_ops(net, ws, c0, nc, s);
+        }
+        tm.stop();
+        for (size_t k = 0; k < pl.outputs.size(); k++)
+            copy_out(outputs[k], ws.outs[k].p, (size_t)pl.outputs[k].per_image * n * sizeof(float), s);
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        return ZB_OK;
+    });
+}
+
+// ---- frames ---------------------------------------------------------------------------------------
+static zb_status frames_make(zb_ctx *ctx, const uint8_t *src, int32_t w, int32_t h, int64_t row_stride, int32_t n,
+                             bool copy, zb_frames **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !out || !src) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/out/pixels is NULL");
+        if (w <= 0 || h <= 0 || n <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "frame width/height/count must be positive");
+        if (row_stride < (int64_t)w * 4 || row_stride % 4)
+            return fail(ZB_ERR_INVALID_ARGUMENT, "row stride must be a multiple of 4 and >= 4*width");
+        CU(cudaSetDevice(ctx->device));
+        auto fr = std::make_unique<zb_frames>();
+        fr->ctx = ctx;
+        fr->f.width = w;
+        fr->f.height = h;
+        fr->f.row_stride = row_stride;
+        fr->f.frame_stride = row_stride * h;
+        fr->f.n = n;
+        if (copy) {
+            if (is_device_ptr(src)) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_frames_upload expects host memory");
+            CU(cudaMalloc((void **)&fr->owned, (size_t)fr->f.frame_stride * n));
+            CU(cudaMemcpyAsync(fr->owned, src, (size_t)fr->f.frame_stride * n, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            fr->f.base = fr->owned;
+        } else {
+            if (!is_device_ptr(src)) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_frames_alias expects device memory");
+            if (((uintptr_t)src) % 4) return fail(ZB_ERR_INVALID_ARGUMENT, "frame base must be 4-byte aligned");
+            fr->f.base = src;
+        }
+        *out = fr.release();
+        return ZB_OK;
+    });
+}
+
+zb_status zb_frames_upload(zb_ctx *ctx, const uint8_t *rgba, int32_t w, int32_t h, int64_t row_stride, int32_t n,
+                           zb_frames **out) {
+    return frames_make(ctx, rgba, w, h, row_stride, n, true, out);
+}
+
+zb_status zb_frames_alias(zb_ctx *ctx, const uint8_t *rgba, int32_t w, int32_t h, int64_t row_stride, int32_t n,
+                          zb_frames **out) {
+    return frames_make(ctx, rgba, w, h, row_stride, n, false, out);
+}
+
+zb_status zb_frames_update(zb_frames *fr, const uint8_t *rgba_host, int32_t first, int32_t count) {
+    return guarded([&]() -> zb_status {
+        if (!fr || !rgba_host || !fr->owned) return fail(ZB_ERR_INVALID_ARGUMENT, "frames must come from zb_frames_upload");
+        if (first < 0 || count < 0 || first + count > fr->f.n) return fail(ZB_ERR_INVALID_ARGUMENT, "frame range out of bounds");
+        CU(cudaSetDevice(fr->ctx->device));
+        CU(cudaMemcpyAsync(fr->owned + (size_t)first * fr->f.frame_stride, rgba_host, (size_t)count * fr->f.frame_stride,
+                           cudaMemcpyHostToDevice, fr->ctx->stream));
+        return ZB_OK;
+    });
+}
+
+void zb_frames_destroy(zb_frames *fr) {
+    if (!fr) return;
+    cudaSetDevice(fr->ctx->device);
+    if (fr->owned) cudaFree(fr->owned);
+    delete fr;
+}
+
+// ---- preprocess --------------------------------------------------------------------------------------
+zb_status zb_preprocess(zb_ctx *ctx, const zb_frames *frames, const zb_view *views, int32_t n, int32_t out_w,
+                        int32_t out_h, float lo, float hi, zb_tensor_layout layout, float *out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !views || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/views/out is NULL");
+        if (out_w <= 0 || out_h <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "bad output resolution");
+        if (!(hi > lo)) return fail(ZB_ERR_INVALID_ARGUMENT, "ColorMapper range must satisfy end > start");
+        check_frames(frames, views, n);
+        if (n == 0) return ZB_OK;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        std::vector<ViewDev> hv(n);
+        for (int i = 0; i < n; i++) hv[i] = view_dev(rrect_from_view(views[i]), views[i].frame, 0);
+        DevBuf dv, dout;
+        dv.reserve(sizeof(ViewDev) * n);
+        CU(cudaMemcpyAsync(dv.p, hv.data(), sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+        const size_t per = (size_t)3 * out_w * out_h;
+        float *d_out = out;
+        const bool dev = is_device_ptr(out);
+        if (!dev) {
+            dout.reserve(per * n * sizeof(float));
+            d_out = dout.as<float>();
+        }
+        Timer tm(ctx, s);
+        launch_sample(frames->f, dv.as<ViewDev>(), n, out_w, out_h, lo, hi,
+                      layout == ZB_NCHW ? SAMPLE_NCHW : SAMPLE_NHWC3, d_out, (long long)per, s);
+        CU(cudaGetLastError());
+        tm.stop();
+        if (!dev) CU(cudaMemcpyAsync(out, d_out, per * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        return ZB_OK;
+    });
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// Detector / Estimator / face pipeline handles
+// ================================================================================================
+struct zb_detector {
+    zb_ctx *ctx;
+    zb_net *net;
+    zb_detector_kind kind;
+    float lo, hi;
+    float thresh = 0.5f;        // Detector::DEFAULT_THRESHOLD (detection.rs:167)
+    float iou = 0.3f;           // NonMaxSuppression::DEFAULT_IOU_THRESH (nms.rs:28)
+    int mode = ZB_NMS_AVERAGE;  // nms.rs:39
+    Workspace ws;
+    DevBuf d_views, d_fit, d_dets, d_counts;
+    PinBuf h_stage, h_counts;
+};
+
+struct zb_estimator {
+    zb_ctx *ctx;
+    zb_net *net;
+    zb_estimator_kind kind;
+    float lo, hi;
+    int num_landmarks;
+    Workspace ws;
+    DevBuf d_views, d_fit, d_lm, d_scalars;
+    PinBuf h_stage;
+};
+
+struct zb_face_pipeline {
+    zb_ctx *ctx;
+    zb_net *det_net, *lm_net;
+    float thresh = 0.5f, iou = 0.3f;
+    int mode = ZB_NMS_AVERAGE;
+    Workspace ws_det, ws_lm;
+    DevBuf d_views, d_fit, d_dets, d_counts, d_lm_views, d_lm_fit, d_rois, d_lm, d_scalars;
+    PinBuf h_stage, h_counts;
+    int cap = 0;
+};
+
+namespace {
+
+DecodeParams decode_params(zb_detector_kind kind, const Plan &pl, float thresh, float iou, int mode, int cap) {
+    DecodeParams p{};
+    p.net_w = pl.in_w;
+    p.net_h = pl.in_h;
+    if (kind == ZB_DET_FACE_SHORT_RANGE) {
+        p.num_params = 16, p.num_kp = 6, p.angle_kind = 0;
+        p.l0_boxes = 2, p.l0_w = 16, p.l0_h = 16, p.l1_boxes = 6, p.l1_w = 8, p.l1_h = 8;
+    } else {
+        p.num_params = 18, p.num_kp = 7, p.angle_kind = 1;
+        p.l0_boxes = 2, p.l0_w = 24, p.l0_h = 24, p.l1_boxes = 6, p.l1_w = 12, p.l1_h = 12;
+    }
+    p.num_anchors = p.l0_boxes * p.l0_w * p.l0_h + p.l1_boxes * p.l1_w * p.l1_h;
+    p.thresh = thresh;
+    p.iou_thresh = iou;
+    p.nms_mode = mode;
+    p.cap = cap;
+    return p;
+}
+
+// `assert_eq!(boxes.shape(), &[1, num_anchors, 16])` etc. (face/detection.rs:107-108), checked at creation.
+void check_detector_net(const zb_net *net, zb_detector_kind kind) {
+    DecodeParams p = decode_params(kind, net->plan, 0.5f, 0.3f, 1, 1);
+    const auto &o = net->plan.outputs;
+    if (o.size() < 2 || o[0].per_image != (int64_t)p.num_anchors * p.num_params || o[1].per_image != p.num_anchors)
+        throw std::runtime_error("bad shape: detector network outputs do not match [1," + std::to_string(p.num_anchors) +
+                                 "," + std::to_string(p.num_params) + "] / [1," + std::to_string(p.num_anchors) + ",1]");
+}
+
+int estimator_landmarks(zb_estimator_kind k) { return k == ZB_EST_FACE_MESH_V1 ? 468 : k == ZB_EST_EYE ? 76 : 21; }
+
+void check_estimator_net(const zb_net *net, zb_estimator_kind kind) {
+    const auto &o = net->plan.outputs;
+    bool ok = false;
+    if (kind == ZB_EST_FACE_MESH_V1) ok = o.size() >= 2 && o[0].per_image == 1404 && o[1].per_image == 1;
+    if (kind == ZB_EST_EYE) ok = o.size() >= 2 && o[0].per_image == 213 && o[1].per_image == 15;
+    if (kind == ZB_EST_HAND)
+        ok = o.size() >= 4 && o[0].per_image == 63 && o[1].per_image == 1 && o[2].per_image == 1 && o[3].per_image == 63;
+    if (!ok) throw std::runtime_error("bad shape: landmark network outputs do not match the estimator kind");
+}
+
+}  // namespace
+
+extern "C" {
+
+zb_status zb_detector_create(zb_ctx *ctx, zb_net *net, zb_detector_kind kind, float lo, float hi, zb_detector **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
+        if (!(hi > lo)) return fail(ZB_ERR_INVALID_ARGUMENT, "ColorMapper range must satisfy end > start");
+        try {
+            check_detector_net(net, kind);
+        } catch (const std::runtime_error &e) {
+            return fail(ZB_ERR_BAD_SHAPE, e.what());
+        }
+        auto d = std::make_unique<zb_detector>();
+        d->ctx = ctx, d->net = net, d->kind = kind, d->lo = lo, d->hi = hi;
+        *out = d.release();
+        return ZB_OK;
+    });
+}
+
+void zb_detector_destroy(zb_detector *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    delete d;
+}
+
+zb_status zb_detector_set_threshold(zb_detector *d, float t) {
+    if (!d) return fail(ZB_ERR_INVALID_ARGUMENT, "detector is NULL");
+    d->thresh = t;
+    return ZB_OK;
+}
+
+zb_status zb_detector_set_nms(zb_detector *d, float iou, zb_nms_mode m) {
+    if (!d) return fail(ZB_ERR_INVALID_ARGUMENT, "detector is NULL");
+    d->iou = iou;
+    d->mode = (int)m;
+    return ZB_OK;
+}
+
+zb_status zb_detector_input_resolution(const zb_detector *d, int32_t *w, int32_t *h) {
+    if (!d) return fail(ZB_ERR_INVALID_ARGUMENT, "detector is NULL");
+    if (w) *w = d->net->plan.in_w;
+    if (h) *h = d->net->plan.in_h;
+    return ZB_OK;
+}
+
+zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_view *views, int32_t n,
+                             zb_detection *out_dets, int32_t *out_counts, int32_t cap, float *raw_boxes,
+                             float *raw_scores) {
+    return guarded([&]() -> zb_status {
+        if (!d) return fail(ZB_ERR_INVALID_ARGUMENT, "detector is NULL");
+        if (cap <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "cap must be positive");
+        check_frames(frames, views, n);
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = d->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const Plan &pl = d->net->plan;
+        const int chunk = std::min(net_chunk(d->net), n);
+        d->ws.ensure(d->net, chunk, n);
+        // host: per-view aspect fit + composition (cheap, exact)
+        d->h_stage.reserve((sizeof(ViewDev) + 4 * sizeof(float)) * n);
+        ViewDev *hv = d->h_stage.as<ViewDev>();
+        float *hfit = reinterpret_cast<float *>(hv + n);
+        for (int i = 0; i < n; i++) {
+            RRectF base = views ? rrect_from_view(views[i]) : full_view(frames->f.width, frames->f.height);
+            RRectF sampled;
+            fit_view(base, pl.in_w, pl.in_h, sampled, hfit + 4 * i);
+            hv[i] = view_dev(sampled, views ? views[i].frame : i, 0);
+        }
+        d->d_views.reserve(sizeof(ViewDev) * n);
+        d->d_fit.reserve(4 * sizeof(float) * n);
+        d->d_dets.reserve(sizeof(DetDev) * (size_t)n * cap);
+        d->d_counts.reserve(sizeof(int) * n);
+        d->h_counts.reserve(sizeof(int) * n);
+        CU(cudaMemcpyAsync(d->d_views.p, hv, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        const DecodeParams dp = decode_params(d->kind, pl, d->thresh, d->iou, d->mode, cap);
+        Timer tm(ctx, s);
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int nc = std::min(chunk, n - c0);
+            launch_sample(frames->f, d->d_views.as<ViewDev>() + c0, nc, pl.in_w, pl.in_h, d->lo, d->hi, SAMPLE_NHWC4,
+                          tensor_ptr(d->net, d->ws, pl.input, c0), pl.tensors[pl.input].img_stride, s);
+            run_ops(d->net, d->ws, c0, nc, s);
+            launch_decode_nms(d->ws.outs[0].as<float>() + (size_t)c0 * pl.outputs[0].per_image,
+                              d->ws.outs[1].as<float>() + (size_t)c0 * pl.outputs[1].per_image,
+                              d->d_fit.as<float>() + 4 * c0, nc, dp, d->d_dets.as<DetDev>() + (size_t)c0 * cap,
+                              d->d_counts.as<int>() + c0, s);
+        }
+        CU(cudaGetLastError());
+        tm.stop();
+        copy_out(out_dets, d->d_dets.p, sizeof(DetDev) * (size_t)n * cap, s);
+        copy_out(out_counts, d->d_counts.p, sizeof(int) * n, s);
+        copy_out(raw_boxes, d->ws.outs[0].p, (size_t)pl.outputs[0].per_image * n * sizeof(float), s);
+        copy_out(raw_scores, d->ws.outs[1].p, (size_t)pl.outputs[1].per_image * n * sizeof(float), s);
+        CU(cudaMemcpyAsync(d->h_counts.p, d->d_counts.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        const int *hc = d->h_counts.as<int>();
+        for (int i = 0; i < n; i++)
+            if (hc[i] > cap)
+                return fail(ZB_ERR_CAPACITY, "view " + std::to_string(i) + " produced " + std::to_string(hc[i]) +
+                                                 " detections; capacity is " + std::to_string(cap));
+        return ZB_OK;
+    });
+}
+
+// ---- estimator -----------------------------------------------------------------------------------------
+zb_status zb_estimator_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, float lo, float hi, zb_estimator **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
+        if (!(hi > lo)) return fail(ZB_ERR_INVALID_ARGUMENT, "ColorMapper range must satisfy end > start");
+        try {
+            check_estimator_net(net, kind);
+        } catch (const std::runtime_error &e) {
+            return fail(ZB_ERR_BAD_SHAPE, e.what());
+        }
+        auto e = std::make_unique<zb_estimator>();
+        e->ctx = ctx, e->net = net, e->kind = kind, e->lo = lo, e->hi = hi;
+        e->num_landmarks = estimator_landmarks(kind);
+        *out = e.release();
+        return ZB_OK;
+    });
+}
+
+void zb_estimator_destroy(zb_estimator *e) {
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    delete e;
+}
+
+int32_t zb_estimator_num_landmarks(const zb_estimator *e) { return e ? e->num_landmarks : 0; }
+
+zb_status zb_estimator_input_resolution(const zb_estimator *e, int32_t *w, int32_t *h) {
+    if (!e) return fail(ZB_ERR_INVALID_ARGUMENT, "estimator is NULL");
+    if (w) *w = e->net->plan.in_w;
+    if (h) *h = e->net->plan.in_h;
+    return ZB_OK;
+}
+
+zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const zb_view *views, const uint8_t *flip_x,
+                                int32_t n, float *out_landmarks, float *out_scalars) {
+    return guarded([&]() -> zb_status {
+        if (!e) return fail(ZB_ERR_INVALID_ARGUMENT, "estimator is NULL");
+        check_frames(frames, views, n);
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = e->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const Plan &pl = e->net->plan;
+        const int chunk = std::min(net_chunk(e->net), n);
+        e->ws.ensure(e->net, chunk, n);
+        e->h_stage.reserve((sizeof(ViewDev) + 4 * sizeof(float)) * n);
+        ViewDev *hv = e->h_stage.as<ViewDev>();
+        float *hfit = reinterpret_cast<float *>(hv + n);
+        for (int i = 0; i < n; i++) {
+            RRectF base = views ? rrect_from_view(views[i]) : full_view(frames->f.width, frames->f.height);
+            RRectF sampled;
+            fit_view(base, pl.in_w, pl.in_h, sampled, hfit + 4 * i);
+            hv[i] = view_dev(sampled, views ? views[i].frame : i, flip_x ? (flip_x[i] != 0) : 0);
+        }
+        const int L = e->num_landmarks;
+        e->d_views.reserve(sizeof(ViewDev) * n);
+        e->d_fit.reserve(4 * sizeof(float) * n);
+        e->d_lm.reserve(sizeof(float) * 3 * (size_t)L * n);
+        e->d_scalars.reserve(sizeof(float) * 2 * n);
+        CU(cudaMemcpyAsync(e->d_views.p, hv, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(e->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        LandmarkParams lp{};
+        lp.kind = (int)e->kind;
+        lp.num_landmarks = L;
+        lp.net_w = pl.in_w;
+        lp.net_h = pl.in_h;
+        lp.track_transform = 0;
+        Timer tm(ctx, s);
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int nc = std::min(chunk, n - c0);
+            launch_sample(frames->f, e->d_views.as<ViewDev>() + c0, nc, pl.in_w, pl.in_h, e->lo, e->hi, SAMPLE_NHWC4,
+                          tensor_ptr(e->net, e->ws, pl.input, c0), pl.tensors[pl.input].img_stride, s);
+            run_ops(e->net, e->ws, c0, nc, s);
+            const int s0 = (int)pl.outputs[0].per_image, s1 = (int)pl.outputs[1].per_image;
+            const int s2 = pl.outputs.size() > 2 ? (int)pl.outputs[2].per_image : 0;
+            launch_landmarks(e->ws.outs[0].as<float>() + (size_t)c0 * s0, s0, e->ws.outs[1].as<float>() + (size_t)c0 * s1,
+                             s1, s2 ? e->ws.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2,
+                             e->d_fit.as<float>() + 4 * c0, e->d_views.as<ViewDev>() + c0, nullptr, nc, lp,
+                             e->d_lm.as<float>() + (size_t)c0 * L * 3, e->d_scalars.as<float>() + 2 * c0, s);
+        }
+        CU(cudaGetLastError());
+        tm.stop();
+        copy_out(out_landmarks, e->d_lm.p, sizeof(float) * 3 * (size_t)L * n, s);
+        copy_out(out_scalars, e->d_scalars.p, sizeof(float) * 2 * n, s);
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        return ZB_OK;
+    });
+}
+
+// ---- fused face pipeline ------------------------------------------------------------------------------
+zb_status zb_face_pipeline_create(zb_ctx *ctx, zb_net *det_net, zb_net *lm_net, zb_face_pipeline **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !det_net || !lm_net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
+        try {
+            check_detector_net(det_net, ZB_DET_FACE_SHORT_RANGE);
+            check_estimator_net(lm_net, ZB_EST_FACE_MESH_V1);
+        } catch (const std::runtime_error &e) {
+            return fail(ZB_ERR_BAD_SHAPE, e.what());
+        }
+        auto p = std::make_unique<zb_face_pipeline>();
+        p->ctx = ctx, p->det_net = det_net, p->lm_net = lm_net;
+        *out = p.release();
+        return ZB_OK;
+    });
+}
+
+void zb_face_pipeline_destroy(zb_face_pipeline *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    delete p;
+}
+
+zb_status zb_face_pipeline_set_threshold(zb_face_pipeline *p, float t, float iou, zb_nms_mode m) {
+    if (!p) return fail(ZB_ERR_INVALID_ARGUMENT, "pipeline is NULL");
+    p->thresh = t, p->iou = iou, p->mode = (int)m;
+    return ZB_OK;
+}
+
+zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
+                               int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_flags,
+                               zb_view *out_rois) {
+    return guarded([&]() -> zb_status {
+        if (!p) return fail(ZB_ERR_INVALID_ARGUMENT, "pipeline is NULL");
+        if (cap <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "cap must be positive");
+        check_frames(frames, nullptr, n);
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = p->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const Plan &dpl = p->det_net->plan, &lpl = p->lm_net->plan;
+        const int chunk = std::min(net_chunk(p->det_net), n);
+        p->ws_det.ensure(p->det_net, chunk, n);
+        p->ws_lm.ensure(p->lm_net, chunk, n);
+        // every whole-frame view is the same rectangle: fit once, replicate with the frame index
+        p->h_stage.reserve((sizeof(ViewDev) + 4 * sizeof(float)) * n);
+        ViewDev *hv = p->h_stage.as<ViewDev>();
+        float *hfit = reinterpret_cast<float *>(hv + n);
+        {
+            RRectF sampled;
+            float fit[4];
+            fit_view(full_view(frames->f.width, frames->f.height), dpl.in_w, dpl.in_h, sampled, fit);
+            for (int i = 0; i < n; i++) {
+                hv[i] = view_dev(sampled, i, 0);
+                memcpy(hfit + 4 * i, fit, sizeof(fit));
+            }
+        }
+        const int L = 468;
+        p->d_views.reserve(sizeof(ViewDev) * n);
+        p->d_fit.reserve(4 * sizeof(float) * n);
+        p->d_dets.reserve(sizeof(DetDev) * (size_t)n * cap);
+        p->d_counts.reserve(sizeof(int) * n);
+        p->d_lm_views.reserve(sizeof(ViewDev) * n);
+        p->d_lm_fit.reserve(4 * sizeof(float) * n);
+        p->d_rois.reserve(sizeof(ViewHost) * n);
+        p->d_lm.reserve(sizeof(float) * 3 * (size_t)L * n);
+        p->d_scalars.reserve(sizeof(float) * 2 * n);
+        p->h_counts.reserve(sizeof(int) * n);
+        CU(cudaMemcpyAsync(p->d_views.p, hv, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(p->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        const DecodeParams dp = decode_params(ZB_DET_FACE_SHORT_RANGE, dpl, p->thresh, p->iou, p->mode, cap);
+        LandmarkParams lp{};
+        lp.kind = ZB_EST_FACE_MESH_V1;
+        lp.num_landmarks = L;
+        lp.net_w = lpl.in_w;
+        lp.net_h = lpl.in_h;
+        lp.track_transform = 1;
+        Timer tm(ctx, s);
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int nc = std::min(chunk, n - c0);
+            // detector
+            launch_sample(frames->f, p->d_views.as<ViewDev>() + c0, nc, dpl.in_w, dpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
+                          tensor_ptr(p->det_net, p->ws_det, dpl.input, c0), dpl.tensors[dpl.input].img_stride, s);
+            run_ops(p->det_net, p->ws_det, c0, nc, s);
+            launch_decode_nms(p->ws_det.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
+                              p->ws_det.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image,
+                              p->d_fit.as<float>() + 4 * c0, nc, dp, p->d_dets.as<DetDev>() + (size_t)c0 * cap,
+                              p->d_counts.as<int>() + c0, s);
+            // RoI -> landmark view (stays on device)
+            launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0, nc,
+                            lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0,
+                            p->d_rois.as<ViewHost>() + c0, s);
+            // landmarks
+            launch_sample(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lpl.in_w, lpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
+                          tensor_ptr(p->lm_net, p->ws_lm, lpl.input, c0), lpl.tensors[lpl.input].img_stride, s);
+            run_ops(p->lm_net, p->ws_lm, c0, nc, s);
+            const int s0 = (int)lpl.outputs[0].per_image, s1 = (int)lpl.outputs[1].per_image;
+            launch_landmarks(p->ws_lm.outs[0].as<float>() + (size_t)c0 * s0, s0,
+                             p->ws_lm.outs[1].as<float>() + (size_t)c0 * s1, s1, nullptr, 0,
+                             p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
+                             p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
+                             p->d_scalars.as<float>() + 2 * c0, s);
+        }
+        CU(cudaGetLastError());
+        tm.stop();
+        copy_out(out_dets, p->d_dets.p, sizeof(DetDev) * (size_t)n * cap, s);
+        copy_out(out_counts, p->d_counts.p, sizeof(int) * n, s);
+        copy_out(out_landmarks, p->d_lm.p, sizeof(float) * 3 * (size_t)L * n, s);
+        if (out_flags) {
+            // scalars are [n][2]; flags want [n]: strided copy
+            CU(cudaMemcpy2DAsync(out_flags, sizeof(float), p->d_scalars.p, 2 * sizeof(float), sizeof(float), n,
+                                 is_device_ptr(out_flags) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        }
+        copy_out(out_rois, p->d_rois.p, sizeof(ViewHost) * n, s);
+        CU(cudaMemcpyAsync(p->h_counts.p, p->d_counts.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        const int *hc = p->h_counts.as<int>();
+        for (int i = 0; i < n; i++)
+            if (hc[i] > cap)
+                return fail(ZB_ERR_CAPACITY, "frame " + std::to_string(i) + " produced " + std::to_string(hc[i]) +
+                                                 " detections; capacity is " + std::to_string(cap));
+        return ZB_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Host-side launch interface of the sm_100a kernels (implemented in kernels_conv.cu and
+// kernels_exact.cu).  Plain structs, no CUDA types beyond cudaStream_t.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.h"
+
+namespace zb {
+
+struct ActDev {
+    int kind;
+    float lo, hi;
+    const float *slope;
+};
+
+struct EpiDev {
+    const float *bias;
+    ActDev act1;
+    const float *res;          // residual tensor base (chunk-local) or nullptr
+    long long res_img_stride;
+    int res_H, res_W, res_Cs;  // residual tensor dims (before pooling)
+    int res_pool;
+    ActDev act2;
+};
+
+struct ConvDev {
+    const float *in;
+    long long in_img_stride;
+    int H, W, Cs_in;
+    float *out;
+    long long out_img_stride;
+    int Ho, Wo, out_pix_stride;
+    const float *w;            // [K][Ns]
+    int K, Ns, Nstore;
+    int kh, kw, sh, sw, pt, pl;
+    int M;                     // images * Ho * Wo
+    EpiDev epi;
+    // fused depthwise producer (OP_DWPW): `w`/K describe the pointwise stage
+    const float *dw_w;         // [kh*kw][Cs_in]
+    const float *dw_b;         // [Cs_in]
+    ActDev act_mid;
+};
+
+enum ConvMode { CONV_GATHER = 0, CONV_PW = 1, CONV_DWPW = 2 };
+
+// Counts one launch per call into *launch_counter when non-null.
+void launch_conv(const ConvDev &p, ConvMode mode, cudaStream_t s);
+void launch_dw(const ConvDev &p, cudaStream_t s);   // uses dw_w/dw_b = nullptr; w = [kh*kw][Cs], epi.bias
+void launch_maxpool2(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                     long long out_img_stride, int n, cudaStream_t s);
+void launch_resize2x(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                     long long out_img_stride, int n, cudaStream_t s);
+void launch_gap(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                long long out_img_stride, int n, cudaStream_t s);
+// out = act2(in + res) ; also used for standalone activations (res == nullptr -> act1 then act2)
+void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                    long long out_img_stride, int out_pix_stride, int Nstore, const EpiDev &epi, int n,
+                    cudaStream_t s);
+void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
+                          cudaStream_t s);
+
+// ---- exact (no-FMA) kernels: kernels_exact.cu -------------------------------------------------
+struct ViewDev {               // composed ViewData::rect + per-view constants
+    int frame;
+    float cx, cy, w, h;        // RotatedRect.rect
+    float cosr, sinr;          // cos/sin of the rotation (f32, computed like the reference)
+    int flip_x;
+    int valid;                 // 0: skip sampling (tensor filled with `lo`)
+};
+
+struct FramesDev {
+    const uint8_t *base;
+    int width, height;
+    long long row_stride;      // bytes
+    long long frame_stride;    // bytes
+    int n;
+};
+
+// Build ViewDev[n] on the device from host-style zb_view records (cos/sin in double, rounded).
+struct ViewHost { int frame; float cx, cy, w, h, radians; };
+
+// image->tensor: NCHW planar f32 [n,3,h,w] / NHWC3 [n,h,w,3] (public layouts) or NHWC4 (internal)
+enum SampleLayout { SAMPLE_NCHW = 0, SAMPLE_NHWC3 = 1, SAMPLE_NHWC4 = 2 };
+void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
+                   SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s);
+
+// Detector front: fit each given view (or whole frame) to the network aspect and compose (detection.rs:224-227).
+// in_views == nullptr -> whole frames [first_frame, first_frame+n).
+void launch_fit_views(const FramesDev &f, const ViewHost *in_views, int first_frame, int n, int net_w, int net_h,
+                      ViewDev *out_views, float *out_fit /*[n][4]: scale, tl.x, tl.y, pad*/, cudaStream_t s);
+
+struct DetDev {                // mirrors zb_detection
+    float confidence, angle, cx, cy, w, h;
+    float kp[14];
+    int num_kp;
+    int anchor;
+};
+
+struct DecodeParams {
+    int num_anchors, num_params, num_kp;
+    int net_w, net_h;
+    int l0_boxes, l0_w, l0_h, l1_boxes, l1_w, l1_h;   // SSD layers (ssd.rs:96-119)
+    int angle_kind;            // 0 face (kp1-kp0 vs X), 1 palm (kp0-kp2 vs Y)
+    float thresh, iou_thresh;
+    int nms_mode;              // 0 remove, 1 average
+    int cap;
+};
+// one CTA per image: sigmoid/threshold/decode -> NMS -> remap (fit: scale, tl.x, tl.y)
+void launch_decode_nms(const float *boxes, const float *scores, const float *fit, int n, const DecodeParams &p,
+                       DetDev *out, int *out_counts, cudaStream_t s);
+
+// Face pipeline glue: best detection -> RoI -> tracker view (landmark.rs:465-466) composed with the full frame.
+void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, int cap, int first_frame, int n,
+                     int net_w, int net_h, ViewDev *out_views, float *out_fit, ViewHost *out_view_rects,
+                     cudaStream_t s);
+
+struct LandmarkParams {
+    int kind;                  // zb_estimator_kind
+    int num_landmarks;
+    int net_w, net_h;
+    int track_transform;       // 1: also apply view_rect.transform_out (LandmarkTracker, landmark.rs:482-486)
+};
+// out0/out1/out2: raw network outputs (per-image strides s0,s1,s2)
+void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
+                      const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
+                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s);
+
+void launch_compose_views(const ViewHost *in_views, const uint8_t *flip, int n, ViewDev *out, cudaStream_t s);
+
+extern long long g_launch_count;   // total kernel launches issued by this library (process-wide)
+
+}  // namespace zb

@@ -1,0 +1,456 @@
+// sm_100a kernels for the CNN forward pass (NHWC f32, FMA allowed).
+//
+//  conv_gemm_kernel  — every full convolution (stems 5x5/3x3 s2, 2x2 s2, 1x1 pointwise, dense heads,
+//                      Gemm) as an implicit GEMM: M = images*Ho*Wo pixels, N = Cout, K = kh*kw*Cs_in.
+//                      A tile gathered (or, for OP_DWPW, COMPUTED by the depthwise stage on the fly so the
+//                      depthwise output never touches HBM), W tile staged in shared memory, register-tiled
+//                      FFMA micro-kernel, fused epilogue: bias -> act1 -> (+ residual, optionally read
+//                      through a 2x2 max-pool and zero channel-pad) -> act2 -> NHWC / head-layout store.
+//  dw_kernel         — standalone depthwise kxk.
+//  small ops         — 2x2 max-pool, bilinear x2 resize (half_pixel), global average pool, eltwise add/act,
+//                      NCHW -> NHWC4 input conversion.
+//
+// Replaces the engine call `ort.session.run` / `plan.run` (crates/zaru/src/nn/mod.rs:496, :528).
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace zb {
+
+long long g_launch_count = 0;
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, const ActDev &a, int n) {
+    switch (a.kind) {
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_PRELU: return v < 0.0f ? v * __ldg(a.slope + n) : v;
+        case ACT_CLIP: return fminf(fmaxf(v, a.lo), a.hi);
+        case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// Residual value for output pixel (img, oy, ox), channel n (n % 4 == 0 when vectorised by the caller).
+__device__ __forceinline__ float residual_at(const EpiDev &e, int img, int oy, int ox, int n) {
+    if (n >= e.res_Cs) return 0.0f;
+    const float *base = e.res + (long long)img * e.res_img_stride;
+    if (!e.res_pool) return __ldg(base + ((long long)oy * e.res_W + ox) * e.res_Cs + n);
+    const float *p = base + ((long long)(2 * oy) * e.res_W + 2 * ox) * e.res_Cs + n;
+    float a = __ldg(p), b = __ldg(p + e.res_Cs);
+    float c = __ldg(p + (long long)e.res_W * e.res_Cs), d = __ldg(p + (long long)e.res_W * e.res_Cs + e.res_Cs);
+    return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+__device__ __forceinline__ float4 residual4_at(const EpiDev &e, int img, int oy, int ox, int n) {
+    if (n >= e.res_Cs) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *base = e.res + (long long)img * e.res_img_stride;
+    if (!e.res_pool) return ldg4(base + ((long long)oy * e.res_W + ox) * e.res_Cs + n);
+    const float *p = base + ((long long)(2 * oy) * e.res_W + 2 * ox) * e.res_Cs + n;
+    float4 a = ldg4(p), b = ldg4(p + e.res_Cs);
+    float4 c = ldg4(p + (long long)e.res_W * e.res_Cs), d = ldg4(p + (long long)e.res_W * e.res_Cs + e.res_Cs);
+    return make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
+                       fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution.  MODE: 0 gather (any kh,kw,stride,pads), 1 pointwise (1x1/s1/p0),
+// 2 fused depthwise producer.
+// ------------------------------------------------------------------------------------------------
+constexpr int BK = 32;
+
+template <int BM, int BN, int TM, int TN, int MODE>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const ConvDev p) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int TXN = BN / TN;
+    constexpr int A_PER_THREAD = (BM * BK / 4) / NT;   // float4 A elements per thread per chunk
+    constexpr int W_PER_THREAD = (BK * BN / 4) / NT;
+    static_assert(NT % BM == 0 || BM % NT == 0, "thread->pixel mapping");
+    static_assert((BM * BK / 4) % NT == 0 && (BK * BN / 4) % NT == 0, "tile divisibility");
+
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Ws[BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TXN, ty = tid / TXN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int HoWo = p.Ho * p.Wo;
+
+    // --- per-thread A-load assignment: element e = tid + i*NT ; m = e % BM ; kq = e / BM ---------------
+    // NT is a multiple of BM (or BM == NT), so every element of this thread has the same pixel m.
+    const int a_m = tid % BM;
+    const int a_kq0 = tid / BM;                 // first k-quad; subsequent ones step by NT/BM
+    constexpr int A_KQ_STEP = NT / BM > 0 ? NT / BM : 1;
+    const int gm = m0 + a_m;
+    const bool a_valid = gm < p.M;
+    int a_img = 0, a_oy = 0, a_ox = 0;
+    if (a_valid) {
+        a_img = gm / HoWo;
+        int r = gm - a_img * HoWo;
+        a_oy = r / p.Wo;
+        a_ox = r - a_oy * p.Wo;
+    }
+    const float *a_base = p.in + (long long)a_img * p.in_img_stride;
+    const int iy0 = a_oy * p.sh - p.pt, ix0 = a_ox * p.sw - p.pl;
+
+    float4 a_reg[A_PER_THREAD];
+    float4 w_reg[W_PER_THREAD];
+
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_PER_THREAD; i++) {
+            const int kq = a_kq0 + i * A_KQ_STEP;
+            const int k = k0 + kq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_valid && k < p.K) {
+                if (MODE == CONV_PW) {
+                    v = ldg4(a_base + ((long long)a_oy * p.W + a_ox) * p.Cs_in + k);
+                } else if (MODE == CONV_GATHER) {
+                    const int tap = k / p.Cs_in, c = k - tap * p.Cs_in;
+                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                    const int iy = iy0 + ky, ix = ix0 + kx;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                        v = ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + c);
+                } else {   // CONV_DWPW: depthwise kh x kw over channels [k, k+4)
+                    v = ldg4(p.dw_b + k);
+                    for (int ky = 0; ky < p.kh; ky++) {
+                        const int iy = iy0 + ky;
+                        if (iy < 0 || iy >= p.H) continue;
+                        for (int kx = 0; kx < p.kw; kx++) {
+                            const int ix = ix0 + kx;
+                            if (ix < 0 || ix >= p.W) continue;
+                            const float4 x = ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + k);
+                            const float4 wv = ldg4(p.dw_w + (ky * p.kw + kx) * p.Cs_in + k);
+                            v.x = fmaf(x.x, wv.x, v.x);
+                            v.y = fmaf(x.y, wv.y, v.y);
+                            v.z = fmaf(x.z, wv.z, v.z);
+                            v.w = fmaf(x.w, wv.w, v.w);
+                        }
+                    }
+                    v.x = apply_act(v.x, p.act_mid, k);
+                    v.y = apply_act(v.y, p.act_mid, k + 1);
+                    v.z = apply_act(v.z, p.act_mid, k + 2);
+                    v.w = apply_act(v.w, p.act_mid, k + 3);
+                }
+            }
+            a_reg[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < W_PER_THREAD; i++) {
+            const int e = tid + i * NT;
+            const int nq = e % (BN / 4), k = e / (BN / 4);
+            const int gk = k0 + k, gn = n0 + nq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < p.K && gn < p.Ns) v = ldg4(p.w + (long long)gk * p.Ns + gn);
+            w_reg[i] = v;
+        }
+    };
+
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int i = 0; i < A_PER_THREAD; i++) {
+            const int kq = a_kq0 + i * A_KQ_STEP;
+            As[kq * 4 + 0][a_m] = a_reg[i].x;
+            As[kq * 4 + 1][a_m] = a_reg[i].y;
+            As[kq * 4 + 2][a_m] = a_reg[i].z;
+            As[kq * 4 + 3][a_m] = a_reg[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < W_PER_THREAD; i++) {
+            const int e = tid + i * NT;
+            const int nq = e % (BN / 4), k = e / (BN / 4);
+            *reinterpret_cast<float4 *>(&Ws[k][nq * 4]) = w_reg[i];
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+    load_chunk(0);
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        store_chunk();
+        __syncthreads();
+        if (k0 + BK < p.K) load_chunk(k0 + BK);
+        const int kmax = min(BK, p.K - k0);
+        for (int kk = 0; kk < kmax; kk += 4) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                const int k = kk + k4;
+                float a[TM], b[TN];
+#pragma unroll
+                for (int i = 0; i < TM; i += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(&As[k][ty * TM + i]);
+                    a[i] = v.x, a[i + 1] = v.y, a[i + 2] = v.z, a[i + 3] = v.w;
+                }
+#pragma unroll
+                for (int j = 0; j < TN; j += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(&Ws[k][tx * TN + j]);
+                    b[j] = v.x, b[j + 1] = v.y, b[j + 2] = v.z, b[j + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < TM; i++)
+#pragma unroll
+                    for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // --- epilogue ------------------------------------------------------------------------------------
+    const EpiDev &e = p.epi;
+    const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0);
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        const int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        const int img = m / HoWo;
+        const int r = m - img * HoWo;
+        const int oy = r / p.Wo, ox = r - oy * p.Wo;
+        float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const int n = n0 + tx * TN + j;
+            if (n >= p.Nstore) continue;
+            float v[4] = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
+            if (n + 3 < p.Ns) {
+                const float4 b = ldg4(e.bias + n);
+                v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (n + q < p.Ns) v[q] += __ldg(e.bias + n + q);
+            }
+            if (e.act1.kind != ACT_NONE) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (n + q < p.Ns) v[q] = apply_act(v[q], e.act1, n + q);
+            }
+            if (e.res) {
+                if ((e.res_Cs % 4) == 0) {
+                    const float4 rr = residual4_at(e, img, oy, ox, n);
+                    v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) v[q] += residual_at(e, img, oy, ox, n + q);
+                }
+            }
+            if (e.act2.kind != ACT_NONE) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (n + q < p.Ns) v[q] = apply_act(v[q], e.act2, n + q);
+            }
+            if (vec_ok) {
+                *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (n + q < p.Nstore) orow[n + q] = v[q];
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+void launch_conv_cfg(const ConvDev &p, ConvMode mode, cudaStream_t s) {
+    dim3 grid((p.M + BM - 1) / BM, (p.Ns + BN - 1) / BN);
+    dim3 block((BM / TM) * (BN / TN));
+    switch (mode) {
+        case CONV_GATHER: conv_gemm_kernel<BM, BN, TM, TN, CONV_GATHER><<<grid, block, 0, s>>>(p); break;
+        case CONV_PW: conv_gemm_kernel<BM, BN, TM, TN, CONV_PW><<<grid, block, 0, s>>>(p); break;
+        case CONV_DWPW: conv_gemm_kernel<BM, BN, TM, TN, CONV_DWPW><<<grid, block, 0, s>>>(p); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standalone depthwise conv: one thread per (output pixel, 4 channels).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dw_kernel(const ConvDev p) {
+    const int cq_n = p.Cs_in / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.M * cq_n) return;
+    const int cq = (int)(idx % cq_n);
+    const int m = (int)(idx / cq_n);
+    const int HoWo = p.Ho * p.Wo;
+    const int img = m / HoWo;
+    const int r = m - img * HoWo;
+    const int oy = r / p.Wo, ox = r - oy * p.Wo;
+    const int c = cq * 4;
+    const float *base = p.in + (long long)img * p.in_img_stride;
+    const int iy0 = oy * p.sh - p.pt, ix0 = ox * p.sw - p.pl;
+    float4 v = ldg4(p.epi.bias + c);
+    for (int ky = 0; ky < p.kh; ky++) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= p.H) continue;
+        for (int kx = 0; kx < p.kw; kx++) {
+            const int ix = ix0 + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const float4 x = ldg4(base + ((long long)iy * p.W + ix) * p.Cs_in + c);
+            const float4 wv = ldg4(p.w + (ky * p.kw + kx) * p.Cs_in + c);
+            v.x = fmaf(x.x, wv.x, v.x);
+            v.y = fmaf(x.y, wv.y, v.y);
+            v.z = fmaf(x.z, wv.z, v.z);
+            v.w = fmaf(x.w, wv.w, v.w);
+        }
+    }
+    const EpiDev &e = p.epi;
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) o[q] = apply_act(o[q], e.act1, c + q);
+    if (e.res) {
+        const float4 rr = residual4_at(e, img, oy, ox, c);
+        o[0] += rr.x, o[1] += rr.y, o[2] += rr.z, o[3] += rr.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) o[q] = apply_act(o[q], e.act2, c + q);
+    float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
+    *reinterpret_cast<float4 *>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float *in, long long in_img_stride, int H, int W, int Cs,
+                                                       float *out, long long out_img_stride, int n) {
+    const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1, cq_n = Cs / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * Ho * Wo * cq_n) return;
+    const int cq = (int)(idx % cq_n);
+    long long m = idx / cq_n;
+    const int ox = (int)(m % Wo);
+    m /= Wo;
+    const int oy = (int)(m % Ho);
+    const int img = (int)(m / Ho);
+    const float *p = in + (long long)img * in_img_stride + ((long long)(2 * oy) * W + 2 * ox) * Cs + cq * 4;
+    const float4 a = ldg4(p), b = ldg4(p + Cs), c = ldg4(p + (long long)W * Cs), d = ldg4(p + (long long)W * Cs + Cs);
+    float4 o = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
+                           fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
+    *reinterpret_cast<float4 *>(out + (long long)img * out_img_stride + ((long long)oy * Wo + ox) * Cs + cq * 4) = o;
+}
+
+// ONNX Resize, mode=linear, coordinate_transformation_mode=half_pixel, scale 2 (palm FPN).
+__global__ void __launch_bounds__(256) resize2x_kernel(const float *in, long long in_img_stride, int H, int W, int Cs,
+                                                       float *out, long long out_img_stride, int n) {
+    const int Ho = 2 * H, Wo = 2 * W, cq_n = Cs / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * Ho * Wo * cq_n) return;
+    const int cq = (int)(idx % cq_n);
+    long long m = idx / cq_n;
+    const int ox = (int)(m % Wo);
+    m /= Wo;
+    const int oy = (int)(m % Ho);
+    const int img = (int)(m / Ho);
+    float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.0f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.0f);
+    int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+    int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float fy = sy - (float)y0, fx = sx - (float)x0;
+    const float *b = in + (long long)img * in_img_stride + cq * 4;
+    const float4 v00 = ldg4(b + ((long long)y0 * W + x0) * Cs), v01 = ldg4(b + ((long long)y0 * W + x1) * Cs);
+    const float4 v10 = ldg4(b + ((long long)y1 * W + x0) * Cs), v11 = ldg4(b + ((long long)y1 * W + x1) * Cs);
+    auto lerp2 = [&](float a00, float a01, float a10, float a11) {
+        const float top = a00 + (a01 - a00) * fx, bot = a10 + (a11 - a10) * fx;
+        return top + (bot - top) * fy;
+    };
+    float4 o = make_float4(lerp2(v00.x, v01.x, v10.x, v11.x), lerp2(v00.y, v01.y, v10.y, v11.y),
+                           lerp2(v00.z, v01.z, v10.z, v11.z), lerp2(v00.w, v01.w, v10.w, v11.w));
+    *reinterpret_cast<float4 *>(out + (long long)img * out_img_stride + ((long long)oy * Wo + ox) * Cs + cq * 4) = o;
+}
+
+__global__ void __launch_bounds__(256) gap_kernel(const float *in, long long in_img_stride, int H, int W, int Cs,
+                                                  float *out, long long out_img_stride, int n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * Cs) return;
+    const int c = (int)(idx % Cs);
+    const int img = (int)(idx / Cs);
+    const float *b = in + (long long)img * in_img_stride + c;
+    float acc = 0.f;
+    const int hw = H * W;
+    for (int i = 0; i < hw; i++) acc += __ldg(b + (long long)i * Cs);
+    out[(long long)img * out_img_stride + c] = acc / (float)hw;
+}
+
+__global__ void __launch_bounds__(256) eltwise_kernel(const float *in, long long in_img_stride, int H, int W, int Cs,
+                                                      float *out, long long out_img_stride, int out_pix_stride,
+                                                      int Nstore, const EpiDev e, int n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * H * W * Cs) return;
+    const int c = (int)(idx % Cs);
+    long long m = idx / Cs;
+    const int ox = (int)(m % W);
+    m /= W;
+    const int oy = (int)(m % H);
+    const int img = (int)(m / H);
+    if (c >= Nstore) return;
+    float v = __ldg(in + (long long)img * in_img_stride + ((long long)oy * W + ox) * Cs + c);
+    v = apply_act(v, e.act1, c);
+    if (e.res) v += residual_at(e, img, oy, ox, c);
+    v = apply_act(v, e.act2, c);
+    out[(long long)img * out_img_stride + ((long long)oy * W + ox) * out_pix_stride + c] = v;
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float *in, int n, int H, int W, float *out,
+                                                            long long out_img_stride) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long hw = (long long)H * W;
+    if (idx >= (long long)n * hw) return;
+    const int img = (int)(idx / hw);
+    const long long pix = idx - (long long)img * hw;
+    const float *b = in + (long long)img * 3 * hw + pix;
+    float4 o = make_float4(__ldg(b), __ldg(b + hw), __ldg(b + 2 * hw), 0.f);
+    *reinterpret_cast<float4 *>(out + (long long)img * out_img_stride + pix * 4) = o;
+}
+
+inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+}  // namespace
+
+void launch_conv(const ConvDev &p, ConvMode mode, cudaStream_t s) {
+    g_launch_count++;
+    if (p.Ns <= 32) launch_conv_cfg<128, 32, 4, 4>(p, mode, s);
+    else if (p.Ns <= 64) launch_conv_cfg<128, 64, 8, 4>(p, mode, s);
+    else launch_conv_cfg<64, 128, 4, 8>(p, mode, s);
+}
+
+void launch_dw(const ConvDev &p, cudaStream_t s) {
+    g_launch_count++;
+    long long total = (long long)p.M * (p.Cs_in / 4);
+    dw_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
+}
+
+void launch_maxpool2(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                     long long out_img_stride, int n, cudaStream_t s) {
+    g_launch_count++;
+    long long total = (long long)n * ((H - 2) / 2 + 1) * ((W - 2) / 2 + 1) * (Cs / 4);
+    maxpool2_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride, n);
+}
+
+void launch_resize2x(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                     long long out_img_stride, int n, cudaStream_t s) {
+    g_launch_count++;
+    long long total = (long long)n * 4 * H * W * (Cs / 4);
+    resize2x_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride, n);
+}
+
+void launch_gap(const float *in, long long in_img_stride, int H, int W, int Cs, float *out, long long out_img_stride,
+                int n, cudaStream_t s) {
+    g_launch_count++;
+    gap_kernel<<<blocks_for((long long)n * Cs, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride, n);
+}
+
+void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int Cs, float *out,
+                    long long out_img_stride, int out_pix_stride, int Nstore, const EpiDev &epi, int n,
+                    cudaStream_t s) {
+    g_launch_count++;
+    long long total = (long long)n * H * W * Cs;
+    eltwise_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride,
+                                                          out_pix_stride, Nstore, epi, n);
+}
+
+void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
+                          cudaStream_t s) {
+    g_launch_count++;
+    nchw_to_nhwc4_kernel<<<blocks_for((long long)n * H * W, 256), 256, 0, s>>>(in_nchw, n, H, W, out, out_img_stride);
+}
+
+}  // namespace zb

@@ -1,0 +1,461 @@
+// sm_100a kernels whose arithmetic must reproduce the reference's scalar f32 code bit for bit:
+// image->tensor sampling, SSD decode + NMS + remap, RoI/view algebra, landmark unpacking.
+// THIS FILE IS COMPILED WITH -fmad=false: every mul/add/sub/div rounds separately, like Rust.
+//
+//   sample_kernel ....... Cnn image_map closure + sample + ViewData::image_coord + ColorMapper::map
+//                         (crates/zaru/src/nn/mod.rs:54-73, :156-166; image/mod.rs:224-247)
+//   decode_nms_kernel ... extract_outputs / extract_detection (face/detection.rs:96-157,
+//                         hand/detection.rs:108-179), Anchors::calculate (detection/ssd.rs:96-119),
+//                         NonMaxSuppression::process (detection/nms.rs:59-145), Rect::iou
+//                         (zaru-image/src/rect.rs:193-214), remap (detection.rs:245-267)
+//   face_roi_kernel ..... examples/facemesh.rs:49-54 + LandmarkTracker::track (landmark.rs:465-466)
+//                         + Estimator::estimate_impl view fitting (landmark.rs:320-323)
+//   landmarks_kernel .... Network::extract impls + Estimator remap (landmark.rs:336-345) + tracker
+//                         transform_out (landmark.rs:482-486)
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "geom.h"
+#include "kernels.h"
+
+namespace zb {
+namespace {
+
+__device__ __forceinline__ float sigmoid_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// Rust `as u32` on a rounded f32 kept in float form (saturating, NaN -> 0), then `as f32`.
+__device__ __forceinline__ float sat_u32_as_f32(float v) {
+    if (!(v > 0.0f)) return 0.0f;                 // negatives and NaN -> 0
+    if (v >= 4294967296.0f) return 4294967296.0f; // u32::MAX as f32
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
+                                                     int out_h, float lo, float hi, int layout,
+                                                     float *__restrict__ out, long long out_img_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int img = blockIdx.z;
+    if (x >= out_w) return;
+    const ViewDev v = views[img];
+
+    unsigned rgba = 0u;   // Color::NONE
+    if (v.valid) {
+        const int xs = v.flip_x ? (out_w - 1 - x) : x;
+        // sample(): x = (u * view_w).round() as u32 with u = x as f32 / w as f32   (nn/mod.rs:54-58)
+        const float u = (float)xs / (float)out_w;
+        const float vv = (float)y / (float)out_h;
+        const float sx = sat_u32_as_f32(roundf(u * v.w));
+        const float sy = sat_u32_as_f32(roundf(vv * v.h));
+        // ViewData::image_coord (image/mod.rs:224-241)
+        RRectF rr;
+        rr.r.cx = v.cx, rr.r.cy = v.cy, rr.r.w = v.w, rr.r.h = v.h;
+        rr.c = v.cosr, rr.s = v.sinr, rr.rad = 0.f;
+        float px, py;
+        transform_out(rr, sx + 0.5f, sy + 0.5f, px, py);
+        const float fx = roundf(px - 0.5f), fy = roundf(py - 0.5f);
+        const bool reject = fx < 0.0f || fy < 0.0f || ceilf(fx) >= 4294967296.0f || ceilf(fy) >= 4294967296.0f;
+        if (!reject) {
+            // `x.round() as u32`: NaN -> 0
+            const unsigned ix = (fx == fx) ? (unsigned)fx : 0u;
+            const unsigned iy = (fy == fy) ? (unsigned)fy : 0u;
+            if (ix < (unsigned)f.width && iy < (unsigned)f.height) {
+                const uint8_t *p = f.base + (long long)v.frame * f.frame_stride + (long long)iy * f.row_stride +
+                                   (long long)ix * 4;
+                rgba = __ldg(reinterpret_cast<const unsigned *>(p));
+            }
+        }
+    }
+    // ColorMapper::map (nn/mod.rs:156-166): col as f32 * ((end - start) / 255.0) + start
+    const float adjust = (hi - lo) / 255.0f;
+    const float r = (float)(rgba & 0xFFu) * adjust + lo;
+    const float g = (float)((rgba >> 8) & 0xFFu) * adjust + lo;
+    const float b = (float)((rgba >> 16) & 0xFFu) * adjust + lo;
+    float *o = out + (long long)img * out_img_stride;
+    const long long pix = (long long)y * out_w + x;
+    if (layout == SAMPLE_NHWC4) {
+        *reinterpret_cast<float4 *>(o + pix * 4) = make_float4(r, g, b, 0.0f);
+    } else if (layout == SAMPLE_NHWC3) {
+        o[pix * 3 + 0] = r, o[pix * 3 + 1] = g, o[pix * 3 + 2] = b;
+    } else {
+        const long long hw = (long long)out_w * out_h;
+        o[pix] = r, o[hw + pix] = g, o[2 * hw + pix] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Detection decode for anchor i, field f:
+//   0 cx, 1 cy, 2 w, 3 h, 4 angle, 5+2k kp_k.x, 6+2k kp_k.y   (network-input pixel units)
+// ------------------------------------------------------------------------------------------------
+struct AnchorXY { float x, y; };
+
+__device__ __forceinline__ AnchorXY anchor_of(const DecodeParams &p, int i) {
+    // Anchors::calculate (ssd.rs:96-119): layers in order, y-major, x, then boxes_per_cell copies.
+    int w = p.l0_w, h = p.l0_h, b = p.l0_boxes;
+    const int n0 = p.l0_w * p.l0_h * p.l0_boxes;
+    if (i >= n0) {
+        i -= n0;
+        w = p.l1_w, h = p.l1_h, b = p.l1_boxes;
+    }
+    const int cell = i / b;
+    const int cy = cell / w, cx = cell - cy * w;
+    AnchorXY a;
+    a.x = ((float)cx + 0.5f) / (float)w;
+    a.y = ((float)cy + 0.5f) / (float)h;
+    return a;
+}
+
+// Vec2::signed_angle_to (zaru-linalg vector.rs:568-573)
+__device__ __forceinline__ float signed_angle_to(float ax, float ay, float bx, float by) {
+    const float perp = ax * by - ay * bx;
+    const float dot = (0.0f + ax * bx) + ay * by;
+    return -atan2f(perp, dot);
+}
+
+__device__ float decode_field(const DecodeParams &p, const float *__restrict__ bp, int anchor, int field) {
+    const AnchorXY a = anchor_of(p, anchor);
+    const float isx = (float)p.net_w, isy = (float)p.net_h;
+    const float cx = bp[0] + a.x * isx;
+    const float cy = bp[1] + a.y * isy;
+    if (field == 0) return cx;
+    if (field == 1) return cy;
+    if (field == 2) return bp[2];
+    if (field == 3) return bp[3];
+    if (field == 4) {
+        // keypoint k = (b[4+2k], b[5+2k]) + center * input_size   (center already in pixels: SURVEY F4)
+        if (p.angle_kind == 0) {
+            const float lx = bp[4] + cx * isx, ly = bp[5] + cy * isy;
+            const float rx = bp[6] + cx * isx, ry = bp[7] + cy * isy;
+            return signed_angle_to(rx - lx, ry - ly, 1.0f, 0.0f);
+        }
+        const float wx = bp[4] + cx * isx, wy = bp[5] + cy * isy;      // Wrist = kp 0
+        const float fx = bp[8] + cx * isx, fy = bp[9] + cy * isy;      // MiddleFingerMcp = kp 2
+        return signed_angle_to(wx - fx, wy - fy, 0.0f, 1.0f);
+    }
+    const int k = field - 5;
+    return (k & 1) ? (bp[4 + k] + cy * isy) : (bp[4 + k] + cx * isx);
+}
+
+// f32::total_cmp key (zaru-image/src/num.rs:5-28)
+__device__ __forceinline__ int total_key(float v) {
+    int b = __float_as_int(v);
+    return b ^ (int)(((unsigned)(b >> 31)) >> 1);
+}
+
+// Rect::iou (rect.rs:193-214) on (cx, cy, w, h)
+__device__ __forceinline__ float rect_area_span(float minx, float miny, float maxx, float maxy) {
+    // Rect::bounding([min,max]) -> span_inner -> from_top_left(x_min, y_min, x_max - x_min, y_max - y_min); area = w*h
+    return (maxx - minx) * (maxy - miny);
+}
+__device__ __forceinline__ float iou_ref(float4 a, float4 b) {
+    const float ax = a.x - a.z * 0.5f, ay = a.y - a.w * 0.5f;
+    const float bx = b.x - b.z * 0.5f, by = b.y - b.w * 0.5f;
+    const float minx = fmaxf(ax, bx), miny = fmaxf(ay, by);
+    const float maxx = fminf(ax + a.z, bx + b.z), maxy = fminf(ay + a.w, by + b.w);
+    float inter = 0.0f;
+    if (!(minx > maxx || miny > maxy)) inter = rect_area_span(minx, miny, maxx, maxy);
+    const float uni = a.z * a.w + b.z * b.w - inter;
+    return inter / uni;
+}
+
+// Order-preserving block compaction helper: returns the exclusive prefix of `flag` over the block and the total.
+__device__ __forceinline__ int block_excl_scan(int flag, int *warp_sums, int &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < nw; w++) {
+        const int s = warp_sums[w];
+        if (w < wid) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    total = tot;
+    return base + in_warp;
+}
+
+// One CTA per image.  Dynamic smem: A * (int idx + float conf + float4 box + int order + int rem + int tmp)
+__global__ void __launch_bounds__(256) decode_nms_kernel(const float *__restrict__ boxes,
+                                                         const float *__restrict__ scores,
+                                                         const float *__restrict__ fit, const DecodeParams p,
+                                                         DetDev *__restrict__ out, int *__restrict__ out_counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = p.num_anchors;
+    float4 *c_box = reinterpret_cast<float4 *>(smem_raw);
+    float *c_conf = reinterpret_cast<float *>(c_box + A);
+    int *c_idx = reinterpret_cast<int *>(c_conf + A);
+    int *rem = c_idx + A;      // remaining candidates, ascending (confidence, index)
+    int *tmp = rem + A;        // scratch for compaction
+    int *members = tmp + A;    // cluster members (ascending), seed excluded
+    __shared__ int warp_sums[8];
+
+    const int img = blockIdx.x;
+    const float *bx = boxes + (long long)img * A * p.num_params;
+    const float *sc = scores + (long long)img * A;
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    // 1. sigmoid + threshold, compact in anchor order  (face/detection.rs:109-113: `if conf < thresh {continue}`)
+    int n = 0;
+    for (int base = 0; base < A; base += T) {
+        const int i = base + tid;
+        float conf = 0.f;
+        int keep = 0;
+        if (i < A) {
+            conf = sigmoid_ref(sc[i]);
+            keep = !(conf < p.thresh);
+        }
+        int tot;
+        const int pos = block_excl_scan(keep, warp_sums, tot);
+        if (keep) {
+            c_idx[n + pos] = i;
+            c_conf[n + pos] = conf;
+            const float *bp = bx + (long long)i * p.num_params;
+            c_box[n + pos] = make_float4(decode_field(p, bp, i, 0), decode_field(p, bp, i, 1), bp[2], bp[3]);
+        }
+        n += tot;
+    }
+    __syncthreads();
+
+    // 2. stable ascending rank sort by TotalF32(confidence)  (nms.rs:66; tie order fixed as stable)
+    for (int c = tid; c < n; c += T) {
+        const int kc = total_key(c_conf[c]);
+        int rank = 0;
+        for (int d = 0; d < n; d++) {
+            const int kd = total_key(c_conf[d]);
+            rank += (kd < kc) || (kd == kc && d < c);
+        }
+        rem[rank] = c;
+    }
+    __syncthreads();
+
+    // 3. greedy seed loop
+    const float scale = fit[img * 4 + 0], tlx = fit[img * 4 + 1], tly = fit[img * 4 + 2];
+    const int nfields = 5 + 2 * p.num_kp;
+    int n_rem = n, n_out = 0;
+    while (n_rem > 0) {
+        const int seed = rem[n_rem - 1];
+        const float4 sbox = c_box[seed];
+        n_rem -= 1;
+        __syncthreads();
+        // classify the remaining candidates against the seed, preserving order
+        int n_keep = 0, n_mem = 0;
+        for (int base = 0; base < n_rem; base += T) {
+            const int j = base + tid;
+            int c = -1, is_mem = 0, is_keep = 0;
+            if (j < n_rem) {
+                c = rem[j];
+                const float iou = iou_ref(sbox, c_box[c]);
+                if (p.nms_mode == 1) {
+                    is_mem = iou >= p.iou_thresh;      // nms.rs:86
+                    is_keep = !is_mem;
+                } else {
+                    is_keep = iou < p.iou_thresh;      // nms.rs:73 (NaN is dropped)
+                }
+            }
+            int tk, tm;
+            const int pk = block_excl_scan(is_keep, warp_sums, tk);
+            const int pm = block_excl_scan(is_mem, warp_sums, tm);
+            if (is_keep) tmp[n_keep + pk] = c;
+            if (is_mem) members[n_mem + pm] = c;
+            n_keep += tk;
+            n_mem += tm;
+        }
+        __syncthreads();
+        for (int j = tid; j < n_keep; j += T) rem[j] = tmp[j];
+        n_rem = n_keep;
+
+        // output
+        if (n_out < p.cap) {
+            DetDev *o = out + (long long)img * p.cap + n_out;
+            if (tid < nfields) {
+                float val;
+                const float *sbp = bx + (long long)c_idx[seed] * p.num_params;
+                if (p.nms_mode == 1) {
+                    // confidence-weighted average over [seed, members ascending]  (nms.rs:93-131)
+                    float acc = 0.0f, divisor = 0.0f;
+                    {
+                        const float factor = c_conf[seed];
+                        divisor = divisor + factor;
+                        acc = acc + decode_field(p, sbp, c_idx[seed], tid) * factor;
+                    }
+                    for (int j = 0; j < n_mem; j++) {
+                        const int c = members[j];
+                        const float factor = c_conf[c];
+                        divisor = divisor + factor;
+                        acc = acc + decode_field(p, bx + (long long)c_idx[c] * p.num_params, c_idx[c], tid) * factor;
+                    }
+                    val = acc / divisor;
+                } else {
+                    val = decode_field(p, sbp, c_idx[seed], tid);
+                }
+                // remap to the caller's coordinates (detection.rs:245-267)
+                if (tid == 0) o->cx = val * scale + tlx;
+                else if (tid == 1) o->cy = val * scale + tly;
+                else if (tid == 2) o->w = val * scale;
+                else if (tid == 3) o->h = val * scale;
+                else if (tid == 4) o->angle = val;
+                else {
+                    const int k = tid - 5;
+                    o->kp[k] = val * scale + ((k & 1) ? tly : tlx);
+                }
+            } else if (tid == nfields) {
+                o->confidence = c_conf[seed];
+                o->num_kp = p.num_kp;
+                o->anchor = c_idx[seed];
+            } else if (tid > nfields && tid <= nfields + (14 - 2 * p.num_kp)) {
+                o->kp[2 * p.num_kp + (tid - nfields - 1)] = 0.0f;
+            }
+        }
+        n_out += 1;
+        __syncthreads();
+    }
+    if (tid == 0) out_counts[img] = n_out;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) face_roi_kernel(const FramesDev f, const DetDev *__restrict__ dets,
+                                                       const int *__restrict__ counts, int cap, int first_frame,
+                                                       int n, int net_w, int net_h, ViewDev *__restrict__ out_views,
+                                                       float *__restrict__ out_fit, ViewHost *__restrict__ out_rects) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cnt = min(counts[i], cap);
+    ViewDev v;
+    v.frame = first_frame + i;
+    v.flip_x = 0;
+    v.valid = cnt > 0;
+    v.cx = v.cy = 0.f, v.w = v.h = 1.f, v.cosr = 1.f, v.sinr = 0.f;
+    float fit0 = 1.f, fit1 = 0.f, fit2 = 0.f;
+    ViewHost vr;
+    vr.frame = first_frame + i;
+    vr.cx = vr.cy = vr.w = vr.h = 0.f, vr.radians = 0.f;
+    if (cnt > 0) {
+        // detections.iter().max_by_key(|det| TotalF32(det.confidence()))  -> last maximum (facemesh.rs:49-52)
+        const DetDev *d = dets + (long long)i * cap;
+        int best = 0;
+        int bk = __float_as_int(d[0].confidence);
+        bk ^= (int)(((unsigned)(bk >> 31)) >> 1);
+        for (int j = 1; j < cnt; j++) {
+            int k = __float_as_int(d[j].confidence);
+            k ^= (int)(((unsigned)(k >> 31)) >> 1);
+            if (k >= bk) bk = k, best = j;
+        }
+        const float aspect = aspect_as_f32((unsigned)net_w, (unsigned)net_h);
+        // tracker.set_roi(detection.bounding_rect()); view_rect = roi.map(grow_to_fit_aspect)  (landmark.rs:465)
+        RectF roi;
+        roi.cx = d[best].cx, roi.cy = d[best].cy, roi.w = d[best].w, roi.h = d[best].h;
+        const RectF view_rect = grow_to_fit_aspect(roi, aspect);
+        vr.cx = view_rect.cx, vr.cy = view_rect.cy, vr.w = view_rect.w, vr.h = view_rect.h;
+        // full_image.view(view_rect)   (landmark.rs:466; rotation 0 -> cos 1, sin 0 exactly)
+        const RRectF full = full_view(f.width, f.height);
+        const RRectF v1 = view_compose(full, view_rect, 0.0f, 1.0f, 0.0f);
+        // Estimator::estimate_impl: rect = view.rect().grow_to_fit_aspect(..); view = image.view(rect)  (:320-323)
+        const RectF r1 = rect_from_top_left(0.0f, 0.0f, v1.r.w, v1.r.h);
+        const RectF r2 = grow_to_fit_aspect(r1, aspect);
+        const RRectF v2 = view_compose(v1, r2, 0.0f, 1.0f, 0.0f);
+        v.cx = v2.r.cx, v.cy = v2.r.cy, v.w = v2.r.w, v.h = v2.r.h;
+        fit0 = r2.w / (float)net_w;   // scale = rect.width() / input_res.width()   (:336)
+        fit1 = rect_x(r2);
+        fit2 = rect_y(r2);
+    }
+    out_views[i] = v;
+    out_fit[i * 4 + 0] = fit0, out_fit[i * 4 + 1] = fit1, out_fit[i * 4 + 2] = fit2, out_fit[i * 4 + 3] = 0.f;
+    if (out_rects) out_rects[i] = vr;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict__ out0, int s0,
+                                                        const float *__restrict__ out1, int s1,
+                                                        const float *__restrict__ out2, int s2,
+                                                        const float *__restrict__ fit,
+                                                        const ViewDev *__restrict__ views,
+                                                        const ViewHost *__restrict__ view_rects, int n,
+                                                        const LandmarkParams p, float *__restrict__ landmarks,
+                                                        float *__restrict__ scalars) {
+    const int img = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int valid = views ? views[img].valid : 1;
+    if (l == 0 && scalars) {
+        float a = 0.f, b = 0.f;
+        if (p.kind == 0) a = valid ? sigmoid_ref(out1[(long long)img * s1]) : -1.0f;  // mediapipe.rs:60
+        if (p.kind == 2) a = out1[(long long)img * s1], b = out2[(long long)img * s2]; // hand/landmark.rs:310-311
+        scalars[img * 2 + 0] = a, scalars[img * 2 + 1] = b;
+    }
+    if (l >= p.num_landmarks) return;
+    const float *src;
+    if (p.kind == 1) {
+        // eye.rs:51-63: iris (out1, 5 pts) -> positions[..5]; contour (out0, 71 pts) -> positions[5..]
+        src = (l < 5) ? out1 + (long long)img * s1 + 3 * l : out0 + (long long)img * s0 + 3 * (l - 5);
+    } else {
+        src = out0 + (long long)img * s0 + 3 * l;
+    }
+    float x = src[0], y = src[1], z = src[2];
+    if (views && views[img].flip_x) {
+        // EyeLandmarks::flip_horizontal_in_place (eye.rs:121-125) in network-input coordinates
+        const float half = (float)p.net_w / 2.0f;
+        x = -(x - half) + half;
+    }
+    const float scale = fit[img * 4 + 0], tlx = fit[img * 4 + 1], tly = fit[img * 4 + 2];
+    x = x * scale, y = y * scale, z = z * scale;   // landmark.rs:339 (z is scaled too)
+    x = x + tlx;
+    y = y + tly;
+    if (p.track_transform && view_rects) {
+        // LandmarkTracker::track: view_rect.transform_out([p.x, p.y])  (landmark.rs:482-486)
+        const ViewHost vr = view_rects[img];
+        RRectF rr;
+        rr.r.cx = vr.cx, rr.r.cy = vr.cy, rr.r.w = vr.w, rr.r.h = vr.h;
+        rr.rad = vr.radians;
+        rr.c = (vr.radians == 0.0f) ? 1.0f : (float)cos((double)vr.radians);
+        rr.s = (vr.radians == 0.0f) ? 0.0f : (float)sin((double)vr.radians);
+        float ox, oy;
+        transform_out(rr, x, y, ox, oy);
+        x = ox, y = oy;
+    }
+    float *o = landmarks + ((long long)img * p.num_landmarks + l) * 3;
+    if (!valid) x = y = z = 0.f;
+    o[0] = x, o[1] = y, o[2] = z;
+}
+
+}  // namespace
+
+void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
+                   SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s) {
+    g_launch_count++;
+    dim3 block(128);
+    dim3 grid((out_w + 127) / 128, out_h, n);
+    sample_kernel<<<grid, block, 0, s>>>(f, views, out_w, out_h, lo, hi, (int)layout, out, out_img_stride);
+}
+
+void launch_decode_nms(const float *boxes, const float *scores, const float *fit, int n, const DecodeParams &p,
+                       DetDev *out, int *out_counts, cudaStream_t s) {
+    g_launch_count++;
+    const size_t smem = (size_t)p.num_anchors * (sizeof(float4) + sizeof(float) + 4 * sizeof(int));
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    decode_nms_kernel<<<n, 256, smem, s>>>(boxes, scores, fit, p, out, out_counts);
+}
+
+void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, int cap, int first_frame, int n,
+                     int net_w, int net_h, ViewDev *out_views, float *out_fit, ViewHost *out_view_rects,
+                     cudaStream_t s) {
+    g_launch_count++;
+    face_roi_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, dets, counts, cap, first_frame, n, net_w, net_h, out_views,
+                                                    out_fit, out_view_rects);
+}
+
+void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
+                      const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
+                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s) {
+    g_launch_count++;
+    dim3 grid((p.num_landmarks + 127) / 128, n);
+    landmarks_kernel<<<grid, 128, 0, s>>>(out0, s0, out1, s1, out2, s2, fit, views, view_rects, n, p, landmarks,
+                                          scalars);
+}
+
+}  // namespace zb

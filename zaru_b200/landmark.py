@@ -1,0 +1,143 @@
+"""Host-side mirror of `zaru::landmark` (crates/zaru/src/landmark.rs) and the landmark networks
+(`face::landmark::mediapipe::FaceMeshV1`, `face::eye::EyeNetwork`, `hand::landmark::LiteNetwork`)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi, context, model_path
+from .nn import Cnn, CnnInputShape, ColorMapper, NeuralNetwork
+
+
+class Landmarks:
+    """landmark.rs:17-90: positions [L,3] float32."""
+
+    def __init__(self, positions: np.ndarray):
+        self._positions = positions
+
+    def len(self):
+        return self._positions.shape[0]
+
+    def positions(self):
+        return self._positions
+
+
+class Estimate:
+    def __init__(self, positions, scalars):
+        self._landmarks = Landmarks(positions)
+        self._scalars = scalars
+
+    def landmarks(self):
+        return self._landmarks
+
+    def landmarks_mut(self):
+        return self._landmarks
+
+
+class LandmarkResultV1(Estimate):
+    """mediapipe.rs:118-192."""
+    NUM_LANDMARKS = 468
+
+    def confidence(self):
+        return np.float32(self._scalars[0])
+
+
+class EyeLandmarks(Estimate):
+    """eye.rs:67-125."""
+    NUM_LANDMARKS = 76
+
+    def iris_center(self):
+        return self._landmarks.positions()[0]
+
+
+class HandLandmarkResult(Estimate):
+    """hand/landmark.rs LandmarkResult."""
+    NUM_LANDMARKS = 21
+
+    def presence(self):
+        return np.float32(self._scalars[0])
+
+    def confidence(self):
+        return self.presence()
+
+    def raw_handedness(self):
+        return np.float32(self._scalars[1])
+
+
+class Network:
+    """`landmark::Network` (landmark.rs:239-250)."""
+    onnx = None
+    kind = None
+    color_range = (-1.0, 1.0)
+    result = Estimate
+    _cnn_cache = {}
+
+    def cnn(self) -> Cnn:
+        key = (type(self).__name__, model_path(self.onnx))
+        if key not in Network._cnn_cache:
+            Network._cnn_cache[key] = Cnn(NeuralNetwork.from_path(model_path(self.onnx)), CnnInputShape.NCHW,
+                                          ColorMapper.linear(*self.color_range))
+        return Network._cnn_cache[key]
+
+
+class FaceMeshV1(Network):
+    onnx = "face_landmark.onnx"
+    kind = _ffi.ZB_EST_FACE_MESH_V1
+    color_range = (-1.0, 1.0)
+    result = LandmarkResultV1
+
+
+class EyeNetwork(Network):
+    onnx = "iris_landmark.onnx"
+    kind = _ffi.ZB_EST_EYE
+    color_range = (-1.0, 1.0)
+    result = EyeLandmarks
+
+
+class HandLiteNetwork(Network):
+    onnx = "hand_landmark_lite.onnx"
+    kind = _ffi.ZB_EST_HAND
+    color_range = (0.0, 1.0)
+    result = HandLandmarkResult
+
+
+class Estimator:
+    """Neural-network based landmark estimator (landmark.rs:256-349), batched over views."""
+
+    def __init__(self, network: Network):
+        self.network = network
+        self._cnn = network.cnn()
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_estimator_create(context(), self._cnn.nn._h, network.kind, network.color_range[0],
+                                                  network.color_range[1], C.byref(h)))
+        self._h = h
+        self._L = _ffi.lib().zb_estimator_num_landmarks(h)
+
+    def input_resolution(self):
+        return self._cnn.input_resolution()
+
+    def estimate(self, image):
+        """`Estimator::estimate(&image)` (landmark.rs:310)."""
+        view = image.as_view()
+        batch, idx = view.image().device()
+        return self.estimate_views(batch, [view.to_zb_view(idx)])[0]
+
+    def estimate_views(self, batch, zviews, flip_x=None):
+        n = len(zviews)
+        arr = (_ffi.zb_view * n)(*zviews)
+        lm = np.empty((n, self._L, 3), np.float32)
+        sc = np.empty((n, 2), np.float32)
+        flips = None
+        if flip_x is not None:
+            flips = (C.c_uint8 * n)(*[1 if f else 0 for f in flip_x])
+        _ffi.check(_ffi.lib().zb_estimator_estimate(self._h, batch._h, arr, flips, n, lm.ctypes.data, sc.ctypes.data))
+        return [self.network.result(lm[i], sc[i]) for i in range(n)]
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ffi.lib().zb_estimator_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -1,0 +1,67 @@
+"""The fused per-frame face pipeline: detect -> best detection -> RoI -> face mesh, all on device.
+
+Composition taken from the reference's example loop (crates/zaru/examples/facemesh.rs:36-55:
+`detector.detect(&image)`, `tracker.set_roi(best.bounding_rect())`) followed by one
+`LandmarkTracker::track` step on the same frame (crates/zaru/src/landmark.rs:456-501).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi, context
+from .detection import Detection, Detections, ShortRangeNetwork
+from .landmark import FaceMeshV1
+
+
+class FacePipelineResult:
+    def __init__(self, detections, landmarks, flags, rois):
+        self.detections = detections      # list[Detections], frame coordinates
+        self.landmarks = landmarks        # [n,468,3] float32, frame coordinates
+        self.face_flags = flags           # [n] sigmoid(face_flag); -1 where no face was detected
+        self.rois = rois                  # [n,5]: view_rect (cx, cy, w, h, radians) used for the mesh
+
+
+class FacePipeline:
+    def __init__(self, capacity: int = 16, detector_network=None, landmark_network=None):
+        self._det = (detector_network or ShortRangeNetwork()).cnn()
+        self._lm = (landmark_network or FaceMeshV1()).cnn()
+        self._cap = capacity
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_face_pipeline_create(context(), self._det.nn._h, self._lm.nn._h, C.byref(h)))
+        self._h = h
+        self._bufs = None
+
+    def set_threshold(self, det_thresh=0.5, iou_thresh=0.3, mode=_ffi.ZB_NMS_AVERAGE):
+        _ffi.check(_ffi.lib().zb_face_pipeline_set_threshold(self._h, det_thresh, iou_thresh, mode))
+
+    def _buffers(self, n):
+        if self._bufs is None or self._bufs[0] != n:
+            self._bufs = (n, (_ffi.zb_detection * (n * self._cap))(), (C.c_int32 * n)(),
+                          np.empty((n, 468, 3), np.float32), np.empty(n, np.float32), (_ffi.zb_view * n)())
+        return self._bufs
+
+    def run_raw(self, batch, n=None):
+        """One pass over `n` frames; results land in reusable host buffers (no Python unpacking)."""
+        n = len(batch) if n is None else n
+        _, dets, counts, lm, flags, rois = self._buffers(n)
+        _ffi.check(_ffi.lib().zb_face_pipeline_run(self._h, batch._h, n, dets, counts, self._cap, lm.ctypes.data,
+                                                   flags.ctypes.data, rois))
+        return dets, counts, lm, flags, rois
+
+    def run(self, batch, n=None) -> FacePipelineResult:
+        n = len(batch) if n is None else n
+        dets, counts, lm, flags, rois = self.run_raw(batch, n)
+        out = [Detections(Detection(dets[i * self._cap + k]) for k in range(min(counts[i], self._cap)))
+               for i in range(n)]
+        r = np.array([[v.cx, v.cy, v.w, v.h, v.radians] for v in rois], np.float32).reshape(n, 5)
+        return FacePipelineResult(out, lm.copy(), flags.copy(), r)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ffi.lib().zb_face_pipeline_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
