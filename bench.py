@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the full face pipeline (BlazeFace -> NMS -> crop -> face mesh) on synthetic
+1080p frames, BASELINE.json config 4: batch 1024 per GPU, frames resident in HBM.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what every field means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_W, FRAME_H = 1920, 1080
+FRAME_BYTES = FRAME_W * FRAME_H * 4
+ALG_MB_PER_FRAME = 12.82      # block-fused network traffic 12.61 MB + 0.21 MB sampled pixels
+ALG_MFLOP_PER_FRAME = 131.48
+METRIC = "frames/sec face detect+landmark (1080p)"
+UNIT = "frames/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path (numpy restatement + cv2.dnn, 1 thread per worker)
+# ------------------------------------------------------------------------------------------------
+_worker_frames = None
+
+
+def _cpu_worker_init(seed0, count):
+    global _worker_frames
+    import cv2
+    cv2.setNumThreads(1)
+    from zaru_b200 import synth
+    _worker_frames = [synth.s_face_frame(seed0 + i)[0] for i in range(count)]
+    from tests.oracle_pipeline import face_pipeline
+    face_pipeline(_worker_frames[0])   # load + warm the networks
+
+
+def _cpu_worker_run(n):
+    from tests.oracle_pipeline import face_pipeline
+    for i in range(n):
+        face_pipeline(_worker_frames[i % len(_worker_frames)])
+    return n
+
+
+def cpu_baseline_single(budget_s=15.0):
+    """Oracle pipeline on ONE host core over distinct S-face frames for ~budget_s seconds."""
+    _cpu_worker_init(5000, 8)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < budget_s:
+        n += _cpu_worker_run(4)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} 1080p S-face frames in {dt:.1f} s: oracle (numpy restatement + cv2.dnn, 1 thread) of "
+                      "sample->BlazeFace->NMS->crop->face mesh; ort/tract cannot be built here"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 16
+    ctx = mp.get_context("spawn")
+    pools = [ctx.Pool(1, initializer=_cpu_worker_init, initargs=(9000 + 8 * w, 8)) for w in range(cores)]
+
+    def step():
+        rs = [p.apply_async(_cpu_worker_run, (per_worker,)) for p in pools]
+        return sum(r.get() for r in rs)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        frames += step()
+    dt = time.perf_counter() - t0
+    for p in pools:
+        p.terminate()
+    value = frames / dt
+    sample = (f"{per_worker * cores} 1080p S-face frames per step over {cores} worker processes "
+              "(one oracle Detector+Estimator per worker, cv2.dnn 1 thread each; mirrors rayon map_init, "
+              "eval_face_recognition.rs:67-70)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config4: full face pipeline on synthetic 1080p frames (CPU reference arm, bounded sample)",
+                       "frames_per_step": per_worker * cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import zaru_b200
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+
+    zaru_b200.load_library()
+    zaru_b200.context(local)
+    res = Resolution(FRAME_W, FRAME_H)
+    batch_n = args.batch
+
+    # --- inputs: `unique` distinct S-face frames per rank, tiled to the batch, resident in HBM -----------
+    t0 = time.perf_counter()
+    uniq = np.stack([synth.s_face_frame(1000 * rank + i)[0] for i in range(args.unique)])
+    d_uniq = torch.from_numpy(uniq).cuda()
+    idx = torch.arange(batch_n, device="cuda") % args.unique
+    d_frames = d_uniq[idx].contiguous()            # [batch,1080,1920,4] uint8, 8.49 GB at batch 1024 (> 126 MB L2)
+    del d_uniq
+    torch.cuda.synchronize()
+    batch = ImageBatch.alias_device(res, d_frames.data_ptr(), batch_n, keepalive=d_frames)
+    log(f"[rank {rank}] inputs ready in {time.perf_counter() - t0:.1f} s ({batch_n} frames, {args.unique} distinct)")
+
+    pipe = FacePipeline(capacity=args.cap)
+    if args.chunk:
+        pipe._det.nn.set_chunk(args.chunk)
+        pipe._lm.nn.set_chunk(args.chunk)
+
+    def barrier():
+        zaru_b200.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # --- device-resident throughput (`value`) ---------------------------------------------------------
+    for _ in range(args.warmup):
+        pipe.run_raw(batch, batch_n)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = zaru_b200.launch_count()
+    wall0 = time.perf_counter()
+    zaru_b200.timer_start()
+    for _ in range(args.steps):
+        dets, counts, lm, flags, rois = pipe.run_raw(batch, batch_n)
+    dev_ms = zaru_b200.timer_stop_ms()
+    zaru_b200.sync()
+    torch.cuda.synchronize()
+    wall_ms = 1000.0 * (time.perf_counter() - wall0)
+    launches = zaru_b200.launch_count() - launches0
+    barrier()
+    n_with_face = int((flags >= 0).sum())
+    t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = t.tolist()
+
+    # --- end to end through the public API with HOST frames (`e2e`) -------------------------------------
+    e2e_n = min(args.e2e_batch, batch_n)
+    h_frames = torch.empty((e2e_n, FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory()
+    h_frames.copy_(d_frames[:e2e_n])
+    e2e_batch = ImageBatch.from_rgba8(res, h_frames.numpy())
+    h_ptr = h_frames.numpy()
+
+    def e2e_step():
+        e2e_batch.update(h_ptr, 0)                 # host -> device copy of this step's frames (pinned memory)
+        return pipe.run_raw(e2e_batch, e2e_n)      # includes the device -> host copy of the results
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    zaru_b200.sync()
+    e2e_ms = 1000.0 * (time.perf_counter() - e0)
+    te = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms_max = te.item()
+    clock_info = clocks.stop() if rank == 0 else None
+    d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
+
+    # --- per-kernel CUDA-event profile of one step (roofline block) -------------------------------------
+    prof = None
+    if rank == 0:
+        zaru_b200.profile_begin()
+        pipe.run_raw(batch, batch_n)
+        prof = zaru_b200.profile_end()
+
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    value = world * batch_n * args.steps / (dev_ms_max / 1000.0)
+    e2e_value = world * e2e_n * args.steps / (e2e_ms_max / 1000.0)
+    peak, peak_src = peaks()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    total_ms = sum(v["ms"] for v in prof.values())
+    achieved = top[1]["bytes"] / (top[1]["ms"] / 1000.0) / 1e9
+    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
+                   "GBps": round(v["bytes"] / (v["ms"] / 1000.0) / 1e9, 1) if v["ms"] > 0 else None,
+                   "TFLOPs": round(v["flops"] / (v["ms"] / 1000.0) / 1e12, 2) if v["ms"] > 0 else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    pipeline_gbs = value / world * ALG_MB_PER_FRAME * 1e6 / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark",
+                   "batch_per_gpu": batch_n, "frame": "1920x1080 RGBA8", "distinct_frames": args.unique,
+                   "l2_policy": f"inputs larger than L2 ({batch_n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
+                   "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "64")), "frames_with_face": n_with_face,
+                   "timing": "CUDA events on the library stream around the K steps, max over ranks"},
+        "wall_ms_per_step": wall_ms_max / args.steps,
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n * FRAME_BYTES, "d2h_bytes_per_step": d2h,
+                "batch_per_gpu": e2e_n, "ms_per_step": e2e_ms_max / args.steps,
+                "note": "pinned host frames -> zb_frames_update (H2D) -> zb_face_pipeline_run -> results D2H, every step"},
+        "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "share_of_step": top[1]["ms"] / total_ms,
+                     "pipeline": {"achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
+                                  "model": f"{ALG_MB_PER_FRAME} MB algorithmic bytes per frame (SURVEY §8d) x frames/s per GPU"}},
+        "kernels": kernels,
+        "clocks": clock_info,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_single(args.cpu_budget)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zaru_b200", choices=["zaru_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--e2e-batch", type=int, default=256)
+    ap.add_argument("--unique", type=int, default=32)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--cap", type=int, default=16)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "zaru_b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

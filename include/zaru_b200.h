@@ -154,6 +154,14 @@ zb_status zb_detector_detect(zb_detector *det, const zb_frames *frames, const zb
                              int32_t n, zb_detection *out_dets, int32_t *out_counts, int32_t cap,
                              float *raw_boxes, float *raw_scores);
 
+/* `network.extract(&outputs, thresh, ..)` + `nms.process(..)` + remap on caller-supplied head
+ * tensors (detection.rs:231-267): raw_boxes [n,A,P], raw_scores [n,A,1] (host_or_device).
+ * views (optional): the views the tensors were computed from, used for the remap; NULL keeps
+ * network-input coordinates (scale 1, offset 0).                                              */
+zb_status zb_detector_extract(zb_detector *det, const float *raw_boxes, const float *raw_scores,
+                              const zb_view *views, int32_t n, zb_detection *out_dets,
+                              int32_t *out_counts, int32_t cap);
+
 /* ---- zaru::landmark::Estimator (crates/zaru/src/landmark.rs:256-349) ----------------------- */
 zb_status zb_estimator_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, float lo, float hi,
                               zb_estimator **out);
@@ -202,6 +210,14 @@ zb_status zb_plan_from_onnx(const void *onnx_bytes, size_t len, int32_t fuse_dwp
 /* Device time (ms, CUDA events on the handle's own stream) of the last *_run/_detect/_estimate
  * call, excluding host<->device result copies.                                                */
 float zb_last_device_ms(zb_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream: start, (any number of calls), stop -> ms.      */
+zb_status zb_timer_start(zb_ctx *ctx);
+zb_status zb_timer_stop(zb_ctx *ctx, float *ms);
+/* Per-launch profiler: between begin and end every kernel launch on `ctx` is bracketed by CUDA
+ * events on its launch stream; end returns JSON {kernel class: {launches, ms, bytes, flops}}
+ * where bytes/flops are the ALGORITHMIC work of those launches (DESIGN.md "roofline").        */
+zb_status zb_profile_begin(zb_ctx *ctx);
+zb_status zb_profile_end(zb_ctx *ctx, char *json, size_t cap, size_t *needed);
 
 #ifdef __cplusplus
 }

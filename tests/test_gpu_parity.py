@@ -1,0 +1,407 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star / SURVEY §8d): preprocessing tensor bit-exact; identical
+post-NMS detection sets; boxes / keypoints / landmarks within 1e-3 NORMALISED units (pixels of the
+network input / input size); scores and flags within 1e-3 absolute; angles within 1e-3 rad.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import zaru_b200
+    zaru_b200.load_library()
+    zaru_b200.context()
+    return zaru_b200
+
+
+def _oimg(rgba):
+    from oracle.image import Image
+    return Image(rgba)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1/a2: image -> tensor, bit exact
+# ------------------------------------------------------------------------------------------------
+def _views_for(img_w, img_h, rng, k):
+    from oracle.geometry import Rect, RotatedRect
+    out = [RotatedRect(Rect.from_top_left(0, 0, img_w, img_h), 0.0)]
+    for _ in range(k):
+        w, h = rng.uniform(8, 1.4 * img_w), rng.uniform(8, 1.4 * img_h)
+        cx, cy = rng.uniform(-0.2 * img_w, 1.2 * img_w), rng.uniform(-0.2 * img_h, 1.2 * img_h)
+        out.append(RotatedRect(Rect.from_center(cx, cy, w, h), rng.choice([0.0, 0.0, rng.uniform(-3.2, 3.2), math.pi / 2])))
+    return out
+
+
+@pytest.mark.parametrize("size,net", [((1280, 720), (128, 128)), ((535, 535), (192, 192)), ((97, 61), (64, 64)),
+                                      ((1920, 1080), (224, 224))])
+def test_preprocess_bit_exact(zb, size, net):
+    import ctypes as C
+    from oracle.image import image_to_tensor
+    from zaru_b200 import _ffi
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.rect import Resolution
+    rng = np.random.default_rng(size[0] * 7 + net[0])
+    W, H = size
+    px = rng.integers(0, 256, size=(H, W, 4), dtype=np.uint8)
+    oimg = _oimg(px)
+    batch = ImageBatch.from_rgba8(Resolution(W, H), px[None])
+    views = _views_for(W, H, rng, 12)
+    zviews = (_ffi.zb_view * len(views))(*[_ffi.zb_view(0, float(v.rect.cx), float(v.rect.cy), float(v.rect.w),
+                                                      float(v.rect.h), float(v.radians)) for v in views])
+    for lo, hi, layout in [(-1.0, 1.0, _ffi.ZB_NCHW), (0.0, 1.0, _ffi.ZB_NHWC)]:
+        out = np.empty((len(views), 3, net[1], net[0]) if layout == _ffi.ZB_NCHW else (len(views), net[1], net[0], 3), np.float32)
+        _ffi.check(_ffi.lib().zb_preprocess(zb.context(), batch._h, zviews, len(views), net[0], net[1], lo, hi, layout,
+                                            out.ctypes.data))
+        for i, v in enumerate(views):
+            want = image_to_tensor(oimg.view(v), net[0], net[1], lo, hi, "NCHW" if layout == _ffi.ZB_NCHW else "NHWC")[0]
+            assert np.array_equal(out[i].view(np.uint32), want.view(np.uint32)), f"view {i} {v} differs"
+
+
+def test_preprocess_letterbox_worked_example(zb):
+    """1080p -> 128x128: rows 0..27 and 100..127 are letterbox (-1.0), source px = (15x, 15y-420)."""
+    from zaru_b200.image import Image
+    from zaru_b200.detection import ShortRangeNetwork
+    from zaru_b200.rect import AspectRatio
+    rng = np.random.default_rng(3)
+    px = rng.integers(0, 256, size=(1080, 1920, 4), dtype=np.uint8)
+    img = Image(px)
+    cnn = ShortRangeNetwork().cnn()
+    rect = img.rect().grow_to_fit_aspect(AspectRatio.SQUARE)
+    t = cnn.tensor(img.view(rect))
+    assert t.shape == (1, 3, 128, 128)
+    assert (t[0, :, :28, :] == -1.0).all() and (t[0, :, 100:, :] == -1.0).all()
+    adjust = (np.float32(1.0) - np.float32(-1.0)) / np.float32(255.0)
+    for (x, y) in [(0, 28), (127, 99), (64, 64)]:
+        want = px[15 * y - 420, 15 * x, :3].astype(np.float32) * adjust + np.float32(-1.0)
+        assert np.array_equal(t[0, :, y, x], want)
+
+
+# ------------------------------------------------------------------------------------------------
+# a3: network forward, all five graphs
+# ------------------------------------------------------------------------------------------------
+NETS = [("face_detection_short_range", -1.0, 128), ("face_landmark", -1.0, 192), ("iris_landmark", -1.0, 64),
+        ("palm_detection_lite", 0.0, 192), ("hand_landmark_lite", 0.0, 224)]
+
+
+@pytest.mark.parametrize("name,lo,size", NETS)
+def test_network_forward_matches_oracle(zb, assets_dir, name, lo, size, sad_linus_cropped):
+    from oracle import nn as onn
+    from oracle.image import image_to_tensor
+    from zaru_b200.nn import NeuralNetwork
+    path = os.path.join(assets_dir, "onnx", name + ".onnx")
+    net = NeuralNetwork.from_path(path)
+    onet = onn.NeuralNetwork(path, backend="cv2")
+    assert [s for _, s in net.outputs()] == [[1 if d in (None, 0) else d for d in s] for _, s in onet.outputs()]
+    rng = np.random.default_rng(5)
+    x = np.empty((5, 3, size, size), np.float32)
+    x[0] = image_to_tensor(_oimg(sad_linus_cropped).as_view(), size, size, lo, 1.0)[0]
+    x[1:3] = rng.uniform(lo, 1.0, size=(2, 3, size, size))
+    # smooth random images (closer to natural statistics than white noise)
+    coarse = rng.uniform(lo, 1.0, size=(2, 3, 8, 8)).astype(np.float32)
+    x[3:5] = np.repeat(np.repeat(coarse, size // 8, axis=2), size // 8, axis=3)
+    got = net.estimate(x)
+    want = onet.estimate(x)
+    want2 = onet.estimate(x[:1], backend="torch")
+    for k, (g, r) in enumerate(zip(got, want)):
+        assert g.shape == r.shape
+        # raw head tensors are in network-input pixel units (or logits): normalise coordinates by input size
+        err = float(np.abs(g - r).max())
+        noise = float(np.abs(want2[k] - r[:1]).max())   # oracle-vs-oracle floor on the fixture image
+        limit = max(TOL * size, 4 * noise) if g.shape[-1] > 2 else max(5e-3, 4 * noise)
+        assert err <= limit, (name, k, err, noise)
+
+
+def test_network_forward_chunking_is_invisible(zb, assets_dir):
+    from zaru_b200.nn import NeuralNetwork
+    net = NeuralNetwork.from_path(os.path.join(assets_dir, "onnx", "face_detection_short_range.onnx"))
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1, 1, size=(7, 3, 128, 128)).astype(np.float32)
+    net.set_chunk(64)
+    a = net.estimate(x)
+    net.set_chunk(3)   # ragged last chunk
+    b = net.estimate(x)
+    net.set_chunk(1)
+    c = net.estimate(x)
+    for u, v, w in zip(a, b, c):
+        assert np.array_equal(u, v) and np.array_equal(u, w)
+
+
+# ------------------------------------------------------------------------------------------------
+# a6-a9: decode + NMS + remap
+# ------------------------------------------------------------------------------------------------
+def _check_dets(got, want, size, what=""):
+    assert len(got) == len(want), f"{what}: {len(got)} detections, oracle has {len(want)}"
+    for g, w in zip(got, want):
+        assert g.anchor == w.anchor, f"{what}: cluster seeds differ ({g.anchor} vs {w.anchor})"
+        gv, wv = g.as_vector(), w.as_vector()
+        assert abs(gv[0] - wv[0]) <= TOL, (what, "confidence", gv[0], wv[0])
+        assert abs(gv[1] - wv[1]) <= TOL, (what, "angle", gv[1], wv[1])
+        assert np.abs(gv[2:] - wv[2:]).max() <= TOL * size, (what, "coords", np.abs(gv[2:] - wv[2:]).max())
+
+
+@pytest.mark.parametrize("kind", ["face", "palm"])
+@pytest.mark.parametrize("mode", ["average", "remove"])
+def test_extract_nms_matches_oracle_on_random_heads(zb, kind, mode):
+    """Decode+NMS in isolation on synthetic head tensors: exercises dense clusters, ties, both modes."""
+    from oracle import detection as od
+    from zaru_b200 import detection as zd
+    from zaru_b200 import _ffi
+    onet = od.ShortRangeNetwork() if kind == "face" else od.PalmLiteNetwork()
+    znet = zd.ShortRangeNetwork() if kind == "face" else zd.PalmLiteNetwork()
+    A = len(onet.anchors())
+    P = onet.num_params
+    size = 128 if kind == "face" else 192
+    rng = np.random.default_rng(11 if kind == "face" else 12)
+    n = 6
+    boxes = rng.normal(0, 6, size=(n, A, P)).astype(np.float32)
+    boxes[..., 2:4] = rng.uniform(10, 60, size=(n, A, 2))
+    scores = rng.normal(-4.0, 2.0, size=(n, A, 1)).astype(np.float32)
+    scores[1] = -50.0                                   # empty set
+    scores[2, :40] = 3.0                                # exact ties (saturating-free) inside one frame
+    scores[3] = rng.normal(0.5, 1.0, size=(A, 1))       # hundreds of candidates
+    scores[4, ::7] = 20.0                               # sigmoid saturates to 1.0 -> many equal confidences
+    det = zd.Detector(znet, capacity=A)
+    det.nms_mut().set_mode(zd.SuppressionMode.Average if mode == "average" else zd.SuppressionMode.Remove)
+    got = det.extract(boxes, scores)
+    for i in range(n):
+        cand = []
+        onet.extract([boxes[i:i + 1], scores[i:i + 1]], 0.5, cand)
+        nms = od.NonMaxSuppression()
+        nms.set_mode(mode)
+        want = nms.process(cand)
+        _check_dets(got[i], want, size, f"{kind}/{mode}/item{i}")
+        if mode == "average" and want:
+            # in-tree arithmetic: identical op order; only exp()/atan2() may differ from glibc in the last bit
+            gv = np.stack([g.as_vector() for g in got[i]])
+            wv = np.stack([w.as_vector() for w in want])
+            np.testing.assert_array_max_ulp(gv[:, 2:6], wv[:, 2:6], maxulp=4)
+    assert len(got[1]) == 0
+
+
+def test_extract_threshold_iou_and_capacity(zb):
+    from oracle import detection as od
+    from zaru_b200 import detection as zd
+    from zaru_b200 import _ffi
+    rng = np.random.default_rng(13)
+    A = 896
+    boxes = rng.normal(0, 4, size=(1, A, 16)).astype(np.float32)
+    boxes[..., 2:4] = 30.0
+    scores = rng.normal(0, 2, size=(1, A, 1)).astype(np.float32)
+    det = zd.Detector(zd.ShortRangeNetwork(), capacity=A)
+    for thresh, iou in [(0.3, 0.3), (0.7, 0.1), (0.5, 0.0), (0.9, 0.9)]:
+        det.set_threshold(thresh)
+        det.nms_mut().set_iou_thresh(iou)
+        got = det.extract(boxes, scores)[0]
+        cand = []
+        od.ShortRangeNetwork().extract([boxes, scores], thresh, cand)
+        nms = od.NonMaxSuppression()
+        nms.set_iou_thresh(iou)
+        _check_dets(got, nms.process(cand), 128, f"t{thresh}/iou{iou}")
+    small = zd.Detector(zd.ShortRangeNetwork(), capacity=2)
+    small.set_threshold(0.5)
+    small.nms_mut().set_iou_thresh(0.9)
+    with pytest.raises(_ffi.ZaruError) as e:
+        small.extract(boxes, scores)
+    assert e.value.status == _ffi.ZB_ERR_CAPACITY
+
+
+def test_detects_face_reference_assertion(zb, sad_linus_full):
+    """Port of face/detection.rs:164-173 `detects_face`, plus parity with the oracle."""
+    from oracle.detection import Detector as ODetector, ShortRangeNetwork as ONet
+    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200.image import Image
+    det = Detector(ShortRangeNetwork())
+    dets = det.detect(Image(sad_linus_full))
+    assert len(dets) >= 1, "no detection"
+    d = dets[0]
+    assert d.confidence() >= 0.8, d.confidence()
+    assert abs(math.degrees(float(d.angle()))) < 5.0
+    want = ODetector(ONet()).detect(_oimg(sad_linus_full))
+    _check_dets(dets, want, 128 * (1280 / 128), "sad_linus")   # remapped coords: tolerance scales with the view
+
+
+def test_detector_batch_on_synthetic_1080p(zb):
+    from oracle.detection import Detector as ODetector, ShortRangeNetwork as ONet
+    from zaru_b200 import synth
+    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.rect import Resolution
+    n = 6
+    frames = np.stack([synth.s_face_frame(100 + i)[0] for i in range(n)])
+    frames[n - 1] = synth.s_face_frame(7, allow_empty=False)[0]
+    batch = ImageBatch.from_rgba8(Resolution(1920, 1080), frames)
+    det = Detector(ShortRangeNetwork())
+    got = det.detect_batch(batch, want_raw=True)
+    raw_b, raw_s = det.last_raw
+    odet = ODetector(ONet())
+    total = 0
+    for i in range(n):
+        want = odet.detect(_oimg(frames[i]))
+        margin = float(np.abs(odet.last_raw[1]).min())
+        assert np.abs(raw_s[i] - odet.last_raw[1][0]).max() < 5e-3
+        if margin < 1e-2:
+            continue   # a logit within 1e-2 of the threshold: set identity is not required
+        _check_dets(got[i], want, 128 * 15.0, f"frame{i}")
+        total += len(want)
+    assert total >= 3
+
+
+def test_detector_on_views_and_rotations(zb, sad_linus_full):
+    from oracle.detection import Detector as ODetector, ShortRangeNetwork as ONet
+    from oracle.geometry import Rect as ORect, RotatedRect as ORR
+    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200.image import Image
+    from zaru_b200.rect import Rect, RotatedRect
+    img, oimg = Image(sad_linus_full), _oimg(sad_linus_full)
+    det, odet = Detector(ShortRangeNetwork()), ODetector(ONet())
+    for (cx, cy, w, h, rad) in [(700, 400, 600, 500, 0.0), (700, 420, 700, 700, 0.2), (640, 360, 1280, 720, -0.15)]:
+        got = det.detect(img.view(RotatedRect(Rect.from_center(cx, cy, w, h), rad)))
+        want = odet.detect(oimg.view(ORR(ORect.from_center(cx, cy, w, h), rad)))
+        _check_dets(got, want, 128 * max(w, h) / 128, f"view{(cx, cy, w, h, rad)}")
+
+
+# ------------------------------------------------------------------------------------------------
+# a10: landmark estimators
+# ------------------------------------------------------------------------------------------------
+def test_estimates_landmarks_reference_assertions(zb, sad_linus_cropped):
+    """Port of mediapipe.rs:603-624 (`estimates_landmarks_upright/rotated/rotated2`) + oracle parity."""
+    from oracle.geometry import RotatedRect as ORR, f32
+    from oracle.landmark import Estimator as OEst, FaceLandmarks, FaceMeshV1 as ONet
+    from zaru_b200.image import Image
+    from zaru_b200.landmark import Estimator, FaceMeshV1
+    from zaru_b200.rect import RotatedRect
+    img, oimg = Image(sad_linus_cropped), _oimg(sad_linus_cropped)
+    est = Estimator(FaceMeshV1())
+    for deg, expected in [(0.0, 0.0), (10.0, -10.0), (-10.0, 10.0)]:
+        rad = float(np.radians(f32(deg)))
+        view = img.as_view() if deg == 0.0 else img.view(RotatedRect(img.rect(), rad))
+        oview = oimg.as_view() if deg == 0.0 else oimg.view(ORR(oimg.rect(), rad))
+        r = est.estimate(view)
+        assert r.confidence() > 0.9
+        fl = FaceLandmarks()
+        fl.positions[:] = r.landmarks().positions()
+        for angle in (fl.rotation_radians(), fl.left_eye().radians, fl.right_eye().radians):
+            assert abs(math.degrees(float(angle)) - expected) < 5.0
+        assert fl.left_eye().center()[0] < fl.right_eye().center()[0]
+        want = OEst(ONet()).estimate(oview)
+        scale = 535.0 / 192.0
+        assert abs(float(r.confidence()) - float(want.face_flag)) <= TOL
+        assert np.abs(r.landmarks().positions() - want.positions).max() <= TOL * 192 * scale
+
+
+@pytest.mark.parametrize("which", ["eye", "hand"])
+def test_eye_and_hand_estimators_match_oracle(zb, which, sad_linus_cropped, sad_linus_full):
+    from oracle.geometry import Rect as ORect, RotatedRect as ORR
+    from oracle.landmark import Estimator as OEst, EyeNetwork as OEye, HandLiteNetwork as OHand
+    from zaru_b200.image import Image
+    from zaru_b200.landmark import Estimator, EyeNetwork, HandLiteNetwork
+    from zaru_b200.rect import Rect, RotatedRect
+    if which == "eye":
+        px, net, onet, size = sad_linus_cropped, EyeNetwork(), OEye(), 64
+        rois = [(200, 235, 90, 60, 0.0), (335, 235, 96, 64, 0.05), (268, 260, 300, 300, -0.3)]
+    else:
+        px, net, onet, size = sad_linus_full, HandLiteNetwork(), OHand(), 224
+        rois = [(640, 360, 600, 600, 0.0), (640, 360, 500, 400, 0.35), (300, 300, 420, 420, -0.35)]
+    img, oimg = Image(px), _oimg(px)
+    est = Estimator(net)
+    for (cx, cy, w, h, rad) in rois:
+        r = est.estimate(img.view(RotatedRect(Rect.from_center(cx, cy, w, h), rad)))
+        want = OEst(onet).estimate(oimg.view(ORR(ORect.from_center(cx, cy, w, h), rad)))
+        scale = max(w, h) / size
+        assert np.abs(r.landmarks().positions() - want.positions).max() <= TOL * size * scale
+        if which == "hand":
+            assert abs(float(r.presence()) - float(want.presence)) <= TOL
+            assert abs(float(r.raw_handedness()) - float(want.raw_handedness)) <= TOL
+
+
+def test_right_eye_flip_rule(zb, sad_linus_cropped):
+    """flip_x: tensor mirrored left-right, x un-mirrored in network coordinates (eye.rs:121-125)."""
+    from oracle.image import image_to_tensor
+    from oracle.landmark import EyeNetwork as OEye
+    from oracle.geometry import AspectRatio, Rect as ORect, f32
+    from zaru_b200.image import Image
+    from zaru_b200.landmark import Estimator, EyeNetwork
+    from zaru_b200.rect import Rect
+    img, oimg = Image(sad_linus_cropped), _oimg(sad_linus_cropped)
+    roi = (335.0, 235.0, 96.0, 96.0)
+    est = Estimator(EyeNetwork())
+    view = img.view(Rect.from_center(*roi))
+    batch, idx = img.device()
+    got = est.estimate_views(batch, [view.to_zb_view(idx)], flip_x=[True])[0].landmarks().positions()
+    oview = oimg.view(ORect.from_center(*roi))
+    t = image_to_tensor(oview, 64, 64, -1.0, 1.0)[:, :, :, ::-1].copy()
+    onet = OEye()
+    out = onet.cnn().nn.estimate(t)
+    e = onet.new_estimate()
+    onet.extract(out, e)
+    e.positions[:, 0] = -(e.positions[:, 0] - f32(32.0)) + f32(32.0)
+    scale = f32(96.0) / f32(64.0)
+    e.positions *= scale
+    assert np.abs(got - e.positions).max() <= TOL * 64 * float(scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# full face pipeline (config 4 shape, small batch)
+# ------------------------------------------------------------------------------------------------
+def test_face_pipeline_matches_oracle(zb):
+    from tests.oracle_pipeline import face_pipeline
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    seeds = [200, 201, 202, 203, 204]
+    frames = np.stack([synth.s_face_frame(s)[0] for s in seeds] + [synth.s_face_frame(1, allow_empty=True)[0] * 0 + 90])
+    batch = ImageBatch.from_rgba8(Resolution(1920, 1080), frames)
+    pipe = FacePipeline()
+    res = pipe.run(batch)
+    checked = 0
+    for i in range(len(frames)):
+        dets, lm, flag, view_rect, raw = face_pipeline(frames[i])
+        if float(np.abs(raw[1]).min()) < 1e-2:
+            continue
+        _check_dets(res.detections[i], dets, 128 * 15.0, f"frame{i}")
+        if not dets:
+            assert res.face_flags[i] == -1.0
+            continue
+        assert np.allclose(res.rois[i, :4], np.asarray(view_rect.rect.as_tuple(), np.float32), atol=TOL * 128 * 15)
+        scale = float(view_rect.rect.w) / 192.0
+        assert abs(float(res.face_flags[i]) - float(flag)) <= 2e-3
+        assert np.abs(res.landmarks[i] - lm).max() <= TOL * 192 * scale + 15.0 * TOL * 128, i
+        checked += 1
+    assert checked >= 3
+    assert len(res.detections[-1]) == 0 and res.face_flags[-1] == -1.0
+
+
+def test_pipeline_properties_at_batch(zb):
+    """Size-independent properties at a larger batch: permutation equivariance and determinism."""
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    uniq = np.stack([synth.s_face_frame(300 + i)[0] for i in range(8)])
+    n = 96
+    order = np.random.default_rng(0).integers(0, 8, size=n)
+    batch = ImageBatch.from_rgba8(Resolution(1920, 1080), uniq[order])
+    pipe = FacePipeline()
+    a = pipe.run(batch)
+    b = pipe.run(batch)
+    assert np.array_equal(a.landmarks, b.landmarks) and np.array_equal(a.face_flags, b.face_flags)
+    first = {}
+    for i, u in enumerate(order):
+        if u not in first:
+            first[u] = i
+            continue
+        j = first[u]
+        assert len(a.detections[i]) == len(a.detections[j])
+        for x, y in zip(a.detections[i], a.detections[j]):
+            assert np.array_equal(x.as_vector(), y.as_vector())
+        assert np.array_equal(a.landmarks[i], a.landmarks[j])

@@ -54,3 +54,25 @@ def last_device_ms() -> float:
 
 def sync():
     _ffi.check(_ffi.lib().zb_sync(context()))
+
+
+def timer_start():
+    _ffi.check(_ffi.lib().zb_timer_start(context()))
+
+
+def timer_stop_ms() -> float:
+    ms = C.c_float()
+    _ffi.check(_ffi.lib().zb_timer_stop(context(), C.byref(ms)))
+    return float(ms.value)
+
+
+def profile_begin():
+    _ffi.check(_ffi.lib().zb_profile_begin(context()))
+
+
+def profile_end() -> dict:
+    """Stop profiling; {kernel class: {launches, ms, bytes, flops}} (CUDA events per launch)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    _ffi.check(_ffi.lib().zb_profile_end(context(), buf, len(buf), None))
+    return json.loads(buf.value.decode())

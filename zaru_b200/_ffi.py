@@ -69,6 +69,7 @@ SIGNATURES = {
     "zb_detector_set_nms": (i32, [P, f32, i32]),
     "zb_detector_input_resolution": (i32, [P, C.POINTER(i32), C.POINTER(i32)]),
     "zb_detector_detect": (i32, [P, P, P, i32, P, P, i32, P, P]),
+    "zb_detector_extract": (i32, [P, P, P, P, i32, P, P, i32]),
     "zb_estimator_create": (i32, [P, P, i32, f32, f32, PP]),
     "zb_estimator_destroy": (None, [P]),
     "zb_estimator_num_landmarks": (i32, [P]),
@@ -82,6 +83,10 @@ SIGNATURES = {
     "zb_net_weights": (i32, [P, C.POINTER(C.POINTER(C.c_float)), C.POINTER(sz)]),
     "zb_plan_from_onnx": (i32, [P, sz, i32, C.c_char_p, sz, C.POINTER(sz), P, sz, C.POINTER(sz)]),
     "zb_last_device_ms": (f32, [P]),
+    "zb_timer_start": (i32, [P]),
+    "zb_timer_stop": (i32, [P, C.POINTER(f32)]),
+    "zb_profile_begin": (i32, [P]),
+    "zb_profile_end": (i32, [P, C.c_char_p, sz, C.POINTER(sz)]),
 }
 
 _lib = None

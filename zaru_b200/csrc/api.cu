@@ -112,13 +112,48 @@ struct PinBuf {
 
 }  // namespace
 
+struct ProfRec {
+    const char *cls;
+    cudaEvent_t a, b;
+    double bytes, flops;
+};
+
 struct zb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float last_ms = 0.f;
     int default_chunk = 64;
+    // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t prof_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
 };
+
+namespace {
+// Wraps one kernel launch; when profiling is on, brackets it with CUDA events on the launch stream.
+template <class F>
+void prof_launch(zb_ctx *ctx, cudaStream_t s, const char *cls, double bytes, double flops, F &&f) {
+    if (!ctx->prof_on) {
+        f();
+        return;
+    }
+    cudaEvent_t a = ctx->prof_event(), b = ctx->prof_event();
+    CU(cudaEventRecord(a, s));
+    f();
+    CU(cudaEventRecord(b, s));
+    ctx->prof.push_back({cls, a, b, bytes, flops});
+}
+}  // namespace
 
 struct zb_net {
     zb_ctx *ctx = nullptr;
@@ -198,6 +233,18 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, cudaStream_t s) {
             e.res_pool = op.res_pool;
         }
         const int out_pix = to.Cs;
+        zb_ctx *ctx = net->ctx;
+        // algorithmic work of this launch (true channel counts, f32; weights excluded): DESIGN.md §roofline
+        double bytes = 4.0 * nc * ((double)ti.H * ti.W * ti.C + (double)to.H * to.W * to.C);
+        if (op.res >= 0 && op.res != op.in) {
+            const TensorInfo &tr = pl.tensors[op.res];
+            bytes += 4.0 * nc * (double)tr.H * tr.W * tr.C;
+        }
+        double flops = 0;
+        const double opix = (double)nc * to.H * to.W;
+        if (op.kind == OP_CONV) flops = 2.0 * opix * op.N * op.kh * op.kw * ti.C;
+        if (op.kind == OP_DW) flops = 2.0 * opix * op.kh * op.kw * ti.C;
+        if (op.kind == OP_DWPW) flops = 2.0 * opix * (op.kh * op.kw * ti.C + (double)ti.C * op.N);
         switch (op.kind) {
             case OP_CONV:
             case OP_DW:
@@ -222,26 +269,38 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, cudaStream_t s) {
                 if (op.kind == OP_CONV) {
                     p.w = W + op.w_off;
                     const bool pw = op.kh == 1 && op.kw == 1 && op.sh == 1 && op.sw == 1 && op.pt == 0 && op.pl == 0;
-                    launch_conv(p, pw ? CONV_PW : CONV_GATHER, s);
+                    prof_launch(ctx, s, pw ? "conv_gemm<pw>" : "conv_gemm<gather>", bytes, flops,
+                                [&] { launch_conv(p, pw ? CONV_PW : CONV_GATHER, s); });
                 } else if (op.kind == OP_DW) {
                     p.w = W + op.w_off;
-                    launch_dw(p, s);
+                    prof_launch(ctx, s, "dw", bytes, flops, [&] { launch_dw(p, s); });
                 } else {
                     p.w = W + op.w2_off;
                     p.epi.bias = W + op.b2_off;
                     p.dw_w = W + op.w_off;
                     p.dw_b = W + op.b_off;
                     p.act_mid = act_dev(op.act_mid, W);
-                    launch_conv(p, CONV_DWPW, s);
+                    prof_launch(ctx, s, "conv_gemm<dwpw>", bytes, flops, [&] { launch_conv(p, CONV_DWPW, s); });
                 }
                 break;
             }
-            case OP_MAXPOOL: launch_maxpool2(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); break;
-            case OP_RESIZE: launch_resize2x(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); break;
-            case OP_GAP: launch_gap(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); break;
+            case OP_MAXPOOL:
+                prof_launch(ctx, s, "maxpool2", bytes, 0,
+                            [&] { launch_maxpool2(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); });
+                break;
+            case OP_RESIZE:
+                prof_launch(ctx, s, "resize2x", bytes, 0,
+                            [&] { launch_resize2x(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); });
+                break;
+            case OP_GAP:
+                prof_launch(ctx, s, "gap", bytes, 0,
+                            [&] { launch_gap(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, nc, s); });
+                break;
             case OP_ADD:
             case OP_ACT:
-                launch_eltwise(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, out_pix, op.Nstore, e, nc, s);
+                prof_launch(ctx, s, "eltwise", bytes, 0, [&] {
+                    launch_eltwise(in, ti.img_stride, ti.H, ti.W, ti.Cs, out, to.img_stride, out_pix, op.Nstore, e, nc, s);
+                });
                 break;
             default: throw std::runtime_error("internal: unknown op kind");
         }
@@ -338,6 +397,8 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&ctx->ev0));
         CU(cudaEventCreate(&ctx->ev1));
+        CU(cudaEventCreate(&ctx->ev2));
+        CU(cudaEventCreate(&ctx->ev3));
         if (const char *c = getenv("ZB_CHUNK")) {
             int v = atoi(c);
             if (v > 0) ctx->default_chunk = v;
@@ -353,6 +414,9 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream), cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -368,6 +432,73 @@ zb_status zb_sync(zb_ctx *ctx) {
 int64_t zb_launch_count(zb_ctx *) { return g_launch_count; }
 
 float zb_last_device_ms(zb_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+
+zb_status zb_timer_start(zb_ctx *ctx) {
+    return guarded([&]() -> zb_status {
+        if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaEventRecord(ctx->ev2, ctx->stream));
+        return ZB_OK;
+    });
+}
+
+zb_status zb_timer_stop(zb_ctx *ctx, float *ms) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !ms) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/ms is NULL");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaEventRecord(ctx->ev3, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev3));
+        CU(cudaEventElapsedTime(ms, ctx->ev2, ctx->ev3));
+        return ZB_OK;
+    });
+}
+
+zb_status zb_profile_begin(zb_ctx *ctx) {
+    if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    ctx->prof.clear();
+    ctx->ev_used = 0;
+    ctx->prof_on = true;
+    return ZB_OK;
+}
+
+zb_status zb_profile_end(zb_ctx *ctx, char *json, size_t cap, size_t *needed) {
+    return guarded([&]() -> zb_status {
+        if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->prof_on = false;
+        struct Agg { long long launches = 0; double ms = 0, bytes = 0, flops = 0; };
+        std::vector<std::pair<std::string, Agg>> agg;
+        for (auto &r : ctx->prof) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, r.a, r.b));
+            Agg *a = nullptr;
+            for (auto &kv : agg)
+                if (kv.first == r.cls) a = &kv.second;
+            if (!a) {
+                agg.push_back({r.cls, Agg{}});
+                a = &agg.back().second;
+            }
+            a->launches++, a->ms += ms, a->bytes += r.bytes, a->flops += r.flops;
+        }
+        std::string s = "{";
+        char buf[256];
+        for (size_t i = 0; i < agg.size(); i++) {
+            snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%lld,\"ms\":%.6f,\"bytes\":%.1f,\"flops\":%.1f}", i ? "," : "",
+                     agg[i].first.c_str(), agg[i].second.launches, agg[i].second.ms, agg[i].second.bytes,
+                     agg[i].second.flops);
+            s += buf;
+        }
+        s += "}";
+        if (needed) *needed = s.size() + 1;
+        if (json && cap > 0) {
+            size_t n = std::min(cap - 1, s.size());
+            memcpy(json, s.data(), n);
+            json[n] = 0;
+        }
+        return ZB_OK;
+    });
+}
 
 // ---- networks ------------------------------------------------------------------------------------
 zb_status zb_net_load(zb_ctx *ctx, const void *onnx, size_t len, zb_net **out) {
@@ -789,6 +920,63 @@ zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_v
     });
 }
 
+zb_status zb_detector_extract(zb_detector *d, const float *raw_boxes, const float *raw_scores, const zb_view *views,
+                              int32_t n, zb_detection *out_dets, int32_t *out_counts, int32_t cap) {
+    return guarded([&]() -> zb_status {
+        if (!d || !raw_boxes || !raw_scores) return fail(ZB_ERR_INVALID_ARGUMENT, "detector/raw tensors are NULL");
+        if (cap <= 0 || n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "cap must be positive, n non-negative");
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = d->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const Plan &pl = d->net->plan;
+        const DecodeParams dp = decode_params(d->kind, pl, d->thresh, d->iou, d->mode, cap);
+        const size_t nb = (size_t)n * dp.num_anchors * dp.num_params, ns = (size_t)n * dp.num_anchors;
+        DevBuf db, ds;
+        const float *pb = raw_boxes, *ps = raw_scores;
+        if (!is_device_ptr(raw_boxes)) {
+            db.reserve(nb * sizeof(float));
+            CU(cudaMemcpyAsync(db.p, raw_boxes, nb * sizeof(float), cudaMemcpyHostToDevice, s));
+            pb = db.as<float>();
+        }
+        if (!is_device_ptr(raw_scores)) {
+            ds.reserve(ns * sizeof(float));
+            CU(cudaMemcpyAsync(ds.p, raw_scores, ns * sizeof(float), cudaMemcpyHostToDevice, s));
+            ps = ds.as<float>();
+        }
+        d->h_stage.reserve(4 * sizeof(float) * n);
+        float *hfit = d->h_stage.as<float>();
+        for (int i = 0; i < n; i++) {
+            if (views) {
+                RRectF sampled;
+                fit_view(rrect_from_view(views[i]), pl.in_w, pl.in_h, sampled, hfit + 4 * i);
+            } else {
+                hfit[4 * i] = 1.0f, hfit[4 * i + 1] = 0.0f, hfit[4 * i + 2] = 0.0f, hfit[4 * i + 3] = 0.0f;
+            }
+        }
+        d->d_fit.reserve(4 * sizeof(float) * n);
+        d->d_dets.reserve(sizeof(DetDev) * (size_t)n * cap);
+        d->d_counts.reserve(sizeof(int) * n);
+        d->h_counts.reserve(sizeof(int) * n);
+        CU(cudaMemcpyAsync(d->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        Timer tm(ctx, s);
+        launch_decode_nms(pb, ps, d->d_fit.as<float>(), n, dp, d->d_dets.as<DetDev>(), d->d_counts.as<int>(), s);
+        CU(cudaGetLastError());
+        tm.stop();
+        copy_out(out_dets, d->d_dets.p, sizeof(DetDev) * (size_t)n * cap, s);
+        copy_out(out_counts, d->d_counts.p, sizeof(int) * n, s);
+        CU(cudaMemcpyAsync(d->h_counts.p, d->d_counts.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        const int *hc = d->h_counts.as<int>();
+        for (int i = 0; i < n; i++)
+            if (hc[i] > cap)
+                return fail(ZB_ERR_CAPACITY, "item " + std::to_string(i) + " produced " + std::to_string(hc[i]) +
+                                                 " detections; capacity is " + std::to_string(cap));
+        return ZB_OK;
+    });
+}
+
 // ---- estimator -----------------------------------------------------------------------------------------
 zb_status zb_estimator_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, float lo, float hi, zb_estimator **out) {
     return guarded([&]() -> zb_status {
@@ -960,27 +1148,38 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
             // detector
-            launch_sample(frames->f, p->d_views.as<ViewDev>() + c0, nc, dpl.in_w, dpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
-                          tensor_ptr(p->det_net, p->ws_det, dpl.input, c0), dpl.tensors[dpl.input].img_stride, s);
+            prof_launch(ctx, s, "sample", 16.0 * nc * dpl.in_w * dpl.in_h, 0, [&] {
+                launch_sample(frames->f, p->d_views.as<ViewDev>() + c0, nc, dpl.in_w, dpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
+                              tensor_ptr(p->det_net, p->ws_det, dpl.input, c0), dpl.tensors[dpl.input].img_stride, s);
+            });
             run_ops(p->det_net, p->ws_det, c0, nc, s);
-            launch_decode_nms(p->ws_det.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
-                              p->ws_det.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image,
-                              p->d_fit.as<float>() + 4 * c0, nc, dp, p->d_dets.as<DetDev>() + (size_t)c0 * cap,
-                              p->d_counts.as<int>() + c0, s);
+            prof_launch(ctx, s, "decode_nms", 4.0 * nc * dp.num_anchors * (dp.num_params + 1), 0, [&] {
+                launch_decode_nms(p->ws_det.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
+                                  p->ws_det.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image,
+                                  p->d_fit.as<float>() + 4 * c0, nc, dp, p->d_dets.as<DetDev>() + (size_t)c0 * cap,
+                                  p->d_counts.as<int>() + c0, s);
+            });
             // RoI -> landmark view (stays on device)
-            launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0, nc,
-                            lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0,
-                            p->d_rois.as<ViewHost>() + c0, s);
+            prof_launch(ctx, s, "face_roi", 128.0 * nc, 0, [&] {
+                launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0,
+                                nc, lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0,
+                                p->d_lm_fit.as<float>() + 4 * c0, p->d_rois.as<ViewHost>() + c0, s);
+            });
             // landmarks
-            launch_sample(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lpl.in_w, lpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
-                          tensor_ptr(p->lm_net, p->ws_lm, lpl.input, c0), lpl.tensors[lpl.input].img_stride, s);
+            prof_launch(ctx, s, "sample", 16.0 * nc * lpl.in_w * lpl.in_h, 0, [&] {
+                launch_sample(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lpl.in_w, lpl.in_h, -1.0f, 1.0f,
+                              SAMPLE_NHWC4, tensor_ptr(p->lm_net, p->ws_lm, lpl.input, c0),
+                              lpl.tensors[lpl.input].img_stride, s);
+            });
             run_ops(p->lm_net, p->ws_lm, c0, nc, s);
             const int s0 = (int)lpl.outputs[0].per_image, s1 = (int)lpl.outputs[1].per_image;
-            launch_landmarks(p->ws_lm.outs[0].as<float>() + (size_t)c0 * s0, s0,
-                             p->ws_lm.outs[1].as<float>() + (size_t)c0 * s1, s1, nullptr, 0,
-                             p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
-                             p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
-                             p->d_scalars.as<float>() + 2 * c0, s);
+            prof_launch(ctx, s, "landmarks", 8.0 * nc * (3 * L + 1), 0, [&] {
+                launch_landmarks(p->ws_lm.outs[0].as<float>() + (size_t)c0 * s0, s0,
+                                 p->ws_lm.outs[1].as<float>() + (size_t)c0 * s1, s1, nullptr, 0,
+                                 p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
+                                 p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
+                                 p->d_scalars.as<float>() + 2 * c0, s);
+            });
         }
         CU(cudaGetLastError());
         tm.stop();

@@ -21,7 +21,9 @@
 namespace zb {
 namespace {
 
-__device__ __forceinline__ float sigmoid_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+// num.rs:6-8 `1.0 / (1.0 + (-v).exp())`.  Rust's f32::exp is glibc expf (< 0.51 ulp, i.e. correctly rounded
+// in practice); CUDA's expf is only 2-ulp accurate, so evaluate exp in f64 and round once.
+__device__ __forceinline__ float sigmoid_ref(float v) { return 1.0f / (1.0f + (float)exp((double)(-v))); }
 
 // Rust `as u32` on a rounded f32 kept in float form (saturating, NaN -> 0), then `as f32`.
 __device__ __forceinline__ float sat_u32_as_f32(float v) {
@@ -110,7 +112,7 @@ __device__ __forceinline__ AnchorXY anchor_of(const DecodeParams &p, int i) {
 __device__ __forceinline__ float signed_angle_to(float ax, float ay, float bx, float by) {
     const float perp = ax * by - ay * bx;
     const float dot = (0.0f + ax * bx) + ay * by;
-    return -atan2f(perp, dot);
+    return -(float)atan2((double)perp, (double)dot);   // glibc atan2f is correctly rounded in practice
 }
 
 __device__ float decode_field(const DecodeParams &p, const float *__restrict__ bp, int anchor, int field) {

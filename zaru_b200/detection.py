@@ -161,6 +161,20 @@ class Detector:
         self._push_params()
         return self._run(batch, None, len(batch) if n is None else n, want_raw)
 
+    def extract(self, raw_boxes: np.ndarray, raw_scores: np.ndarray, zviews=None):
+        """`network.extract` + NMS + remap on caller-supplied head tensors (detection.rs:231-267)."""
+        self._push_params()
+        raw_boxes = np.ascontiguousarray(raw_boxes, np.float32)
+        raw_scores = np.ascontiguousarray(raw_scores, np.float32)
+        n = raw_boxes.shape[0]
+        dets = (_ffi.zb_detection * (n * self._cap))()
+        counts = (C.c_int32 * n)()
+        arr = (_ffi.zb_view * n)(*zviews) if zviews is not None else None
+        _ffi.check(_ffi.lib().zb_detector_extract(self._h, raw_boxes.ctypes.data, raw_scores.ctypes.data, arr, n,
+                                                  dets, counts, self._cap))
+        return [Detections(Detection(dets[i * self._cap + k]) for k in range(min(counts[i], self._cap)))
+                for i in range(n)]
+
     def _run(self, batch, views, n, want_raw):
         dets = (_ffi.zb_detection * (n * self._cap))()
         counts = (C.c_int32 * n)()
