@@ -62,3 +62,45 @@ def test_bad_models_are_reported():
     assert e.value.status in (_ffi.ZB_ERR_BAD_MODEL, _ffi.ZB_ERR_UNSUPPORTED_OP)
     with pytest.raises(_ffi.ZaruError):
         lower_onnx(b"")
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_arena_allocation_never_aliases_live_tensors(assets_dir, name):
+    _, raw = _load(assets_dir, name)
+    plan, _ = lower_onnx(raw)
+    T, ops = plan["tensors"], plan["ops"]
+    split = plan["split"]
+    assert all(op["stage"] == (1 if i >= split else 0) for i, op in enumerate(ops))
+    used = {}
+    for i, op in enumerate(ops):
+        for t in (op["in"], op["res"], op["out"]):
+            if t >= 0:
+                used.setdefault(t, []).append(i)
+    live = []
+    for t, idxs in used.items():
+        ti = T[t]
+        if ti["buffer"] >= 0:
+            continue
+        lo, hi = min(idxs), max(idxs)
+        if ti["def_op"] < 0:
+            lo = -1
+        # stage-0 ops repeat per chunk before stage 1 starts: anything read in stage 1 must live in the batch arena
+        if hi >= split:
+            assert ti["arena"] == 1, ti
+        else:
+            assert ti["arena"] == 0, ti
+        size = ti["H"] * ti["W"] * ti["Cs"]
+        live.append((t, ti["arena"], lo, hi, ti["offset"], ti["offset"] + size))
+        cap = plan["arena1_per_image"] if ti["arena"] else plan["arena_per_image"]
+        assert ti["offset"] + size <= cap and ti["offset"] % 64 == 0
+    for a in live:
+        for b in live:
+            if a[0] >= b[0] or a[1] != b[1]:
+                continue
+            overlap_time = not (a[3] < b[2] or b[3] < a[2])
+            # boundary tensors are written chunk by chunk during ALL of stage 0: treat them as live from op 0
+            if a[1] == 1 and (a[2] < split or b[2] < split):
+                overlap_time = overlap_time or (min(a[2], b[2]) < split and max(a[2], b[2]) < split) or \
+                    not (a[3] < split and b[2] >= split) and not (b[3] < split and a[2] >= split) and overlap_time
+            if overlap_time:
+                assert a[5] <= b[4] or b[5] <= a[4], f"tensors {T[a[0]]['name']} and {T[b[0]]['name']} overlap"

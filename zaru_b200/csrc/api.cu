@@ -126,6 +126,7 @@ struct zb_ctx {
     int default_chunk = 64;
     // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
     bool prof_on = false;
+    bool prof_detail = false;            // ZB_PROF_DETAIL=1: one profile row per layer instead of per kernel class
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -166,17 +167,19 @@ struct zb_net {
 };
 
 struct Workspace {
-    DevBuf arena;
+    DevBuf arena;                        // stage-0 activations of ONE chunk
     int cap = 0;                         // images per chunk the arena can hold
+    DevBuf arena1;                       // boundary + stage-1 activations of the WHOLE batch
     std::vector<DevBuf> outs;            // graph outputs for the whole batch
     int out_images = 0;
     void ensure(const zb_net *net, int chunk, int n) {
         if (chunk > cap) {
-            arena.reserve((size_t)net->plan.arena_per_image * chunk * sizeof(float));
+            arena.reserve(std::max<size_t>(16, (size_t)net->plan.arena_per_image * chunk * sizeof(float)));
             cap = chunk;
         }
         if (outs.size() != net->plan.outputs.size()) outs.resize(net->plan.outputs.size());
         if (n > out_images) {
+            arena1.reserve(std::max<size_t>(16, (size_t)net->plan.arena1_per_image * n * sizeof(float)));
             for (size_t k = 0; k < outs.size(); k++)
                 outs[k].reserve((size_t)net->plan.outputs[k].per_image * n * sizeof(float));
             out_images = n;
@@ -206,15 +209,19 @@ ActDev act_dev(const ActSpec &a, const float *weights) {
 // Pointer of tensor `t` for the chunk starting at image c0 (arena slot or graph-output row).
 float *tensor_ptr(const zb_net *net, Workspace &ws, int t, int c0) {
     const TensorInfo &ti = net->plan.tensors[t];
-    if (ti.buffer < 0) return ws.arena.as<float>() + (size_t)ti.offset * ws.cap;
+    if (ti.buffer < 0 && ti.arena == 0) return ws.arena.as<float>() + (size_t)ti.offset * ws.cap;
+    if (ti.buffer < 0)   // batch arena: region sized for out_images images, image c0 first
+        return ws.arena1.as<float>() + (size_t)ti.offset * ws.out_images + (size_t)c0 * ti.img_stride;
     return ws.outs[ti.buffer].as<float>() + (size_t)c0 * net->plan.outputs[ti.buffer].per_image + ti.offset;
 }
 
-// Runs the plan's ops for `nc` images whose NHWC4 input already sits in the arena input slot.
-void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, cudaStream_t s) {
+// Runs the plan's ops of one stage for images [c0, c0+nc): stage 0 once per chunk (its NHWC4 input already sits
+// in the arena input slot), stage 1 once for the whole batch (c0 = 0, nc = n).
+void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaStream_t s) {
     const Plan &pl = net->plan;
     const float *W = net->d_weights;
     for (const Op &op : pl.ops) {
+        if (op.stage != stage) continue;
         const TensorInfo &ti = pl.tensors[op.in];
         const TensorInfo &to = pl.tensors[op.out];
         const float *in = tensor_ptr(net, ws, op.in, c0);
@@ -269,7 +276,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, cudaStream_t s) {
                 if (op.kind == OP_CONV) {
                     p.w = W + op.w_off;
                     const bool pw = op.kh == 1 && op.kw == 1 && op.sh == 1 && op.sw == 1 && op.pt == 0 && op.pl == 0;
-                    prof_launch(ctx, s, pw ? "conv_gemm<pw>" : "conv_gemm<gather>", bytes, flops,
+                    prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : pw ? "conv_gemm<pw>" : "conv_gemm<gather>", bytes, flops,
                                 [&] { launch_conv(p, pw ? CONV_PW : CONV_GATHER, s); });
                 } else if (op.kind == OP_DW) {
                     p.w = W + op.w_off;
@@ -280,7 +287,8 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, cudaStream_t s) {
                     p.dw_w = W + op.w_off;
                     p.dw_b = W + op.b_off;
                     p.act_mid = act_dev(op.act_mid, W);
-                    prof_launch(ctx, s, "conv_gemm<dwpw>", bytes, flops, [&] { launch_conv(p, CONV_DWPW, s); });
+                    prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "conv_gemm<dwpw>", bytes, flops,
+                                [&] { launch_conv(p, CONV_DWPW, s); });
                 }
                 break;
             }
@@ -399,6 +407,7 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         CU(cudaEventCreate(&ctx->ev1));
         CU(cudaEventCreate(&ctx->ev2));
         CU(cudaEventCreate(&ctx->ev3));
+        if (const char *c = getenv("ZB_PROF_DETAIL")) ctx->prof_detail = atoi(c) != 0;
         if (const char *c = getenv("ZB_CHUNK")) {
             int v = atoi(c);
             if (v > 0) ctx->default_chunk = v;
@@ -482,7 +491,7 @@ zb_status zb_profile_end(zb_ctx *ctx, char *json, size_t cap, size_t *needed) {
             a->launches++, a->ms += ms, a->bytes += r.bytes, a->flops += r.flops;
         }
         std::string s = "{";
-        char buf[256];
+        char buf[512];
         for (size_t i = 0; i < agg.size(); i++) {
             snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%lld,\"ms\":%.6f,\"bytes\":%.1f,\"flops\":%.1f}", i ? "," : "",
                      agg[i].first.c_str(), agg[i].second.launches, agg[i].second.ms, agg[i].second.bytes,
@@ -625,8 +634,9 @@ zb_status zb_net_estimate(zb_net *net, const float *input, int32_t n, float *con
             const int nc = std::min(chunk, n - c0);
             launch_nchw_to_nhwc4(d_in + in_elems * c0, nc, pl.in_h, pl.in_w, tensor_ptr(net, ws, pl.input, c0),
                                  pl.tensors[pl.input].img_stride, s);
-            run_ops(net, ws, c0, nc, s);
+            run_ops(net, ws, c0, nc, 0, s);
         }
+        run_ops(net, ws, 0, n, 1, s);
         tm.stop();
         for (size_t k = 0; k < pl.outputs.size(); k++)
             copy_out(outputs[k], ws.outs[k].p, (size_t)pl.outputs[k].per_image * n * sizeof(float), s);
@@ -896,12 +906,11 @@ zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_v
             const int nc = std::min(chunk, n - c0);
             launch_sample(frames->f, d->d_views.as<ViewDev>() + c0, nc, pl.in_w, pl.in_h, d->lo, d->hi, SAMPLE_NHWC4,
                           tensor_ptr(d->net, d->ws, pl.input, c0), pl.tensors[pl.input].img_stride, s);
-            run_ops(d->net, d->ws, c0, nc, s);
-            launch_decode_nms(d->ws.outs[0].as<float>() + (size_t)c0 * pl.outputs[0].per_image,
-                              d->ws.outs[1].as<float>() + (size_t)c0 * pl.outputs[1].per_image,
-                              d->d_fit.as<float>() + 4 * c0, nc, dp, d->d_dets.as<DetDev>() + (size_t)c0 * cap,
-                              d->d_counts.as<int>() + c0, s);
+            run_ops(d->net, d->ws, c0, nc, 0, s);
         }
+        run_ops(d->net, d->ws, 0, n, 1, s);
+        launch_decode_nms(d->ws.outs[0].as<float>(), d->ws.outs[1].as<float>(), d->d_fit.as<float>(), n, dp,
+                          d->d_dets.as<DetDev>(), d->d_counts.as<int>(), s);
         CU(cudaGetLastError());
         tm.stop();
         copy_out(out_dets, d->d_dets.p, sizeof(DetDev) * (size_t)n * cap, s);
@@ -1049,13 +1058,15 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
             const int nc = std::min(chunk, n - c0);
             launch_sample(frames->f, e->d_views.as<ViewDev>() + c0, nc, pl.in_w, pl.in_h, e->lo, e->hi, SAMPLE_NHWC4,
                           tensor_ptr(e->net, e->ws, pl.input, c0), pl.tensors[pl.input].img_stride, s);
-            run_ops(e->net, e->ws, c0, nc, s);
+            run_ops(e->net, e->ws, c0, nc, 0, s);
+        }
+        run_ops(e->net, e->ws, 0, n, 1, s);
+        {
             const int s0 = (int)pl.outputs[0].per_image, s1 = (int)pl.outputs[1].per_image;
             const int s2 = pl.outputs.size() > 2 ? (int)pl.outputs[2].per_image : 0;
-            launch_landmarks(e->ws.outs[0].as<float>() + (size_t)c0 * s0, s0, e->ws.outs[1].as<float>() + (size_t)c0 * s1,
-                             s1, s2 ? e->ws.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2,
-                             e->d_fit.as<float>() + 4 * c0, e->d_views.as<ViewDev>() + c0, nullptr, nc, lp,
-                             e->d_lm.as<float>() + (size_t)c0 * L * 3, e->d_scalars.as<float>() + 2 * c0, s);
+            launch_landmarks(e->ws.outs[0].as<float>(), s0, e->ws.outs[1].as<float>(), s1,
+                             s2 ? e->ws.outs[2].as<float>() : nullptr, s2, e->d_fit.as<float>(),
+                             e->d_views.as<ViewDev>(), nullptr, n, lp, e->d_lm.as<float>(), e->d_scalars.as<float>(), s);
         }
         CU(cudaGetLastError());
         tm.stop();
@@ -1145,40 +1156,42 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         lp.net_h = lpl.in_h;
         lp.track_transform = 1;
         Timer tm(ctx, s);
+        // detector, stage 0 (large activations): per chunk so they stay L2-resident
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
-            // detector
             prof_launch(ctx, s, "sample", 16.0 * nc * dpl.in_w * dpl.in_h, 0, [&] {
                 launch_sample(frames->f, p->d_views.as<ViewDev>() + c0, nc, dpl.in_w, dpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
                               tensor_ptr(p->det_net, p->ws_det, dpl.input, c0), dpl.tensors[dpl.input].img_stride, s);
             });
-            run_ops(p->det_net, p->ws_det, c0, nc, s);
-            prof_launch(ctx, s, "decode_nms", 4.0 * nc * dp.num_anchors * (dp.num_params + 1), 0, [&] {
-                launch_decode_nms(p->ws_det.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
-                                  p->ws_det.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image,
-                                  p->d_fit.as<float>() + 4 * c0, nc, dp, p->d_dets.as<DetDev>() + (size_t)c0 * cap,
-                                  p->d_counts.as<int>() + c0, s);
-            });
-            // RoI -> landmark view (stays on device)
-            prof_launch(ctx, s, "face_roi", 128.0 * nc, 0, [&] {
-                launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0,
-                                nc, lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0,
-                                p->d_lm_fit.as<float>() + 4 * c0, p->d_rois.as<ViewHost>() + c0, s);
-            });
-            // landmarks
+            run_ops(p->det_net, p->ws_det, c0, nc, 0, s);
+        }
+        // detector, stage 1 (deep, spatially tiny layers) + decode/NMS + RoI: once for the whole batch
+        run_ops(p->det_net, p->ws_det, 0, n, 1, s);
+        prof_launch(ctx, s, "decode_nms", 4.0 * n * dp.num_anchors * (dp.num_params + 1), 0, [&] {
+            launch_decode_nms(p->ws_det.outs[0].as<float>(), p->ws_det.outs[1].as<float>(), p->d_fit.as<float>(), n, dp,
+                              p->d_dets.as<DetDev>(), p->d_counts.as<int>(), s);
+        });
+        prof_launch(ctx, s, "face_roi", 128.0 * n, 0, [&] {
+            launch_face_roi(frames->f, p->d_dets.as<DetDev>(), p->d_counts.as<int>(), cap, 0, n, lpl.in_w, lpl.in_h,
+                            p->d_lm_views.as<ViewDev>(), p->d_lm_fit.as<float>(), p->d_rois.as<ViewHost>(), s);
+        });
+        // landmarks, stage 0 per chunk, stage 1 per batch
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int nc = std::min(chunk, n - c0);
             prof_launch(ctx, s, "sample", 16.0 * nc * lpl.in_w * lpl.in_h, 0, [&] {
                 launch_sample(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lpl.in_w, lpl.in_h, -1.0f, 1.0f,
                               SAMPLE_NHWC4, tensor_ptr(p->lm_net, p->ws_lm, lpl.input, c0),
                               lpl.tensors[lpl.input].img_stride, s);
             });
-            run_ops(p->lm_net, p->ws_lm, c0, nc, s);
+            run_ops(p->lm_net, p->ws_lm, c0, nc, 0, s);
+        }
+        run_ops(p->lm_net, p->ws_lm, 0, n, 1, s);
+        {
             const int s0 = (int)lpl.outputs[0].per_image, s1 = (int)lpl.outputs[1].per_image;
-            prof_launch(ctx, s, "landmarks", 8.0 * nc * (3 * L + 1), 0, [&] {
-                launch_landmarks(p->ws_lm.outs[0].as<float>() + (size_t)c0 * s0, s0,
-                                 p->ws_lm.outs[1].as<float>() + (size_t)c0 * s1, s1, nullptr, 0,
-                                 p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
-                                 p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
-                                 p->d_scalars.as<float>() + 2 * c0, s);
+            prof_launch(ctx, s, "landmarks", 8.0 * n * (3 * L + 1), 0, [&] {
+                launch_landmarks(p->ws_lm.outs[0].as<float>(), s0, p->ws_lm.outs[1].as<float>(), s1, nullptr, 0,
+                                 p->d_lm_fit.as<float>(), p->d_lm_views.as<ViewDev>(), p->d_rois.as<ViewHost>(), n, lp,
+                                 p->d_lm.as<float>(), p->d_scalars.as<float>(), s);
             });
         }
         CU(cudaGetLastError());

@@ -13,6 +13,8 @@
 // Replaces the engine call `ort.session.run` / `plan.run` (crates/zaru/src/nn/mod.rs:496, :528).
 #include <cuda_runtime.h>
 
+#include <stdexcept>
+
 #include "kernels.h"
 
 namespace zb {
@@ -59,18 +61,71 @@ __device__ __forceinline__ float4 residual4_at(const EpiDev &e, int img, int oy,
 // Implicit-GEMM convolution.  MODE: 0 gather (any kh,kw,stride,pads), 1 pointwise (1x1/s1/p0),
 // 2 fused depthwise producer.
 // ------------------------------------------------------------------------------------------------
-constexpr int BK = 32;
 
-template <int BM, int BN, int TM, int TN, int MODE>
+// Depthwise KSxKS over channels [k, k+4) for one output pixel.  All loads of a row (KS=5) or of the whole
+// window (KS=3) are issued before the FMAs that consume them, so one thread keeps 9 (5) independent
+// 128-bit loads in flight instead of a dependent load->FMA chain.
+template <int KS>
+__device__ __forceinline__ float4 dw_window(const ConvDev &p, const float *__restrict__ a_base, int iy0, int ix0, int k) {
+    float4 v = ldg4(p.dw_b + k);
+    if (KS == 3) {
+        float4 x[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+            const int iy = iy0 + ky;
+            const bool rowok = iy >= 0 && iy < p.H;
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int ix = ix0 + kx;
+                x[ky * 3 + kx] = (rowok && ix >= 0 && ix < p.W) ? ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + k)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const float4 wv = ldg4(p.dw_w + t * p.Cs_in + k);
+            v.x = fmaf(x[t].x, wv.x, v.x);
+            v.y = fmaf(x[t].y, wv.y, v.y);
+            v.z = fmaf(x[t].z, wv.z, v.z);
+            v.w = fmaf(x[t].w, wv.w, v.w);
+        }
+    } else {
+#pragma unroll 1
+        for (int ky = 0; ky < KS; ky++) {
+            const int iy = iy0 + ky;
+            if (iy < 0 || iy >= p.H) continue;
+            float4 x[KS];
+#pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+                const int ix = ix0 + kx;
+                x[kx] = (ix >= 0 && ix < p.W) ? ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + k)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+                const float4 wv = ldg4(p.dw_w + (ky * KS + kx) * p.Cs_in + k);
+                v.x = fmaf(x[kx].x, wv.x, v.x);
+                v.y = fmaf(x[kx].y, wv.y, v.y);
+                v.z = fmaf(x[kx].z, wv.z, v.z);
+                v.w = fmaf(x[kx].w, wv.w, v.w);
+            }
+        }
+    }
+    return v;
+}
+
+template <int BM, int BN, int TM, int TN, int BK, int MODE, int KS>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const ConvDev p) {
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int TXN = BN / TN;
-    constexpr int A_PER_THREAD = (BM * BK / 4) / NT;   // float4 A elements per thread per chunk
-    constexpr int W_PER_THREAD = (BK * BN / 4) / NT;
-    static_assert(NT % BM == 0 || BM % NT == 0, "thread->pixel mapping");
-    static_assert((BM * BK / 4) % NT == 0 && (BK * BN / 4) % NT == 0, "tile divisibility");
+    constexpr int QP = BK / 4;                          // k-quads (float4) per pixel per chunk
+    constexpr int A_PER_THREAD = (BM * QP) / NT;        // float4 A elements per thread per chunk
+    constexpr int W_TOTAL = BK * BN / 4;
+    constexpr int W_PER_THREAD = (W_TOTAL + NT - 1) / NT;
+    constexpr int AKP = BK + 4;                         // As row stride: rows stay 16-byte aligned
+    static_assert((BM * QP) % NT == 0 && NT % QP == 0, "tile divisibility");
 
-    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float As[BM][AKP];         // pixel-major: one STS.128 per produced float4
     __shared__ __align__(16) float Ws[BK][BN];
 
     const int tid = threadIdx.x;
@@ -78,57 +133,48 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int HoWo = p.Ho * p.Wo;
 
-    // --- per-thread A-load assignment: element e = tid + i*NT ; m = e % BM ; kq = e / BM ---------------
-    // NT is a multiple of BM (or BM == NT), so every element of this thread has the same pixel m.
-    const int a_m = tid % BM;
-    const int a_kq0 = tid / BM;                 // first k-quad; subsequent ones step by NT/BM
-    constexpr int A_KQ_STEP = NT / BM > 0 ? NT / BM : 1;
-    const int gm = m0 + a_m;
-    const bool a_valid = gm < p.M;
-    int a_img = 0, a_oy = 0, a_ox = 0;
-    if (a_valid) {
-        a_img = gm / HoWo;
-        int r = gm - a_img * HoWo;
-        a_oy = r / p.Wo;
-        a_ox = r - a_oy * p.Wo;
+    // --- per-thread A-load assignment: element e = tid + i*NT ; kq = e % QP (same for every i) ; m = e / QP.
+    // Consecutive lanes cover consecutive channel quads of one pixel, so a warp's 128-bit loads are contiguous.
+    const int a_kq = tid % QP;
+    const int a_mb = tid / QP;
+    long long a_off[A_PER_THREAD];                      // element offset of the image (PW: of the pixel)
+    int a_yx[A_PER_THREAD];                             // (iy0 << 16) | (ix0 & 0xffff); invalid pixel: a_off < 0
+#pragma unroll
+    for (int i = 0; i < A_PER_THREAD; i++) {
+        const int gm = m0 + a_mb + i * (NT / QP);
+        if (gm < p.M) {
+            const int img = gm / HoWo;
+            const int r = gm - img * HoWo;
+            const int oy = r / p.Wo, ox = r - oy * p.Wo;
+            a_off[i] = (long long)img * p.in_img_stride;
+            if (MODE == CONV_PW) a_off[i] += ((long long)oy * p.W + ox) * p.Cs_in;
+            a_yx[i] = ((oy * p.sh - p.pt) << 16) | ((ox * p.sw - p.pl) & 0xffff);
+        } else {
+            a_off[i] = -1;
+            a_yx[i] = 0;
+        }
     }
-    const float *a_base = p.in + (long long)a_img * p.in_img_stride;
-    const int iy0 = a_oy * p.sh - p.pt, ix0 = a_ox * p.sw - p.pl;
 
     float4 a_reg[A_PER_THREAD];
     float4 w_reg[W_PER_THREAD];
 
     auto load_chunk = [&](int k0) {
+        const int k = k0 + a_kq * 4;
 #pragma unroll
         for (int i = 0; i < A_PER_THREAD; i++) {
-            const int kq = a_kq0 + i * A_KQ_STEP;
-            const int k = k0 + kq * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a_valid && k < p.K) {
+            if (a_off[i] >= 0 && k < p.K) {
+                const int iy0 = a_yx[i] >> 16, ix0 = (int)(short)(a_yx[i] & 0xffff);
                 if (MODE == CONV_PW) {
-                    v = ldg4(a_base + ((long long)a_oy * p.W + a_ox) * p.Cs_in + k);
+                    v = ldg4(p.in + a_off[i] + k);
                 } else if (MODE == CONV_GATHER) {
                     const int tap = k / p.Cs_in, c = k - tap * p.Cs_in;
                     const int ky = tap / p.kw, kx = tap - ky * p.kw;
                     const int iy = iy0 + ky, ix = ix0 + kx;
                     if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                        v = ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + c);
-                } else {   // CONV_DWPW: depthwise kh x kw over channels [k, k+4)
-                    v = ldg4(p.dw_b + k);
-                    for (int ky = 0; ky < p.kh; ky++) {
-                        const int iy = iy0 + ky;
-                        if (iy < 0 || iy >= p.H) continue;
-                        for (int kx = 0; kx < p.kw; kx++) {
-                            const int ix = ix0 + kx;
-                            if (ix < 0 || ix >= p.W) continue;
-                            const float4 x = ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + k);
-                            const float4 wv = ldg4(p.dw_w + (ky * p.kw + kx) * p.Cs_in + k);
-                            v.x = fmaf(x.x, wv.x, v.x);
-                            v.y = fmaf(x.y, wv.y, v.y);
-                            v.z = fmaf(x.z, wv.z, v.z);
-                            v.w = fmaf(x.w, wv.w, v.w);
-                        }
-                    }
+                        v = ldg4(p.in + a_off[i] + ((long long)iy * p.W + ix) * p.Cs_in + c);
+                } else {   // CONV_DWPW: depthwise KS x KS over channels [k, k+4)
+                    v = dw_window<KS == 0 ? 3 : KS>(p, p.in + a_off[i], iy0, ix0, k);
                     v.x = apply_act(v.x, p.act_mid, k);
                     v.y = apply_act(v.y, p.act_mid, k + 1);
                     v.z = apply_act(v.z, p.act_mid, k + 2);
@@ -140,28 +186,22 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
 #pragma unroll
         for (int i = 0; i < W_PER_THREAD; i++) {
             const int e = tid + i * NT;
-            const int nq = e % (BN / 4), k = e / (BN / 4);
-            const int gk = k0 + k, gn = n0 + nq * 4;
+            const int nq = e % (BN / 4), kr = e / (BN / 4);
+            const int gk = k0 + kr, gn = n0 + nq * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gk < p.K && gn < p.Ns) v = ldg4(p.w + (long long)gk * p.Ns + gn);
+            if (e < W_TOTAL && gk < p.K && gn < p.Ns) v = ldg4(p.w + (long long)gk * p.Ns + gn);
             w_reg[i] = v;
         }
     };
 
     auto store_chunk = [&]() {
 #pragma unroll
-        for (int i = 0; i < A_PER_THREAD; i++) {
-            const int kq = a_kq0 + i * A_KQ_STEP;
-            As[kq * 4 + 0][a_m] = a_reg[i].x;
-            As[kq * 4 + 1][a_m] = a_reg[i].y;
-            As[kq * 4 + 2][a_m] = a_reg[i].z;
-            As[kq * 4 + 3][a_m] = a_reg[i].w;
-        }
+        for (int i = 0; i < A_PER_THREAD; i++)
+            *reinterpret_cast<float4 *>(&As[a_mb + i * (NT / QP)][a_kq * 4]) = a_reg[i];
 #pragma unroll
         for (int i = 0; i < W_PER_THREAD; i++) {
             const int e = tid + i * NT;
-            const int nq = e % (BN / 4), k = e / (BN / 4);
-            *reinterpret_cast<float4 *>(&Ws[k][nq * 4]) = w_reg[i];
+            if (e < W_TOTAL) *reinterpret_cast<float4 *>(&Ws[e / (BN / 4)][(e % (BN / 4)) * 4]) = w_reg[i];
         }
     };
 
@@ -177,26 +217,27 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
         __syncthreads();
         if (k0 + BK < p.K) load_chunk(k0 + BK);
         const int kmax = min(BK, p.K - k0);
+#pragma unroll 2
         for (int kk = 0; kk < kmax; kk += 4) {
+            float a4[TM][4], b4[4][TN];
 #pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) {
-                const int k = kk + k4;
-                float a[TM], b[TN];
+            for (int i = 0; i < TM; i++) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[ty * TM + i][kk]);
+                a4[i][0] = v.x, a4[i][1] = v.y, a4[i][2] = v.z, a4[i][3] = v.w;
+            }
 #pragma unroll
-                for (int i = 0; i < TM; i += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(&As[k][ty * TM + i]);
-                    a[i] = v.x, a[i + 1] = v.y, a[i + 2] = v.z, a[i + 3] = v.w;
-                }
+            for (int q = 0; q < 4; q++)
 #pragma unroll
                 for (int j = 0; j < TN; j += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(&Ws[k][tx * TN + j]);
-                    b[j] = v.x, b[j + 1] = v.y, b[j + 2] = v.z, b[j + 3] = v.w;
+                    const float4 v = *reinterpret_cast<const float4 *>(&Ws[kk + q][tx * TN + j]);
+                    b4[q][j] = v.x, b4[q][j + 1] = v.y, b4[q][j + 2] = v.z, b4[q][j + 3] = v.w;
                 }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
 #pragma unroll
                 for (int i = 0; i < TM; i++)
 #pragma unroll
-                    for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-            }
+                    for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a4[i][q], b4[q][j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -255,15 +296,25 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
     }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, int BKT>
 void launch_conv_cfg(const ConvDev &p, ConvMode mode, cudaStream_t s) {
     dim3 grid((p.M + BM - 1) / BM, (p.Ns + BN - 1) / BN);
     dim3 block((BM / TM) * (BN / TN));
     switch (mode) {
-        case CONV_GATHER: conv_gemm_kernel<BM, BN, TM, TN, CONV_GATHER><<<grid, block, 0, s>>>(p); break;
-        case CONV_PW: conv_gemm_kernel<BM, BN, TM, TN, CONV_PW><<<grid, block, 0, s>>>(p); break;
-        case CONV_DWPW: conv_gemm_kernel<BM, BN, TM, TN, CONV_DWPW><<<grid, block, 0, s>>>(p); break;
+        case CONV_GATHER: conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_GATHER, 0><<<grid, block, 0, s>>>(p); break;
+        case CONV_PW: conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_PW, 0><<<grid, block, 0, s>>>(p); break;
+        case CONV_DWPW:
+            if (p.kh == 3 && p.kw == 3) conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_DWPW, 3><<<grid, block, 0, s>>>(p);
+            else if (p.kh == 5 && p.kw == 5) conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_DWPW, 5><<<grid, block, 0, s>>>(p);
+            else throw std::runtime_error("unsupported op: fused depthwise kernel other than 3x3 / 5x5");
+            break;
     }
+}
+
+template <int BM, int BN, int TM, int TN>
+void launch_conv_tile(const ConvDev &p, ConvMode mode, cudaStream_t s) {
+    if (p.K <= 16) launch_conv_cfg<BM, BN, TM, TN, 16>(p, mode, s);
+    else launch_conv_cfg<BM, BN, TM, TN, 32>(p, mode, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,9 +458,10 @@ inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total +
 
 void launch_conv(const ConvDev &p, ConvMode mode, cudaStream_t s) {
     g_launch_count++;
-    if (p.Ns <= 32) launch_conv_cfg<128, 32, 4, 4>(p, mode, s);
-    else if (p.Ns <= 64) launch_conv_cfg<128, 64, 8, 4>(p, mode, s);
-    else launch_conv_cfg<64, 128, 4, 8>(p, mode, s);
+    if (p.Ns <= 16) launch_conv_tile<256, 16, 4, 4>(p, mode, s);
+    else if (p.Ns <= 32) launch_conv_tile<128, 32, 4, 4>(p, mode, s);
+    else if (p.Ns <= 64) launch_conv_tile<128, 64, 8, 4>(p, mode, s);
+    else launch_conv_tile<64, 128, 4, 8>(p, mode, s);
 }
 
 void launch_dw(const ConvDev &p, cudaStream_t s) {

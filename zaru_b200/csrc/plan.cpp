@@ -567,60 +567,78 @@ struct Lowerer {
         for (auto &ti : plan.tensors)
             if (ti.exact && ti.buffer < 0 && ti.last_use >= 0 && ti.Cs % 4 != 0)
                 unsupported("exact-layout tensor '" + ti.name + "' consumed by another op");
-        // arena allocation (first fit over per-image element offsets)
+        // stage split: the longest suffix of ops whose outputs are all small runs once per batch (stage 1)
+        plan.split = (int)plan.ops.size();
+        if (opt.batch_stage_bytes > 0) {
+            while (plan.split > 0) {
+                const TensorInfo &to = plan.tensors[plan.ops[plan.split - 1].out];
+                if ((int64_t)to.H * to.W * to.Cs * 4 > opt.batch_stage_bytes) break;
+                plan.split--;
+            }
+        }
+        for (size_t i = 0; i < plan.ops.size(); i++) plan.ops[i].stage = (int)i >= plan.split ? 1 : 0;
+        for (auto &ti : plan.tensors) ti.arena = 0;
+        for (size_t i = plan.split; i < plan.ops.size(); i++) {
+            const Op &op = plan.ops[i];
+            for (int t : {op.in, op.in2, op.res, op.out})
+                if (t >= 0) plan.tensors[t].arena = 1;
+        }
+        // arena allocation (first fit over per-image element offsets), one pass per arena
         struct Block { int64_t off, size; };
-        std::vector<Block> free_list;
-        int64_t arena_end = 0;
-        std::vector<std::pair<int, int>> live;  // (last_use, tensor)
-        auto alloc = [&](int64_t size) {
-            for (size_t i = 0; i < free_list.size(); i++) {
-                if (free_list[i].size >= size) {
-                    int64_t off = free_list[i].off;
-                    free_list[i].off += size;
-                    free_list[i].size -= size;
-                    if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
-                    return off;
-                }
-            }
-            int64_t off = arena_end;
-            arena_end += size;
-            return off;
-        };
-        auto release = [&](int64_t off, int64_t size) {
-            free_list.push_back({off, size});
-            std::sort(free_list.begin(), free_list.end(), [](const Block &a, const Block &b) { return a.off < b.off; });
-            for (size_t i = 0; i + 1 < free_list.size();) {
-                if (free_list[i].off + free_list[i].size == free_list[i + 1].off) {
-                    free_list[i].size += free_list[i + 1].size;
-                    free_list.erase(free_list.begin() + i + 1);
-                } else i++;
-            }
-            if (!free_list.empty() && free_list.back().off + free_list.back().size == arena_end) {
-                arena_end = free_list.back().off;
-                free_list.pop_back();
-            }
-        };
         auto slot = [&](const TensorInfo &ti) { return (int64_t)round_up((int)((int64_t)ti.H * ti.W * ti.Cs), 64); };
-        {
-            TensorInfo &ti = plan.tensors[plan.input];
-            ti.offset = alloc(slot(ti));
-            live.push_back({ti.last_use, plan.input});
-        }
-        for (size_t i = 0; i < plan.ops.size(); i++) {
-            for (size_t k = 0; k < live.size();) {
-                if (live[k].first < (int)i) {
-                    const TensorInfo &ti = plan.tensors[live[k].second];
-                    release(ti.offset, slot(ti));
-                    live.erase(live.begin() + k);
-                } else k++;
+        for (int arena = 0; arena < 2; arena++) {
+            std::vector<Block> free_list;
+            int64_t arena_end = 0, arena_max = 0;
+            std::vector<std::pair<int, int>> live;  // (last_use, tensor)
+            auto alloc = [&](int64_t size) {
+                for (size_t i = 0; i < free_list.size(); i++) {
+                    if (free_list[i].size >= size) {
+                        int64_t off = free_list[i].off;
+                        free_list[i].off += size;
+                        free_list[i].size -= size;
+                        if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
+                        return off;
+                    }
+                }
+                int64_t off = arena_end;
+                arena_end += size;
+                arena_max = std::max(arena_max, arena_end);
+                return off;
+            };
+            auto release = [&](int64_t off, int64_t size) {
+                free_list.push_back({off, size});
+                std::sort(free_list.begin(), free_list.end(), [](const Block &a, const Block &b) { return a.off < b.off; });
+                for (size_t i = 0; i + 1 < free_list.size();) {
+                    if (free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+                        free_list[i].size += free_list[i + 1].size;
+                        free_list.erase(free_list.begin() + i + 1);
+                    } else i++;
+                }
+                if (!free_list.empty() && free_list.back().off + free_list.back().size == arena_end) {
+                    arena_end = free_list.back().off;
+                    free_list.pop_back();
+                }
+            };
+            if (plan.tensors[plan.input].arena == arena) {
+                TensorInfo &ti = plan.tensors[plan.input];
+                ti.offset = alloc(slot(ti));
+                live.push_back({ti.last_use, plan.input});
             }
-            TensorInfo &to = plan.tensors[plan.ops[i].out];
-            if (to.buffer >= 0) continue;
-            to.offset = alloc(slot(to));
-            live.push_back({std::max(to.last_use, (int)i), plan.ops[i].out});
-            plan.arena_per_image = std::max(plan.arena_per_image, arena_end);
+            for (size_t i = 0; i < plan.ops.size(); i++) {
+                for (size_t k = 0; k < live.size();) {
+                    if (live[k].first < (int)i) {
+                        const TensorInfo &ti = plan.tensors[live[k].second];
+                        release(ti.offset, slot(ti));
+                        live.erase(live.begin() + k);
+                    } else k++;
+                }
+                TensorInfo &to = plan.tensors[plan.ops[i].out];
+                if (to.buffer >= 0 || to.arena != arena) continue;
+                to.offset = alloc(slot(to));
+                live.push_back({std::max(to.last_use, (int)i), plan.ops[i].out});
+            }
+            (arena == 0 ? plan.arena_per_image : plan.arena1_per_image) = arena_max;
         }
-        plan.arena_per_image = std::max(plan.arena_per_image, arena_end);
 
         // weights
         for (size_t i = 0; i < plan.ops.size(); i++) {
@@ -672,6 +690,13 @@ struct Lowerer {
             }
             if (op.act1.kind == ACT_PRELU) op.act1.slope_off = pack_vec(s.slope1, op.N, std::max(op.Ns, round_up(op.N, 4)), "slope");
             if (op.act2.kind == ACT_PRELU) op.act2.slope_off = pack_vec(s.slope2, op.N, std::max(op.Ns, round_up(op.N, 4)), "slope");
+            {
+                static const char *kn[] = {"conv", "dw", "maxpool", "resize", "gap", "add", "act", "dwpw"};
+                std::ostringstream lb;
+                lb << kn[op.kind] << op.kh << "x" << op.kw << " " << ti.H << "x" << ti.W << "x" << ti.C << "->" << to.H << "x"
+                   << to.W << "x" << op.N << " s" << op.sh << (op.stage ? " [batch]" : " [chunk]");
+                op.label = lb.str();
+            }
             if (op.res >= 0) {
                 const TensorInfo &tr = plan.tensors[op.res];
                 int rh = op.res_pool ? (tr.H - 2) / 2 + 1 : tr.H, rw = op.res_pool ? (tr.W - 2) / 2 + 1 : tr.W;
@@ -733,19 +758,20 @@ std::string Plan::to_json() const {
     std::ostringstream os;
     os.precision(9);
     os << "{\"input\":" << input << ",\"in_h\":" << in_h << ",\"in_w\":" << in_w
-       << ",\"arena_per_image\":" << arena_per_image << ",\"macs_per_image\":" << macs_per_image
+       << ",\"arena_per_image\":" << arena_per_image << ",\"arena1_per_image\":" << arena1_per_image
+       << ",\"split\":" << split << ",\"macs_per_image\":" << macs_per_image
        << ",\"num_weights\":" << weights.size() << ",\"tensors\":[";
     for (size_t i = 0; i < tensors.size(); i++) {
         const auto &t = tensors[i];
         os << (i ? "," : "") << "{\"name\":\"" << t.name << "\",\"C\":" << t.C << ",\"H\":" << t.H << ",\"W\":" << t.W
-           << ",\"Cs\":" << t.Cs << ",\"exact\":" << (t.exact ? 1 : 0) << ",\"buffer\":" << t.buffer
+           << ",\"Cs\":" << t.Cs << ",\"exact\":" << (t.exact ? 1 : 0) << ",\"buffer\":" << t.buffer << ",\"arena\":" << t.arena
            << ",\"offset\":" << t.offset << ",\"img_stride\":" << t.img_stride << ",\"def_op\":" << t.def_op
            << ",\"last_use\":" << t.last_use << "}";
     }
     os << "],\"ops\":[";
     for (size_t i = 0; i < ops.size(); i++) {
         const auto &o = ops[i];
-        os << (i ? "," : "") << "{\"kind\":" << o.kind << ",\"in\":" << o.in << ",\"out\":" << o.out
+        os << (i ? "," : "") << "{\"kind\":" << o.kind << ",\"stage\":" << o.stage << ",\"in\":" << o.in << ",\"out\":" << o.out
            << ",\"kh\":" << o.kh << ",\"kw\":" << o.kw << ",\"sh\":" << o.sh << ",\"sw\":" << o.sw << ",\"pt\":" << o.pt
            << ",\"pl\":" << o.pl << ",\"K\":" << o.K << ",\"N\":" << o.N << ",\"Ns\":" << o.Ns
            << ",\"Nstore\":" << o.Nstore << ",\"w_off\":" << o.w_off << ",\"b_off\":" << o.b_off

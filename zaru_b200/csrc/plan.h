@@ -39,6 +39,7 @@ struct TensorInfo {
     int Cs = 0;                   // channel (pixel) stride in elements; channels [C,Cs) are zero
     bool exact = false;           // Cs == C required (feeds a graph output)
     int buffer = -1;              // -1: arena ; >=0: graph output index
+    int arena = 0;                // 0: chunk arena (stage-0 internal) ; 1: batch arena (boundary + stage-1 tensors)
     int64_t offset = 0;           // per-image element offset inside arena slot / output row
     int64_t img_stride = 0;       // elements between consecutive images
     int def_op = -1, last_use = -1;
@@ -60,7 +61,9 @@ struct Op {
     int res = -1;                 // residual tensor id (added after act1)
     int res_pool = 0;             // residual read through a 2x2/s2 max-pool
     ActSpec act2;                 // after residual add
+    int stage = 0;                // 0: run per chunk (large activations stay L2-resident) ; 1: run once per batch
     std::string src_nodes;        // ONNX node names folded into this op (debug)
+    std::string label;            // "dwpw 64x64x24->28 s1" (profiling detail)
 };
 
 struct OutputInfo {
@@ -77,13 +80,18 @@ struct Plan {
     std::string input_name;
     int input = -1;               // tensor id of the network input (NHWC4)
     int in_c = 3, in_h = 0, in_w = 0;
-    int64_t arena_per_image = 0;  // elements
+    int64_t arena_per_image = 0;  // elements, chunk arena (stage 0)
+    int64_t arena1_per_image = 0; // elements, batch arena (stage 1 + boundary tensors)
+    int split = 0;                // first stage-1 op
     double macs_per_image = 0;
     std::string to_json() const;
 };
 
 struct LowerOptions {
     bool fuse_dwpw = true;        // merge depthwise -> pointwise pairs into OP_DWPW
+    // Ops whose per-image output is at most this many bytes (and everything after them) run once per BATCH
+    // instead of once per chunk: the deep, spatially tiny layers need the whole batch to fill 148 SMs.
+    int64_t batch_stage_bytes = 100 * 1024;
 };
 
 // Throws std::runtime_error ("unsupported op ...") for graphs outside the implemented set.
