@@ -1,0 +1,74 @@
+// Device helpers shared by kernels_conv.cu and kernels_thin.cu: activations, vector loads, residual reads.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace zb {
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, const ActDev &a, int n) {
+    switch (a.kind) {
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_PRELU: return v < 0.0f ? v * __ldg(a.slope + n) : v;
+        case ACT_CLIP: return fminf(fmaxf(v, a.lo), a.hi);
+        case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// Activation on 4 consecutive channels starting at n (n % 4 == 0): ONE uniform branch per group of four
+// instead of a switch per element (the per-element switch tripled the instruction count of the thin layers).
+__device__ __forceinline__ void act4(float (&v)[4], const ActDev &a, int n) {
+    if (a.kind == ACT_NONE) return;
+    if (a.kind == ACT_RELU) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], 0.0f);
+    } else if (a.kind == ACT_PRELU) {
+        const float4 s = ldg4(a.slope + n);
+        v[0] = v[0] < 0.0f ? v[0] * s.x : v[0];
+        v[1] = v[1] < 0.0f ? v[1] * s.y : v[1];
+        v[2] = v[2] < 0.0f ? v[2] * s.z : v[2];
+        v[3] = v[3] < 0.0f ? v[3] * s.w : v[3];
+    } else if (a.kind == ACT_CLIP) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = fminf(fmaxf(v[q], a.lo), a.hi);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = 1.0f / (1.0f + expf(-v[q]));
+    }
+}
+__device__ __forceinline__ void act4(float4 &v, const ActDev &a, int n) {
+    if (a.kind == ACT_NONE) return;
+    float t[4] = {v.x, v.y, v.z, v.w};
+    act4(t, a, n);
+    v = make_float4(t[0], t[1], t[2], t[3]);
+}
+
+// Residual value for output pixel (img, oy, ox), channel n (n % 4 == 0 when vectorised by the caller).
+__device__ __forceinline__ float residual_at(const EpiDev &e, int img, int oy, int ox, int n) {
+    if (n >= e.res_Cs) return 0.0f;
+    const float *base = e.res + (long long)img * e.res_img_stride;
+    if (!e.res_pool) return __ldg(base + ((long long)oy * e.res_W + ox) * e.res_Cs + n);
+    const float *p = base + ((long long)(2 * oy) * e.res_W + 2 * ox) * e.res_Cs + n;
+    float a = __ldg(p), b = __ldg(p + e.res_Cs);
+    float c = __ldg(p + (long long)e.res_W * e.res_Cs), d = __ldg(p + (long long)e.res_W * e.res_Cs + e.res_Cs);
+    return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+__device__ __forceinline__ float4 residual4_at(const EpiDev &e, int img, int oy, int ox, int n) {
+    if (n >= e.res_Cs) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *base = e.res + (long long)img * e.res_img_stride;
+    if (!e.res_pool) return ldg4(base + ((long long)oy * e.res_W + ox) * e.res_Cs + n);
+    const float *p = base + ((long long)(2 * oy) * e.res_W + 2 * ox) * e.res_Cs + n;
+    float4 a = ldg4(p), b = ldg4(p + e.res_Cs);
+    float4 c = ldg4(p + (long long)e.res_W * e.res_Cs), d = ldg4(p + (long long)e.res_W * e.res_Cs + e.res_Cs);
+    return make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
+                       fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
+}
+
+
+}  // namespace
+}  // namespace zb

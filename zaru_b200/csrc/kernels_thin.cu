@@ -1,0 +1,212 @@
+// sm_100a thin fused block kernel (see the comment on dwpw_thin_kernel).  Split from kernels_conv.cu so the
+// two translation units compile in parallel.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "conv_common.cuh"
+#include "kernels.h"
+
+namespace zb {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Thin fused block: depthwise 3x3 -> (mid act) -> pointwise 1x1 -> bias -> act1 -> +residual -> act2 for
+// layers with few channels on large maps (Cs_in <= 48, Cout <= 64: the first blocks of every network).
+// One CTA = one TW x TH output tile of one image, one thread = one output pixel:
+//   * the input halo tile is staged ONCE in shared memory with coalesced 128-bit loads (pixel stride padded
+//     to CS+4 words so the per-pixel 128-bit reads below are bank-conflict free);
+//   * the depthwise result (CS values) and the pointwise accumulators (NP values) live in registers;
+//   * depthwise / pointwise weights, bias and PReLU slopes are read from shared memory as warp broadcasts;
+//   * the residual (same tensor as the input in every Blaze-style block, optionally through the 2x2 max-pool
+//     of stride-2 blocks) is taken from the staged tile, so each input element is read from HBM/L2 once.
+// ------------------------------------------------------------------------------------------------
+template <int CS, int S, int NP, int TW, int TH>
+__global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int tiles_x, int tiles_y, int NSP) {
+    constexpr int NT = TW * TH;
+    constexpr int PS = CS + 4;                       // padded pixel stride in words
+    constexpr int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
+    constexpr int CQ = CS / 4;
+    extern __shared__ __align__(16) float smem[];
+    float *s_in = smem;                              // [IH][IW][PS]
+    float *s_dww = s_in + IH * IW * PS;              // [9][CS]
+    float *s_dwb = s_dww + 9 * CS;                   // [CS]
+    float *s_pw = s_dwb + CS;                        // [CS][NSP]
+    float *s_pb = s_pw + CS * NSP;                   // [NSP]
+    float *s_sl = s_pb + NSP;                        // [NSP] act2 PReLU slopes (if any)
+
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const int tile_x = b % tiles_x;
+    b /= tiles_x;
+    const int tile_y = b % tiles_y;
+    const int img = b / tiles_y;
+    const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+    const int iy_org = oy0 * S - p.pt, ix_org = ox0 * S - p.pl;
+    const float *in_img = p.in + (long long)img * p.in_img_stride;
+
+    // --- stage input halo tile + weights -------------------------------------------------------------
+    for (int e = tid; e < IH * IW * CQ; e += NT) {
+        const int q = e % CQ, pix = e / CQ;
+        const int ty = pix / IW, tx = pix - ty * IW;
+        const int iy = iy_org + ty, ix = ix_org + tx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = ldg4(in_img + ((long long)iy * p.W + ix) * CS + q * 4);
+        *reinterpret_cast<float4 *>(s_in + pix * PS + q * 4) = v;
+    }
+    for (int e = tid; e < 9 * CS / 4; e += NT) reinterpret_cast<float4 *>(s_dww)[e] = ldg4(p.dw_w + e * 4);
+    for (int e = tid; e < CS / 4; e += NT) reinterpret_cast<float4 *>(s_dwb)[e] = ldg4(p.dw_b + e * 4);
+    for (int e = tid; e < CS * NSP / 4; e += NT) {
+        const int k = e / (NSP / 4), nq = e - k * (NSP / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nq * 4 < p.Ns) v = ldg4(p.w + (long long)k * p.Ns + nq * 4);
+        reinterpret_cast<float4 *>(s_pw)[e] = v;
+    }
+    for (int e = tid; e < NSP; e += NT) {
+        s_pb[e] = e < p.Ns ? __ldg(p.epi.bias + e) : 0.f;
+        s_sl[e] = (p.epi.act2.kind == ACT_PRELU && e < p.Ns) ? __ldg(p.epi.act2.slope + e) : 0.f;
+    }
+    __syncthreads();
+
+    const int tx = tid % TW, ty = tid / TW;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy >= p.Ho || ox >= p.Wo) return;
+
+    // --- depthwise 3x3 into registers ------------------------------------------------------------------
+    float dwo[CS];
+    const float *s_px = s_in + ((ty * S) * IW + tx * S) * PS;
+#pragma unroll
+    for (int q = 0; q < CQ; q++) {
+        float4 v = *reinterpret_cast<const float4 *>(s_dwb + q * 4);
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const float4 x = *reinterpret_cast<const float4 *>(s_px + ((t / 3) * IW + (t % 3)) * PS + q * 4);
+            const float4 wv = *reinterpret_cast<const float4 *>(s_dww + t * CS + q * 4);
+            v.x = fmaf(x.x, wv.x, v.x);
+            v.y = fmaf(x.y, wv.y, v.y);
+            v.z = fmaf(x.z, wv.z, v.z);
+            v.w = fmaf(x.w, wv.w, v.w);
+        }
+        act4(v, p.act_mid, q * 4);
+        dwo[q * 4 + 0] = v.x, dwo[q * 4 + 1] = v.y, dwo[q * 4 + 2] = v.z, dwo[q * 4 + 3] = v.w;
+    }
+
+    // --- pointwise in passes of NP output channels --------------------------------------------------------
+    const EpiDev &e = p.epi;
+    const bool res_smem = e.res == p.in;               // Blaze-style skip: residual is the block input
+    float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+    for (int n0 = 0; n0 < p.Nstore; n0 += NP) {
+        float acc[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4 *>(s_pb + n0 + j);
+            acc[j] = bv.x, acc[j + 1] = bv.y, acc[j + 2] = bv.z, acc[j + 3] = bv.w;
+        }
+#pragma unroll
+        for (int k = 0; k < CS; k++) {
+            const float a = dwo[k];
+#pragma unroll
+            for (int j = 0; j < NP; j += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(s_pw + k * NSP + n0 + j);
+                acc[j] = fmaf(a, wv.x, acc[j]);
+                acc[j + 1] = fmaf(a, wv.y, acc[j + 1]);
+                acc[j + 2] = fmaf(a, wv.z, acc[j + 2]);
+                acc[j + 3] = fmaf(a, wv.w, acc[j + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j += 4) {
+            const int n = n0 + j;
+            if (n >= p.Nstore) break;
+            float v[4] = {acc[j], acc[j + 1], acc[j + 2], acc[j + 3]};
+            act4(v, e.act1, n);
+            if (e.res) {
+                float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (res_smem) {
+                    if (n < CS) {
+                        if (!e.res_pool) {
+                            // stride-1 block: centre pixel of the 3x3 window (pads 1,1)
+                            rr = *reinterpret_cast<const float4 *>(s_px + (p.pt * IW + p.pl) * PS + n);
+                        } else {
+                            // stride-2 block: 2x2 max-pool of input rows/cols (2oy, 2oy+1) x (2ox, 2ox+1)
+                            const float *r0 = s_in + ((2 * ty + p.pt) * IW + 2 * tx + p.pl) * PS + n;
+                            const float4 a0 = *reinterpret_cast<const float4 *>(r0);
+                            const float4 a1 = *reinterpret_cast<const float4 *>(r0 + PS);
+                            const float4 a2 = *reinterpret_cast<const float4 *>(r0 + IW * PS);
+                            const float4 a3 = *reinterpret_cast<const float4 *>(r0 + IW * PS + PS);
+                            rr = make_float4(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)), fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)),
+                                             fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z)), fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w)));
+                        }
+                    }
+                } else {
+                    rr = residual4_at(e, img, oy, ox, n);
+                }
+                v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+            }
+            if (e.act2.kind == ACT_PRELU) {
+                const float4 sl = *reinterpret_cast<const float4 *>(s_sl + n);
+                v[0] = v[0] < 0.f ? v[0] * sl.x : v[0];
+                v[1] = v[1] < 0.f ? v[1] * sl.y : v[1];
+                v[2] = v[2] < 0.f ? v[2] * sl.z : v[2];
+                v[3] = v[3] < 0.f ? v[3] * sl.w : v[3];
+            } else {
+                act4(v, e.act2, n);
+            }
+            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+template <int CS, int S, int NP>
+bool launch_thin_cfg(const ConvDev &p, cudaStream_t s) {
+    constexpr int TW = S == 1 ? 32 : 16, TH = 8;
+    constexpr int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
+    const int NSP = (p.Ns + NP - 1) / NP * NP;
+    const size_t smem = sizeof(float) * ((size_t)IH * IW * (CS + 4) + 9 * CS + CS + (size_t)CS * NSP + 2 * NSP);
+    if (smem > 200 * 1024) return false;
+    auto kern = dwpw_thin_kernel<CS, S, NP, TW, TH>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        configured = smem;
+    }
+    const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
+    const int images = p.M / (p.Ho * p.Wo);
+    kern<<<(unsigned)(tiles_x * tiles_y * images), TW * TH, smem, s>>>(p, tiles_x, tiles_y, NSP);
+    return true;
+}
+
+template <int CS>
+bool launch_thin_cs(const ConvDev &p, cudaStream_t s) {
+    if (p.sh == 1) return p.Ns <= 16 ? launch_thin_cfg<CS, 1, 16>(p, s) : launch_thin_cfg<CS, 1, 32>(p, s);
+    return p.Ns <= 16 ? launch_thin_cfg<CS, 2, 16>(p, s) : launch_thin_cfg<CS, 2, 32>(p, s);
+}
+
+}  // namespace
+
+// Returns false when the layer is outside the thin kernel's envelope (the GEMM-tile kernel handles it).
+bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
+    static const bool disabled = getenv("ZB_NO_THIN") && atoi(getenv("ZB_NO_THIN")) != 0;
+    if (disabled) return false;
+    if (p.kh != 3 || p.kw != 3 || p.sh != p.sw || (p.sh != 1 && p.sh != 2)) return false;
+    if (p.Cs_in > 48 || p.Ns > 64 || p.Ns % 4 || p.Nstore != p.Ns || p.out_pix_stride != p.Ns) return false;
+    if (p.Ho * p.Wo < 1024) return false;            // small maps: tile quantisation wastes the CTA
+    if (p.sh == 1 && !(p.pt == 1 && p.pl == 1)) return false;
+    if (p.sh == 2 && !(p.pt == 0 && p.pl == 0)) return false;
+    if (p.epi.res && p.epi.res == p.in && p.epi.res_Cs != p.Cs_in) return false;
+    if (p.M % (p.Ho * p.Wo)) return false;
+    switch (p.Cs_in) {
+        case 16: return launch_thin_cs<16>(p, s);
+        case 24: return launch_thin_cs<24>(p, s);
+        case 32: return launch_thin_cs<32>(p, s);
+        case 40: return launch_thin_cs<40>(p, s);
+        case 48: return launch_thin_cs<48>(p, s);
+        default: return false;
+    }
+}
+
+
+}  // namespace zb
