@@ -215,13 +215,33 @@ float *tensor_ptr(const zb_net *net, Workspace &ws, int t, int c0) {
     return ws.outs[ti.buffer].as<float>() + (size_t)c0 * net->plan.outputs[ti.buffer].per_image + ti.offset;
 }
 
-// Runs the plan's ops of one stage for images [c0, c0+nc): stage 0 once per chunk (its NHWC4 input already sits
-// in the arena input slot), stage 1 once for the whole batch (c0 = 0, nc = n).
-void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaStream_t s) {
+// Where the network input comes from when it is sampled from frames (Cnn::estimate path).
+struct StemInput {
+    const FramesDev *frames;
+    const ViewDev *views;      // device array, already offset to image c0
+    float lo, hi;
+};
+
+// Runs the plan's ops of one stage for images [c0, c0+nc): stage 0 once per chunk, stage 1 once for the whole
+// batch (c0 = 0, nc = n).  With `stem` the network input is sampled from the frames: fused into the stem
+// convolution when the first layer allows it, otherwise written to the arena input slot by the sample kernel.
+// Without `stem` the NHWC4 input already sits in the arena input slot.
+void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaStream_t s, const StemInput *stem = nullptr) {
     const Plan &pl = net->plan;
     const float *W = net->d_weights;
-    for (const Op &op : pl.ops) {
+    bool input_ready = stem == nullptr;
+    for (size_t op_index = 0; op_index < pl.ops.size(); op_index++) {
+        const Op &op = pl.ops[op_index];
         if (op.stage != stage) continue;
+        const bool first_conv = op_index == 0 && op.kind == OP_CONV && op.in == pl.input && pl.tensors[pl.input].last_use == 0;
+        if (!input_ready && !first_conv) {   // no fusable stem: materialise the sampled input tensor now
+            const TensorInfo &tin = pl.tensors[pl.input];
+            prof_launch(net->ctx, s, "sample", 16.0 * nc * tin.H * tin.W, 0, [&] {
+                launch_sample(*stem->frames, stem->views, nc, tin.W, tin.H, stem->lo, stem->hi, SAMPLE_NHWC4,
+                              tensor_ptr(net, ws, pl.input, c0), tin.img_stride, s);
+            });
+            input_ready = true;
+        }
         const TensorInfo &ti = pl.tensors[op.in];
         const TensorInfo &to = pl.tensors[op.out];
         const float *in = tensor_ptr(net, ws, op.in, c0);
@@ -275,6 +295,25 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                 p.epi = e;
                 if (op.kind == OP_CONV) {
                     p.w = W + op.w_off;
+                    // first layer: fused sample+stem kernel (or stem on the NHWC4 tensor); input tensor used only here
+                    if (first_conv && stem_supported(p)) {
+                        // algorithmic bytes: one RGBA texel per sampled input pixel + the stem output
+                        const double sbytes = stem ? 4.0 * nc * ti.H * ti.W + 4.0 * nc * (double)to.H * to.W * to.C : bytes;
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "stem(+sample)", sbytes, flops, [&] {
+                            FramesDev none{};
+                            launch_stem(stem ? *stem->frames : none, stem ? stem->views : nullptr, stem ? stem->lo : 0.f,
+                                        stem ? stem->hi : 1.f, p, s);
+                        });
+                        input_ready = true;
+                        break;
+                    }
+                    if (!input_ready) {
+                        prof_launch(ctx, s, "sample", 16.0 * nc * ti.H * ti.W, 0, [&] {
+                            launch_sample(*stem->frames, stem->views, nc, ti.W, ti.H, stem->lo, stem->hi, SAMPLE_NHWC4,
+                                          tensor_ptr(net, ws, pl.input, c0), ti.img_stride, s);
+                        });
+                        input_ready = true;
+                    }
                     const bool pw = op.kh == 1 && op.kw == 1 && op.sh == 1 && op.sw == 1 && op.pt == 0 && op.pl == 0;
                     prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : pw ? "conv_gemm<pw>" : "conv_gemm<gather>", bytes, flops,
                                 [&] { launch_conv(p, pw ? CONV_PW : CONV_GATHER, s); });
@@ -904,9 +943,8 @@ zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_v
         Timer tm(ctx, s);
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
-            launch_sample(frames->f, d->d_views.as<ViewDev>() + c0, nc, pl.in_w, pl.in_h, d->lo, d->hi, SAMPLE_NHWC4,
-                          tensor_ptr(d->net, d->ws, pl.input, c0), pl.tensors[pl.input].img_stride, s);
-            run_ops(d->net, d->ws, c0, nc, 0, s);
+            const StemInput si{&frames->f, d->d_views.as<ViewDev>() + c0, d->lo, d->hi};
+            run_ops(d->net, d->ws, c0, nc, 0, s, &si);
         }
         run_ops(d->net, d->ws, 0, n, 1, s);
         launch_decode_nms(d->ws.outs[0].as<float>(), d->ws.outs[1].as<float>(), d->d_fit.as<float>(), n, dp,
@@ -1056,9 +1094,8 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
         Timer tm(ctx, s);
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
-            launch_sample(frames->f, e->d_views.as<ViewDev>() + c0, nc, pl.in_w, pl.in_h, e->lo, e->hi, SAMPLE_NHWC4,
-                          tensor_ptr(e->net, e->ws, pl.input, c0), pl.tensors[pl.input].img_stride, s);
-            run_ops(e->net, e->ws, c0, nc, 0, s);
+            const StemInput si{&frames->f, e->d_views.as<ViewDev>() + c0, e->lo, e->hi};
+            run_ops(e->net, e->ws, c0, nc, 0, s, &si);
         }
         run_ops(e->net, e->ws, 0, n, 1, s);
         {
@@ -1159,11 +1196,8 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         // detector, stage 0 (large activations): per chunk so they stay L2-resident
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
-            prof_launch(ctx, s, "sample", 16.0 * nc * dpl.in_w * dpl.in_h, 0, [&] {
-                launch_sample(frames->f, p->d_views.as<ViewDev>() + c0, nc, dpl.in_w, dpl.in_h, -1.0f, 1.0f, SAMPLE_NHWC4,
-                              tensor_ptr(p->det_net, p->ws_det, dpl.input, c0), dpl.tensors[dpl.input].img_stride, s);
-            });
-            run_ops(p->det_net, p->ws_det, c0, nc, 0, s);
+            const StemInput si{&frames->f, p->d_views.as<ViewDev>() + c0, -1.0f, 1.0f};
+            run_ops(p->det_net, p->ws_det, c0, nc, 0, s, &si);
         }
         // detector, stage 1 (deep, spatially tiny layers) + decode/NMS + RoI: once for the whole batch
         run_ops(p->det_net, p->ws_det, 0, n, 1, s);
@@ -1178,12 +1212,8 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         // landmarks, stage 0 per chunk, stage 1 per batch
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
-            prof_launch(ctx, s, "sample", 16.0 * nc * lpl.in_w * lpl.in_h, 0, [&] {
-                launch_sample(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lpl.in_w, lpl.in_h, -1.0f, 1.0f,
-                              SAMPLE_NHWC4, tensor_ptr(p->lm_net, p->ws_lm, lpl.input, c0),
-                              lpl.tensors[lpl.input].img_stride, s);
-            });
-            run_ops(p->lm_net, p->ws_lm, c0, nc, 0, s);
+            const StemInput si{&frames->f, p->d_lm_views.as<ViewDev>() + c0, -1.0f, 1.0f};
+            run_ops(p->lm_net, p->ws_lm, c0, nc, 0, s, &si);
         }
         run_ops(p->lm_net, p->ws_lm, 0, n, 1, s);
         {

@@ -77,7 +77,7 @@ struct FramesDev {
     int n;
 };
 
-// Build ViewDev[n] on the device from host-style zb_view records (cos/sin in double, rounded).
+// Host-style view record (same layout as zb_view).
 struct ViewHost { int frame; float cx, cy, w, h, radians; };
 
 // image->tensor: NCHW planar f32 [n,3,h,w] / NHWC3 [n,h,w,3] (public layouts) or NHWC4 (internal)
@@ -85,10 +85,9 @@ enum SampleLayout { SAMPLE_NCHW = 0, SAMPLE_NHWC3 = 1, SAMPLE_NHWC4 = 2 };
 void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
                    SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s);
 
-// Detector front: fit each given view (or whole frame) to the network aspect and compose (detection.rs:224-227).
-// in_views == nullptr -> whole frames [first_frame, first_frame+n).
-void launch_fit_views(const FramesDev &f, const ViewHost *in_views, int first_frame, int n, int net_w, int net_h,
-                      ViewDev *out_views, float *out_fit /*[n][4]: scale, tl.x, tl.y, pad*/, cudaStream_t s);
+// Fused sampling + stem conv (views != nullptr) or stem conv on an NHWC4 tensor (views == nullptr).
+bool stem_supported(const ConvDev &p);
+bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s);
 
 struct DetDev {                // mirrors zb_detection
     float confidence, angle, cx, cy, w, h;
@@ -125,8 +124,6 @@ struct LandmarkParams {
 void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
                       const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
                       const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s);
-
-void launch_compose_views(const ViewHost *in_views, const uint8_t *flip, int n, ViewDev *out, cudaStream_t s);
 
 extern long long g_launch_count;   // total kernel launches issued by this library (process-wide)
 

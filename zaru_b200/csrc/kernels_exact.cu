@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "geom.h"
 #include "kernels.h"
 
@@ -33,24 +35,19 @@ __device__ __forceinline__ float sat_u32_as_f32(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
-                                                     int out_h, float lo, float hi, int layout,
-                                                     float *__restrict__ out, long long out_img_stride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    const int img = blockIdx.z;
-    if (x >= out_w) return;
-    const ViewDev v = views[img];
-
+// One sampled, colour-mapped pixel of the network input tensor: (r, g, b, 0).
+//   sample(): x = (u * view_w).round() as u32 with u = x as f32 / w as f32          (nn/mod.rs:54-58)
+//   ViewData::image_coord: transform_out(x+0.5, y+0.5), round(p-0.5), bounds          (image/mod.rs:224-241)
+//   ColorMapper::map: col as f32 * ((end - start) / 255.0) + start                   (nn/mod.rs:156-166)
+__device__ __forceinline__ float4 sample_pixel(const FramesDev &f, const ViewDev &v, int x, int y, int out_w, int out_h,
+                                               float lo, float adjust) {
     unsigned rgba = 0u;   // Color::NONE
     if (v.valid) {
         const int xs = v.flip_x ? (out_w - 1 - x) : x;
-        // sample(): x = (u * view_w).round() as u32 with u = x as f32 / w as f32   (nn/mod.rs:54-58)
         const float u = (float)xs / (float)out_w;
         const float vv = (float)y / (float)out_h;
         const float sx = sat_u32_as_f32(roundf(u * v.w));
         const float sy = sat_u32_as_f32(roundf(vv * v.h));
-        // ViewData::image_coord (image/mod.rs:224-241)
         RRectF rr;
         rr.r.cx = v.cx, rr.r.cy = v.cy, rr.r.w = v.w, rr.r.h = v.h;
         rr.c = v.cosr, rr.s = v.sinr, rr.rad = 0.f;
@@ -69,21 +66,158 @@ __global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const Vi
             }
         }
     }
-    // ColorMapper::map (nn/mod.rs:156-166): col as f32 * ((end - start) / 255.0) + start
+    return make_float4((float)(rgba & 0xFFu) * adjust + lo, (float)((rgba >> 8) & 0xFFu) * adjust + lo,
+                       (float)((rgba >> 16) & 0xFFu) * adjust + lo, 0.0f);
+}
+
+__global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
+                                                     int out_h, float lo, float hi, int layout,
+                                                     float *__restrict__ out, long long out_img_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int img = blockIdx.z;
+    if (x >= out_w) return;
+    const ViewDev v = views[img];
     const float adjust = (hi - lo) / 255.0f;
-    const float r = (float)(rgba & 0xFFu) * adjust + lo;
-    const float g = (float)((rgba >> 8) & 0xFFu) * adjust + lo;
-    const float b = (float)((rgba >> 16) & 0xFFu) * adjust + lo;
+    const float4 c = sample_pixel(f, v, x, y, out_w, out_h, lo, adjust);
     float *o = out + (long long)img * out_img_stride;
     const long long pix = (long long)y * out_w + x;
     if (layout == SAMPLE_NHWC4) {
-        *reinterpret_cast<float4 *>(o + pix * 4) = make_float4(r, g, b, 0.0f);
+        *reinterpret_cast<float4 *>(o + pix * 4) = c;
     } else if (layout == SAMPLE_NHWC3) {
-        o[pix * 3 + 0] = r, o[pix * 3 + 1] = g, o[pix * 3 + 2] = b;
+        o[pix * 3 + 0] = c.x, o[pix * 3 + 1] = c.y, o[pix * 3 + 2] = c.z;
     } else {
         const long long hw = (long long)out_w * out_h;
-        o[pix] = r, o[hw + pix] = g, o[2 * hw + pix] = b;
+        o[pix] = c.x, o[hw + pix] = c.y, o[2 * hw + pix] = c.z;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused image->tensor sampling + stem convolution (KS x KS, stride 2, 3 -> N <= 64 channels) + bias + act.
+// The sampled network-input tile a CTA needs is produced straight into shared memory (bit-exact sampler
+// above), so the [n,h,w,3] input tensor never exists in HBM; with `views == nullptr` the tile is read from
+// an NHWC4 tensor instead (NeuralNetwork::estimate on caller tensors).  One thread = one output pixel, all
+// N accumulators in registers, weights read from shared memory as warp broadcasts.  The convolution uses
+// explicit fmaf (this translation unit is built with -fmad=false for the sampler's sake).
+// ------------------------------------------------------------------------------------------------
+template <int KS, int NP>
+__global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const ViewDev *__restrict__ views, float lo, float hi,
+                                                   const ConvDev p, int tiles_x, int tiles_y, int NSP) {
+    constexpr int TW = 32, TH = 8, NT = 256;
+    constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
+    extern __shared__ __align__(16) float smem[];
+    float4 *s_in = reinterpret_cast<float4 *>(smem);            // [IH][IW] (r,g,b,0)
+    float *s_w = smem + IH * IW * 4;                           // [KS*KS*4][NSP]  (row 4*tap+ci)
+    float *s_b = s_w + KS * KS * 4 * NSP;                      // [NSP]
+    float *s_sl = s_b + NSP;                                   // [NSP]
+
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const int tile_x = b % tiles_x;
+    b /= tiles_x;
+    const int tile_y = b % tiles_y;
+    const int img = b / tiles_y;
+    const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+    const int iy_org = oy0 * 2 - p.pt, ix_org = ox0 * 2 - p.pl;
+
+    if (views) {
+        const ViewDev v = views[img];
+        const float adjust = (hi - lo) / 255.0f;
+        for (int e = tid; e < IH * IW; e += NT) {
+            const int ty = e / IW, tx = e - ty * IW;
+            const int iy = iy_org + ty, ix = ix_org + tx;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);     // conv zero padding (NOT the letterbox colour)
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) c = sample_pixel(f, v, ix, iy, p.W, p.H, lo, adjust);
+            s_in[e] = c;
+        }
+    } else {
+        const float *in_img = p.in + (long long)img * p.in_img_stride;
+        for (int e = tid; e < IH * IW; e += NT) {
+            const int ty = e / IW, tx = e - ty * IW;
+            const int iy = iy_org + ty, ix = ix_org + tx;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                c = __ldg(reinterpret_cast<const float4 *>(in_img + ((long long)iy * p.W + ix) * 4));
+            s_in[e] = c;
+        }
+    }
+    for (int e = tid; e < KS * KS * 4 * NSP / 4; e += NT) {
+        const int k = e / (NSP / 4), nq = e - k * (NSP / 4);
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nq * 4 < p.Ns) wv = __ldg(reinterpret_cast<const float4 *>(p.w + (long long)k * p.Ns + nq * 4));
+        reinterpret_cast<float4 *>(s_w)[e] = wv;
+    }
+    for (int e = tid; e < NSP; e += NT) {
+        s_b[e] = e < p.Ns ? __ldg(p.epi.bias + e) : 0.f;
+        s_sl[e] = (p.epi.act1.kind == ACT_PRELU && e < p.Ns) ? __ldg(p.epi.act1.slope + e) : 0.f;
+    }
+    __syncthreads();
+
+    const int tx = tid % TW, ty = tid / TW;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy >= p.Ho || ox >= p.Wo) return;
+    float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+    const float4 *s_px = s_in + (ty * 2) * IW + tx * 2;
+    const int act = p.epi.act1.kind;
+    for (int n0 = 0; n0 < p.Nstore; n0 += NP) {
+        float acc[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j++) acc[j] = s_b[n0 + j];
+#pragma unroll
+        for (int t = 0; t < KS * KS; t++) {
+            const float4 x = s_px[(t / KS) * IW + (t % KS)];
+            const float xs[3] = {x.x, x.y, x.z};
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++) {
+#pragma unroll
+                for (int j = 0; j < NP; j += 4) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(s_w + (t * 4 + ci) * NSP + n0 + j);
+                    acc[j] = fmaf(xs[ci], wv.x, acc[j]);
+                    acc[j + 1] = fmaf(xs[ci], wv.y, acc[j + 1]);
+                    acc[j + 2] = fmaf(xs[ci], wv.z, acc[j + 2]);
+                    acc[j + 3] = fmaf(xs[ci], wv.w, acc[j + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j += 4) {
+            const int n = n0 + j;
+            if (n >= p.Nstore) break;
+            float v[4] = {acc[j], acc[j + 1], acc[j + 2], acc[j + 3]};
+            if (act == ACT_RELU) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], 0.0f);
+            } else if (act == ACT_PRELU) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[q] = v[q] < 0.0f ? v[q] * s_sl[n + q] : v[q];
+            } else if (act == ACT_CLIP) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[q] = fminf(fmaxf(v[q], p.epi.act1.lo), p.epi.act1.hi);
+            }
+            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+template <int KS, int NP>
+bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
+    constexpr int TW = 32, TH = 8;
+    constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
+    const int NSP = (p.Ns + NP - 1) / NP * NP;
+    const size_t smem = sizeof(float) * ((size_t)IH * IW * 4 + (size_t)KS * KS * 4 * NSP + 2 * NSP);
+    auto kern = stem_kernel<KS, NP>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        configured = smem;
+    }
+    const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
+    const int images = p.M / (p.Ho * p.Wo);
+    kern<<<(unsigned)(tiles_x * tiles_y * images), 256, smem, s>>>(f, views, lo, hi, p, tiles_x, tiles_y, NSP);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,6 +563,31 @@ void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, i
     dim3 block(128);
     dim3 grid((out_w + 127) / 128, out_h, n);
     sample_kernel<<<grid, block, 0, s>>>(f, views, out_w, out_h, lo, hi, (int)layout, out, out_img_stride);
+}
+
+// Stem conv (KS x KS, stride 2, Cin = 3 in an NHWC4 tensor or sampled on the fly from `views`).
+// Returns false when the layer is outside the kernel's envelope.
+bool stem_supported(const ConvDev &p) {
+    static const bool disabled = getenv("ZB_NO_STEM") && atoi(getenv("ZB_NO_STEM")) != 0;
+    if (disabled) return false;
+    if (p.Cs_in != 4 || p.sh != 2 || p.sw != 2 || p.kh != p.kw || (p.kh != 3 && p.kh != 5)) return false;
+    if (p.Ns > 64 || p.Ns % 4 || p.Nstore != p.Ns || p.out_pix_stride != p.Ns || p.epi.res || p.epi.act2.kind != ACT_NONE)
+        return false;
+    if (p.epi.act1.kind == ACT_SIGMOID || p.M % (p.Ho * p.Wo)) return false;
+    return true;
+}
+
+bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
+    if (!stem_supported(p)) return false;
+    g_launch_count++;
+    if (p.kh == 3) {
+        if (p.Ns <= 16) return launch_stem_cfg<3, 16>(f, views, lo, hi, p, s);
+        if (p.Ns == 24) return launch_stem_cfg<3, 24>(f, views, lo, hi, p, s);
+        return launch_stem_cfg<3, 32>(f, views, lo, hi, p, s);
+    }
+    if (p.Ns <= 16) return launch_stem_cfg<5, 16>(f, views, lo, hi, p, s);
+    if (p.Ns == 24) return launch_stem_cfg<5, 24>(f, views, lo, hi, p, s);
+    return launch_stem_cfg<5, 32>(f, views, lo, hi, p, s);
 }
 
 void launch_decode_nms(const float *boxes, const float *scores, const float *fit, int n, const DecodeParams &p,
