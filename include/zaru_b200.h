@@ -206,6 +206,12 @@ zb_status zb_plan_from_onnx(const void *onnx_bytes, size_t len, int32_t fuse_dwp
                             size_t cap, size_t *needed, float *weights, size_t weights_cap,
                             size_t *weights_needed);
 
+/* Unit-test hook for the tcgen05 path: D[128,N] = A[128,K] * B[N,K]^T (row-major host arrays) through
+ * the same shared-memory descriptors / TMEM read-back the fused blocks use; nsplit 1 = single TF32
+ * MMA, 3 = 3xTF32 (FP32-level accuracy).                                                        */
+zb_status zb_debug_tc_gemm(zb_ctx *ctx, const float *A, const float *B, float *D, int32_t N, int32_t K,
+                           int32_t nsplit);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------- */
 /* Device time (ms, CUDA events on the handle's own stream) of the last *_run/_detect/_estimate
  * call, excluding host<->device result copies.                                                */

@@ -125,6 +125,8 @@ struct zb_ctx {
     float last_ms = 0.f;
     int default_chunk = 64;
     // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
+    int tc_mode = 1;                     // ZB_TC: 0 = SIMT only, 1 = tcgen05 3xTF32 for fused blocks with K >= tc_min_k
+    int tc_min_k = 56;                   // ZB_TC_MIN_K
     bool prof_on = false;
     bool prof_detail = false;            // ZB_PROF_DETAIL=1: one profile row per layer instead of per kernel class
     std::vector<ProfRec> prof;
@@ -326,8 +328,16 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     p.dw_w = W + op.w_off;
                     p.dw_b = W + op.b_off;
                     p.act_mid = act_dev(op.act_mid, W);
-                    prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "conv_gemm<dwpw>", bytes, flops,
-                                [&] { launch_conv(p, CONV_DWPW, s); });
+                    // kernel choice for fused blocks: tcgen05 (3xTF32) for the wide ones, SIMT thin/tile otherwise
+                    const bool use_tc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_tc_supported(p, op.NP) &&
+                                        p.K >= ctx->tc_min_k;
+                    if (use_tc) {
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_tc<tcgen05>", bytes, flops,
+                                    [&] { launch_dwpw_tc(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
+                    } else {
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "conv_gemm<dwpw>", bytes, flops,
+                                    [&] { launch_conv(p, CONV_DWPW, s); });
+                    }
                 }
                 break;
             }
@@ -447,6 +457,8 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         CU(cudaEventCreate(&ctx->ev2));
         CU(cudaEventCreate(&ctx->ev3));
         if (const char *c = getenv("ZB_PROF_DETAIL")) ctx->prof_detail = atoi(c) != 0;
+        if (const char *c = getenv("ZB_TC")) ctx->tc_mode = atoi(c);
+        if (const char *c = getenv("ZB_TC_MIN_K")) ctx->tc_min_k = atoi(c);
         if (const char *c = getenv("ZB_CHUNK")) {
             int v = atoi(c);
             if (v > 0) ctx->default_chunk = v;
@@ -497,6 +509,27 @@ zb_status zb_timer_stop(zb_ctx *ctx, float *ms) {
         CU(cudaEventRecord(ctx->ev3, ctx->stream));
         CU(cudaEventSynchronize(ctx->ev3));
         CU(cudaEventElapsedTime(ms, ctx->ev2, ctx->ev3));
+        return ZB_OK;
+    });
+}
+
+// D[128,N] = A[128,K] * B[N,K]^T on the tcgen05 path (nsplit 1 = raw TF32 operands, 3 = 3xTF32). Host pointers.
+zb_status zb_debug_tc_gemm(zb_ctx *ctx, const float *A, const float *B, float *D, int32_t N, int32_t K, int32_t nsplit) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !A || !B || !D) return fail(ZB_ERR_INVALID_ARGUMENT, "NULL argument");
+        CU(cudaSetDevice(ctx->device));
+        DevBuf da, db, dd;
+        da.reserve(sizeof(float) * 128 * K);
+        db.reserve(sizeof(float) * N * K);
+        dd.reserve(sizeof(float) * 128 * N);
+        cudaStream_t s = ctx->stream;
+        CU(cudaMemcpyAsync(da.p, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(db.p, B, sizeof(float) * N * K, cudaMemcpyHostToDevice, s));
+        if (!launch_tc_gemm_test(da.as<float>(), db.as<float>(), dd.as<float>(), N, K, nsplit, s))
+            return fail(ZB_ERR_INVALID_ARGUMENT, "unsupported N/K for the tcgen05 test GEMM");
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(D, dd.p, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
         return ZB_OK;
     });
 }

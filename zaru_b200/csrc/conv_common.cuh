@@ -70,5 +70,58 @@ __device__ __forceinline__ float4 residual4_at(const EpiDev &e, int img, int oy,
 }
 
 
+// Depthwise KSxKS over channels [k, k+4) for one output pixel.  All loads of a row (KS=5) or of the whole
+// window (KS=3) are issued before the FMAs that consume them, so one thread keeps 9 (5) independent
+// 128-bit loads in flight instead of a dependent load->FMA chain.
+template <int KS>
+__device__ __forceinline__ float4 dw_window(const ConvDev &p, const float *__restrict__ a_base, int iy0, int ix0, int k) {
+    float4 v = ldg4(p.dw_b + k);
+    if (KS == 3) {
+        float4 x[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+            const int iy = iy0 + ky;
+            const bool rowok = iy >= 0 && iy < p.H;
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int ix = ix0 + kx;
+                x[ky * 3 + kx] = (rowok && ix >= 0 && ix < p.W) ? ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + k)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const float4 wv = ldg4(p.dw_w + t * p.Cs_in + k);
+            v.x = fmaf(x[t].x, wv.x, v.x);
+            v.y = fmaf(x[t].y, wv.y, v.y);
+            v.z = fmaf(x[t].z, wv.z, v.z);
+            v.w = fmaf(x[t].w, wv.w, v.w);
+        }
+    } else {
+#pragma unroll 1
+        for (int ky = 0; ky < KS; ky++) {
+            const int iy = iy0 + ky;
+            if (iy < 0 || iy >= p.H) continue;
+            float4 x[KS];
+#pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+                const int ix = ix0 + kx;
+                x[kx] = (ix >= 0 && ix < p.W) ? ldg4(a_base + ((long long)iy * p.W + ix) * p.Cs_in + k)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+                const float4 wv = ldg4(p.dw_w + (ky * KS + kx) * p.Cs_in + k);
+                v.x = fmaf(x[kx].x, wv.x, v.x);
+                v.y = fmaf(x[kx].y, wv.y, v.y);
+                v.z = fmaf(x[kx].z, wv.z, v.z);
+                v.w = fmaf(x[kx].w, wv.w, v.w);
+            }
+        }
+    }
+    return v;
+}
+
+
 }  // namespace
 }  // namespace zb

@@ -60,6 +60,11 @@ void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int 
 void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
                           cudaStream_t s);
 
+// ---- tensor-core path: kernels_tc.cu ------------------------------------------------------------
+bool dwpw_tc_supported(const ConvDev &p, int NP);
+bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
+bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s);
+
 // ---- exact (no-FMA) kernels: kernels_exact.cu -------------------------------------------------
 struct ViewDev {               // composed ViewData::rect + per-view constants
     int frame;

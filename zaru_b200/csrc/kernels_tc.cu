@@ -1,0 +1,309 @@
+// sm_100a tensor-core path: the pointwise (1x1) contraction of the fused depthwise->pointwise blocks on
+// tcgen05.mma (kind::tf32) with the accumulator in TMEM.
+//
+//   dwpw_tc_kernel: one CTA = 128 output pixels (UMMA M = 128) x all output channels.
+//     1. 256 threads produce the depthwise result for their pixels straight into shared memory in the UMMA
+//        K-major canonical layout (tc_common.cuh), split into TF32 hi/lo parts;
+//     2. the pre-split pointwise weights (hi/lo, same layout, packed at load time) are copied next to it;
+//     3. ONE thread issues the K/8 x 3 tcgen05.mma instructions (3xTF32: lo*hi + hi*lo + hi*hi, FP32
+//        accumulation in TMEM) and commits them to an mbarrier;
+//     4. all 8 warps read their TMEM lanes back (tcgen05.ld 32x32b) and run the fused epilogue
+//        (bias -> act1 -> +residual [channel-pad, 2x2 max-pool] -> act2) with 128-bit stores.
+//   3xTF32 keeps the contraction at FP32-level accuracy (the reference is pure f32; plain TF32/BF16 operands
+//   move BlazeFace logits by up to 1e-3), at 3x a negligible MMA cost: these layers are bound by
+//   the depthwise producer and the epilogue, not by the tensor pipe.
+//
+//   tc_gemm_test_kernel: D[128,N] = A[128,K] * B[N,K]^T through the same descriptors (unit test of the path).
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdlib>
+
+#include "conv_common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace zb {
+namespace {
+
+using namespace tc;
+
+constexpr int TC_M = 128;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tc_gemm_test_kernel(const float *__restrict__ A, const float *__restrict__ B,
+                                                           float *__restrict__ D, int N, int K, int nsplit) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int KQ = K / 4;
+    float *sA_hi = reinterpret_cast<float *>(smem_raw);
+    float *sA_lo = sA_hi + (size_t)KQ * TC_M * 4;
+    float *sB_hi = sA_lo + (size_t)KQ * TC_M * 4;
+    float *sB_lo = sB_hi + (size_t)KQ * N * 4;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t ncols = tmem_cols_for(N);
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) mbar_init(&mbar, 1);
+    for (int e = tid; e < TC_M * K; e += 128) {
+        const int m = e / K, k = e - m * K;
+        float hi, lo;
+        split_tf32(A[e], hi, lo);
+        if (nsplit == 1) hi = A[e];   // raw FP32 bits: shows what the hardware does with un-rounded operands
+        sA_hi[((size_t)(k / 4) * TC_M + m) * 4 + (k & 3)] = hi;
+        sA_lo[((size_t)(k / 4) * TC_M + m) * 4 + (k & 3)] = lo;
+    }
+    for (int e = tid; e < N * K; e += 128) {
+        const int n = e / K, k = e - n * K;
+        float hi, lo;
+        split_tf32(B[e], hi, lo);
+        if (nsplit == 1) hi = B[e];
+        sB_hi[((size_t)(k / 4) * N + n) * 4 + (k & 3)] = hi;
+        sB_lo[((size_t)(k / 4) * N + n) * 4 + (k & 3)] = lo;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_tf32(TC_M, N);
+        uint32_t acc = 0;
+        for (int pass = 0; pass < nsplit; pass++) {
+            // pass order: lo*hi, hi*lo, hi*hi (small terms first); nsplit == 1: hi*hi only
+            const float *a = (nsplit == 3 && pass == 0) ? sA_lo : sA_hi;
+            const float *b = (nsplit == 3 && pass == 1) ? sB_lo : sB_hi;
+            for (int j = 0; j < K / 8; j++) {
+                const uint64_t ad = make_smem_desc(smem_u32(a) + (uint32_t)(2 * j) * TC_M * 16, TC_M * 16, 128);
+                const uint64_t bd = make_smem_desc(smem_u32(b) + (uint32_t)(2 * j) * N * 16, (uint32_t)N * 16, 128);
+                umma_tf32(tmem, ad, bd, idesc, acc);
+                acc = 1;
+            }
+        }
+        umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + (tid & 31);
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (c0 + i < N) D[(size_t)row * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused depthwise KSxKS -> pointwise on tcgen05.  p.K = Cs_in (multiple of 8), NP = N padded to 16.
+// w_hi / w_lo: [K/4][NP][4] TF32-split pointwise weights.  KC = K-chunk resident in smem per MMA batch.
+// ------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const float *__restrict__ w_hi,
+                                                      const float *__restrict__ w_lo, int NP, int KC, int Kpad) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int KQC = KC / 4;
+    float *sA_hi = reinterpret_cast<float *>(smem_raw);          // [KQC][128][4]
+    float *sA_lo = sA_hi + (size_t)KQC * TC_M * 4;
+    float *sB_hi = sA_lo + (size_t)KQC * TC_M * 4;               // [KQC][NP][4]
+    float *sB_lo = sB_hi + (size_t)KQC * NP * 4;
+    __shared__ __align__(16) int4 rowinfo[TC_M];                 // {img offset lo, hi, iy0, ix0}; iy0 == INT_MIN: no pixel
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_M;
+    const int HoWo = p.Ho * p.Wo;
+    const uint32_t ncols = tmem_cols_for(NP);
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) mbar_init(&mbar, 1);
+    if (tid < TC_M) {
+        const int gm = m0 + tid;
+        int4 ri = make_int4(0, 0, INT_MIN, 0);
+        if (gm < p.M) {
+            const int img = gm / HoWo;
+            const int r = gm - img * HoWo;
+            const int oy = r / p.Wo, ox = r - oy * p.Wo;
+            const long long off = (long long)img * p.in_img_stride;
+            ri = make_int4((int)(off & 0xffffffffll), (int)(off >> 32), oy * p.sh - p.pt, ox * p.sw - p.pl);
+        }
+        rowinfo[tid] = ri;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = make_idesc_tf32(TC_M, NP);
+
+    uint32_t acc_flag = 0, phase = 0;
+    for (int kc0 = 0; kc0 < Kpad; kc0 += KC) {
+        // --- B chunk: straight copy (already in UMMA layout, already split) -----------------------------
+        {
+            const float4 *gh = reinterpret_cast<const float4 *>(w_hi) + (size_t)(kc0 / 4) * NP;
+            const float4 *gl = reinterpret_cast<const float4 *>(w_lo) + (size_t)(kc0 / 4) * NP;
+            for (int e = tid; e < KQC * NP; e += 256) {
+                reinterpret_cast<float4 *>(sB_hi)[e] = __ldg(gh + e);
+                reinterpret_cast<float4 *>(sB_lo)[e] = __ldg(gl + e);
+            }
+        }
+        // --- A chunk: depthwise producer --------------------------------------------------------------------
+        for (int e = tid; e < TC_M * KQC; e += 256) {
+            const int r8 = e & 7, g = e >> 3;
+            const int kq = g % KQC, mg = g / KQC;
+            const int m = mg * 8 + r8;
+            const int k = kc0 + kq * 4;
+            const int4 ri = rowinfo[m];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ri.z != INT_MIN && k < p.K) {
+                const long long off = ((long long)ri.y << 32) | (unsigned)ri.x;
+                v = dw_window<KS>(p, p.in + off, ri.z, ri.w, k);
+                act4(v, p.act_mid, k);
+            }
+            float4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x);
+            split_tf32(v.y, hi.y, lo.y);
+            split_tf32(v.z, hi.z, lo.z);
+            split_tf32(v.w, hi.w, lo.w);
+            *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * TC_M + m) * 4) = hi;
+            *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * TC_M + m) * 4) = lo;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+#pragma unroll 1
+            for (int pass = 0; pass < 3; pass++) {
+                const float *a = pass == 0 ? sA_lo : sA_hi;
+                const float *b = pass == 1 ? sB_lo : sB_hi;
+                const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
+                for (int j = 0; j < KC / 8; j++) {
+                    const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * TC_M * 16, TC_M * 16, 128);
+                    const uint64_t bd = make_smem_desc(b0 + (uint32_t)(2 * j) * NP * 16, (uint32_t)NP * 16, 128);
+                    umma_tf32(tmem, ad, bd, idesc, acc_flag);
+                    acc_flag = 1;
+                }
+            }
+            umma_commit(&mbar);
+        }
+        // everybody waits for the MMAs before the smem tiles are overwritten / the accumulator is read
+        mbar_wait(&mbar, phase);
+        phase ^= 1;
+        tc_fence_after();
+    }
+
+    // --- epilogue: warp w owns TMEM lanes 32*(w%4).., columns [half*NP/2, (half+1)*NP/2) ---------------------
+    const EpiDev &e = p.epi;
+    const int row = (warp & 3) * 32 + lane;
+    const int m = m0 + row;
+    const int half = warp >> 2;
+    const int cbeg = half * (NP / 2), cend = cbeg + NP / 2;
+    int img = 0, oy = 0, ox = 0, r = 0;
+    const bool rowok = m < p.M;
+    if (rowok) {
+        img = m / HoWo;
+        r = m - img * HoWo;
+        oy = r / p.Wo;
+        ox = r - oy * p.Wo;
+    }
+    float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
+    const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0);
+    for (int c0 = cbeg; c0 < cend; c0 += 8) {
+        float v8[8];
+        tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v8);
+        if (!rowok) continue;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int n = c0 + 4 * h;
+            if (n >= p.Nstore) continue;
+            float v[4] = {v8[4 * h], v8[4 * h + 1], v8[4 * h + 2], v8[4 * h + 3]};
+            if (n + 3 < p.Ns) {
+                const float4 b = ldg4(e.bias + n);
+                v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (n + q < p.Ns) v[q] += __ldg(e.bias + n + q);
+            }
+            act4(v, e.act1, n);
+            if (e.res) {
+                if ((e.res_Cs % 4) == 0) {
+                    const float4 rr = residual4_at(e, img, oy, ox, n);
+                    v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) v[q] += residual_at(e, img, oy, ox, n + q);
+                }
+            }
+            act4(v, e.act2, n);
+            if (vec_ok) {
+                *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (n + q < p.Nstore) orow[n + q] = v[q];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+size_t dwpw_tc_smem(int KC, int NP) { return sizeof(float) * 2 * ((size_t)KC * TC_M + (size_t)KC * NP) + 1024; }
+
+template <int KS>
+bool launch_dwpw_tc_ks(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    const int KC = p.K <= 64 ? p.K : 64;                       // K chunk resident in shared memory
+    const int Kpad = (p.K + KC - 1) / KC * KC;                 // packed weights are zero-padded to this many rows
+    const size_t smem = dwpw_tc_smem(KC, NP);
+    if (smem > 220 * 1024) return false;
+    auto kern = dwpw_tc_kernel<KS>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        configured = smem;
+    }
+    kern<<<(unsigned)((p.M + TC_M - 1) / TC_M), 256, smem, s>>>(p, w_hi, w_lo, NP, KC, Kpad);
+    return true;
+}
+
+}  // namespace
+
+bool dwpw_tc_supported(const ConvDev &p, int NP) {
+    if (!((p.kh == 3 && p.kw == 3) || (p.kh == 5 && p.kw == 5))) return false;
+    if (p.K % 8 || p.K < 8 || p.K > 1024 || NP % 16 || NP < 16 || NP > 256) return false;
+    return true;
+}
+
+bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    if (!dwpw_tc_supported(p, NP)) return false;
+    g_launch_count++;
+    return p.kh == 3 ? launch_dwpw_tc_ks<3>(p, w_hi, w_lo, NP, s) : launch_dwpw_tc_ks<5>(p, w_hi, w_lo, NP, s);
+}
+
+// D[128,N] = A[128,K] * B[N,K]^T on tcgen05 (nsplit 1: raw TF32, 3: 3xTF32).  Device pointers.
+bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s) {
+    if (N % 16 || N < 16 || N > 256 || K % 8 || K < 8) return false;
+    const size_t smem = sizeof(float) * 2 * ((size_t)K * TC_M + (size_t)K * N) + 1024;
+    if (smem > 220 * 1024) return false;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        configured = smem;
+    }
+    g_launch_count++;
+    tc_gemm_test_kernel<<<1, 128, smem, s>>>(A, B, D, N, K, nsplit);
+    return true;
+}
+
+}  // namespace zb

@@ -15,6 +15,18 @@ namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// cvt.rna.tf32.f32 on the host: round to nearest (ties away) to a 10-bit mantissa, kept in an FP32 container.
+inline float rna_tf32(float x) {
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    if ((b & 0x7f800000u) == 0x7f800000u) return x;
+    b += 0x1000u;
+    b &= 0xffffe000u;
+    float r;
+    memcpy(&r, &b, 4);
+    return r;
+}
+
 // A graph value during lowering.
 struct Value {
     enum Kind { NONE, MATERIAL, VIRT, FLAT, CONSTANT } kind = NONE;
@@ -681,6 +693,21 @@ struct Lowerer {
                     for (int co = 0; co < op.N; co++)
                         for (int ci = 0; ci < C; ci++) w2[(size_t)ci * op.Ns + co] = s.w2->f[(size_t)co * C + ci];
                     op.w2_off = push_weights(w2);
+                    // tensor-core copy: K-major UMMA canonical layout, split into TF32 hi + lo (3xTF32)
+                    op.NP = round_up(op.Ns, 16);
+                    // rows padded (with zeros) to a multiple of the 64-deep K chunk the kernel keeps in smem
+                    const int kpad = op.K <= 64 ? op.K : round_up(op.K, 64);
+                    std::vector<float> whi((size_t)kpad * op.NP, 0.f), wlo((size_t)kpad * op.NP, 0.f);
+                    for (int co = 0; co < op.N; co++)
+                        for (int ci = 0; ci < C; ci++) {
+                            const float v = s.w2->f[(size_t)co * C + ci];
+                            const float hi = rna_tf32(v);
+                            const size_t idx = ((size_t)(ci / 4) * op.NP + co) * 4 + (ci & 3);
+                            whi[idx] = hi;
+                            wlo[idx] = rna_tf32(v - hi);
+                        }
+                    op.wtc_hi_off = push_weights(whi);
+                    op.wtc_lo_off = push_weights(wlo);
                     op.b2_off = pack_vec(s.b2, op.N, op.Ns, "bias");
                     if (op.act_mid.kind == ACT_PRELU) op.act_mid.slope_off = pack_vec(s.slope_mid, C, Cs, "slope");
                 }
@@ -775,6 +802,7 @@ std::string Plan::to_json() const {
            << ",\"kh\":" << o.kh << ",\"kw\":" << o.kw << ",\"sh\":" << o.sh << ",\"sw\":" << o.sw << ",\"pt\":" << o.pt
            << ",\"pl\":" << o.pl << ",\"K\":" << o.K << ",\"N\":" << o.N << ",\"Ns\":" << o.Ns
            << ",\"Nstore\":" << o.Nstore << ",\"w_off\":" << o.w_off << ",\"b_off\":" << o.b_off
+           << ",\"wtc_hi_off\":" << o.wtc_hi_off << ",\"wtc_lo_off\":" << o.wtc_lo_off << ",\"NP\":" << o.NP
            << ",\"w2_off\":" << o.w2_off << ",\"b2_off\":" << o.b2_off << ",\"res\":" << o.res
            << ",\"res_pool\":" << o.res_pool << ",";
         json_act(os, "act_mid", o.act_mid);

@@ -56,6 +56,8 @@ struct Op {
     int Nstore = 0;               // columns written to `out`
     int64_t w_off = -1, b_off = -1;      // CONV / DW weights, bias
     int64_t w2_off = -1, b2_off = -1;    // DWPW: pointwise weights, bias
+    int64_t wtc_hi_off = -1, wtc_lo_off = -1;   // DWPW: pointwise weights, TF32 hi/lo split, UMMA layout [K/4][NP][4]
+    int NP = 0;                   // DWPW: Cout padded to a multiple of 16 (UMMA N)
     ActSpec act_mid;              // DWPW: activation between dw and pw
     ActSpec act1;                 // after bias
     int res = -1;                 // residual tensor id (added after act1)

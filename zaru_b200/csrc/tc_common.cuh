@@ -1,0 +1,115 @@
+// tcgen05 / TMEM building blocks for sm_100a (inline PTX; no CUTLASS dependency).
+//
+// Operand layout used throughout: K-major, SWIZZLE_NONE ("interleave") canonical layout for 4-byte (TF32)
+// elements.  A tile of R rows x K columns lives in shared memory as [K/4][R][4 floats]:
+//     offset(row, k) = (k / 4) * (R * 16 B) + row * 16 B + (k % 4) * 4 B
+// so a core matrix (8 rows x 16 B) is 128 contiguous bytes, consecutive 8-row groups are SBO = 128 B apart
+// and the two 16-byte K chunks one MMA (K = 8 for kind::tf32) consumes are LBO = R * 16 B apart.
+// Descriptor bit fields follow the PTX ISA "shared memory matrix descriptor" / "instruction descriptor"
+// tables (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS tree).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace zb {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor: start address, leading/stride byte offsets (16-byte units),
+// version = 1 (Blackwell), base offset 0, layout type 0 = SWIZZLE_NONE.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// 32-bit instruction descriptor for kind::tf32: D = F32, A = B = TF32, both K-major, dense, M x N.
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // c_format = F32
+    d |= 2u << 7;                       // a_format = TF32
+    d |= 2u << 10;                      // b_format = TF32
+    d |= (uint32_t)(N >> 3) << 17;      // n_dim
+    d |= (uint32_t)(M >> 4) << 24;      // m_dim
+    return d;
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {       // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Make generic-proxy shared-memory writes visible to the async proxy (the tensor core reads smem through it).
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one M x N x 8 TF32 MMA.  Issued by ONE thread.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// Arrive on `bar` when every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// TMEM -> registers: lane (base + laneid) of the warp's 32-lane slice, 8 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Round-to-nearest FP32 -> TF32 (10-bit mantissa), result kept in an FP32 container.
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// x = hi + lo with hi, lo both TF32-representable: the 3xTF32 split (hi*hi + hi*lo + lo*hi ~ FP32 product).
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
+}
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
+
+}  // namespace tc
+}  // namespace zb
