@@ -127,6 +127,7 @@ struct zb_ctx {
     // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
     int tc_mode = 1;                     // ZB_TC: 0 = SIMT only, 1 = tcgen05 3xTF32 for fused blocks with K >= tc_min_k
     int tc_min_k = 56;                   // ZB_TC_MIN_K
+    int tc_min_ctas = 600;               // ZB_TC_MIN_CTAS
     bool prof_on = false;
     bool prof_detail = false;            // ZB_PROF_DETAIL=1: one profile row per layer instead of per kernel class
     std::vector<ProfRec> prof;
@@ -329,8 +330,9 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     p.dw_b = W + op.b_off;
                     p.act_mid = act_dev(op.act_mid, W);
                     // kernel choice for fused blocks: tcgen05 (3xTF32) for the wide ones, SIMT thin/tile otherwise
+                    // (measured: the tcgen05 kernel has the higher per-CTA latency, so it needs >= ~2 waves of CTAs)
                     const bool use_tc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_tc_supported(p, op.NP) &&
-                                        p.K >= ctx->tc_min_k;
+                                        p.K >= ctx->tc_min_k && p.M >= ctx->tc_min_ctas * 128;
                     if (use_tc) {
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_tc<tcgen05>", bytes, flops,
                                     [&] { launch_dwpw_tc(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
@@ -459,6 +461,7 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         if (const char *c = getenv("ZB_PROF_DETAIL")) ctx->prof_detail = atoi(c) != 0;
         if (const char *c = getenv("ZB_TC")) ctx->tc_mode = atoi(c);
         if (const char *c = getenv("ZB_TC_MIN_K")) ctx->tc_min_k = atoi(c);
+        if (const char *c = getenv("ZB_TC_MIN_CTAS")) ctx->tc_min_ctas = atoi(c);
         if (const char *c = getenv("ZB_CHUNK")) {
             int v = atoi(c);
             if (v > 0) ctx->default_chunk = v;

@@ -19,6 +19,13 @@ __device__ __forceinline__ float apply_act(float v, const ActDev &a, int n) {
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Activation on 4 consecutive channels starting at n (n % 4 == 0): ONE uniform branch per group of four
 // instead of a switch per element (the per-element switch tripled the instruction count of the thin layers).
 __device__ __forceinline__ void act4(float (&v)[4], const ActDev &a, int n) {

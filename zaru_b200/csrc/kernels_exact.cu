@@ -39,6 +39,33 @@ __device__ __forceinline__ float sat_u32_as_f32(float v) {
 //   sample(): x = (u * view_w).round() as u32 with u = x as f32 / w as f32          (nn/mod.rs:54-58)
 //   ViewData::image_coord: transform_out(x+0.5, y+0.5), round(p-0.5), bounds          (image/mod.rs:224-241)
 //   ColorMapper::map: col as f32 * ((end - start) / 255.0) + start                   (nn/mod.rs:156-166)
+// Address of the source texel for tensor pixel (x, y), or nullptr when it reads Color::NONE.
+__device__ __forceinline__ const unsigned *sample_address(const FramesDev &f, const ViewDev &v, int x, int y, int out_w,
+                                                          int out_h) {
+    if (!v.valid) return nullptr;
+    const int xs = v.flip_x ? (out_w - 1 - x) : x;
+    const float u = (float)xs / (float)out_w;
+    const float vv = (float)y / (float)out_h;
+    const float sx = sat_u32_as_f32(roundf(u * v.w));
+    const float sy = sat_u32_as_f32(roundf(vv * v.h));
+    RRectF rr;
+    rr.r.cx = v.cx, rr.r.cy = v.cy, rr.r.w = v.w, rr.r.h = v.h;
+    rr.c = v.cosr, rr.s = v.sinr, rr.rad = 0.f;
+    float px, py;
+    transform_out(rr, sx + 0.5f, sy + 0.5f, px, py);
+    const float fx = roundf(px - 0.5f), fy = roundf(py - 0.5f);
+    if (fx < 0.0f || fy < 0.0f || ceilf(fx) >= 4294967296.0f || ceilf(fy) >= 4294967296.0f) return nullptr;
+    const unsigned ix = (fx == fx) ? (unsigned)fx : 0u;   // `x.round() as u32`: NaN -> 0
+    const unsigned iy = (fy == fy) ? (unsigned)fy : 0u;
+    if (ix >= (unsigned)f.width || iy >= (unsigned)f.height) return nullptr;
+    return reinterpret_cast<const unsigned *>(f.base + (long long)v.frame * f.frame_stride + (long long)iy * f.row_stride +
+                                              (long long)ix * 4);
+}
+__device__ __forceinline__ float4 color_map(unsigned rgba, float lo, float adjust) {
+    return make_float4((float)(rgba & 0xFFu) * adjust + lo, (float)((rgba >> 8) & 0xFFu) * adjust + lo,
+                       (float)((rgba >> 16) & 0xFFu) * adjust + lo, 0.0f);
+}
+
 __device__ __forceinline__ float4 sample_pixel(const FramesDev &f, const ViewDev &v, int x, int y, int out_w, int out_h,
                                                float lo, float adjust) {
     unsigned rgba = 0u;   // Color::NONE
@@ -123,12 +150,27 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
     if (views) {
         const ViewDev v = views[img];
         const float adjust = (hi - lo) / 255.0f;
-        for (int e = tid; e < IH * IW; e += NT) {
-            const int ty = e / IW, tx = e - ty * IW;
-            const int iy = iy_org + ty, ix = ix_org + tx;
-            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);     // conv zero padding (NOT the letterbox colour)
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) c = sample_pixel(f, v, ix, iy, p.W, p.H, lo, adjust);
-            s_in[e] = c;
+        // batches of 4 texels per thread: all addresses first, then all (independent) loads, then convert+store
+        for (int e0 = tid; e0 < IH * IW; e0 += 4 * NT) {
+            const unsigned *addr[4];
+            bool inside[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * NT;
+                const int ty = e / IW, tx = e - ty * IW;
+                const int iy = iy_org + ty, ix = ix_org + tx;
+                inside[u] = e < IH * IW && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                addr[u] = inside[u] ? sample_address(f, v, ix, iy, p.W, p.H) : nullptr;
+            }
+            unsigned rgba[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) rgba[u] = addr[u] ? __ldg(addr[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * NT;
+                if (e < IH * IW)   // conv zero padding outside the tensor (NOT the letterbox colour)
+                    s_in[e] = inside[u] ? color_map(rgba[u], lo, adjust) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     } else {
         const float *in_img = p.in + (long long)img * p.in_img_stride;

@@ -101,6 +101,45 @@ __global__ void __launch_bounds__(128) tc_gemm_test_kernel(const float *__restri
 // Fused depthwise KSxKS -> pointwise on tcgen05.  p.K = Cs_in (multiple of 8), NP = N padded to 16.
 // w_hi / w_lo: [K/4][NP][4] TF32-split pointwise weights.  KC = K-chunk resident in smem per MMA batch.
 // ------------------------------------------------------------------------------------------------
+// Epilogue for `NC` consecutive accumulator columns of one output pixel (one thread).
+template <int NC>
+__device__ __forceinline__ void tc_epilogue_cols(const ConvDev &p, const float (&acc)[NC], int c0, int img, int oy, int ox,
+                                                 float *orow, bool vec_ok) {
+    const EpiDev &e = p.epi;
+#pragma unroll
+    for (int h = 0; h < NC / 4; h++) {
+        const int n = c0 + 4 * h;
+        if (n >= p.Nstore) continue;
+        float v[4] = {acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]};
+        if (n + 3 < p.Ns) {
+            const float4 b = ldg4(e.bias + n);
+            v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (n + q < p.Ns) v[q] += __ldg(e.bias + n + q);
+        }
+        act4(v, e.act1, n);
+        if (e.res) {
+            if ((e.res_Cs % 4) == 0) {
+                const float4 rr = residual4_at(e, img, oy, ox, n);
+                v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[q] += residual_at(e, img, oy, ox, n + q);
+            }
+        }
+        act4(v, e.act2, n);
+        if (vec_ok) {
+            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (n + q < p.Nstore) orow[n + q] = v[q];
+        }
+    }
+}
+
 template <int KS>
 __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const float *__restrict__ w_hi,
                                                       const float *__restrict__ w_lo, int NP, int KC, int Kpad) {
@@ -111,15 +150,23 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
     float *sB_hi = sA_lo + (size_t)KQC * TC_M * 4;               // [KQC][NP][4]
     float *sB_lo = sB_hi + (size_t)KQC * NP * 4;
     __shared__ __align__(16) int4 rowinfo[TC_M];                 // {img offset lo, hi, iy0, ix0}; iy0 == INT_MIN: no pixel
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar_mma, mbar_b;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TC_M;
     const int HoWo = p.Ho * p.Wo;
     const uint32_t ncols = tmem_cols_for(NP);
+    const uint32_t b_bytes = (uint32_t)KQC * NP * 16;            // one K chunk of one weight half
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
-    if (tid == 0) mbar_init(&mbar, 1);
+    if (tid == 0) {
+        mbar_init(&mbar_mma, 1);
+        mbar_init(&mbar_b, 1);
+        // first weight chunk: two TMA bulk copies (already in UMMA layout, already TF32-split)
+        mbar_expect_tx(&mbar_b, 2 * b_bytes);
+        bulk_copy_g2s(sB_hi, w_hi, b_bytes, &mbar_b);
+        bulk_copy_g2s(sB_lo, w_lo, b_bytes, &mbar_b);
+    }
     if (tid < TC_M) {
         const int gm = m0 + tid;
         int4 ri = make_int4(0, 0, INT_MIN, 0);
@@ -138,43 +185,54 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = make_idesc_tf32(TC_M, NP);
 
+    // depthwise producer for element e of the current chunk: 8 rows x consecutive channel quads per warp, so both
+    // the 128-bit global loads (8 pixels x 64 B) and the 128-bit smem stores (8 rows x 16 B = one core matrix)
+    // are contiguous.
+    auto produce = [&](int e, int kc0) -> float4 {
+        const int r8 = e & 7, g = e >> 3;
+        const int kq = g % KQC, mg = g / KQC;
+        const int m = mg * 8 + r8;
+        const int k = kc0 + kq * 4;
+        const int4 ri = rowinfo[m];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ri.z != INT_MIN && k < p.K) {
+            const long long off = ((long long)ri.y << 32) | (unsigned)ri.x;
+            v = dw_window<KS>(p, p.in + off, ri.z, ri.w, k);
+            act4(v, p.act_mid, k);
+        }
+        return v;
+    };
+    auto store_split = [&](int e, const float4 &v) {
+        const int r8 = e & 7, g = e >> 3;
+        const int kq = g % KQC, mg = g / KQC;
+        const int m = mg * 8 + r8;
+        float4 hi, lo;
+        split_tf32(v.x, hi.x, lo.x);
+        split_tf32(v.y, hi.y, lo.y);
+        split_tf32(v.z, hi.z, lo.z);
+        split_tf32(v.w, hi.w, lo.w);
+        *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * TC_M + m) * 4) = hi;
+        *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * TC_M + m) * 4) = lo;
+    };
+
     uint32_t acc_flag = 0, phase = 0;
+    const int n_elem = TC_M * KQC;
     for (int kc0 = 0; kc0 < Kpad; kc0 += KC) {
-        // --- B chunk: straight copy (already in UMMA layout, already split) -----------------------------
-        {
-            const float4 *gh = reinterpret_cast<const float4 *>(w_hi) + (size_t)(kc0 / 4) * NP;
-            const float4 *gl = reinterpret_cast<const float4 *>(w_lo) + (size_t)(kc0 / 4) * NP;
-            for (int e = tid; e < KQC * NP; e += 256) {
-                reinterpret_cast<float4 *>(sB_hi)[e] = __ldg(gh + e);
-                reinterpret_cast<float4 *>(sB_lo)[e] = __ldg(gl + e);
-            }
+        // --- A chunk: two elements in flight per thread (all their loads are issued before the FMAs) --------
+        int e = tid;
+        for (; e + 256 < n_elem; e += 512) {
+            const float4 v0 = produce(e, kc0);
+            const float4 v1 = produce(e + 256, kc0);
+            store_split(e, v0);
+            store_split(e + 256, v1);
         }
-        // --- A chunk: depthwise producer --------------------------------------------------------------------
-        for (int e = tid; e < TC_M * KQC; e += 256) {
-            const int r8 = e & 7, g = e >> 3;
-            const int kq = g % KQC, mg = g / KQC;
-            const int m = mg * 8 + r8;
-            const int k = kc0 + kq * 4;
-            const int4 ri = rowinfo[m];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ri.z != INT_MIN && k < p.K) {
-                const long long off = ((long long)ri.y << 32) | (unsigned)ri.x;
-                v = dw_window<KS>(p, p.in + off, ri.z, ri.w, k);
-                act4(v, p.act_mid, k);
-            }
-            float4 hi, lo;
-            split_tf32(v.x, hi.x, lo.x);
-            split_tf32(v.y, hi.y, lo.y);
-            split_tf32(v.z, hi.z, lo.z);
-            split_tf32(v.w, hi.w, lo.w);
-            *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * TC_M + m) * 4) = hi;
-            *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * TC_M + m) * 4) = lo;
-        }
+        if (e < n_elem) store_split(e, produce(e, kc0));
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
         if (tid == 0) {
+            mbar_wait(&mbar_b, phase);                       // weights of this chunk have landed (TMA)
 #pragma unroll 1
             for (int pass = 0; pass < 3; pass++) {
                 const float *a = pass == 0 ? sA_lo : sA_hi;
@@ -187,16 +245,20 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
                     acc_flag = 1;
                 }
             }
-            umma_commit(&mbar);
+            umma_commit(&mbar_mma);
         }
         // everybody waits for the MMAs before the smem tiles are overwritten / the accumulator is read
-        mbar_wait(&mbar, phase);
-        phase ^= 1;
+        mbar_wait(&mbar_mma, phase);
         tc_fence_after();
+        phase ^= 1;
+        if (tid == 0 && kc0 + KC < Kpad) {                   // prefetch the next weight chunk behind the next producer pass
+            mbar_expect_tx(&mbar_b, 2 * b_bytes);
+            bulk_copy_g2s(sB_hi, w_hi + (size_t)((kc0 + KC) / 4) * NP * 4, b_bytes, &mbar_b);
+            bulk_copy_g2s(sB_lo, w_lo + (size_t)((kc0 + KC) / 4) * NP * 4, b_bytes, &mbar_b);
+        }
     }
 
     // --- epilogue: warp w owns TMEM lanes 32*(w%4).., columns [half*NP/2, (half+1)*NP/2) ---------------------
-    const EpiDev &e = p.epi;
     const int row = (warp & 3) * 32 + lane;
     const int m = m0 + row;
     const int half = warp >> 2;
@@ -211,42 +273,22 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
     }
     float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
     const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0);
-    for (int c0 = cbeg; c0 < cend; c0 += 8) {
-        float v8[8];
-        tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v8);
-        if (!rowok) continue;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int n = c0 + 4 * h;
-            if (n >= p.Nstore) continue;
-            float v[4] = {v8[4 * h], v8[4 * h + 1], v8[4 * h + 2], v8[4 * h + 3]};
-            if (n + 3 < p.Ns) {
-                const float4 b = ldg4(e.bias + n);
-                v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (n + q < p.Ns) v[q] += __ldg(e.bias + n + q);
-            }
-            act4(v, e.act1, n);
-            if (e.res) {
-                if ((e.res_Cs % 4) == 0) {
-                    const float4 rr = residual4_at(e, img, oy, ox, n);
-                    v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) v[q] += residual_at(e, img, oy, ox, n + q);
-                }
-            }
-            act4(v, e.act2, n);
-            if (vec_ok) {
-                *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (n + q < p.Nstore) orow[n + q] = v[q];
-            }
-        }
+    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    int c0 = cbeg;
+    for (; c0 + 32 <= cend; c0 += 32) {
+        float v[32];
+        tmem_ld32(tbase + (uint32_t)c0, v);
+        if (rowok) tc_epilogue_cols<32>(p, v, c0, img, oy, ox, orow, vec_ok);
+    }
+    for (; c0 + 16 <= cend; c0 += 16) {
+        float v[16];
+        tmem_ld16(tbase + (uint32_t)c0, v);
+        if (rowok) tc_epilogue_cols<16>(p, v, c0, img, oy, ox, orow, vec_ok);
+    }
+    for (; c0 + 8 <= cend; c0 += 8) {
+        float v[8];
+        tmem_ld8(tbase + (uint32_t)c0, v);
+        if (rowok) tc_epilogue_cols<8>(p, v, c0, img, oy, ox, orow, vec_ok);
     }
     tc_fence_before();
     __syncthreads();
@@ -257,7 +299,8 @@ size_t dwpw_tc_smem(int KC, int NP) { return sizeof(float) * 2 * ((size_t)KC * T
 
 template <int KS>
 bool launch_dwpw_tc_ks(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
-    const int KC = p.K <= 64 ? p.K : 64;                       // K chunk resident in shared memory
+    static const int kc_max = getenv("ZB_TC_KC") ? atoi(getenv("ZB_TC_KC")) : 32;
+    const int KC = p.K <= kc_max ? p.K : kc_max;               // K chunk resident in shared memory
     const int Kpad = (p.K + KC - 1) / KC * KC;                 // packed weights are zero-padded to this many rows
     const size_t smem = dwpw_tc_smem(KC, NP);
     if (smem > 220 * 1024) return false;

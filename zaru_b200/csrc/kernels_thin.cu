@@ -45,27 +45,28 @@ __global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int 
     const int iy_org = oy0 * S - p.pt, ix_org = ox0 * S - p.pl;
     const float *in_img = p.in + (long long)img * p.in_img_stride;
 
-    // --- stage input halo tile + weights -------------------------------------------------------------
+    // --- stage input halo tile + weights with cp.async (LDGSTS): every copy of the CTA is in flight at once
+    // instead of one dependent LDG->STS round trip per loop iteration; out-of-image pixels are zero-filled.
     for (int e = tid; e < IH * IW * CQ; e += NT) {
         const int q = e % CQ, pix = e / CQ;
         const int ty = pix / IW, tx = pix - ty * IW;
         const int iy = iy_org + ty, ix = ix_org + tx;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = ldg4(in_img + ((long long)iy * p.W + ix) * CS + q * 4);
-        *reinterpret_cast<float4 *>(s_in + pix * PS + q * 4) = v;
+        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const float *src = ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img;
+        cp_async16(s_in + pix * PS + q * 4, src, ok ? 16 : 0);
     }
-    for (int e = tid; e < 9 * CS / 4; e += NT) reinterpret_cast<float4 *>(s_dww)[e] = ldg4(p.dw_w + e * 4);
-    for (int e = tid; e < CS / 4; e += NT) reinterpret_cast<float4 *>(s_dwb)[e] = ldg4(p.dw_b + e * 4);
+    for (int e = tid; e < 9 * CS / 4; e += NT) cp_async16(s_dww + e * 4, p.dw_w + e * 4, 16);
+    for (int e = tid; e < CS / 4; e += NT) cp_async16(s_dwb + e * 4, p.dw_b + e * 4, 16);
     for (int e = tid; e < CS * NSP / 4; e += NT) {
         const int k = e / (NSP / 4), nq = e - k * (NSP / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nq * 4 < p.Ns) v = ldg4(p.w + (long long)k * p.Ns + nq * 4);
-        reinterpret_cast<float4 *>(s_pw)[e] = v;
+        const bool ok = nq * 4 < p.Ns;
+        cp_async16(s_pw + e * 4, ok ? p.w + (long long)k * p.Ns + nq * 4 : p.w, ok ? 16 : 0);
     }
     for (int e = tid; e < NSP; e += NT) {
         s_pb[e] = e < p.Ns ? __ldg(p.epi.bias + e) : 0.f;
         s_sl[e] = (p.epi.act2.kind == ACT_PRELU && e < p.Ns) ? __ldg(p.epi.act2.slope + e) : 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const int tx = tid % TW, ty = tid / TW;

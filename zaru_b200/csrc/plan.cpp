@@ -696,7 +696,7 @@ struct Lowerer {
                     // tensor-core copy: K-major UMMA canonical layout, split into TF32 hi + lo (3xTF32)
                     op.NP = round_up(op.Ns, 16);
                     // rows padded (with zeros) to a multiple of the 64-deep K chunk the kernel keeps in smem
-                    const int kpad = op.K <= 64 ? op.K : round_up(op.K, 64);
+                    const int kpad = round_up(op.K, 64);   // any chunk size in {16, 32, 64} divides it
                     std::vector<float> whi((size_t)kpad * op.NP, 0.f), wlo((size_t)kpad * op.NP, 0.f);
                     for (int co = 0; co < op.N; co++)
                         for (int ci = 0; ci < C; ci++) {
