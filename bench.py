@@ -182,7 +182,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import zaru_b200
-    from zaru_b200 import synth
+    from zaru_b200 import shard, synth
     from zaru_b200.image import ImageBatch
     from zaru_b200.pipeline import FacePipeline
     from zaru_b200.rect import Resolution
@@ -194,7 +194,10 @@ def run_gpu(args):
 
     # --- inputs: `unique` distinct S-face frames per rank, tiled to the batch, resident in HBM -----------
     t0 = time.perf_counter()
-    uniq = np.stack([synth.s_face_frame(1000 * rank + i)[0] for i in range(args.unique)])
+    # independent streams shard round-robin over the GPUs (stream s -> rank s % world); every rank owns
+    # `unique` distinct synthetic streams and no data-path collective is needed
+    my_streams = shard.streams_for_rank(args.unique * world, world, rank)
+    uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in my_streams])
     d_uniq = torch.from_numpy(uniq).cuda()
     idx = torch.arange(batch_n, device="cuda") % args.unique
     d_frames = d_uniq[idx].contiguous()            # [batch,1080,1920,4] uint8, 8.49 GB at batch 1024 (> 126 MB L2)
@@ -233,10 +236,7 @@ def run_gpu(args):
     launches = zaru_b200.launch_count() - launches0
     barrier()
     n_with_face = int((flags >= 0).sum())
-    t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, wall_ms_max = t.tolist()
+    dev_ms_max, wall_ms_max = shard.max_over_ranks([dev_ms, wall_ms], dist, "cuda")
 
     # --- end to end through the public API with HOST frames (`e2e`) -------------------------------------
     e2e_n = min(args.e2e_batch, batch_n)
@@ -257,10 +257,7 @@ def run_gpu(args):
         e2e_step()
     zaru_b200.sync()
     e2e_ms = 1000.0 * (time.perf_counter() - e0)
-    te = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms_max = te.item()
+    (e2e_ms_max,) = shard.max_over_ranks([e2e_ms], dist, "cuda")
     clock_info = clocks.stop() if rank == 0 else None
     d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
 

@@ -1,0 +1,78 @@
+"""Generate tests/golden/*.npz: oracle outputs on the reference's own fixture images and on synthetic frames.
+
+Run in the build container (needs /root/reference/3rdparty or the staged assets):
+    python tools/gen_golden.py
+The vectors pin (a) the oracle against drift (CPU test) and (b) the CUDA path (GPU test) on inputs whose
+expected results the reference's tests describe (face/detection.rs:164-173, mediapipe.rs:603-624).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.detection import Detector, ShortRangeNetwork  # noqa: E402
+from oracle.geometry import RotatedRect, f32  # noqa: E402
+from oracle.image import Image, image_to_tensor  # noqa: E402
+from oracle.landmark import Estimator, FaceMeshV1  # noqa: E402
+from tests.oracle_pipeline import face_pipeline  # noqa: E402
+from zaru_b200 import synth  # noqa: E402
+
+
+def dets_array(dets):
+    return np.stack([np.concatenate([d.as_vector(), [np.float32(d.anchor)]]) for d in dets]).astype(np.float32) \
+        if dets else np.zeros((0, 19), np.float32)
+
+
+def main():
+    out = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    assets = synth.assets_dir()
+    full = synth.load_image_rgba(os.path.join(assets, "img", "sad_linus.jpg"))
+    crop = synth.load_image_rgba(os.path.join(assets, "img", "sad_linus_cropped.jpg"))
+
+    # --- detects_face fixture ---------------------------------------------------------------------
+    det = Detector(ShortRangeNetwork())
+    dets = det.detect(Image(full))
+    img = Image(full)
+    rect = img.rect().grow_to_fit_aspect(det.input_resolution().aspect_ratio())
+    tensor = image_to_tensor(img.view(rect), 128, 128, -1.0, 1.0)
+    np.savez_compressed(os.path.join(out, "sad_linus_detect.npz"),
+                        image_sha=np.frombuffer(__import__("hashlib").sha256(full.tobytes()).digest(), np.uint8),
+                        tensor_sha=np.frombuffer(__import__("hashlib").sha256(tensor.tobytes()).digest(), np.uint8),
+                        tensor_rows=tensor[0, :, ::16, ::8].copy(),      # a sparse probe of the sampled tensor
+                        raw_boxes=det.last_raw[0], raw_scores=det.last_raw[1], detections=dets_array(dets))
+
+    # --- estimates_landmarks_{upright,rotated,rotated2} ----------------------------------------------
+    cimg = Image(crop)
+    lm = {}
+    for name, deg in [("upright", 0.0), ("rot_p10", 10.0), ("rot_m10", -10.0)]:
+        view = cimg.as_view() if deg == 0.0 else cimg.view(RotatedRect(cimg.rect(), np.radians(f32(deg))))
+        e = Estimator(FaceMeshV1()).estimate(view)
+        lm[f"{name}_positions"] = e.positions.copy()
+        lm[f"{name}_flag"] = np.float32(e.face_flag)
+        lm[f"{name}_rotation"] = np.float32(e.rotation_radians())
+    np.savez_compressed(os.path.join(out, "sad_linus_landmarks.npz"),
+                        image_sha=np.frombuffer(__import__("hashlib").sha256(crop.tobytes()).digest(), np.uint8), **lm)
+
+    # --- synthetic S-face frames through the whole pipeline --------------------------------------------
+    recs = {}
+    seeds = [7, 200, 201, 203, 300, 301]
+    for s in seeds:
+        frame = synth.s_face_frame(s, allow_empty=(s != 7))[0]
+        dets, lms, flag, view_rect, raw = face_pipeline(frame)
+        recs[f"s{s}_frame_sha"] = np.frombuffer(__import__("hashlib").sha256(frame.tobytes()).digest(), np.uint8)
+        recs[f"s{s}_detections"] = dets_array(dets)
+        recs[f"s{s}_margin"] = np.float32(np.abs(raw[1]).min())
+        recs[f"s{s}_flag"] = np.float32(flag)
+        recs[f"s{s}_landmarks"] = lms if lms is not None else np.zeros((0, 3), np.float32)
+        recs[f"s{s}_roi"] = np.asarray(view_rect.rect.as_tuple(), np.float32) if view_rect is not None else np.zeros(4, np.float32)
+    np.savez_compressed(os.path.join(out, "s_face_pipeline.npz"), seeds=np.asarray(seeds), **recs)
+    for f in sorted(os.listdir(out)):
+        print(f, os.path.getsize(os.path.join(out, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -337,8 +337,9 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_tc<tcgen05>", bytes, flops,
                                     [&] { launch_dwpw_tc(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
                     } else {
-                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "conv_gemm<dwpw>", bytes, flops,
-                                    [&] { launch_conv(p, CONV_DWPW, s); });
+                        prof_launch(ctx, s,
+                                    ctx->prof_detail ? op.label.c_str() : dwpw_thin_supported(p) ? "dwpw_thin" : "conv_gemm<dwpw>",
+                                    bytes, flops, [&] { launch_conv(p, CONV_DWPW, s); });
                     }
                 }
                 break;

@@ -60,6 +60,8 @@ void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int 
 void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
                           cudaStream_t s);
 
+bool dwpw_thin_supported(const ConvDev &p);   // kernels_thin.cu: would launch_conv(CONV_DWPW) take the thin kernel?
+
 // ---- tensor-core path: kernels_tc.cu ------------------------------------------------------------
 bool dwpw_tc_supported(const ConvDev &p, int NP);
 bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);

@@ -189,7 +189,7 @@ bool launch_thin_cs(const ConvDev &p, cudaStream_t s) {
 }  // namespace
 
 // Returns false when the layer is outside the thin kernel's envelope (the GEMM-tile kernel handles it).
-bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
+bool dwpw_thin_supported(const ConvDev &p) {
     static const bool disabled = getenv("ZB_NO_THIN") && atoi(getenv("ZB_NO_THIN")) != 0;
     if (disabled) return false;
     if (p.kh != 3 || p.kw != 3 || p.sh != p.sw || (p.sh != 1 && p.sh != 2)) return false;
@@ -199,6 +199,11 @@ bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
     if (p.sh == 2 && !(p.pt == 0 && p.pl == 0)) return false;
     if (p.epi.res && p.epi.res == p.in && p.epi.res_Cs != p.Cs_in) return false;
     if (p.M % (p.Ho * p.Wo)) return false;
+    return p.Cs_in == 16 || p.Cs_in == 24 || p.Cs_in == 32 || p.Cs_in == 40 || p.Cs_in == 48;
+}
+
+bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
+    if (!dwpw_thin_supported(p)) return false;
     switch (p.Cs_in) {
         case 16: return launch_thin_cs<16>(p, s);
         case 24: return launch_thin_cs<24>(p, s);
