@@ -168,6 +168,10 @@ def run_gpu(args):
     import numpy as np
     import torch
 
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (e.g. "NCCL version ...") go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -310,7 +314,7 @@ def run_gpu(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_budget)
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -26,6 +26,21 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src,
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Packed FP32 FMA (Blackwell FFMA2: two fused multiply-adds per issued instruction; each lane rounds exactly
+// like fmaf, so results are bit-identical to the scalar form while the FMA issue slots are halved).
+// Measured (round 1): neutral in the thin kernel, SLOWER in the stem and GEMM-tile kernels (the (a,a) broadcast
+// pairs cost extra moves and registers), so only the thin kernel uses it.
+__device__ __forceinline__ void fma4(float4 &acc, const float4 &x, const float4 &w) {          // acc += x * w
+    const float2 lo = __ffma2_rn(make_float2(x.x, x.y), make_float2(w.x, w.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(make_float2(x.z, x.w), make_float2(w.z, w.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void fma4s(float2 &acc_lo, float2 &acc_hi, float a, const float4 &w) {   // acc += a * w
+    const float2 aa = make_float2(a, a);
+    acc_lo = __ffma2_rn(aa, make_float2(w.x, w.y), acc_lo);
+    acc_hi = __ffma2_rn(aa, make_float2(w.z, w.w), acc_hi);
+}
+
 // Activation on 4 consecutive channels starting at n (n % 4 == 0): ONE uniform branch per group of four
 // instead of a switch per element (the per-element switch tripled the instruction count of the thin layers).
 __device__ __forceinline__ void act4(float (&v)[4], const ActDev &a, int n) {

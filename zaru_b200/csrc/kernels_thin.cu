@@ -83,10 +83,7 @@ __global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int 
         for (int t = 0; t < 9; t++) {
             const float4 x = *reinterpret_cast<const float4 *>(s_px + ((t / 3) * IW + (t % 3)) * PS + q * 4);
             const float4 wv = *reinterpret_cast<const float4 *>(s_dww + t * CS + q * 4);
-            v.x = fmaf(x.x, wv.x, v.x);
-            v.y = fmaf(x.y, wv.y, v.y);
-            v.z = fmaf(x.z, wv.z, v.z);
-            v.w = fmaf(x.w, wv.w, v.w);
+            fma4(v, x, wv);
         }
         act4(v, p.act_mid, q * 4);
         dwo[q * 4 + 0] = v.x, dwo[q * 4 + 1] = v.y, dwo[q * 4 + 2] = v.z, dwo[q * 4 + 3] = v.w;
@@ -97,11 +94,11 @@ __global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int 
     const bool res_smem = e.res == p.in;               // Blaze-style skip: residual is the block input
     float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
     for (int n0 = 0; n0 < p.Nstore; n0 += NP) {
-        float acc[NP];
+        float2 acc[NP / 2];
 #pragma unroll
         for (int j = 0; j < NP; j += 4) {
             const float4 bv = *reinterpret_cast<const float4 *>(s_pb + n0 + j);
-            acc[j] = bv.x, acc[j + 1] = bv.y, acc[j + 2] = bv.z, acc[j + 3] = bv.w;
+            acc[j / 2] = make_float2(bv.x, bv.y), acc[j / 2 + 1] = make_float2(bv.z, bv.w);
         }
 #pragma unroll
         for (int k = 0; k < CS; k++) {
@@ -109,17 +106,14 @@ __global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int 
 #pragma unroll
             for (int j = 0; j < NP; j += 4) {
                 const float4 wv = *reinterpret_cast<const float4 *>(s_pw + k * NSP + n0 + j);
-                acc[j] = fmaf(a, wv.x, acc[j]);
-                acc[j + 1] = fmaf(a, wv.y, acc[j + 1]);
-                acc[j + 2] = fmaf(a, wv.z, acc[j + 2]);
-                acc[j + 3] = fmaf(a, wv.w, acc[j + 3]);
+                fma4s(acc[j / 2], acc[j / 2 + 1], a, wv);
             }
         }
 #pragma unroll
         for (int j = 0; j < NP; j += 4) {
             const int n = n0 + j;
             if (n >= p.Nstore) break;
-            float v[4] = {acc[j], acc[j + 1], acc[j + 2], acc[j + 3]};
+            float v[4] = {acc[j / 2].x, acc[j / 2].y, acc[j / 2 + 1].x, acc[j / 2 + 1].y};
             act4(v, e.act1, n);
             if (e.res) {
                 float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
