@@ -333,7 +333,11 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     // (measured: the tcgen05 kernel has the higher per-CTA latency, so it needs >= ~2 waves of CTAs)
                     const bool use_tc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_tc_supported(p, op.NP) &&
                                         p.K >= ctx->tc_min_k && p.M >= ctx->tc_min_ctas * 128;
-                    if (use_tc) {
+                    const bool use_ttc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_ttc_supported(p, op.NP);
+                    if (use_ttc) {
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_ttc<tcgen05>", bytes, flops,
+                                    [&] { launch_dwpw_ttc(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
+                    } else if (use_tc) {
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_tc<tcgen05>", bytes, flops,
                                     [&] { launch_dwpw_tc(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
                     } else {

@@ -65,6 +65,8 @@ bool dwpw_thin_supported(const ConvDev &p);   // kernels_thin.cu: would launch_c
 // ---- tensor-core path: kernels_tc.cu ------------------------------------------------------------
 bool dwpw_tc_supported(const ConvDev &p, int NP);
 bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
+bool dwpw_ttc_supported(const ConvDev &p, int NP);   // thin blocks: smem tile + sliding-window dw + tcgen05 pw
+bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
 bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s);
 
 // ---- exact (no-FMA) kernels: kernels_exact.cu -------------------------------------------------

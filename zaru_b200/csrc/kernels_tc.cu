@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
         const int kq = g % KQC, mg = g / KQC;
         const int m = mg * 8 + r8;
         float4 hi, lo;
-        split_tf32(v.x, hi.x, lo.x);
-        split_tf32(v.y, hi.y, lo.y);
-        split_tf32(v.z, hi.z, lo.z);
-        split_tf32(v.w, hi.w, lo.w);
+        split_tf32_fast(v.x, hi.x, lo.x);
+        split_tf32_fast(v.y, hi.y, lo.y);
+        split_tf32_fast(v.z, hi.z, lo.z);
+        split_tf32_fast(v.w, hi.w, lo.w);
         *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * TC_M + m) * 4) = hi;
         *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * TC_M + m) * 4) = lo;
     };
@@ -247,8 +247,11 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
             }
             umma_commit(&mbar_mma);
         }
-        // everybody waits for the MMAs before the smem tiles are overwritten / the accumulator is read
-        mbar_wait(&mbar_mma, phase);
+        // ONE thread polls the mbarrier (a 256-thread try_wait spin loop burns the issue slots the other resident
+        // CTAs need); everybody else parks at the hardware barrier until the MMAs have completed.
+        if (tid == 0) mbar_wait(&mbar_mma, phase);
+        tc_fence_before();
+        __syncthreads();
         tc_fence_after();
         phase ^= 1;
         if (tid == 0 && kc0 + KC < Kpad) {                   // prefetch the next weight chunk behind the next producer pass
@@ -295,6 +298,297 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Thin fused block on the tensor core ("tile-tc"): depthwise 3x3 (stride 1, pads 1) -> pointwise -> epilogue for
+// Cs_in <= 48 on large maps.  One CTA = a 32 x TH output tile of one image (M = 32*TH = 256 or 128 rows).
+//   1. input halo tile -> shared memory by cp.async (each input element read from L2/HBM once per CTA);
+//   2. depthwise by SLIDING WINDOW: one work item = 4 horizontally adjacent pixels x one channel quad, so the
+//      3x6 window is loaded once for 4 outputs (18 instead of 36 LDS.128) and the 9 weight quads once;
+//   3. results are TF32-split and stored straight into the UMMA K-major A tile ([k/4][row][4], chunk stride
+//      padded to (M+1)*16 B through the descriptor's LBO so the stores are bank-conflict free);
+//   4. pointwise weights (pre-split, UMMA layout) arrive by TMA bulk copy; one thread issues the 3xTF32
+//      tcgen05.mma chain per 128-row half, accumulators in TMEM;
+//   5. every thread reads its own pixel's row back (tcgen05.ld) and applies bias / residual (from the staged
+//      tile) / activation, storing N contiguous floats.
+// ------------------------------------------------------------------------------------------------
+template <int CS, int TH, int NBUF>
+__global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const float *__restrict__ w_hi,
+                                                       const float *__restrict__ w_lo, int NP, int tiles_x, int tiles_y,
+                                                       int total_tiles, int poll_all) {
+    constexpr int TW = 32, M = TW * TH, NT = 256;
+    constexpr int PS = CS + 4, IW = TW + 2, IH = TH + 2, CQ = CS / 4;
+    constexpr int HALVES = M / 128;
+    constexpr int IN_TILE = IH * IW * PS;                            // floats per staged input tile
+    constexpr uint32_t LBO_A = (M + 1) * 16;                         // padded chunk stride of the A tile (bytes)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *sA_hi = reinterpret_cast<float *>(smem_raw);              // [CQ][(M+1)][4]
+    float *sA_lo = sA_hi + CQ * (M + 1) * 4;
+    float *sB_hi = sA_lo + CQ * (M + 1) * 4;                         // [CQ][NP][4]  (TMA destination, 16 B aligned)
+    float *sB_lo = sB_hi + CQ * NP * 4;
+    float *s_in0 = sB_lo + CQ * NP * 4;                              // NBUF x [IH][IW][PS]
+    float *s_dww = s_in0 + NBUF * IN_TILE;                           // [9][CS]
+    float *s_dwb = s_dww + 9 * CS;                                   // [CS]
+    float *s_pb = s_dwb + CS;                                        // [NP]
+    float *s_sl = s_pb + NP;                                         // [NP]
+    __shared__ __align__(8) uint64_t mbar_mma, mbar_b;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ncols = tmem_cols_for(HALVES * NP);
+    const uint32_t b_bytes = (uint32_t)CQ * NP * 16;
+
+    // ---- once per (persistent) CTA: TMEM, barriers, pointwise weights by TMA, depthwise weights, bias, slopes ----
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) {
+        mbar_init(&mbar_mma, 1);
+        mbar_init(&mbar_b, 1);
+        mbar_expect_tx(&mbar_b, 2 * b_bytes);
+        bulk_copy_g2s(sB_hi, w_hi, b_bytes, &mbar_b);
+        bulk_copy_g2s(sB_lo, w_lo, b_bytes, &mbar_b);
+    }
+    for (int e = tid; e < 9 * CQ; e += NT) cp_async16(s_dww + e * 4, p.dw_w + e * 4, 16);
+    for (int e = tid; e < CQ; e += NT) cp_async16(s_dwb + e * 4, p.dw_b + e * 4, 16);
+    for (int e = tid; e < NP; e += NT) {
+        s_pb[e] = e < p.Ns ? __ldg(p.epi.bias + e) : 0.f;
+        s_sl[e] = (p.epi.act2.kind == ACT_PRELU && e < p.Ns) ? __ldg(p.epi.act2.slope + e) : 0.f;
+    }
+
+    // stage the input halo tile of `tile` into buffer `buf` (cp.async: returns immediately)
+    auto tile_coords = [&](int tile, int &tile_x, int &tile_y, int &img) {
+        if (NBUF == 1) {
+            tile_x = blockIdx.x, tile_y = blockIdx.y, img = blockIdx.z;
+        } else {
+            int t = tile;
+            tile_x = t % tiles_x;
+            t /= tiles_x;
+            tile_y = t % tiles_y;
+            img = t / tiles_y;
+        }
+    };
+    // stage the input halo tile of `tile` into buffer `buf` (cp.async: returns immediately)
+    auto issue_fill = [&](int tile, int buf) {
+        int tile_x, tile_y, img;
+        tile_coords(tile, tile_x, tile_y, img);
+        const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+        const float *in_img = p.in + (long long)img * p.in_img_stride;
+        float *dst = s_in0 + buf * IN_TILE;
+        for (int e = tid; e < IH * IW * CQ; e += NT) {
+            const int q = e % CQ, pix = e / CQ;
+            const int ty = pix / IW, tx = pix - ty * IW;
+            const int iy = oy0 - 1 + ty, ix = ox0 - 1 + tx;
+            const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            cp_async16(dst + pix * PS + q * 4, ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img, ok ? 16 : 0);
+        }
+    };
+
+    // NBUF == 1: 3-D grid (tile_x, tile_y, image), one tile per CTA, no index divisions;
+    // NBUF == 2: 1-D persistent grid looping over linear tile ids.
+    int tile = NBUF == 1 ? ((int)blockIdx.z * tiles_y + (int)blockIdx.y) * tiles_x + (int)blockIdx.x : (int)blockIdx.x;
+    const int tile_step = NBUF == 1 ? total_tiles : (int)gridDim.x;
+    int buf = 0;
+    uint32_t phase = 0;
+    if (tile < total_tiles) issue_fill(tile, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = make_idesc_tf32(128, NP);
+    const EpiDev &e = p.epi;
+    const bool res_smem = e.res == p.in && !e.res_pool;
+    bool weights_ready = false;
+
+    for (; tile < total_tiles; tile += tile_step, buf ^= (NBUF - 1)) {
+        const int next = NBUF == 2 ? tile + tile_step : total_tiles;
+        cp_async_wait_all();                   // this tile's input has landed ...
+        tc_fence_before();
+        __syncthreads();                       // ... for everybody; previous tile's epilogue is finished
+        tc_fence_after();
+        if (next < total_tiles) issue_fill(next, buf ^ 1);   // (persistent variant) prefetch behind this tile's compute
+        const float *s_in = s_in0 + buf * IN_TILE;
+
+        // --- depthwise, sliding window: item = (strip of 4 pixels along x, channel quad) -----------------------
+        constexpr int STRIPS = TH * (TW / 4);
+        for (int it = tid; it < STRIPS * CQ; it += NT) {
+            const int q = it % CQ, strip = it / CQ;
+            const int sy = strip / (TW / 4), sx = (strip % (TW / 4)) * 4;
+            const float4 bias = *reinterpret_cast<const float4 *>(s_dwb + q * 4);
+            float4 v[4] = {bias, bias, bias, bias};
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                float4 x[6];
+                const float *row = s_in + ((sy + ky) * IW + sx) * PS + q * 4;
+#pragma unroll
+                for (int c = 0; c < 6; c++) x[c] = *reinterpret_cast<const float4 *>(row + c * PS);
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(s_dww + (ky * 3 + kx) * CS + q * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v[i].x = fmaf(x[i + kx].x, wv.x, v[i].x);
+                        v[i].y = fmaf(x[i + kx].y, wv.y, v[i].y);
+                        v[i].z = fmaf(x[i + kx].z, wv.z, v[i].z);
+                        v[i].w = fmaf(x[i + kx].w, wv.w, v[i].w);
+                    }
+                }
+            }
+            const int m = sy * TW + sx;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                act4(v[i], p.act_mid, q * 4);
+                float4 hi, lo;
+                split_tf32_fast(v[i].x, hi.x, lo.x);
+                split_tf32_fast(v[i].y, hi.y, lo.y);
+                split_tf32_fast(v[i].z, hi.z, lo.z);
+                split_tf32_fast(v[i].w, hi.w, lo.w);
+                *reinterpret_cast<float4 *>(sA_hi + (q * (M + 1) + m + i) * 4) = hi;
+                *reinterpret_cast<float4 *>(sA_lo + (q * (M + 1) + m + i) * 4) = lo;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            if (!weights_ready) mbar_wait(&mbar_b, 0), weights_ready = true;   // weights landed (first tile only)
+#pragma unroll 1
+            for (int half = 0; half < HALVES; half++) {
+                uint32_t acc_flag = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; pass++) {
+                    const uint32_t a0 = smem_u32(pass == 0 ? sA_lo : sA_hi) + (uint32_t)half * 128 * 16;
+                    const uint32_t b0 = smem_u32(pass == 1 ? sB_lo : sB_hi);
+#pragma unroll
+                    for (int j = 0; j < CS / 8; j++) {
+                        const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * LBO_A, LBO_A, 128);
+                        const uint64_t bd = make_smem_desc(b0 + (uint32_t)(2 * j) * NP * 16, (uint32_t)NP * 16, 128);
+                        umma_tf32(tmem + (uint32_t)half * NP, ad, bd, idesc, acc_flag);
+                        acc_flag = 1;
+                    }
+                }
+            }
+            umma_commit(&mbar_mma);
+        }
+        if (poll_all) {
+            mbar_wait(&mbar_mma, phase);             // every thread polls the mbarrier itself
+        } else {
+            if (tid == 0) mbar_wait(&mbar_mma, phase);   // one poller; the rest park at bar.sync
+            tc_fence_before();
+            __syncthreads();
+        }
+        phase ^= 1;
+        tc_fence_after();
+
+        // --- epilogue: thread t owns row (t % 128) of half (t / 128); with M = 128 the upper warps take the
+        // upper half of the columns of the same rows.
+        int tile_x, tile_y, img;
+        tile_coords(tile, tile_x, tile_y, img);
+        const int row = (warp & 3) * 32 + lane;
+        const int half = HALVES == 2 ? (warp >> 2) : 0;
+        const int m = half * 128 + row;
+        const int ty = m / TW, tx = m % TW;
+        const int oy = tile_y * TH + ty, ox = tile_x * TW + tx;
+        const bool ok = oy < p.Ho && ox < p.Wo;
+        const int cbeg = HALVES == 2 ? 0 : (warp >> 2) * (NP / 2);
+        const int cend = HALVES == 2 ? NP : cbeg + NP / 2;
+        float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+        const float *s_center = s_in + ((ty + 1) * IW + tx + 1) * PS;
+        const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)half * NP;
+        for (int c0 = cbeg; c0 < cend; c0 += 8) {
+            float v8[8];
+            tmem_ld8(tbase + (uint32_t)c0, v8);
+            if (!ok) continue;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int n = c0 + 4 * h;
+                if (n >= p.Nstore) continue;
+                const float4 bv = *reinterpret_cast<const float4 *>(s_pb + n);
+                float v[4] = {v8[4 * h] + bv.x, v8[4 * h + 1] + bv.y, v8[4 * h + 2] + bv.z, v8[4 * h + 3] + bv.w};
+                act4(v, e.act1, n);
+                if (e.res) {
+                    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (res_smem) {
+                        if (n < CS) rr = *reinterpret_cast<const float4 *>(s_center + n);
+                    } else {
+                        rr = residual4_at(e, img, oy, ox, n);
+                    }
+                    v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+                }
+                if (e.act2.kind == ACT_PRELU) {
+                    const float4 sl = *reinterpret_cast<const float4 *>(s_sl + n);
+                    v[0] = v[0] < 0.f ? v[0] * sl.x : v[0];
+                    v[1] = v[1] < 0.f ? v[1] * sl.y : v[1];
+                    v[2] = v[2] < 0.f ? v[2] * sl.z : v[2];
+                    v[3] = v[3] < 0.f ? v[3] * sl.w : v[3];
+                } else {
+                    act4(v, e.act2, n);
+                }
+                *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+    cp_async_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+template <int CS, int TH, int NBUF>
+size_t ttc_smem(int NP) {
+    constexpr int M = 32 * TH, CQ = CS / 4;
+    return sizeof(float) * (2 * (size_t)CQ * (M + 1) * 4 + 2 * (size_t)CQ * NP * 4 + NBUF * (size_t)(TH + 2) * 34 * (CS + 4) +
+                            10 * CS + 2 * (size_t)NP) + 1024;
+}
+
+template <int CS, int TH, int NBUF>
+bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    const size_t smem = ttc_smem<CS, TH, NBUF>(NP);
+    auto kern = dwpw_ttc_kernel<CS, TH, NBUF>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        configured = smem;
+    }
+    const int tiles_x = (p.Wo + 31) / 32, tiles_y = (p.Ho + TH - 1) / TH;
+    const int images = p.M / (p.Ho * p.Wo);
+    const int total = tiles_x * tiles_y * images;
+    // persistent CTAs: as many as fit on the 148 SMs, each looping over tiles
+    static int per_sm = 0, num_sms = 0;
+    static size_t per_sm_smem = 0;
+    if (per_sm == 0 || per_sm_smem != smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+        if (per_sm < 1) per_sm = 1;
+        per_sm_smem = smem;
+    }
+    // NBUF == 2: persistent CTAs (as many as fit on the SMs) looping over tiles with the next input tile
+    // prefetched; NBUF == 1: one tile per CTA (measured faster: more resident CTAs overlap the serial phases)
+    static const int poll_all = getenv("ZB_TC_POLL_ALL") ? atoi(getenv("ZB_TC_POLL_ALL")) : 1;
+    if (NBUF == 1) {
+        kern<<<dim3(tiles_x, tiles_y, images), 256, smem, s>>>(p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
+    } else {
+        const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
+        kern<<<(unsigned)grid, 256, smem, s>>>(p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
+    }
+    return true;
+}
+
+template <int CS>
+bool launch_ttc_cs(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    // tile height: 8 rows (M = 256) when three CTAs still fit in one SM's shared memory, else 4 rows (M = 128)
+    static const bool persist = getenv("ZB_TTC_PERSIST") && atoi(getenv("ZB_TTC_PERSIST")) != 0;
+    if (persist) {
+        if (ttc_smem<CS, 8, 2>(NP) <= 110 * 1024 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 2>(p, w_hi, w_lo, NP, s);
+        return launch_ttc_cfg<CS, 4, 2>(p, w_hi, w_lo, NP, s);
+    }
+    if (ttc_smem<CS, 8, 1>(NP) <= 74 * 1024 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 1>(p, w_hi, w_lo, NP, s);
+    return launch_ttc_cfg<CS, 4, 1>(p, w_hi, w_lo, NP, s);
+}
+
 size_t dwpw_tc_smem(int KC, int NP) { return sizeof(float) * 2 * ((size_t)KC * TC_M + (size_t)KC * NP) + 1024; }
 
 template <int KS>
@@ -329,6 +623,32 @@ bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     if (!dwpw_tc_supported(p, NP)) return false;
     g_launch_count++;
     return p.kh == 3 ? launch_dwpw_tc_ks<3>(p, w_hi, w_lo, NP, s) : launch_dwpw_tc_ks<5>(p, w_hi, w_lo, NP, s);
+}
+
+bool dwpw_ttc_supported(const ConvDev &p, int NP) {
+    static const bool disabled = getenv("ZB_NO_TTC") && atoi(getenv("ZB_NO_TTC")) != 0;
+    if (disabled) return false;
+    if (p.kh != 3 || p.kw != 3 || p.sh != 1 || p.sw != 1 || p.pt != 1 || p.pl != 1) return false;
+    // measured per layer against the SIMT thin kernel (same box, batch 1024): Cs 16 loses (1.17 vs 1.07 ms on the
+    // 96x96x16 blocks), Cs 24 ties, Cs >= 32 wins (0.78 vs 0.92 ms on 48x48x32, 0.18 vs 0.23 ms on 32x32x36)
+    static const int min_cs = getenv("ZB_TTC_MIN_CS") ? atoi(getenv("ZB_TTC_MIN_CS")) : 24;
+    if (!(p.Cs_in == 16 || p.Cs_in == 24 || p.Cs_in == 32 || p.Cs_in == 40 || p.Cs_in == 48) || p.Cs_in < min_cs) return false;
+    if (p.K != p.Cs_in || NP % 16 || NP < 16 || NP > 64 || p.Ns % 4 || p.Nstore != p.Ns || p.out_pix_stride != p.Ns) return false;
+    if (p.Ho * p.Wo < 1024 || p.Wo < 32 || p.Ho % 4 || p.M % (p.Ho * p.Wo)) return false;
+    if (p.epi.res && p.epi.res == p.in && p.epi.res_Cs != p.Cs_in) return false;
+    return true;
+}
+
+bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    if (!dwpw_ttc_supported(p, NP)) return false;
+    g_launch_count++;
+    switch (p.Cs_in) {
+        case 16: return launch_ttc_cs<16>(p, w_hi, w_lo, NP, s);
+        case 24: return launch_ttc_cs<24>(p, w_hi, w_lo, NP, s);
+        case 32: return launch_ttc_cs<32>(p, w_hi, w_lo, NP, s);
+        case 40: return launch_ttc_cs<40>(p, w_hi, w_lo, NP, s);
+        default: return launch_ttc_cs<48>(p, w_hi, w_lo, NP, s);
+    }
 }
 
 // D[128,N] = A[128,K] * B[N,K]^T on tcgen05 (nsplit 1: raw TF32, 3: 3xTF32).  Device pointers.
