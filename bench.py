@@ -262,6 +262,27 @@ def run_gpu(args):
     zaru_b200.sync()
     e2e_ms = 1000.0 * (time.perf_counter() - e0)
     (e2e_ms_max,) = shard.max_over_ranks([e2e_ms], dist, "cuda")
+    # --- e2e, zero-copy variant: frames stay in pinned host memory, the sampler reads texels across PCIe -----
+    zc_n = batch_n
+    zc_ms_max = None
+    try:
+        reps = (zc_n + e2e_n - 1) // e2e_n
+        h_big = torch.empty((zc_n, FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory()
+        for r in range(reps):
+            lo_i, hi_i = r * e2e_n, min(zc_n, (r + 1) * e2e_n)
+            h_big[lo_i:hi_i].copy_(h_frames[:hi_i - lo_i])
+        zc_batch = ImageBatch.alias_pinned_host(res, h_big.data_ptr(), zc_n, keepalive=h_big)
+        for _ in range(max(1, args.warmup // 2)):
+            pipe.run_raw(zc_batch, zc_n)
+        barrier()
+        z0 = time.perf_counter()
+        for _ in range(args.steps):
+            pipe.run_raw(zc_batch, zc_n)
+        zaru_b200.sync()
+        zc_ms = 1000.0 * (time.perf_counter() - z0)
+        (zc_ms_max,) = shard.max_over_ranks([zc_ms], dist, "cuda")
+    except Exception as ex:   # pinned allocation of the full batch can fail on small hosts
+        log(f"[rank {rank}] zero-copy e2e skipped: {ex}")
     clock_info = clocks.stop() if rank == 0 else None
     d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
 
@@ -281,6 +302,23 @@ def run_gpu(args):
 
     value = world * batch_n * args.steps / (dev_ms_max / 1000.0)
     e2e_value = world * e2e_n * args.steps / (e2e_ms_max / 1000.0)
+    e2e_copy = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n * FRAME_BYTES, "d2h_bytes_per_step": d2h,
+                "batch_per_gpu": e2e_n, "ms_per_step": e2e_ms_max / args.steps,
+                "note": "pinned host frames -> zb_frames_update (explicit H2D of whole frames) -> zb_face_pipeline_run -> results D2H"}
+    e2e_best = e2e_copy
+    if zc_ms_max is not None:
+        zc_value = world * zc_n * args.steps / (zc_ms_max / 1000.0)
+        # bytes that cross PCIe: one 32-byte sector per sampled texel is the upper bound (128x128 + 192x192 samples)
+        e2e_zc = {"value": zc_value, "unit": UNIT, "h2d_bytes_per_step": zc_n * (128 * 128 + 192 * 192) * 32,
+                  "d2h_bytes_per_step": zc_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24), "batch_per_gpu": zc_n,
+                  "ms_per_step": zc_ms_max / args.steps,
+                  "note": "frames stay in PINNED HOST memory (zb_frames_alias on the pinned pointer); the sampling kernels "
+                          "read the texels they need across PCIe inside the timed region (zero-copy), results D2H; "
+                          "h2d bytes = upper bound, one 32 B sector per sampled texel"}
+        if zc_value > e2e_value:
+            e2e_best = dict(e2e_zc, explicit_copy=e2e_copy)
+        else:
+            e2e_best = dict(e2e_copy, zero_copy=e2e_zc)
     peak, peak_src = peaks()
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     total_ms = sum(v["ms"] for v in prof.values())
@@ -301,9 +339,7 @@ def run_gpu(args):
                    "timing": "CUDA events on the library stream around the K steps, max over ranks"},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n * FRAME_BYTES, "d2h_bytes_per_step": d2h,
-                "batch_per_gpu": e2e_n, "ms_per_step": e2e_ms_max / args.steps,
-                "note": "pinned host frames -> zb_frames_update (H2D) -> zb_face_pipeline_run -> results D2H, every step"},
+        "e2e": e2e_best,
         "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "share_of_step": top[1]["ms"] / total_ms,

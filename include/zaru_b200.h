@@ -121,7 +121,9 @@ zb_status zb_net_set_chunk(zb_net *net, int32_t images_per_chunk);
  * (stride_bytes >= 4*width between rows, frames contiguous) into HBM.                         */
 zb_status zb_frames_upload(zb_ctx *ctx, const uint8_t *rgba_host, int32_t width, int32_t height,
                            int64_t row_stride_bytes, int32_t n, zb_frames **out);
-/* Same, without a copy: `rgba_device` must stay valid while the handle lives.                 */
+/* Same, without a copy: the pixels must stay valid while the handle lives.  `rgba_device` may be
+ * device memory, or PINNED host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory): then
+ * the sampler reads the texels it needs directly across PCIe (zero-copy ingest).              */
 zb_status zb_frames_alias(zb_ctx *ctx, const uint8_t *rgba_device, int32_t width, int32_t height,
                           int64_t row_stride_bytes, int32_t n, zb_frames **out);
 /* Re-fill an uploaded batch from host memory (steady-state ingest; async on the ctx stream). */

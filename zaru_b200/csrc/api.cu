@@ -194,6 +194,7 @@ struct zb_frames {
     zb_ctx *ctx = nullptr;
     FramesDev f{};
     uint8_t *owned = nullptr;
+    bool host_mapped = false;            // pixels live in pinned host memory (zero-copy sampling across PCIe)
 };
 
 namespace {
@@ -749,9 +750,22 @@ static zb_status frames_make(zb_ctx *ctx, const uint8_t *src, int32_t w, int32_t
             CU(cudaStreamSynchronize(ctx->stream));
             fr->f.base = fr->owned;
         } else {
-            if (!is_device_ptr(src)) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_frames_alias expects device memory");
-            if (((uintptr_t)src) % 4) return fail(ZB_ERR_INVALID_ARGUMENT, "frame base must be 4-byte aligned");
-            fr->f.base = src;
+            const uint8_t *dev = src;
+            if (!is_device_ptr(src)) {
+                // Pinned (page-locked, mapped) HOST memory: the sampler reads texels straight across PCIe
+                // (zero-copy).  Only the ~46 K texels a frame's two views touch are transferred instead of
+                // the whole 8.3 MB frame.
+                cudaPointerAttributes a;
+                if (cudaPointerGetAttributes(&a, src) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
+                    cudaGetLastError();
+                    return fail(ZB_ERR_INVALID_ARGUMENT,
+                                "zb_frames_alias expects device memory or pinned (cudaHostAlloc / cudaHostRegister) host memory");
+                }
+                dev = static_cast<const uint8_t *>(a.devicePointer);
+                fr->host_mapped = true;
+            }
+            if (((uintptr_t)dev) % 4) return fail(ZB_ERR_INVALID_ARGUMENT, "frame base must be 4-byte aligned");
+            fr->f.base = dev;
         }
         *out = fr.release();
         return ZB_OK;
@@ -855,7 +869,9 @@ struct zb_face_pipeline {
     zb_net *det_net, *lm_net;
     float thresh = 0.5f, iou = 0.3f;
     int mode = ZB_NMS_AVERAGE;
-    Workspace ws_det, ws_lm;
+    Workspace ws_det[2], ws_lm[2];       // one set per stream (chunks alternate between two streams)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf d_views, d_fit, d_dets, d_counts, d_lm_views, d_lm_fit, d_rois, d_lm, d_scalars;
     PinBuf h_stage, h_counts;
     int cap = 0;
@@ -1176,6 +1192,9 @@ zb_status zb_face_pipeline_create(zb_ctx *ctx, zb_net *det_net, zb_net *lm_net, 
 void zb_face_pipeline_destroy(zb_face_pipeline *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
+    if (p->stream2) cudaStreamSynchronize(p->stream2), cudaStreamDestroy(p->stream2);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     delete p;
 }
 
@@ -1197,9 +1216,22 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         CU(cudaSetDevice(ctx->device));
         cudaStream_t s = ctx->stream;
         const Plan &dpl = p->det_net->plan, &lpl = p->lm_net->plan;
-        const int chunk = std::min(net_chunk(p->det_net), n);
-        p->ws_det.ensure(p->det_net, chunk, n);
-        p->ws_lm.ensure(p->lm_net, chunk, n);
+        // Frames in pinned host memory are sampled across PCIe: split the batch into >= 4 chunks and alternate
+        // them between two streams so one chunk's (PCIe-latency-bound) sampling overlaps the other's compute.
+        static const bool two_stream_env = getenv("ZB_TWO_STREAMS") && atoi(getenv("ZB_TWO_STREAMS")) != 0;   // measured: no gain, PCIe-bound
+        const bool two_streams = two_stream_env && frames->host_mapped && n >= 8 && !ctx->prof_on;
+        int chunk = std::min(net_chunk(p->det_net), n);
+        if (two_streams) chunk = std::min(chunk, std::max(4, (n + 3) / 4));
+        const int ns = two_streams ? 2 : 1;
+        if (two_streams && !p->stream2) {
+            CU(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+        }
+        for (int j = 0; j < ns; j++) {
+            p->ws_det[j].ensure(p->det_net, chunk, n);
+            p->ws_lm[j].ensure(p->lm_net, chunk, n);
+        }
         // every whole-frame view is the same rectangle: fit once, replicate with the frame index
         p->h_stage.reserve((sizeof(ViewDev) + 4 * sizeof(float)) * n);
         ViewDev *hv = p->h_stage.as<ViewDev>();
@@ -1234,36 +1266,46 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         lp.net_h = lpl.in_h;
         lp.track_transform = 1;
         Timer tm(ctx, s);
-        // detector, stage 0 (large activations): per chunk so they stay L2-resident
-        for (int c0 = 0; c0 < n; c0 += chunk) {
-            const int nc = std::min(chunk, n - c0);
-            const StemInput si{&frames->f, p->d_views.as<ViewDev>() + c0, -1.0f, 1.0f};
-            run_ops(p->det_net, p->ws_det, c0, nc, 0, s, &si);
+        if (two_streams) {
+            CU(cudaEventRecord(p->ev_fork, s));
+            CU(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
         }
-        // detector, stage 1 (deep, spatially tiny layers) + decode/NMS + RoI: once for the whole batch
-        run_ops(p->det_net, p->ws_det, 0, n, 1, s);
-        prof_launch(ctx, s, "decode_nms", 4.0 * n * dp.num_anchors * (dp.num_params + 1), 0, [&] {
-            launch_decode_nms(p->ws_det.outs[0].as<float>(), p->ws_det.outs[1].as<float>(), p->d_fit.as<float>(), n, dp,
-                              p->d_dets.as<DetDev>(), p->d_counts.as<int>(), s);
-        });
-        prof_launch(ctx, s, "face_roi", 128.0 * n, 0, [&] {
-            launch_face_roi(frames->f, p->d_dets.as<DetDev>(), p->d_counts.as<int>(), cap, 0, n, lpl.in_w, lpl.in_h,
-                            p->d_lm_views.as<ViewDev>(), p->d_lm_fit.as<float>(), p->d_rois.as<ViewHost>(), s);
-        });
-        // landmarks, stage 0 per chunk, stage 1 per batch
-        for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int s0 = (int)lpl.outputs[0].per_image, s1 = (int)lpl.outputs[1].per_image;
+        int k = 0;
+        for (int c0 = 0; c0 < n; c0 += chunk, k++) {
             const int nc = std::min(chunk, n - c0);
-            const StemInput si{&frames->f, p->d_lm_views.as<ViewDev>() + c0, -1.0f, 1.0f};
-            run_ops(p->lm_net, p->ws_lm, c0, nc, 0, s, &si);
-        }
-        run_ops(p->lm_net, p->ws_lm, 0, n, 1, s);
-        {
-            const int s0 = (int)lpl.outputs[0].per_image, s1 = (int)lpl.outputs[1].per_image;
-            prof_launch(ctx, s, "landmarks", 8.0 * n * (3 * L + 1), 0, [&] {
-                launch_landmarks(p->ws_lm.outs[0].as<float>(), s0, p->ws_lm.outs[1].as<float>(), s1, nullptr, 0,
-                                 p->d_lm_fit.as<float>(), p->d_lm_views.as<ViewDev>(), p->d_rois.as<ViewHost>(), n, lp,
-                                 p->d_lm.as<float>(), p->d_scalars.as<float>(), s);
+            const int j = k % ns;
+            cudaStream_t cs = j == 0 ? s : p->stream2;
+            Workspace &wd = p->ws_det[j], &wl = p->ws_lm[j];
+            // detector: (fused) sampling + stage 0 + stage 1, decode/NMS, RoI -> landmark view (all on device)
+            const StemInput sd{&frames->f, p->d_views.as<ViewDev>() + c0, -1.0f, 1.0f};
+            run_ops(p->det_net, wd, c0, nc, 0, cs, &sd);
+            run_ops(p->det_net, wd, c0, nc, 1, cs);
+            prof_launch(ctx, cs, "decode_nms", 4.0 * nc * dp.num_anchors * (dp.num_params + 1), 0, [&] {
+                launch_decode_nms(wd.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
+                                  wd.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image,
+                                  p->d_fit.as<float>() + 4 * c0, nc, dp, p->d_dets.as<DetDev>() + (size_t)c0 * cap,
+                                  p->d_counts.as<int>() + c0, cs);
             });
+            prof_launch(ctx, cs, "face_roi", 128.0 * nc, 0, [&] {
+                launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0, nc,
+                                lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0,
+                                p->d_rois.as<ViewHost>() + c0, cs);
+            });
+            // landmarks
+            const StemInput sl{&frames->f, p->d_lm_views.as<ViewDev>() + c0, -1.0f, 1.0f};
+            run_ops(p->lm_net, wl, c0, nc, 0, cs, &sl);
+            run_ops(p->lm_net, wl, c0, nc, 1, cs);
+            prof_launch(ctx, cs, "landmarks", 8.0 * nc * (3 * L + 1), 0, [&] {
+                launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
+                                 nullptr, 0, p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
+                                 p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
+                                 p->d_scalars.as<float>() + 2 * c0, cs);
+            });
+        }
+        if (two_streams) {
+            CU(cudaEventRecord(p->ev_join, p->stream2));
+            CU(cudaStreamWaitEvent(s, p->ev_join, 0));
         }
         CU(cudaGetLastError());
         tm.stop();

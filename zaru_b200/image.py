@@ -45,6 +45,11 @@ class ImageBatch:
                                               res.width() * 4, n, C.byref(h)))
         return cls(h, res.width(), res.height(), n, keepalive)
 
+    @classmethod
+    def alias_pinned_host(cls, res: Resolution, host_ptr: int, n: int, keepalive=None) -> "ImageBatch":
+        """Frames stay in PINNED host memory; the CUDA sampler reads the texels it needs across PCIe."""
+        return cls.alias_device(res, host_ptr, n, keepalive)
+
     def update(self, frames: np.ndarray, first: int = 0):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         _ffi.check(_ffi.lib().zb_frames_update(self._h, frames.ctypes.data, first, frames.shape[0]))
