@@ -126,7 +126,7 @@ struct zb_ctx {
     int default_chunk = 1024;
     // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
     int tc_mode = 1;                     // ZB_TC: 0 = SIMT only, 1 = tcgen05 3xTF32 for fused blocks with K >= tc_min_k
-    int tc_min_k = 72;                   // ZB_TC_MIN_K
+    int tc_min_k = 48;                   // ZB_TC_MIN_K
     int tc_min_ctas = 600;               // ZB_TC_MIN_CTAS
     bool prof_on = false;
     bool prof_detail = false;            // ZB_PROF_DETAIL=1: one profile row per layer instead of per kernel class

@@ -140,14 +140,17 @@ __device__ __forceinline__ void tc_epilogue_cols(const ConvDev &p, const float (
     }
 }
 
-template <int KS>
+// STRIP (3x3, stride 1, Wo % 4 == 0): the producer's work item is 4 horizontally adjacent pixels x one channel
+// quad, so the 3x6 input window is loaded once for 4 outputs (4.5 instead of 9 global loads per output quad).
+template <int KS, bool STRIP>
 __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const float *__restrict__ w_hi,
                                                       const float *__restrict__ w_lo, int NP, int KC, int Kpad) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int KQC = KC / 4;
-    float *sA_hi = reinterpret_cast<float *>(smem_raw);          // [KQC][128][4]
-    float *sA_lo = sA_hi + (size_t)KQC * TC_M * 4;
-    float *sB_hi = sA_lo + (size_t)KQC * TC_M * 4;               // [KQC][NP][4]
+    constexpr int A_ROWS = TC_M + 1;                             // chunk stride padded by one row: conflict-free stores
+    float *sA_hi = reinterpret_cast<float *>(smem_raw);          // [KQC][129][4]
+    float *sA_lo = sA_hi + (size_t)KQC * A_ROWS * 4;
+    float *sB_hi = sA_lo + (size_t)KQC * A_ROWS * 4;             // [KQC][NP][4]
     float *sB_lo = sB_hi + (size_t)KQC * NP * 4;
     __shared__ __align__(16) int4 rowinfo[TC_M];                 // {img offset lo, hi, iy0, ix0}; iy0 == INT_MIN: no pixel
     __shared__ __align__(8) uint64_t mbar_mma, mbar_b;
@@ -211,22 +214,78 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
         split_tf32_fast(v.y, hi.y, lo.y);
         split_tf32_fast(v.z, hi.z, lo.z);
         split_tf32_fast(v.w, hi.w, lo.w);
-        *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * TC_M + m) * 4) = hi;
-        *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * TC_M + m) * 4) = lo;
+        *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * A_ROWS + m) * 4) = hi;
+        *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * A_ROWS + m) * 4) = lo;
+    };
+    // strip item: rows m..m+3 are 4 consecutive pixels of one image row (Wo % 4 == 0), channel quad kq
+    auto produce_strip = [&](int it, int kc0) {
+        const int kq = it % KQC, strip = it / KQC;
+        const int m = strip * 4;
+        const int k = kc0 + kq * 4;
+        const int4 ri = rowinfo[m];
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ri.z != INT_MIN && k < p.K) {
+            const long long off = ((long long)ri.y << 32) | (unsigned)ri.x;
+            const float *base = p.in + off + k;
+            const float4 bias = ldg4(p.dw_b + k);
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = bias;
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const int iy = ri.z + ky;
+                const bool rowok = iy >= 0 && iy < p.H;
+                float4 x[6];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const int ix = ri.w + c;
+                    x[c] = (rowok && ix >= 0 && ix < p.W) ? ldg4(base + ((long long)iy * p.W + ix) * p.Cs_in)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const float4 wv = ldg4(p.dw_w + (ky * 3 + kx) * p.Cs_in + k);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v[i].x = fmaf(x[i + kx].x, wv.x, v[i].x);
+                        v[i].y = fmaf(x[i + kx].y, wv.y, v[i].y);
+                        v[i].z = fmaf(x[i + kx].z, wv.z, v[i].z);
+                        v[i].w = fmaf(x[i + kx].w, wv.w, v[i].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) act4(v[i], p.act_mid, k);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float4 hi, lo;
+            split_tf32_fast(v[i].x, hi.x, lo.x);
+            split_tf32_fast(v[i].y, hi.y, lo.y);
+            split_tf32_fast(v[i].z, hi.z, lo.z);
+            split_tf32_fast(v[i].w, hi.w, lo.w);
+            *reinterpret_cast<float4 *>(sA_hi + ((size_t)kq * A_ROWS + m + i) * 4) = hi;
+            *reinterpret_cast<float4 *>(sA_lo + ((size_t)kq * A_ROWS + m + i) * 4) = lo;
+        }
     };
 
     uint32_t acc_flag = 0, phase = 0;
     const int n_elem = TC_M * KQC;
     for (int kc0 = 0; kc0 < Kpad; kc0 += KC) {
-        // --- A chunk: two elements in flight per thread (all their loads are issued before the FMAs) --------
-        int e = tid;
-        for (; e + 256 < n_elem; e += 512) {
-            const float4 v0 = produce(e, kc0);
-            const float4 v1 = produce(e + 256, kc0);
-            store_split(e, v0);
-            store_split(e + 256, v1);
+        if (STRIP) {
+            for (int it = tid; it < (TC_M / 4) * KQC; it += 256) produce_strip(it, kc0);
+        } else {
+            // --- A chunk: two elements in flight per thread (all their loads are issued before the FMAs) ----
+            int e = tid;
+            for (; e + 256 < n_elem; e += 512) {
+                const float4 v0 = produce(e, kc0);
+                const float4 v1 = produce(e + 256, kc0);
+                store_split(e, v0);
+                store_split(e + 256, v1);
+            }
+            if (e < n_elem) store_split(e, produce(e, kc0));
         }
-        if (e < n_elem) store_split(e, produce(e, kc0));
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -239,7 +298,7 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
                 const float *b = pass == 1 ? sB_lo : sB_hi;
                 const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
                 for (int j = 0; j < KC / 8; j++) {
-                    const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * TC_M * 16, TC_M * 16, 128);
+                    const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * A_ROWS * 16, A_ROWS * 16, 128);
                     const uint64_t bd = make_smem_desc(b0 + (uint32_t)(2 * j) * NP * 16, (uint32_t)NP * 16, 128);
                     umma_tf32(tmem, ad, bd, idesc, acc_flag);
                     acc_flag = 1;
@@ -589,16 +648,16 @@ bool launch_ttc_cs(const ConvDev &p, const float *w_hi, const float *w_lo, int N
     return launch_ttc_cfg<CS, 4, 1>(p, w_hi, w_lo, NP, s);
 }
 
-size_t dwpw_tc_smem(int KC, int NP) { return sizeof(float) * 2 * ((size_t)KC * TC_M + (size_t)KC * NP) + 1024; }
+size_t dwpw_tc_smem(int KC, int NP) { return sizeof(float) * 2 * ((size_t)KC * (TC_M + 1) + (size_t)KC * NP) + 1024; }
 
-template <int KS>
+template <int KS, bool STRIP>
 bool launch_dwpw_tc_ks(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
     static const int kc_max = getenv("ZB_TC_KC") ? atoi(getenv("ZB_TC_KC")) : 32;
     const int KC = p.K <= kc_max ? p.K : kc_max;               // K chunk resident in shared memory
     const int Kpad = (p.K + KC - 1) / KC * KC;                 // packed weights are zero-padded to this many rows
     const size_t smem = dwpw_tc_smem(KC, NP);
     if (smem > 220 * 1024) return false;
-    auto kern = dwpw_tc_kernel<KS>;
+    auto kern = dwpw_tc_kernel<KS, STRIP>;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -622,7 +681,10 @@ bool dwpw_tc_supported(const ConvDev &p, int NP) {
 bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
     if (!dwpw_tc_supported(p, NP)) return false;
     g_launch_count++;
-    return p.kh == 3 ? launch_dwpw_tc_ks<3>(p, w_hi, w_lo, NP, s) : launch_dwpw_tc_ks<5>(p, w_hi, w_lo, NP, s);
+    static const bool no_strip = getenv("ZB_TC_NO_STRIP") && atoi(getenv("ZB_TC_NO_STRIP")) != 0;
+    if (p.kh == 5) return launch_dwpw_tc_ks<5, false>(p, w_hi, w_lo, NP, s);
+    const bool strip = !no_strip && p.sh == 1 && p.sw == 1 && p.Wo % 4 == 0 && (p.Ho * p.Wo) % 4 == 0;
+    return strip ? launch_dwpw_tc_ks<3, true>(p, w_hi, w_lo, NP, s) : launch_dwpw_tc_ks<3, false>(p, w_hi, w_lo, NP, s);
 }
 
 bool dwpw_ttc_supported(const ConvDev &p, int NP) {
