@@ -405,3 +405,25 @@ def test_pipeline_properties_at_batch(zb):
         for x, y in zip(a.detections[i], a.detections[j]):
             assert np.array_equal(x.as_vector(), y.as_vector())
         assert np.array_equal(a.landmarks[i], a.landmarks[j])
+
+
+def test_fused_sampling_is_bit_identical_to_sample_then_forward(zb, sad_linus_full):
+    """The stem kernel samples frames on the fly (separable tables for unrotated views, per-texel math for
+    rotated ones).  Feeding the network the tensor produced by the bit-exact `zb_preprocess` must give exactly
+    the same head tensors as the fused path: same conv code, only the source of the input differs."""
+    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200.image import Image
+    from zaru_b200.rect import AspectRatio, Rect, RotatedRect
+    img = Image(sad_linus_full)
+    det = Detector(ShortRangeNetwork())
+    cnn = ShortRangeNetwork().cnn()
+    batch, idx = img.device()
+    views = [img.as_view(), img.view(Rect.from_center(700, 400, 500, 333)),
+             img.view(RotatedRect(Rect.from_center(640, 360, 900, 700), 0.3)),
+             img.view(Rect.from_center(100, 100, 400, 400))]            # partly outside the image
+    for v in views:
+        det.detect_views(batch, [v.to_zb_view(idx)], want_raw=True)
+        raw_b, raw_s = det.last_raw
+        fit = v.view(v.rect().grow_to_fit_aspect(AspectRatio.SQUARE))
+        boxes, scores = cnn.nn.estimate(cnn.tensor(fit))
+        assert np.array_equal(raw_b, boxes) and np.array_equal(raw_s, scores)

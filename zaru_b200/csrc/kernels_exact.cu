@@ -127,16 +127,38 @@ __global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const Vi
 // N accumulators in registers, weights read from shared memory as warp broadcasts.  The convolution uses
 // explicit fmaf (this translation unit is built with -fmad=false for the sampler's sake).
 // ------------------------------------------------------------------------------------------------
-template <int KS, int NP>
+// For an UNROTATED view (cos == 1, sin == 0) the source coordinate of tensor pixel (x, y) is separable:
+//   transform_out gives px = ((0 + 1*dx) + (-0)*dy + hx) + tlx = (dx + hx) + tlx  exactly (adding a signed zero
+//   never changes dx, and 0 + dx is never -0), and likewise py depends on y only.
+// So one table entry per tile column / row replaces ~200 instructions of f32 division, rounding and bounds
+// checks per sampled texel.  Returns the source column (row) or -1 when the texel reads Color::NONE.
+__device__ __forceinline__ int sample_axis(float view_pos_center, float view_extent, int t, int out_n, int flip, int limit) {
+    // view_pos_center / view_extent: RotatedRect centre and size along this axis
+    const int ts = flip ? (out_n - 1 - t) : t;
+    const float u = (float)ts / (float)out_n;
+    const float sc = sat_u32_as_f32(roundf(u * view_extent));
+    const float h = view_extent * 0.5f;
+    const float d = (sc + 0.5f) - h;
+    const float tl = view_pos_center - view_extent * 0.5f;
+    const float pp = ((0.0f + d) + h) + tl;           // same operation order as transform_out with c = 1, s = 0
+    const float fr = roundf(pp - 0.5f);
+    if (fr < 0.0f || ceilf(fr) >= 4294967296.0f) return -1;
+    const unsigned i = (fr == fr) ? (unsigned)fr : 0u;
+    return i < (unsigned)limit ? (int)i : -1;
+}
+
+template <int KS, int NP, int PPT>
 __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const ViewDev *__restrict__ views, float lo, float hi,
                                                    const ConvDev p, int tiles_x, int tiles_y, int NSP) {
-    constexpr int TW = 32, TH = 8, NT = 256;
+    constexpr int TW = 32, TH = 8 * PPT, NT = 256;               // PPT output pixels per thread (rows ty, ty+8)
     constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
     extern __shared__ __align__(16) float smem[];
     float4 *s_in = reinterpret_cast<float4 *>(smem);            // [IH][IW] (r,g,b,0)
     float *s_w = smem + IH * IW * 4;                           // [KS*KS*4][NSP]  (row 4*tap+ci)
     float *s_b = s_w + KS * KS * 4 * NSP;                      // [NSP]
     float *s_sl = s_b + NSP;                                   // [NSP]
+    int *s_col = reinterpret_cast<int *>(s_sl + NSP);          // [IW] source column per tile column (-1: NONE)
+    int *s_row = s_col + IW;                                   // [IH]
 
     const int tid = threadIdx.x;
     int b = blockIdx.x;
@@ -150,26 +172,68 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
     if (views) {
         const ViewDev v = views[img];
         const float adjust = (hi - lo) / 255.0f;
-        // batches of 4 texels per thread: all addresses first, then all (independent) loads, then convert+store
-        for (int e0 = tid; e0 < IH * IW; e0 += 4 * NT) {
-            const unsigned *addr[4];
-            bool inside[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * NT;
-                const int ty = e / IW, tx = e - ty * IW;
-                const int iy = iy_org + ty, ix = ix_org + tx;
-                inside[u] = e < IH * IW && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                addr[u] = inside[u] ? sample_address(f, v, ix, iy, p.W, p.H) : nullptr;
+        const bool separable = v.valid && v.cosr == 1.0f && v.sinr == 0.0f;
+        if (separable) {
+            // tile column / row -> source column / row, -2 marks conv padding (outside the tensor)
+            for (int e = tid; e < IW + IH; e += NT) {
+                if (e < IW) {
+                    const int ix = ix_org + e;
+                    s_col[e] = (ix >= 0 && ix < p.W) ? sample_axis(v.cx, v.w, ix, p.W, v.flip_x, f.width) : -2;
+                } else {
+                    const int iy = iy_org + (e - IW);
+                    s_row[e - IW] = (iy >= 0 && iy < p.H) ? sample_axis(v.cy, v.h, iy, p.H, 0, f.height) : -2;
+                }
             }
-            unsigned rgba[4];
+            __syncthreads();
+            const uint8_t *fbase = f.base + (long long)v.frame * f.frame_stride;
+            for (int e0 = tid; e0 < IH * IW; e0 += 4 * NT) {
+                unsigned rgba[4];
+                int kind[4];                                   // 0: conv padding, 1: Color::NONE, 2: texel
 #pragma unroll
-            for (int u = 0; u < 4; u++) rgba[u] = addr[u] ? __ldg(addr[u]) : 0u;
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * NT;
+                    rgba[u] = 0u;
+                    kind[u] = 0;
+                    if (e < IH * IW) {
+                        const int ty = e / IW, tx = e - ty * IW;
+                        const int sc = s_col[tx], sr = s_row[ty];
+                        if (sc != -2 && sr != -2) {
+                            kind[u] = 1;
+                            if (sc >= 0 && sr >= 0) {
+                                kind[u] = 2;
+                                rgba[u] = __ldg(reinterpret_cast<const unsigned *>(fbase + (long long)sr * f.row_stride + (long long)sc * 4));
+                            }
+                        }
+                    }
+                }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * NT;
-                if (e < IH * IW)   // conv zero padding outside the tensor (NOT the letterbox colour)
-                    s_in[e] = inside[u] ? color_map(rgba[u], lo, adjust) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * NT;
+                    if (e < IH * IW) s_in[e] = kind[u] ? color_map(rgba[u], lo, adjust) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
+            // general (rotated) view: per-texel coordinate math, batches of 4 texels per thread
+            for (int e0 = tid; e0 < IH * IW; e0 += 4 * NT) {
+                const unsigned *addr[4];
+                bool inside[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * NT;
+                    const int ty = e / IW, tx = e - ty * IW;
+                    const int iy = iy_org + ty, ix = ix_org + tx;
+                    inside[u] = e < IH * IW && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    addr[u] = inside[u] ? sample_address(f, v, ix, iy, p.W, p.H) : nullptr;
+                }
+                unsigned rgba[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) rgba[u] = addr[u] ? __ldg(addr[u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * NT;
+                    if (e < IH * IW)   // conv zero padding outside the tensor (NOT the letterbox colour)
+                        s_in[e] = inside[u] ? color_map(rgba[u], lo, adjust) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
         }
     } else {
@@ -196,58 +260,71 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
     __syncthreads();
 
     const int tx = tid % TW, ty = tid / TW;
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    if (oy >= p.Ho || ox >= p.Wo) return;
-    float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
-    const float4 *s_px = s_in + (ty * 2) * IW + tx * 2;
+    const int ox = ox0 + tx;
+    if (ox >= p.Wo) return;
     const int act = p.epi.act1.kind;
     for (int n0 = 0; n0 < p.Nstore; n0 += NP) {
-        float acc[NP];
+        float acc[PPT][NP];
 #pragma unroll
-        for (int j = 0; j < NP; j++) acc[j] = s_b[n0 + j];
+        for (int i = 0; i < PPT; i++)
+#pragma unroll
+            for (int j = 0; j < NP; j++) acc[i][j] = s_b[n0 + j];
 #pragma unroll
         for (int t = 0; t < KS * KS; t++) {
-            const float4 x = s_px[(t / KS) * IW + (t % KS)];
-            const float xs[3] = {x.x, x.y, x.z};
+            float xs[PPT][3];
+#pragma unroll
+            for (int i = 0; i < PPT; i++) {
+                const float4 x = s_in[((ty + 8 * i) * 2 + t / KS) * IW + tx * 2 + (t % KS)];
+                xs[i][0] = x.x, xs[i][1] = x.y, xs[i][2] = x.z;
+            }
 #pragma unroll
             for (int ci = 0; ci < 3; ci++) {
 #pragma unroll
                 for (int j = 0; j < NP; j += 4) {
                     const float4 wv = *reinterpret_cast<const float4 *>(s_w + (t * 4 + ci) * NSP + n0 + j);
-                    acc[j] = fmaf(xs[ci], wv.x, acc[j]);
-                    acc[j + 1] = fmaf(xs[ci], wv.y, acc[j + 1]);
-                    acc[j + 2] = fmaf(xs[ci], wv.z, acc[j + 2]);
-                    acc[j + 3] = fmaf(xs[ci], wv.w, acc[j + 3]);
+#pragma unroll
+                    for (int i = 0; i < PPT; i++) {       // each weight quad feeds PPT pixels
+                        acc[i][j] = fmaf(xs[i][ci], wv.x, acc[i][j]);
+                        acc[i][j + 1] = fmaf(xs[i][ci], wv.y, acc[i][j + 1]);
+                        acc[i][j + 2] = fmaf(xs[i][ci], wv.z, acc[i][j + 2]);
+                        acc[i][j + 3] = fmaf(xs[i][ci], wv.w, acc[i][j + 3]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < NP; j += 4) {
-            const int n = n0 + j;
-            if (n >= p.Nstore) break;
-            float v[4] = {acc[j], acc[j + 1], acc[j + 2], acc[j + 3]};
-            if (act == ACT_RELU) {
+        for (int i = 0; i < PPT; i++) {
+            const int oy = oy0 + ty + 8 * i;
+            if (oy >= p.Ho) continue;
+            float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
 #pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], 0.0f);
-            } else if (act == ACT_PRELU) {
+            for (int j = 0; j < NP; j += 4) {
+                const int n = n0 + j;
+                if (n >= p.Nstore) break;
+                float v[4] = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
+                if (act == ACT_RELU) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = v[q] < 0.0f ? v[q] * s_sl[n + q] : v[q];
-            } else if (act == ACT_CLIP) {
+                    for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], 0.0f);
+                } else if (act == ACT_PRELU) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = fminf(fmaxf(v[q], p.epi.act1.lo), p.epi.act1.hi);
+                    for (int q = 0; q < 4; q++) v[q] = v[q] < 0.0f ? v[q] * s_sl[n + q] : v[q];
+                } else if (act == ACT_CLIP) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) v[q] = fminf(fmaxf(v[q], p.epi.act1.lo), p.epi.act1.hi);
+                }
+                *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
 
-template <int KS, int NP>
+template <int KS, int NP, int PPT>
 bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
-    constexpr int TW = 32, TH = 8;
+    constexpr int TW = 32, TH = 8 * PPT;
     constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
     const int NSP = (p.Ns + NP - 1) / NP * NP;
-    const size_t smem = sizeof(float) * ((size_t)IH * IW * 4 + (size_t)KS * KS * 4 * NSP + 2 * NSP);
-    auto kern = stem_kernel<KS, NP>;
+    const size_t smem = sizeof(float) * ((size_t)IH * IW * 4 + (size_t)KS * KS * 4 * NSP + 2 * NSP + IW + IH);
+    auto kern = stem_kernel<KS, NP, PPT>;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -622,14 +699,16 @@ bool stem_supported(const ConvDev &p) {
 bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
     if (!stem_supported(p)) return false;
     g_launch_count++;
+    // measured: 2 pixels per thread pays for the LDS-bound 5x5 stem (0.79 -> 0.63 ms), not for the 3x3 one
+    static const int ppt = getenv("ZB_STEM_PPT") ? atoi(getenv("ZB_STEM_PPT")) : 0;
     if (p.kh == 3) {
-        if (p.Ns <= 16) return launch_stem_cfg<3, 16>(f, views, lo, hi, p, s);
-        if (p.Ns == 24) return launch_stem_cfg<3, 24>(f, views, lo, hi, p, s);
-        return launch_stem_cfg<3, 32>(f, views, lo, hi, p, s);
+        if (p.Ns <= 16) return ppt == 2 ? launch_stem_cfg<3, 16, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<3, 16, 1>(f, views, lo, hi, p, s);
+        if (p.Ns == 24) return ppt == 2 ? launch_stem_cfg<3, 24, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<3, 24, 1>(f, views, lo, hi, p, s);
+        return launch_stem_cfg<3, 32, 1>(f, views, lo, hi, p, s);
     }
-    if (p.Ns <= 16) return launch_stem_cfg<5, 16>(f, views, lo, hi, p, s);
-    if (p.Ns == 24) return launch_stem_cfg<5, 24>(f, views, lo, hi, p, s);
-    return launch_stem_cfg<5, 32>(f, views, lo, hi, p, s);
+    if (p.Ns <= 16) return ppt != 1 ? launch_stem_cfg<5, 16, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<5, 16, 1>(f, views, lo, hi, p, s);
+    if (p.Ns == 24) return ppt != 1 ? launch_stem_cfg<5, 24, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<5, 24, 1>(f, views, lo, hi, p, s);
+    return launch_stem_cfg<5, 32, 1>(f, views, lo, hi, p, s);
 }
 
 void launch_decode_nms(const float *boxes, const float *scores, const float *fit, int n, const DecodeParams &p,
