@@ -25,6 +25,13 @@ FRAME_W, FRAME_H = 1920, 1080
 FRAME_BYTES = FRAME_W * FRAME_H * 4
 ALG_MB_PER_FRAME = 12.82      # block-fused network traffic 12.61 MB + 0.21 MB sampled pixels
 ALG_MFLOP_PER_FRAME = 131.48
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel classes, from the committed
+# `ncu --set full` captures (profiles/README.md); keyed by profile class, value = (bytes, algorithmic bytes of
+# that same launch) so the ratio can be applied to the live per-launch algorithmic bytes.
+NCU_TRAFFIC = {
+    # dwpw_thin_kernel<16,1,16> on the 1024 x 96x96x16 block: 604.46 MB read + 555.97 MB written
+    "dwpw_thin": (604.462592e6 + 555.972096e6, 2 * 1024 * 96 * 96 * 16 * 4.0),
+}
 METRIC = "frames/sec face detect+landmark (1080p)"
 UNIT = "frames/s"
 
@@ -341,7 +348,12 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "e2e": e2e_best,
         "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # measured DRAM bytes per launch = this class's ncu traffic/algorithmic ratio x live algorithmic bytes
+                     "traffic": (NCU_TRAFFIC[top[0]][0] / NCU_TRAFFIC[top[0]][1] * top[1]["bytes"] / top[1]["launches"]
+                                 if top[0] in NCU_TRAFFIC else None),
+                     "algorithmic_bytes_per_launch": top[1]["bytes"] / top[1]["launches"],
+                     "peak_source": peak_src,
                      "share_of_step": top[1]["ms"] / total_ms,
                      "pipeline": {"achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
                                   "model": f"{ALG_MB_PER_FRAME} MB algorithmic bytes per frame (SURVEY §8d) x frames/s per GPU"}},
