@@ -342,7 +342,7 @@ def run_gpu(args):
         "config": {"workload": "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark",
                    "batch_per_gpu": batch_n, "frame": "1920x1080 RGBA8", "distinct_frames": args.unique,
                    "l2_policy": f"inputs larger than L2 ({batch_n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
-                   "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "64")), "frames_with_face": n_with_face,
+                   "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "1024")), "frames_with_face": n_with_face,
                    "timing": "CUDA events on the library stream around the K steps, max over ranks"},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "gpu_launches": int(launches),

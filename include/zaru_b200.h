@@ -214,6 +214,11 @@ zb_status zb_plan_from_onnx(const void *onnx_bytes, size_t len, int32_t fuse_dwp
 zb_status zb_debug_tc_gemm(zb_ctx *ctx, const float *A, const float *B, float *D, int32_t N, int32_t K,
                            int32_t nsplit);
 
+/* Micro-benchmark hook: average clock cycles per back-to-back tcgen05.mma (kind::tf32, M = 128, K = 8) for an
+ * A-operand layout (leading / stride byte offsets, start offset); `ctas` CTAs run it concurrently.          */
+zb_status zb_debug_mma_rate(zb_ctx *ctx, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t a_off, int32_t iters,
+                            int32_t ksteps, int32_t ctas, float *cycles_per_mma);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------- */
 /* Device time (ms, CUDA events on the handle's own stream) of the last *_run/_detect/_estimate
  * call, excluding host<->device result copies.                                                */

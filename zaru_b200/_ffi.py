@@ -83,6 +83,7 @@ SIGNATURES = {
     "zb_net_weights": (i32, [P, C.POINTER(C.POINTER(C.c_float)), C.POINTER(sz)]),
     "zb_plan_from_onnx": (i32, [P, sz, i32, C.c_char_p, sz, C.POINTER(sz), P, sz, C.POINTER(sz)]),
     "zb_debug_tc_gemm": (i32, [P, P, P, P, i32, i32, i32]),
+    "zb_debug_mma_rate": (i32, [P, i32, i32, i32, i32, i32, i32, i32, P]),
     "zb_last_device_ms": (f32, [P]),
     "zb_timer_start": (i32, [P]),
     "zb_timer_stop": (i32, [P, C.POINTER(f32)]),

@@ -543,6 +543,24 @@ zb_status zb_debug_tc_gemm(zb_ctx *ctx, const float *A, const float *B, float *D
     });
 }
 
+zb_status zb_debug_mma_rate(zb_ctx *ctx, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t a_off, int32_t iters, int32_t ksteps,
+                            int32_t ctas, float *cycles_per_mma) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !cycles_per_mma) return fail(ZB_ERR_INVALID_ARGUMENT, "NULL argument");
+        CU(cudaSetDevice(ctx->device));
+        DevBuf d;
+        d.reserve(sizeof(long long));
+        if (!launch_tc_mma_rate(N, lbo_a, sbo_a, a_off, iters, ksteps, ctas, d.as<long long>(), ctx->stream))
+            return fail(ZB_ERR_INVALID_ARGUMENT, "unsupported MMA micro-benchmark shape");
+        CU(cudaGetLastError());
+        long long cyc = 0;
+        CU(cudaMemcpyAsync(&cyc, d.p, sizeof(cyc), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *cycles_per_mma = (float)((double)cyc / iters);
+        return ZB_OK;
+    });
+}
+
 zb_status zb_profile_begin(zb_ctx *ctx) {
     if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
     ctx->prof.clear();

@@ -67,6 +67,7 @@ bool dwpw_tc_supported(const ConvDev &p, int NP);
 bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
 bool dwpw_ttc_supported(const ConvDev &p, int NP);   // thin blocks: smem tile + sliding-window dw + tcgen05 pw
 bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
+bool launch_tc_mma_rate(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps, int ctas, long long *cycles_dev, cudaStream_t s);
 bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s);
 
 // ---- exact (no-FMA) kernels: kernels_exact.cu -------------------------------------------------

@@ -143,7 +143,7 @@ __device__ __forceinline__ void tc_epilogue_cols(const ConvDev &p, const float (
 // STRIP (3x3, stride 1, Wo % 4 == 0): the producer's work item is 4 horizontally adjacent pixels x one channel
 // quad, so the 3x6 input window is loaded once for 4 outputs (4.5 instead of 9 global loads per output quad).
 template <int KS, bool STRIP>
-__global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const float *__restrict__ w_hi,
+__global__ void __launch_bounds__(256, 3) dwpw_tc_kernel(const ConvDev p, const float *__restrict__ w_hi,
                                                       const float *__restrict__ w_lo, int NP, int KC, int Kpad) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int KQC = KC / 4;
@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
 
     uint32_t acc_flag = 0, phase = 0;
     const int n_elem = TC_M * KQC;
+    const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), A_ROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), A_ROWS * 16, 128);
+    const uint64_t bd_hi = make_smem_desc(smem_u32(sB_hi), (uint32_t)NP * 16, 128), bd_lo = make_smem_desc(smem_u32(sB_lo), (uint32_t)NP * 16, 128);
     for (int kc0 = 0; kc0 < Kpad; kc0 += KC) {
         if (STRIP) {
             for (int it = tid; it < (TC_M / 4) * KQC; it += 256) produce_strip(it, kc0);
@@ -292,16 +294,18 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
         tc_fence_after();
         if (tid == 0) {
             mbar_wait(&mbar_b, phase);                       // weights of this chunk have landed (TMA)
+            // descriptors are built once; each K step only adds its byte offset (>> 4) to the address field, so the
+            // single issuing thread spends ~3 instructions per MMA (it is latency-bound on its own instruction stream)
 #pragma unroll 1
             for (int pass = 0; pass < 3; pass++) {
-                const float *a = pass == 0 ? sA_lo : sA_hi;
-                const float *b = pass == 1 ? sB_lo : sB_hi;
-                const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
+                uint64_t ad = pass == 0 ? ad_lo : ad_hi;
+                uint64_t bd = pass == 1 ? bd_lo : bd_hi;
+#pragma unroll 4
                 for (int j = 0; j < KC / 8; j++) {
-                    const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * A_ROWS * 16, A_ROWS * 16, 128);
-                    const uint64_t bd = make_smem_desc(b0 + (uint32_t)(2 * j) * NP * 16, (uint32_t)NP * 16, 128);
                     umma_tf32(tmem, ad, bd, idesc, acc_flag);
                     acc_flag = 1;
+                    ad += (uint64_t)(2 * A_ROWS);          // 2 K-quads * A_ROWS * 16 B, in 16-byte units
+                    bd += (uint64_t)(2 * NP);
                 }
             }
             umma_commit(&mbar_mma);
@@ -370,16 +374,20 @@ __global__ void __launch_bounds__(256) dwpw_tc_kernel(const ConvDev p, const flo
 //   5. every thread reads its own pixel's row back (tcgen05.ld) and applies bias / residual (from the staged
 //      tile) / activation, storing N contiguous floats.
 // ------------------------------------------------------------------------------------------------
-template <int CS, int TH, int NBUF>
+template <int CS, int TH, int NBUF, int TW>
 __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const float *__restrict__ w_hi,
                                                        const float *__restrict__ w_lo, int NP, int tiles_x, int tiles_y,
                                                        int total_tiles, int poll_all) {
-    constexpr int TW = 32, M = TW * TH, NT = 256;
-    constexpr int PS = CS + 4, IW = TW + 2, IH = TH + 2, CQ = CS / 4;
+    constexpr int M = TW * TH, NT = 256;
+    // pixel stride of the staged tile: CS + 4 words keeps per-pixel 128-bit reads conflict free; for CS == 32 the
+    // pad is replaced by an XOR swizzle of the channel quad with the pixel index (3 KB less shared memory, which
+    // is what lets a third CTA fit on the SM)
+    constexpr bool SWZ = CS == 32;
+    constexpr int PS = SWZ ? CS : CS + 4, IW = TW + 2, IH = TH + 2, CQ = CS / 4;
     constexpr int HALVES = M / 128;
     constexpr int IN_TILE = IH * IW * PS;                            // floats per staged input tile
     constexpr uint32_t LBO_A = (M + 1) * 16;                         // padded chunk stride of the A tile (bytes)
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sA_hi = reinterpret_cast<float *>(smem_raw);              // [CQ][(M+1)][4]
     float *sA_lo = sA_hi + CQ * (M + 1) * 4;
     float *sB_hi = sA_lo + CQ * (M + 1) * 4;                         // [CQ][NP][4]  (TMA destination, 16 B aligned)
@@ -436,7 +444,8 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
             const int ty = pix / IW, tx = pix - ty * IW;
             const int iy = oy0 - 1 + ty, ix = ox0 - 1 + tx;
             const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-            cp_async16(dst + pix * PS + q * 4, ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img, ok ? 16 : 0);
+            cp_async16(dst + pix * PS + (SWZ ? (q ^ (pix & 7)) : q) * 4, ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img,
+                       ok ? 16 : 0);
         }
     };
 
@@ -452,6 +461,8 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = make_idesc_tf32(128, NP);
+    const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), LBO_A, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), LBO_A, 128);
+    const uint64_t bd_hi = make_smem_desc(smem_u32(sB_hi), (uint32_t)NP * 16, 128), bd_lo = make_smem_desc(smem_u32(sB_lo), (uint32_t)NP * 16, 128);
     const EpiDev &e = p.epi;
     const bool res_smem = e.res == p.in && !e.res_pool;
     bool weights_ready = false;
@@ -475,9 +486,10 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
 #pragma unroll
             for (int ky = 0; ky < 3; ky++) {
                 float4 x[6];
-                const float *row = s_in + ((sy + ky) * IW + sx) * PS + q * 4;
+                const int pix0 = (sy + ky) * IW + sx;
 #pragma unroll
-                for (int c = 0; c < 6; c++) x[c] = *reinterpret_cast<const float4 *>(row + c * PS);
+                for (int c = 0; c < 6; c++)
+                    x[c] = *reinterpret_cast<const float4 *>(s_in + (pix0 + c) * PS + (SWZ ? (q ^ ((pix0 + c) & 7)) : q) * 4);
 #pragma unroll
                 for (int kx = 0; kx < 3; kx++) {
                     const float4 wv = *reinterpret_cast<const float4 *>(s_dww + (ky * 3 + kx) * CS + q * 4);
@@ -509,24 +521,26 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
         tc_fence_after();
         if (tid == 0) {
             if (!weights_ready) mbar_wait(&mbar_b, 0), weights_ready = true;   // weights landed (first tile only)
-#pragma unroll 1
+#pragma unroll
             for (int half = 0; half < HALVES; half++) {
                 uint32_t acc_flag = 0;
-#pragma unroll 1
+#pragma unroll
                 for (int pass = 0; pass < 3; pass++) {
-                    const uint32_t a0 = smem_u32(pass == 0 ? sA_lo : sA_hi) + (uint32_t)half * 128 * 16;
-                    const uint32_t b0 = smem_u32(pass == 1 ? sB_lo : sB_hi);
+                    // prebuilt descriptors + 16-byte-unit offsets: ~3 instructions per MMA on the issuing thread
+                    uint64_t ad = (pass == 0 ? ad_lo : ad_hi) + (uint64_t)(half * 128);
+                    uint64_t bd = pass == 1 ? bd_lo : bd_hi;
 #pragma unroll
                     for (int j = 0; j < CS / 8; j++) {
-                        const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * LBO_A, LBO_A, 128);
-                        const uint64_t bd = make_smem_desc(b0 + (uint32_t)(2 * j) * NP * 16, (uint32_t)NP * 16, 128);
                         umma_tf32(tmem + (uint32_t)half * NP, ad, bd, idesc, acc_flag);
                         acc_flag = 1;
+                        ad += (uint64_t)(2 * (LBO_A / 16));
+                        bd += (uint64_t)(2 * NP);
                     }
                 }
             }
             umma_commit(&mbar_mma);
         }
+        if (warp == 0) __syncwarp();                 // lanes 1-31 must not spin (and suspend the warp) while lane 0 issues
         if (poll_all) {
             mbar_wait(&mbar_mma, phase);             // every thread polls the mbarrier itself
         } else {
@@ -550,7 +564,8 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
         const int cbeg = HALVES == 2 ? 0 : (warp >> 2) * (NP / 2);
         const int cend = HALVES == 2 ? NP : cbeg + NP / 2;
         float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
-        const float *s_center = s_in + ((ty + 1) * IW + tx + 1) * PS;
+        const int pix_c = (ty + 1) * IW + tx + 1;
+        const float *s_center = s_in + pix_c * PS;
         const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)half * NP;
         for (int c0 = cbeg; c0 < cend; c0 += 8) {
             float v8[8];
@@ -566,7 +581,7 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
                 if (e.res) {
                     float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (res_smem) {
-                        if (n < CS) rr = *reinterpret_cast<const float4 *>(s_center + n);
+                        if (n < CS) rr = *reinterpret_cast<const float4 *>(s_center + (SWZ ? ((n >> 2) ^ (pix_c & 7)) * 4 : n));
                     } else {
                         rr = residual4_at(e, img, oy, ox, n);
                     }
@@ -591,17 +606,17 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
-template <int CS, int TH, int NBUF>
+template <int CS, int TH, int NBUF, int TW>
 size_t ttc_smem(int NP) {
-    constexpr int M = 32 * TH, CQ = CS / 4;
-    return sizeof(float) * (2 * (size_t)CQ * (M + 1) * 4 + 2 * (size_t)CQ * NP * 4 + NBUF * (size_t)(TH + 2) * 34 * (CS + 4) +
-                            10 * CS + 2 * (size_t)NP) + 1024;
+    constexpr int M = TW * TH, CQ = CS / 4, PS = CS == 32 ? CS : CS + 4;
+    return sizeof(float) * (2 * (size_t)CQ * (M + 1) * 4 + 2 * (size_t)CQ * NP * 4 + NBUF * (size_t)(TH + 2) * (TW + 2) * PS +
+                            10 * CS + 2 * (size_t)NP) + 128;
 }
 
-template <int CS, int TH, int NBUF>
+template <int CS, int TH, int NBUF, int TW>
 bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
-    const size_t smem = ttc_smem<CS, TH, NBUF>(NP);
-    auto kern = dwpw_ttc_kernel<CS, TH, NBUF>;
+    const size_t smem = ttc_smem<CS, TH, NBUF, TW>(NP);
+    auto kern = dwpw_ttc_kernel<CS, TH, NBUF, TW>;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -610,7 +625,7 @@ bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
         }
         configured = smem;
     }
-    const int tiles_x = (p.Wo + 31) / 32, tiles_y = (p.Ho + TH - 1) / TH;
+    const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     const int total = tiles_x * tiles_y * images;
     // persistent CTAs: as many as fit on the 148 SMs, each looping over tiles
@@ -641,11 +656,50 @@ bool launch_ttc_cs(const ConvDev &p, const float *w_hi, const float *w_lo, int N
     // tile height: 8 rows (M = 256) when three CTAs still fit in one SM's shared memory, else 4 rows (M = 128)
     static const bool persist = getenv("ZB_TTC_PERSIST") && atoi(getenv("ZB_TTC_PERSIST")) != 0;
     if (persist) {
-        if (ttc_smem<CS, 8, 2>(NP) <= 110 * 1024 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 2>(p, w_hi, w_lo, NP, s);
-        return launch_ttc_cfg<CS, 4, 2>(p, w_hi, w_lo, NP, s);
+        if (ttc_smem<CS, 8, 2, 32>(NP) <= 110 * 1024 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 2, 32>(p, w_hi, w_lo, NP, s);
+        return launch_ttc_cfg<CS, 4, 2, 32>(p, w_hi, w_lo, NP, s);
     }
-    if (ttc_smem<CS, 8, 1>(NP) <= 74 * 1024 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 1>(p, w_hi, w_lo, NP, s);
-    return launch_ttc_cfg<CS, 4, 1>(p, w_hi, w_lo, NP, s);
+    // maps whose width is a multiple of 16 but not of 32 (48x48): 16 x 8 tiles, no half-empty tile column
+    if (p.Wo % 32 != 0 && p.Wo % 16 == 0 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 1, 16>(p, w_hi, w_lo, NP, s);
+    if (ttc_smem<CS, 8, 1, 32>(NP) <= 74 * 1024 && p.Ho % 8 == 0) return launch_ttc_cfg<CS, 8, 1, 32>(p, w_hi, w_lo, NP, s);
+    return launch_ttc_cfg<CS, 4, 1, 32>(p, w_hi, w_lo, NP, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark: back-to-back tcgen05.mma (kind::tf32, M = 128, K = 8) issue rate for a given operand
+// layout (LBO / SBO / start offset of A).  One thread issues `iters` MMAs and one commit; cycles by clock64.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tc_mma_rate_kernel(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps,
+                                                          long long *cycles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<float *>(smem_raw)[i] = 0.f;
+    const uint32_t ncols = tmem_cols_for(N * ksteps);
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) mbar_init(&mbar, 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, N);
+        const uint32_t a0 = smem_u32(smem_raw) + (uint32_t)a_off, b0 = smem_u32(smem_raw) + 40 * 1024;
+        const long long t0 = clock64();
+        // ksteps = number of accumulators used round-robin (power of two): 1 = every MMA depends on the previous one
+        const uint64_t ad0 = make_smem_desc(a0, lbo_a, sbo_a), ad1 = make_smem_desc(a0 + 2 * lbo_a, lbo_a, sbo_a);
+        const uint64_t bd = make_smem_desc(b0, N * 16, 128);
+#pragma unroll 4
+        for (int i = 0; i < iters; i++) umma_tf32(tmem_slot + (uint32_t)((i & (ksteps - 1)) * N), (i & 1) ? ad1 : ad0, bd, idesc, 1);
+        umma_commit(&mbar);
+        mbar_wait(&mbar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) cycles[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, ncols);
 }
 
 size_t dwpw_tc_smem(int KC, int NP) { return sizeof(float) * 2 * ((size_t)KC * (TC_M + 1) + (size_t)KC * NP) + 1024; }
@@ -693,7 +747,7 @@ bool dwpw_ttc_supported(const ConvDev &p, int NP) {
     if (p.kh != 3 || p.kw != 3 || p.sh != 1 || p.sw != 1 || p.pt != 1 || p.pl != 1) return false;
     // measured per layer against the SIMT thin kernel (same box, batch 1024): Cs 16 loses (1.17 vs 1.07 ms on the
     // 96x96x16 blocks), Cs 24 ties, Cs >= 32 wins (0.78 vs 0.92 ms on 48x48x32, 0.18 vs 0.23 ms on 32x32x36)
-    static const int min_cs = getenv("ZB_TTC_MIN_CS") ? atoi(getenv("ZB_TTC_MIN_CS")) : 24;
+    static const int min_cs = getenv("ZB_TTC_MIN_CS") ? atoi(getenv("ZB_TTC_MIN_CS")) : 32;
     if (!(p.Cs_in == 16 || p.Cs_in == 24 || p.Cs_in == 32 || p.Cs_in == 40 || p.Cs_in == 48) || p.Cs_in < min_cs) return false;
     if (p.K != p.Cs_in || NP % 16 || NP < 16 || NP > 64 || p.Ns % 4 || p.Nstore != p.Ns || p.out_pix_stride != p.Ns) return false;
     if (p.Ho * p.Wo < 1024 || p.Wo < 32 || p.Ho % 4 || p.M % (p.Ho * p.Wo)) return false;
@@ -714,6 +768,18 @@ bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int
 }
 
 // D[128,N] = A[128,K] * B[N,K]^T on tcgen05 (nsplit 1: raw TF32, 3: 3xTF32).  Device pointers.
+bool launch_tc_mma_rate(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps, int ctas, long long *cycles_dev, cudaStream_t s) {
+    if (N % 8 || N < 8 || N > 256 || iters < 1 || ksteps < 1 || (ksteps & (ksteps - 1)) || N * ksteps > 512) return false;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024) != cudaSuccess) return false;
+        configured = true;
+    }
+    g_launch_count++;
+    tc_mma_rate_kernel<<<ctas, 128, 48 * 1024, s>>>(N, lbo_a, sbo_a, a_off, iters, ksteps, cycles_dev);
+    return true;
+}
+
 bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s) {
     if (N % 16 || N < 16 || N > 256 || K % 8 || K < 8) return false;
     const size_t smem = sizeof(float) * 2 * ((size_t)K * TC_M + (size_t)K * N) + 1024;

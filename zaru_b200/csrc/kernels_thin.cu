@@ -152,6 +152,217 @@ __global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-blocked variant of the thin block ("strip"): one thread = PXV vertically adjacent output pixels.
+// ncu on dwpw_thin_kernel<16,1,16> at the bench batch showed the L1/shared pipe 95 % busy (every pixel re-read
+// its 9 taps AND all depthwise + pointwise weights from shared memory: 140 LDS.128 for 400 FMA).  Here
+//   * the (PXV-1)*S+3 input rows of a strip are loaded once and each feeds up to 3 output pixels,
+//   * every weight quad fetched from shared memory is used for PXV pixels,
+// which cuts shared-memory wavefronts per pixel ~3x at PXV = 4.  Lanes run along x with pixel stride CS+4 words
+// (conflict-free 128-bit reads); stride-2 blocks stage even and odd input columns in separate planes so the
+// lane stride stays CS+4 words.  FMA order per output value is the same as in every other kernel of the
+// library (bias, taps row-major; bias, k ascending), so results are bit-identical to them.
+// ------------------------------------------------------------------------------------------------
+template <int CS, int S, int NP, int PXV, int TW, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) dwpw_strip_kernel(const ConvDev p, int tiles_x, int tiles_y) {
+    constexpr int NT = 32 * WARPS;
+    constexpr int SUB = 32 / TW;                       // pixel strips per warp along y
+    constexpr int TH = WARPS * SUB * PXV;              // output rows per CTA
+    constexpr int PS = CS + 4, CQ = CS / 4;
+    constexpr int IH = (TH - 1) * S + 3;
+    constexpr int IW = (TW - 1) * S + 3;               // input columns needed
+    constexpr int PW = S == 1 ? IW : TW + 1;           // columns per plane (S == 2: even plane TW+1, odd plane TW)
+    constexpr int PLANES = S;
+    constexpr int ROWS = (PXV - 1) * S + 3;
+    extern __shared__ __align__(16) float smem[];
+    float *s_in = smem;                                // [IH][PLANES][PW][PS]
+    float *s_dww = s_in + IH * PLANES * PW * PS;       // [9][CS]
+    float *s_dwb = s_dww + 9 * CS;                     // [CS]
+    float *s_pw = s_dwb + CS;                          // [CS][NP]
+    float *s_pb = s_pw + CS * NP;                      // [NP]
+    float *s_sl = s_pb + NP;                           // [NP]
+
+    const int tid = threadIdx.x;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y, img = blockIdx.z;
+    const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+    const int iy_org = oy0 * S - p.pt, ix_org = ox0 * S - p.pl;
+    const float *in_img = p.in + (long long)img * p.in_img_stride;
+
+    for (int e = tid; e < IH * IW * CQ; e += NT) {
+        const int q = e % CQ, pix = e / CQ;
+        const int ty = pix / IW, tx = pix - ty * IW;
+        const int iy = iy_org + ty, ix = ix_org + tx;
+        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const float *src = ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img;
+        const int slot = S == 1 ? (ty * PW + tx) : ((ty * 2 + (tx & 1)) * PW + (tx >> 1));
+        cp_async16(s_in + slot * PS + q * 4, src, ok ? 16 : 0);
+    }
+    for (int e = tid; e < 9 * CQ; e += NT) cp_async16(s_dww + e * 4, p.dw_w + e * 4, 16);
+    for (int e = tid; e < CQ; e += NT) cp_async16(s_dwb + e * 4, p.dw_b + e * 4, 16);
+    for (int e = tid; e < CS * NP / 4; e += NT) {
+        const int k = e / (NP / 4), nq = e - k * (NP / 4);
+        const bool ok = nq * 4 < p.Ns;
+        cp_async16(s_pw + e * 4, ok ? p.w + (long long)k * p.Ns + nq * 4 : p.w, ok ? 16 : 0);
+    }
+    for (int e = tid; e < NP; e += NT) {
+        s_pb[e] = e < p.Ns ? __ldg(p.epi.bias + e) : 0.f;
+        s_sl[e] = (p.epi.act2.kind == ACT_PRELU && e < p.Ns) ? __ldg(p.epi.act2.slope + e) : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tx = lane % TW;
+    const int ty0 = (warp * SUB + lane / TW) * PXV;    // first output row of this thread's strip (tile-local)
+    const int ox = ox0 + tx;
+    if (ox >= p.Wo || oy0 + ty0 >= p.Ho) return;
+
+    // tap (r, kx) of this thread: input row ty0*S + r, input column tx*S + kx
+    auto tap = [&](int r, int kx) -> const float * {
+        const int row = ty0 * S + r;
+        const int slot = S == 1 ? (row * PW + tx + kx) : ((row * 2 + (kx & 1)) * PW + tx + (kx >> 1));
+        return s_in + slot * PS;
+    };
+
+    float2 acc[PXV][NP / 2];
+#pragma unroll
+    for (int j = 0; j < NP; j += 4) {
+        const float4 bv = *reinterpret_cast<const float4 *>(s_pb + j);
+#pragma unroll
+        for (int i = 0; i < PXV; i++) acc[i][j / 2] = make_float2(bv.x, bv.y), acc[i][j / 2 + 1] = make_float2(bv.z, bv.w);
+    }
+
+#pragma unroll 1
+    for (int q = 0; q < CQ; q++) {
+        float4 w9[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) w9[t] = *reinterpret_cast<const float4 *>(s_dww + t * CS + q * 4);
+        const float4 bias = *reinterpret_cast<const float4 *>(s_dwb + q * 4);
+        float4 v[PXV];
+#pragma unroll
+        for (int i = 0; i < PXV; i++) v[i] = bias;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(tap(r, 0) + q * 4);
+            const float4 x1 = *reinterpret_cast<const float4 *>(tap(r, 1) + q * 4);
+            const float4 x2 = *reinterpret_cast<const float4 *>(tap(r, 2) + q * 4);
+#pragma unroll
+            for (int i = 0; i < PXV; i++) {
+                const int ky = r - i * S;
+                if (ky >= 0 && ky < 3) {
+                    fma4(v[i], x0, w9[ky * 3 + 0]);
+                    fma4(v[i], x1, w9[ky * 3 + 1]);
+                    fma4(v[i], x2, w9[ky * 3 + 2]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PXV; i++) act4(v[i], p.act_mid, q * 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const float *wrow = s_pw + (q * 4 + kk) * NP;
+#pragma unroll
+            for (int j = 0; j < NP; j += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(wrow + j);
+#pragma unroll
+                for (int i = 0; i < PXV; i++) {
+                    const float a = kk == 0 ? v[i].x : kk == 1 ? v[i].y : kk == 2 ? v[i].z : v[i].w;
+                    fma4s(acc[i][j / 2], acc[i][j / 2 + 1], a, wv);
+                }
+            }
+        }
+    }
+
+    const EpiDev &e = p.epi;
+    const bool res_smem = e.res == p.in;
+#pragma unroll
+    for (int i = 0; i < PXV; i++) {
+        const int oy = oy0 + ty0 + i;
+        if (oy >= p.Ho) break;
+        float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+#pragma unroll
+        for (int j = 0; j < NP; j += 4) {
+            if (j >= p.Nstore) break;
+            float v4[4] = {acc[i][j / 2].x, acc[i][j / 2].y, acc[i][j / 2 + 1].x, acc[i][j / 2 + 1].y};
+            act4(v4, e.act1, j);
+            if (e.res) {
+                float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (res_smem) {
+                    if (j < CS) {
+                        if (!e.res_pool) {
+                            rr = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl) + j);
+                        } else {
+                            const float4 a0 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl) + j);
+                            const float4 a1 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl + 1) + j);
+                            const float4 a2 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt + 1, p.pl) + j);
+                            const float4 a3 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt + 1, p.pl + 1) + j);
+                            rr = make_float4(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)), fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)),
+                                             fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z)), fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w)));
+                        }
+                    }
+                } else {
+                    rr = residual4_at(e, img, oy, ox, j);
+                }
+                v4[0] += rr.x, v4[1] += rr.y, v4[2] += rr.z, v4[3] += rr.w;
+            }
+            if (e.act2.kind == ACT_PRELU) {
+                const float4 sl = *reinterpret_cast<const float4 *>(s_sl + j);
+                v4[0] = v4[0] < 0.f ? v4[0] * sl.x : v4[0];
+                v4[1] = v4[1] < 0.f ? v4[1] * sl.y : v4[1];
+                v4[2] = v4[2] < 0.f ? v4[2] * sl.z : v4[2];
+                v4[3] = v4[3] < 0.f ? v4[3] * sl.w : v4[3];
+            } else {
+                act4(v4, e.act2, j);
+            }
+            *reinterpret_cast<float4 *>(orow + j) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        }
+    }
+}
+
+template <int CS, int S, int NP, int PXV, int TW, int WARPS>
+bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
+    constexpr int SUB = 32 / TW, TH = WARPS * SUB * PXV;
+    constexpr int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3, PW = S == 1 ? IW : TW + 1;
+    const size_t smem = sizeof(float) * ((size_t)IH * S * PW * (CS + 4) + 10 * CS + (size_t)CS * NP + 2 * NP);
+    auto kern = dwpw_strip_kernel<CS, S, NP, PXV, TW, WARPS>;
+    static bool configured = false;
+    if (smem > 48 * 1024 && !configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        configured = true;
+    }
+    const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
+    const int images = p.M / (p.Ho * p.Wo);
+    kern<<<dim3(tiles_x, tiles_y, images), 32 * WARPS, smem, s>>>(p, tiles_x, tiles_y);
+    return true;
+}
+
+// Envelope of the strip kernel: Cs_in 16 or 24, all output channels in one register pass (PXV * Ns <= 64).
+bool launch_dwpw_strip(const ConvDev &p, cudaStream_t s) {
+    static const bool disabled = getenv("ZB_NO_STRIP") && atoi(getenv("ZB_NO_STRIP")) != 0;
+    if (disabled || p.Ns > 32) return false;
+    const bool wide = p.Wo % 32 == 0 || p.Wo > 64;       // 32-pixel-wide tiles unless that wastes half a tile
+    if (p.Cs_in == 16) {
+        if (p.sh == 1) {
+            if (p.Ns <= 16) return wide ? launch_strip_cfg<16, 1, 16, 4, 32, 4>(p, s) : launch_strip_cfg<16, 1, 16, 4, 16, 2>(p, s);
+            return wide ? launch_strip_cfg<16, 1, 32, 2, 32, 4>(p, s) : launch_strip_cfg<16, 1, 32, 2, 16, 2>(p, s);
+        }
+        if (p.Ns <= 16) return launch_strip_cfg<16, 2, 16, 4, 16, 2>(p, s);
+        return launch_strip_cfg<16, 2, 32, 2, 16, 2>(p, s);
+    }
+    if (p.Cs_in == 24) {
+        if (p.sh == 1) {
+            if (p.Ns <= 24) return wide ? launch_strip_cfg<24, 1, 24, 2, 32, 4>(p, s) : launch_strip_cfg<24, 1, 24, 2, 16, 2>(p, s);
+            return wide ? launch_strip_cfg<24, 1, 32, 2, 32, 4>(p, s) : launch_strip_cfg<24, 1, 32, 2, 16, 2>(p, s);
+        }
+        if (p.Ns <= 24) return launch_strip_cfg<24, 2, 24, 2, 16, 2>(p, s);
+        return launch_strip_cfg<24, 2, 32, 2, 16, 2>(p, s);
+    }
+    return false;
+}
+
 template <int CS, int S, int NP>
 bool launch_thin_cfg(const ConvDev &p, cudaStream_t s) {
     constexpr int TW = S == 1 ? 32 : 16, TH = 8;
@@ -198,6 +409,7 @@ bool dwpw_thin_supported(const ConvDev &p) {
 
 bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
     if (!dwpw_thin_supported(p)) return false;
+    if (launch_dwpw_strip(p, s)) return true;
     switch (p.Cs_in) {
         case 16: return launch_thin_cs<16>(p, s);
         case 24: return launch_thin_cs<24>(p, s);
