@@ -70,13 +70,15 @@ typedef struct zb_detection {
 
 typedef enum zb_detector_kind {
     ZB_DET_FACE_SHORT_RANGE = 0,  /* face/detection.rs:31-59: 16 params, anchors (2,16,16),(6,8,8)   */
-    ZB_DET_PALM = 1               /* hand/detection.rs:49-179: 18 params, anchors (2,24,24),(6,12,12) */
+    ZB_DET_PALM = 1,              /* hand/detection.rs:49-179: 18 params, anchors (2,24,24),(6,12,12) */
+    ZB_DET_FACE_FULL_RANGE = 2    /* face/detection.rs:63-94: 16 params, anchors (1,48,48), 192x192 in  */
 } zb_detector_kind;
 
 typedef enum zb_estimator_kind {
     ZB_EST_FACE_MESH_V1 = 0,      /* face/landmark/mediapipe.rs:44-71: 468 pts + sigmoid(face_flag)   */
     ZB_EST_EYE = 1,               /* face/eye.rs:30-65: 5 iris pts then 71 contour pts                 */
-    ZB_EST_HAND = 2               /* hand/landmark.rs:298-322: 21 pts, presence, raw handedness        */
+    ZB_EST_HAND = 2,              /* hand/landmark.rs:298-322: 21 pts, presence, raw handedness        */
+    ZB_EST_FACE_MESH_V2 = 3       /* face/landmark/mediapipe.rs:81-115: 478 pts, sigmoid(flag), tongueOut */
 } zb_estimator_kind;
 
 typedef enum zb_nms_mode {        /* detection/nms.rs:153-161 */
@@ -190,7 +192,10 @@ zb_status zb_face_pipeline_create(zb_ctx *ctx, zb_net *detector_net, zb_net *lan
 void zb_face_pipeline_destroy(zb_face_pipeline *p);
 zb_status zb_face_pipeline_set_threshold(zb_face_pipeline *p, float det_thresh, float iou_thresh,
                                          zb_nms_mode mode);
-/* out_dets [n][cap], out_counts [n], out_landmarks [n][468][3], out_flags [n] (sigmoid
+int32_t zb_face_pipeline_num_landmarks(const zb_face_pipeline *p);
+/* The detector may be the short- or the full-range BlazeFace and the mesh FaceMeshV1 (L = 468) or FaceMeshV2
+ * (L = 478), recognised by their output shapes; zb_face_pipeline_num_landmarks returns L.
+ * out_dets [n][cap], out_counts [n], out_landmarks [n][L][3], out_flags [n] (sigmoid
  * face_flag; -1 when the frame had no detection), out_rois [n] (the view_rect used).
  * Any output pointer may be NULL to skip that copy.  Pointers: host_or_device.               */
 zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int32_t n,

@@ -190,6 +190,15 @@ class ShortRangeNetwork(SsdNetwork):
     angle_kind = "face"
 
 
+class FullRangeNetwork(SsdNetwork):
+    """face/detection.rs:63-94: one SSD layer, 1 box per cell of a 48x48 grid, 192x192 input."""
+    onnx = "face_detection_full_range.onnx"
+    color_range = (-1.0, 1.0)
+    anchor_layers = [(1, 48, 48)]
+    num_params = 16
+    angle_kind = "face"
+
+
 class PalmLiteNetwork(SsdNetwork):
     """hand/detection.rs:49-73, :115-119."""
     onnx = "palm_detection_lite.onnx"

@@ -77,6 +77,33 @@ class FaceMeshV1(LandmarkNetwork):
         est.positions[:] = np.asarray(outputs[0], np.float32).reshape(-1)[:468 * 3].reshape(468, 3)
 
 
+class FaceLandmarksV2(Estimate):
+    """mediapipe.rs `LandmarkResultV2`: 478 landmarks (468 mesh + 2 x 5 iris), face flag, tongueOut blendshape."""
+
+    def __init__(self):
+        super().__init__(478)
+        self.face_flag = f32(0.0)
+        self.tongue_out = f32(0.0)
+
+    def confidence(self):
+        return self.face_flag
+
+
+class FaceMeshV2(LandmarkNetwork):
+    """mediapipe.rs:81-115 (f16 model: input rounded to f16, outputs widened from f16 by NeuralNetwork.estimate)."""
+    onnx = "face_landmarks_detector.onnx"
+    color_range = (-1.0, 1.0)
+    num_landmarks = 478
+
+    def new_estimate(self):
+        return FaceLandmarksV2()
+
+    def extract(self, outputs, est: FaceLandmarksV2):
+        est.face_flag = sigmoid(np.asarray(outputs[1]).reshape(-1)[0])
+        est.tongue_out = f32(np.asarray(outputs[2]).reshape(-1)[0])      # sigmoid applied inside the model
+        est.positions[:] = np.asarray(outputs[0], np.float32).reshape(-1)[:478 * 3].reshape(478, 3)
+
+
 class EyeLandmarks(Estimate):
     """face/eye.rs:67-125."""
 

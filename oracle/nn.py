@@ -51,7 +51,9 @@ class TorchGraph:
 
         self.torch = torch
         self.g = graph
-        self.consts = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in graph.initializers.items()}
+        # FLOAT16 initializers (face_landmarks_detector.onnx) are widened: the interpreter computes in float32
+        self.consts = {k: torch.from_numpy(np.ascontiguousarray(v.astype(np.float32) if v.dtype == np.float16 else v))
+                       for k, v in graph.initializers.items()}
 
     def run(self, x: np.ndarray, want=None):
         torch = self.torch
@@ -158,13 +160,21 @@ class NeuralNetwork:
         """Run on a float32 [N,3,h,w] tensor, N evaluated one image at a time (reference is batch 1, F5)."""
         backend = backend or self.backend
         outs = None
+        # FLOAT16 graph input: `array.map(|&f| half::f16::from_f32(f))` (nn/mod.rs:487-492); the arithmetic in
+        # between belongs to the (un-vendored) engine - this oracle evaluates it in float32
+        io_f16 = self.graph.elem_types.get(self.graph.inputs[0][0], 1) == 10
+        if io_f16:
+            tensor = np.asarray(tensor, np.float32).astype(np.float16).astype(np.float32)
         for n in range(tensor.shape[0]):
             o = self._run1(tensor[n:n + 1], backend)
             if outs is None:
                 outs = [[] for _ in o]
             for k, v in enumerate(o):
                 outs[k].append(v)
-        return [np.concatenate(v, axis=0) for v in outs]
+        res = [np.concatenate(v, axis=0) for v in outs]
+        if io_f16:   # f16 outputs widened with f32::from (nn/mod.rs:504-508)
+            res = [r.astype(np.float16).astype(np.float32) for r in res]
+        return res
 
     def _run1(self, x, backend):
         names = [n for n, _ in self.graph.outputs]

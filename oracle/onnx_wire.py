@@ -86,6 +86,7 @@ class Graph:
     inputs: list                  # [(name, shape)]
     outputs: list                 # [(name, shape)]
     opset: int = 0
+    elem_types: dict = field(default_factory=dict)   # graph input/output name -> TensorProto.DataType (1 f32, 10 f16)
 
 
 _DTYPES = {1: np.float32, 7: np.int64, 10: np.float16, 6: np.int32, 11: np.float64}
@@ -167,8 +168,8 @@ def _node(buf):
     return n
 
 
-def _value_info(buf):
-    name, shape = "", []
+def _value_info(buf, types=None):
+    name, shape, elem = "", [], 1
     for fno, wt, v in _fields(buf):
         if fno == 1:
             name = bytes(v).decode()
@@ -176,6 +177,8 @@ def _value_info(buf):
             for f2, _, v2 in _fields(v):
                 if f2 == 1:  # tensor_type
                     for f3, _, v3 in _fields(v2):
+                        if f3 == 1:  # elem_type
+                            elem = v3
                         if f3 == 2:  # shape
                             for f4, _, v4 in _fields(v3):
                                 if f4 == 1:  # dim
@@ -184,6 +187,8 @@ def _value_info(buf):
                                         if f5 == 1:
                                             d = _signed(v5)
                                     shape.append(d)
+    if types is not None:
+        types[name] = elem
     return name, shape
 
 
@@ -214,8 +219,8 @@ def load(path_or_bytes) -> Graph:
             name, arr = _tensor(v)
             g.initializers[name] = arr
         elif fno == 11:
-            g.inputs.append(_value_info(v))
+            g.inputs.append(_value_info(v, g.elem_types))
         elif fno == 12:
-            g.outputs.append(_value_info(v))
+            g.outputs.append(_value_info(v, g.elem_types))
     g.inputs = [(n, s) for n, s in g.inputs if n not in g.initializers]
     return g

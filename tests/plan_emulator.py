@@ -57,6 +57,8 @@ def run_plan(plan, w, x_nchw):
     ti = T[plan["input"]]
     x = np.zeros((ti["H"], ti["W"], ti["Cs"]), np.float32)
     x[..., :3] = x_nchw[0].transpose(1, 2, 0)
+    if plan.get("io_f16"):   # FLOAT16 graph input/outputs (Plan::io_f16): round on the way in and on the way out
+        x = x.astype(np.float16).astype(np.float32)
     bufs[plan["input"]] = x
 
     def residual(op, to):
@@ -127,4 +129,6 @@ def run_plan(plan, w, x_nchw):
             # invariant the kernels rely on: padded channels are exactly zero
             assert not v[:, to["C"]:].any(), f"non-zero padded channels in {to['name']}"
             bufs[op["out"]] = v.reshape(Ho, Wo, to["Cs"])
+    if plan.get("io_f16"):
+        outs = [o.astype(np.float16).astype(np.float32) for o in outs]
     return [o.reshape([1] + info["shape"][1:]) for o, info in zip(outs, plan["outputs"])]

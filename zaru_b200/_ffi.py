@@ -20,8 +20,8 @@ ZB_ERR_BAD_SHAPE = -5
 ZB_ERR_CAPACITY = -6
 ZB_ERR_NO_DEVICE = -7
 
-ZB_DET_FACE_SHORT_RANGE, ZB_DET_PALM = 0, 1
-ZB_EST_FACE_MESH_V1, ZB_EST_EYE, ZB_EST_HAND = 0, 1, 2
+ZB_DET_FACE_SHORT_RANGE, ZB_DET_PALM, ZB_DET_FACE_FULL_RANGE = 0, 1, 2
+ZB_EST_FACE_MESH_V1, ZB_EST_EYE, ZB_EST_HAND, ZB_EST_FACE_MESH_V2 = 0, 1, 2, 3
 ZB_NMS_REMOVE, ZB_NMS_AVERAGE = 0, 1
 ZB_NCHW, ZB_NHWC = 0, 1
 ZB_MAX_KEYPOINTS = 7
@@ -78,6 +78,7 @@ SIGNATURES = {
     "zb_face_pipeline_create": (i32, [P, P, P, PP]),
     "zb_face_pipeline_destroy": (None, [P]),
     "zb_face_pipeline_set_threshold": (i32, [P, f32, f32, i32]),
+    "zb_face_pipeline_num_landmarks": (i32, [P]),
     "zb_face_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),
     "zb_net_plan_json": (i32, [P, C.c_char_p, sz, C.POINTER(sz)]),
     "zb_net_weights": (i32, [P, C.POINTER(C.POINTER(C.c_float)), C.POINTER(sz)]),

@@ -242,7 +242,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
             const TensorInfo &tin = pl.tensors[pl.input];
             prof_launch(net->ctx, s, "sample", 16.0 * nc * tin.H * tin.W, 0, [&] {
                 launch_sample(*stem->frames, stem->views, nc, tin.W, tin.H, stem->lo, stem->hi, SAMPLE_NHWC4,
-                              tensor_ptr(net, ws, pl.input, c0), tin.img_stride, s);
+                              tensor_ptr(net, ws, pl.input, c0), tin.img_stride, s, pl.io_f16);
             });
             input_ready = true;
         }
@@ -306,7 +306,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "stem(+sample)", sbytes, flops, [&] {
                             FramesDev none{};
                             launch_stem(stem ? *stem->frames : none, stem ? stem->views : nullptr, stem ? stem->lo : 0.f,
-                                        stem ? stem->hi : 1.f, p, s);
+                                        stem ? stem->hi : 1.f, p, s, stem && pl.io_f16);
                         });
                         input_ready = true;
                         break;
@@ -314,7 +314,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     if (!input_ready) {
                         prof_launch(ctx, s, "sample", 16.0 * nc * ti.H * ti.W, 0, [&] {
                             launch_sample(*stem->frames, stem->views, nc, ti.W, ti.H, stem->lo, stem->hi, SAMPLE_NHWC4,
-                                          tensor_ptr(net, ws, pl.input, c0), ti.img_stride, s);
+                                          tensor_ptr(net, ws, pl.input, c0), ti.img_stride, s, pl.io_f16);
                         });
                         input_ready = true;
                     }
@@ -370,6 +370,13 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
             default: throw std::runtime_error("internal: unknown op kind");
         }
     }
+    // FLOAT16 graph outputs are widened from f16 by the reference (nn/mod.rs:504-508): round once, at the end
+    if (stage == 1 && pl.io_f16)
+        for (size_t k = 0; k < pl.outputs.size(); k++)
+            prof_launch(net->ctx, s, "round_f16", 8.0 * nc * pl.outputs[k].per_image, 0, [&] {
+                launch_round_f16(ws.outs[k].as<float>() + (size_t)c0 * pl.outputs[k].per_image,
+                                 (long long)nc * pl.outputs[k].per_image, s);
+            });
     CU(cudaGetLastError());
 }
 
@@ -732,7 +739,7 @@ zb_status zb_net_estimate(zb_net *net, const float *input, int32_t n, float *con
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
             launch_nchw_to_nhwc4(d_in + in_elems * c0, nc, pl.in_h, pl.in_w, tensor_ptr(net, ws, pl.input, c0),
-                                 pl.tensors[pl.input].img_stride, s);
+                                 pl.tensors[pl.input].img_stride, s, pl.io_f16);
             run_ops(net, ws, c0, nc, 0, s);
         }
         run_ops(net, ws, 0, n, 1, s);
@@ -885,6 +892,8 @@ struct zb_estimator {
 struct zb_face_pipeline {
     zb_ctx *ctx;
     zb_net *det_net, *lm_net;
+    zb_detector_kind det_kind = ZB_DET_FACE_SHORT_RANGE;
+    zb_estimator_kind lm_kind = ZB_EST_FACE_MESH_V1;
     float thresh = 0.5f, iou = 0.3f;
     int mode = ZB_NMS_AVERAGE;
     Workspace ws_det[2], ws_lm[2];       // one set per stream (chunks alternate between two streams)
@@ -904,6 +913,10 @@ DecodeParams decode_params(zb_detector_kind kind, const Plan &pl, float thresh, 
     if (kind == ZB_DET_FACE_SHORT_RANGE) {
         p.num_params = 16, p.num_kp = 6, p.angle_kind = 0;
         p.l0_boxes = 2, p.l0_w = 16, p.l0_h = 16, p.l1_boxes = 6, p.l1_w = 8, p.l1_h = 8;
+    } else if (kind == ZB_DET_FACE_FULL_RANGE) {
+        // FullRangeNetwork (face/detection.rs:63-94): one SSD layer, 1 box per cell of a 48x48 grid
+        p.num_params = 16, p.num_kp = 6, p.angle_kind = 0;
+        p.l0_boxes = 1, p.l0_w = 48, p.l0_h = 48, p.l1_boxes = 0, p.l1_w = 1, p.l1_h = 1;
     } else {
         p.num_params = 18, p.num_kp = 7, p.angle_kind = 1;
         p.l0_boxes = 2, p.l0_w = 24, p.l0_h = 24, p.l1_boxes = 6, p.l1_w = 12, p.l1_h = 12;
@@ -925,12 +938,15 @@ void check_detector_net(const zb_net *net, zb_detector_kind kind) {
                                  "," + std::to_string(p.num_params) + "] / [1," + std::to_string(p.num_anchors) + ",1]");
 }
 
-int estimator_landmarks(zb_estimator_kind k) { return k == ZB_EST_FACE_MESH_V1 ? 468 : k == ZB_EST_EYE ? 76 : 21; }
+int estimator_landmarks(zb_estimator_kind k) {
+    return k == ZB_EST_FACE_MESH_V1 ? 468 : k == ZB_EST_FACE_MESH_V2 ? 478 : k == ZB_EST_EYE ? 76 : 21;
+}
 
 void check_estimator_net(const zb_net *net, zb_estimator_kind kind) {
     const auto &o = net->plan.outputs;
     bool ok = false;
     if (kind == ZB_EST_FACE_MESH_V1) ok = o.size() >= 2 && o[0].per_image == 1404 && o[1].per_image == 1;
+    if (kind == ZB_EST_FACE_MESH_V2) ok = o.size() >= 3 && o[0].per_image == 1434 && o[1].per_image == 1 && o[2].per_image == 1;
     if (kind == ZB_EST_EYE) ok = o.size() >= 2 && o[0].per_image == 213 && o[1].per_image == 15;
     if (kind == ZB_EST_HAND)
         ok = o.size() >= 4 && o[0].per_image == 63 && o[1].per_image == 1 && o[2].per_image == 1 && o[3].per_image == 63;
@@ -1194,14 +1210,20 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
 zb_status zb_face_pipeline_create(zb_ctx *ctx, zb_net *det_net, zb_net *lm_net, zb_face_pipeline **out) {
     return guarded([&]() -> zb_status {
         if (!ctx || !det_net || !lm_net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
+        // detector / mesh generation is recognised by the output shapes: short range (896 anchors) or full range
+        // (2304), FaceMeshV1 (468 points) or FaceMeshV2 (478 points + tongueOut)
+        const zb_detector_kind dk = det_net->plan.outputs.size() >= 2 && det_net->plan.outputs[1].per_image == 2304
+                                        ? ZB_DET_FACE_FULL_RANGE : ZB_DET_FACE_SHORT_RANGE;
+        const zb_estimator_kind lk = !lm_net->plan.outputs.empty() && lm_net->plan.outputs[0].per_image == 1434
+                                         ? ZB_EST_FACE_MESH_V2 : ZB_EST_FACE_MESH_V1;
         try {
-            check_detector_net(det_net, ZB_DET_FACE_SHORT_RANGE);
-            check_estimator_net(lm_net, ZB_EST_FACE_MESH_V1);
+            check_detector_net(det_net, dk);
+            check_estimator_net(lm_net, lk);
         } catch (const std::runtime_error &e) {
             return fail(ZB_ERR_BAD_SHAPE, e.what());
         }
         auto p = std::make_unique<zb_face_pipeline>();
-        p->ctx = ctx, p->det_net = det_net, p->lm_net = lm_net;
+        p->ctx = ctx, p->det_net = det_net, p->lm_net = lm_net, p->det_kind = dk, p->lm_kind = lk;
         *out = p.release();
         return ZB_OK;
     });
@@ -1221,6 +1243,8 @@ zb_status zb_face_pipeline_set_threshold(zb_face_pipeline *p, float t, float iou
     p->thresh = t, p->iou = iou, p->mode = (int)m;
     return ZB_OK;
 }
+
+int32_t zb_face_pipeline_num_landmarks(const zb_face_pipeline *p) { return p ? estimator_landmarks(p->lm_kind) : 0; }
 
 zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
                                int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_flags,
@@ -1263,7 +1287,7 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                 memcpy(hfit + 4 * i, fit, sizeof(fit));
             }
         }
-        const int L = 468;
+        const int L = estimator_landmarks(p->lm_kind);
         p->d_views.reserve(sizeof(ViewDev) * n);
         p->d_fit.reserve(4 * sizeof(float) * n);
         p->d_dets.reserve(sizeof(DetDev) * (size_t)n * cap);
@@ -1276,9 +1300,9 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         p->h_counts.reserve(sizeof(int) * n);
         CU(cudaMemcpyAsync(p->d_views.p, hv, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(p->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
-        const DecodeParams dp = decode_params(ZB_DET_FACE_SHORT_RANGE, dpl, p->thresh, p->iou, p->mode, cap);
+        const DecodeParams dp = decode_params(p->det_kind, dpl, p->thresh, p->iou, p->mode, cap);
         LandmarkParams lp{};
-        lp.kind = ZB_EST_FACE_MESH_V1;
+        lp.kind = p->lm_kind;
         lp.num_landmarks = L;
         lp.net_w = lpl.in_w;
         lp.net_h = lpl.in_h;
@@ -1315,8 +1339,9 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             run_ops(p->lm_net, wl, c0, nc, 0, cs, &sl);
             run_ops(p->lm_net, wl, c0, nc, 1, cs);
             prof_launch(ctx, cs, "landmarks", 8.0 * nc * (3 * L + 1), 0, [&] {
+                const int s2 = p->lm_kind == ZB_EST_FACE_MESH_V2 ? (int)lpl.outputs[2].per_image : 0;
                 launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
-                                 nullptr, 0, p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
+                                 s2 ? wl.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2, p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
                                  p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
                                  p->d_scalars.as<float>() + 2 * c0, cs);
             });

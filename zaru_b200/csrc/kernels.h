@@ -58,7 +58,9 @@ void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int 
                     long long out_img_stride, int out_pix_stride, int Nstore, const EpiDev &epi, int n,
                     cudaStream_t s);
 void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
-                          cudaStream_t s);
+                          cudaStream_t s, int round_f16 = 0);
+// FLOAT16-output networks: round every element to f16 (nearest even) and widen back, in place
+void launch_round_f16(float *data, long long count, cudaStream_t s);
 
 bool dwpw_thin_supported(const ConvDev &p);   // kernels_thin.cu: would launch_conv(CONV_DWPW) take the thin kernel?
 
@@ -93,11 +95,12 @@ struct ViewHost { int frame; float cx, cy, w, h, radians; };
 // image->tensor: NCHW planar f32 [n,3,h,w] / NHWC3 [n,h,w,3] (public layouts) or NHWC4 (internal)
 enum SampleLayout { SAMPLE_NCHW = 0, SAMPLE_NHWC3 = 1, SAMPLE_NHWC4 = 2 };
 void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
-                   SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s);
+                   SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s, int round_f16 = 0);
 
 // Fused sampling + stem conv (views != nullptr) or stem conv on an NHWC4 tensor (views == nullptr).
 bool stem_supported(const ConvDev &p);
-bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s);
+bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s,
+                 int round_f16 = 0);   // round_f16: FLOAT16-input network, sampled values rounded to f16 first
 
 struct DetDev {                // mirrors zb_detection
     float confidence, angle, cx, cy, w, h;

@@ -11,6 +11,7 @@
 //                      NCHW -> NHWC4 input conversion.
 //
 // Replaces the engine call `ort.session.run` / `plan.run` (crates/zaru/src/nn/mod.rs:496, :528).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) eltwise_kernel(const float *in, long long
 }
 
 __global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float *in, int n, int H, int W, float *out,
-                                                            long long out_img_stride) {
+                                                            long long out_img_stride, int f16) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long hw = (long long)H * W;
     if (idx >= (long long)n * hw) return;
@@ -354,7 +355,13 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float *in, int
     const long long pix = idx - (long long)img * hw;
     const float *b = in + (long long)img * 3 * hw + pix;
     float4 o = make_float4(__ldg(b), __ldg(b + hw), __ldg(b + 2 * hw), 0.f);
+    if (f16) o.x = __half2float(__float2half_rn(o.x)), o.y = __half2float(__float2half_rn(o.y)), o.z = __half2float(__float2half_rn(o.z));
     *reinterpret_cast<float4 *>(out + (long long)img * out_img_stride + pix * 4) = o;
+}
+
+__global__ void __launch_bounds__(256) round_f16_kernel(float *data, long long count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) data[i] = __half2float(__float2half_rn(data[i]));
 }
 
 inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
@@ -406,9 +413,14 @@ void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int 
 }
 
 void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
-                          cudaStream_t s) {
+                          cudaStream_t s, int round_f16) {
     g_launch_count++;
-    nchw_to_nhwc4_kernel<<<blocks_for((long long)n * H * W, 256), 256, 0, s>>>(in_nchw, n, H, W, out, out_img_stride);
+    nchw_to_nhwc4_kernel<<<blocks_for((long long)n * H * W, 256), 256, 0, s>>>(in_nchw, n, H, W, out, out_img_stride, round_f16);
+}
+
+void launch_round_f16(float *data, long long count, cudaStream_t s) {
+    g_launch_count++;
+    round_f16_kernel<<<blocks_for(count, 256), 256, 0, s>>>(data, count);
 }
 
 }  // namespace zb

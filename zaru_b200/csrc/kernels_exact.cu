@@ -13,6 +13,7 @@
 //   landmarks_kernel .... Network::extract impls + Estimator remap (landmark.rs:336-345) + tracker
 //                         transform_out (landmark.rs:482-486)
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include <cstdlib>
@@ -61,13 +62,17 @@ __device__ __forceinline__ const unsigned *sample_address(const FramesDev &f, co
     return reinterpret_cast<const unsigned *>(f.base + (long long)v.frame * f.frame_stride + (long long)iy * f.row_stride +
                                               (long long)ix * 4);
 }
-__device__ __forceinline__ float4 color_map(unsigned rgba, float lo, float adjust) {
-    return make_float4((float)(rgba & 0xFFu) * adjust + lo, (float)((rgba >> 8) & 0xFFu) * adjust + lo,
-                       (float)((rgba >> 16) & 0xFFu) * adjust + lo, 0.0f);
+// f16 != 0: the network's input is FLOAT16 - NeuralNetwork::estimate rounds every value with half::f16::from_f32
+// (round to nearest even) before inference (nn/mod.rs:487-492); the device keeps the rounded value in an f32.
+__device__ __forceinline__ float4 color_map(unsigned rgba, float lo, float adjust, int f16 = 0) {
+    float4 c = make_float4((float)(rgba & 0xFFu) * adjust + lo, (float)((rgba >> 8) & 0xFFu) * adjust + lo,
+                           (float)((rgba >> 16) & 0xFFu) * adjust + lo, 0.0f);
+    if (f16) c.x = __half2float(__float2half_rn(c.x)), c.y = __half2float(__float2half_rn(c.y)), c.z = __half2float(__float2half_rn(c.z));
+    return c;
 }
 
 __device__ __forceinline__ float4 sample_pixel(const FramesDev &f, const ViewDev &v, int x, int y, int out_w, int out_h,
-                                               float lo, float adjust) {
+                                               float lo, float adjust, int f16 = 0) {
     unsigned rgba = 0u;   // Color::NONE
     if (v.valid) {
         const int xs = v.flip_x ? (out_w - 1 - x) : x;
@@ -93,20 +98,19 @@ __device__ __forceinline__ float4 sample_pixel(const FramesDev &f, const ViewDev
             }
         }
     }
-    return make_float4((float)(rgba & 0xFFu) * adjust + lo, (float)((rgba >> 8) & 0xFFu) * adjust + lo,
-                       (float)((rgba >> 16) & 0xFFu) * adjust + lo, 0.0f);
+    return color_map(rgba, lo, adjust, f16);
 }
 
 __global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
                                                      int out_h, float lo, float hi, int layout,
-                                                     float *__restrict__ out, long long out_img_stride) {
+                                                     float *__restrict__ out, long long out_img_stride, int f16) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int img = blockIdx.z;
     if (x >= out_w) return;
     const ViewDev v = views[img];
     const float adjust = (hi - lo) / 255.0f;
-    const float4 c = sample_pixel(f, v, x, y, out_w, out_h, lo, adjust);
+    const float4 c = sample_pixel(f, v, x, y, out_w, out_h, lo, adjust, f16);
     float *o = out + (long long)img * out_img_stride;
     const long long pix = (long long)y * out_w + x;
     if (layout == SAMPLE_NHWC4) {
@@ -149,7 +153,7 @@ __device__ __forceinline__ int sample_axis(float view_pos_center, float view_ext
 
 template <int KS, int NP, int PPT>
 __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const ViewDev *__restrict__ views, float lo, float hi,
-                                                   const ConvDev p, int tiles_x, int tiles_y, int NSP) {
+                                                   const ConvDev p, int tiles_x, int tiles_y, int NSP, int f16) {
     constexpr int TW = 32, TH = 8 * PPT, NT = 256;               // PPT output pixels per thread (rows ty, ty+8)
     constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
     extern __shared__ __align__(16) float smem[];
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int e = e0 + u * NT;
-                    if (e < IH * IW) s_in[e] = kind[u] ? color_map(rgba[u], lo, adjust) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e < IH * IW) s_in[e] = kind[u] ? color_map(rgba[u], lo, adjust, f16) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         } else {
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
                 for (int u = 0; u < 4; u++) {
                     const int e = e0 + u * NT;
                     if (e < IH * IW)   // conv zero padding outside the tensor (NOT the letterbox colour)
-                        s_in[e] = inside[u] ? color_map(rgba[u], lo, adjust) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        s_in[e] = inside[u] ? color_map(rgba[u], lo, adjust, f16) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         }
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
 }
 
 template <int KS, int NP, int PPT>
-bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
+bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, int f16, cudaStream_t s) {
     constexpr int TW = 32, TH = 8 * PPT;
     constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
     const int NSP = (p.Ns + NP - 1) / NP * NP;
@@ -335,7 +339,7 @@ bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float h
     }
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
-    kern<<<(unsigned)(tiles_x * tiles_y * images), 256, smem, s>>>(f, views, lo, hi, p, tiles_x, tiles_y, NSP);
+    kern<<<(unsigned)(tiles_x * tiles_y * images), 256, smem, s>>>(f, views, lo, hi, p, tiles_x, tiles_y, NSP, f16);
     return true;
 }
 
@@ -636,6 +640,10 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
     if (l == 0 && scalars) {
         float a = 0.f, b = 0.f;
         if (p.kind == 0) a = valid ? sigmoid_ref(out1[(long long)img * s1]) : -1.0f;  // mediapipe.rs:60
+        if (p.kind == 3) {   // FaceMeshV2 (mediapipe.rs:96-99): sigmoid(face flag); tongueOut is already a probability
+            a = valid ? sigmoid_ref(out1[(long long)img * s1]) : -1.0f;
+            b = out2[(long long)img * s2];
+        }
         if (p.kind == 2) a = out1[(long long)img * s1], b = out2[(long long)img * s2]; // hand/landmark.rs:310-311
         scalars[img * 2 + 0] = a, scalars[img * 2 + 1] = b;
     }
@@ -677,11 +685,11 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
 }  // namespace
 
 void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
-                   SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s) {
+                   SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s, int round_f16) {
     g_launch_count++;
     dim3 block(128);
     dim3 grid((out_w + 127) / 128, out_h, n);
-    sample_kernel<<<grid, block, 0, s>>>(f, views, out_w, out_h, lo, hi, (int)layout, out, out_img_stride);
+    sample_kernel<<<grid, block, 0, s>>>(f, views, out_w, out_h, lo, hi, (int)layout, out, out_img_stride, round_f16);
 }
 
 // Stem conv (KS x KS, stride 2, Cin = 3 in an NHWC4 tensor or sampled on the fly from `views`).
@@ -696,19 +704,19 @@ bool stem_supported(const ConvDev &p) {
     return true;
 }
 
-bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
+bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s, int round_f16) {
     if (!stem_supported(p)) return false;
     g_launch_count++;
     // measured: 2 pixels per thread pays for the LDS-bound 5x5 stem (0.79 -> 0.63 ms), not for the 3x3 one
     static const int ppt = getenv("ZB_STEM_PPT") ? atoi(getenv("ZB_STEM_PPT")) : 0;
     if (p.kh == 3) {
-        if (p.Ns <= 16) return ppt == 2 ? launch_stem_cfg<3, 16, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<3, 16, 1>(f, views, lo, hi, p, s);
-        if (p.Ns == 24) return ppt == 2 ? launch_stem_cfg<3, 24, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<3, 24, 1>(f, views, lo, hi, p, s);
-        return launch_stem_cfg<3, 32, 1>(f, views, lo, hi, p, s);
+        if (p.Ns <= 16) return ppt == 2 ? launch_stem_cfg<3, 16, 2>(f, views, lo, hi, p, round_f16, s) : launch_stem_cfg<3, 16, 1>(f, views, lo, hi, p, round_f16, s);
+        if (p.Ns == 24) return ppt == 2 ? launch_stem_cfg<3, 24, 2>(f, views, lo, hi, p, round_f16, s) : launch_stem_cfg<3, 24, 1>(f, views, lo, hi, p, round_f16, s);
+        return launch_stem_cfg<3, 32, 1>(f, views, lo, hi, p, round_f16, s);
     }
-    if (p.Ns <= 16) return ppt != 1 ? launch_stem_cfg<5, 16, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<5, 16, 1>(f, views, lo, hi, p, s);
-    if (p.Ns == 24) return ppt != 1 ? launch_stem_cfg<5, 24, 2>(f, views, lo, hi, p, s) : launch_stem_cfg<5, 24, 1>(f, views, lo, hi, p, s);
-    return launch_stem_cfg<5, 32, 1>(f, views, lo, hi, p, s);
+    if (p.Ns <= 16) return ppt != 1 ? launch_stem_cfg<5, 16, 2>(f, views, lo, hi, p, round_f16, s) : launch_stem_cfg<5, 16, 1>(f, views, lo, hi, p, round_f16, s);
+    if (p.Ns == 24) return ppt != 1 ? launch_stem_cfg<5, 24, 2>(f, views, lo, hi, p, round_f16, s) : launch_stem_cfg<5, 24, 1>(f, views, lo, hi, p, round_f16, s);
+    return launch_stem_cfg<5, 32, 1>(f, views, lo, hi, p, round_f16, s);
 }
 
 void launch_decode_nms(const float *boxes, const float *scores, const float *fit, int n, const DecodeParams &p,

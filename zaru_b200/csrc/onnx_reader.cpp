@@ -230,6 +230,7 @@ OnnxValueInfo parse_value_info(const uint8_t *d, size_t n) {
                 const uint8_t *s3;
                 size_t l3;
                 while (r3.next(f3, w3, v3, s3, l3)) {
+                    if (f3 == 1 && w3 == 0) vi.elem_type = (int)v3;   // elem_type
                     if (f3 != 2) continue;  // shape
                     Reader r4(s3, l3);
                     int f4, w4;

@@ -58,6 +58,7 @@ struct OnnxNode {
 struct OnnxValueInfo {
     std::string name;
     std::vector<int64_t> shape;
+    int elem_type = 1;             // TensorProto.DataType: 1 = f32, 10 = f16
 };
 
 struct OnnxGraph {

@@ -446,7 +446,9 @@ struct Lowerer {
         if (v.kind == Value::FLAT) return v;
         int t = materialize(name);
         TensorInfo &ti = plan.tensors[t];
-        if (!transposed_nhwc && !(ti.H == 1 && ti.W == 1))
+        // NCHW flattening equals NHWC flattening when there is nothing to permute (1x1 maps, or a single channel:
+        // the classifier head of face_detection_full_range is Reshape([1,1,48,48] -> [1,2304,1]) with no Transpose)
+        if (!transposed_nhwc && !(ti.H == 1 && ti.W == 1) && ti.C != 1)
             unsupported("flattening a spatial NCHW tensor ('" + name + "') without Transpose(0,2,3,1)");
         ti.exact = true;
         Value f;
@@ -737,6 +739,7 @@ struct Lowerer {
         const auto &in = g.inputs[0];
         if (in.shape.size() != 4 || in.shape[1] != 3) unsupported("input that is not [1,3,h,w]");
         plan.input_name = in.name;
+        plan.io_f16 = in.elem_type == 10;
         plan.in_h = (int)in.shape[2];
         plan.in_w = (int)in.shape[3];
         plan.input = new_tensor(in.name, 3, plan.in_h, plan.in_w);
@@ -784,7 +787,7 @@ Plan lower_graph(const OnnxGraph &g, const LowerOptions &opt) {
 std::string Plan::to_json() const {
     std::ostringstream os;
     os.precision(9);
-    os << "{\"input\":" << input << ",\"in_h\":" << in_h << ",\"in_w\":" << in_w
+    os << "{\"input\":" << input << ",\"io_f16\":" << (io_f16 ? 1 : 0) << ",\"in_h\":" << in_h << ",\"in_w\":" << in_w
        << ",\"arena_per_image\":" << arena_per_image << ",\"arena1_per_image\":" << arena1_per_image
        << ",\"split\":" << split << ",\"macs_per_image\":" << macs_per_image
        << ",\"num_weights\":" << weights.size() << ",\"tensors\":[";

@@ -82,6 +82,9 @@ struct Plan {
     std::string input_name;
     int input = -1;               // tensor id of the network input (NHWC4)
     int in_c = 3, in_h = 0, in_w = 0;
+    // graph input / outputs are FLOAT16 (face_landmarks_detector.onnx): NeuralNetwork::estimate rounds the f32
+    // input to f16 and widens the f16 outputs (nn/mod.rs:487-492, :504-508); compute stays FP32 on the device
+    bool io_f16 = false;
     int64_t arena_per_image = 0;  // elements, chunk arena (stage 0)
     int64_t arena1_per_image = 0; // elements, batch arena (stage 1 + boundary tensors)
     int split = 0;                // first stage-1 op

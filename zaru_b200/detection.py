@@ -106,6 +106,13 @@ class ShortRangeNetwork(Network):
     color_range = (-1.0, 1.0)
 
 
+class FullRangeNetwork(Network):
+    """BlazeFace full range (face/detection.rs:63-94): 192x192 input, 2304 anchors."""
+    onnx = "face_detection_full_range.onnx"
+    kind = _ffi.ZB_DET_FACE_FULL_RANGE
+    color_range = (-1.0, 1.0)
+
+
 class PalmLiteNetwork(Network):
     """`hand::detection::LiteNetwork` (hand/detection.rs:49-73)."""
     onnx = "palm_detection_lite.onnx"

@@ -43,6 +43,17 @@ class LandmarkResultV1(Estimate):
         return np.float32(self._scalars[0])
 
 
+class LandmarkResultV2(Estimate):
+    """mediapipe.rs `LandmarkResultV2`: 478 landmarks, face flag, tongueOut blendshape."""
+    NUM_LANDMARKS = 478
+
+    def confidence(self):
+        return np.float32(self._scalars[0])
+
+    def tongue_out(self):
+        return np.float32(self._scalars[1])
+
+
 class EyeLandmarks(Estimate):
     """eye.rs:67-125."""
     NUM_LANDMARKS = 76
@@ -86,6 +97,14 @@ class FaceMeshV1(Network):
     kind = _ffi.ZB_EST_FACE_MESH_V1
     color_range = (-1.0, 1.0)
     result = LandmarkResultV1
+
+
+class FaceMeshV2(Network):
+    """mediapipe.rs:81-115: FLOAT16 model, 256x256 input."""
+    onnx = "face_landmarks_detector.onnx"
+    kind = _ffi.ZB_EST_FACE_MESH_V2
+    color_range = (-1.0, 1.0)
+    result = LandmarkResultV2
 
 
 class EyeNetwork(Network):

@@ -18,7 +18,7 @@ from .landmark import FaceMeshV1
 class FacePipelineResult:
     def __init__(self, detections, landmarks, flags, rois):
         self.detections = detections      # list[Detections], frame coordinates
-        self.landmarks = landmarks        # [n,468,3] float32, frame coordinates
+        self.landmarks = landmarks        # [n,L,3] float32, frame coordinates (L = 468 or 478)
         self.face_flags = flags           # [n] sigmoid(face_flag); -1 where no face was detected
         self.rois = rois                  # [n,5]: view_rect (cx, cy, w, h, radians) used for the mesh
 
@@ -31,6 +31,7 @@ class FacePipeline:
         h = C.c_void_p()
         _ffi.check(_ffi.lib().zb_face_pipeline_create(context(), self._det.nn._h, self._lm.nn._h, C.byref(h)))
         self._h = h
+        self._L = _ffi.lib().zb_face_pipeline_num_landmarks(h)     # 468 (FaceMeshV1) or 478 (FaceMeshV2)
         self._bufs = None
 
     def set_threshold(self, det_thresh=0.5, iou_thresh=0.3, mode=_ffi.ZB_NMS_AVERAGE):
@@ -39,7 +40,7 @@ class FacePipeline:
     def _buffers(self, n):
         if self._bufs is None or self._bufs[0] != n:
             self._bufs = (n, (_ffi.zb_detection * (n * self._cap))(), (C.c_int32 * n)(),
-                          np.empty((n, 468, 3), np.float32), np.empty(n, np.float32), (_ffi.zb_view * n)())
+                          np.empty((n, self._L, 3), np.float32), np.empty(n, np.float32), (_ffi.zb_view * n)())
         return self._bufs
 
     def run_raw(self, batch, n=None):
