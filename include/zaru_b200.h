@@ -202,6 +202,33 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                                zb_detection *out_dets, int32_t *out_counts, int32_t cap,
                                float *out_landmarks, float *out_flags, zb_view *out_rois);
 
+/* ---- LandmarkTracker (landmark.rs:361-502), batched over independent streams ------------------
+ * One tracker owns `streams` RoI slots that live on the device.  zb_tracker_track runs ONE
+ * `LandmarkTracker::track` step for every stream (stream i reads frame i of `frames`):
+ *   view_rect = roi.map(grow_to_fit_aspect) -> Estimator::estimate(full_image.view(view_rect)) ->
+ *   lost if confidence < loss threshold (RoI cleared) -> landmarks mapped to frame coordinates ->
+ *   updated_roi = RotatedRect::bounding(roi.rad + estimate.angle_radians(), landmarks) ->
+ *   roi = updated_roi.grow_rel(roi_padding).
+ * Only face-mesh estimators (ZB_EST_FACE_MESH_V1 / _V2) implement Confidence + angle_radians in the
+ * reference and are accepted here.  Streams without an RoI report tracked = 0 (track() -> None).   */
+typedef struct zb_tracker zb_tracker;
+zb_status zb_tracker_create(zb_ctx *ctx, zb_net *landmark_net, zb_estimator_kind kind, float map_lo, float map_hi,
+                            int32_t streams, zb_tracker **out);
+void zb_tracker_destroy(zb_tracker *t);
+zb_status zb_tracker_set_loss_threshold(zb_tracker *t, float threshold);   /* default 0.5 (landmark.rs:370) */
+zb_status zb_tracker_set_roi_padding(zb_tracker *t, float padding);        /* default 0.3; < 0 or NaN is an error */
+/* set_roi for k streams: rois[j] (frame field ignored, used as-is, no padding) -> stream ids[j];
+ * rois == NULL clears those RoIs.  Host pointers.                                                 */
+zb_status zb_tracker_set_roi(zb_tracker *t, const int32_t *stream_ids, const zb_view *rois, int32_t k);
+/* Current RoI of every stream: rois [streams], has_roi [streams].  Host pointers, either may be NULL. */
+zb_status zb_tracker_roi(zb_tracker *t, zb_view *rois, uint8_t *has_roi);
+/* n must equal `streams`.  out_landmarks [n][L][3] frame coordinates (meaningful only where tracked),
+ * out_confidence [n], out_view_rects [n], out_updated_rois [n] (TrackingResult::updated_roi, before
+ * padding), out_tracked [n] (1 = Some(result)).  Any output may be NULL; host_or_device.           */
+zb_status zb_tracker_track(zb_tracker *t, const zb_frames *frames, int32_t n, float *out_landmarks,
+                           float *out_confidence, zb_view *out_view_rects, zb_view *out_updated_rois,
+                           uint8_t *out_tracked);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 /* JSON description of the lowered plan (fused op list, tensor layouts) of a loaded network and a
  * pointer to its packed host-side weight blob; tests replay the plan on the CPU to validate the

@@ -79,6 +79,7 @@ class FaceMeshV1(LandmarkNetwork):
 
 class FaceLandmarksV2(Estimate):
     """mediapipe.rs `LandmarkResultV2`: 478 landmarks (468 mesh + 2 x 5 iris), face flag, tongueOut blendshape."""
+    LEFT_EYE_OUTER, RIGHT_EYE_OUTER = 33, 263      # same LandmarkIdx enum as V1 (mediapipe.rs:535, :540)
 
     def __init__(self):
         super().__init__(478)
@@ -87,6 +88,15 @@ class FaceLandmarksV2(Estimate):
 
     def confidence(self):
         return self.face_flag
+
+    def rotation_radians(self):
+        """mediapipe.rs:407-421."""
+        le = self.positions[self.LEFT_EYE_OUTER]
+        re = self.positions[self.RIGHT_EYE_OUTER]
+        return signed_angle_to(re[0] - le[0], re[1] - le[1], 1.0, 0.0)
+
+    def angle_radians(self):
+        return self.rotation_radians()
 
 
 class FaceMeshV2(LandmarkNetwork):

@@ -13,10 +13,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle.detection import Detector, ShortRangeNetwork  # noqa: E402
+from oracle.detection import Detector, FullRangeNetwork, ShortRangeNetwork  # noqa: E402
 from oracle.geometry import RotatedRect, f32  # noqa: E402
 from oracle.image import Image, image_to_tensor  # noqa: E402
-from oracle.landmark import Estimator, FaceMeshV1  # noqa: E402
+from oracle.landmark import Estimator, FaceMeshV1, FaceMeshV2  # noqa: E402
 from tests.oracle_pipeline import face_pipeline  # noqa: E402
 from zaru_b200 import synth  # noqa: E402
 
@@ -70,6 +70,16 @@ def main():
         recs[f"s{s}_landmarks"] = lms if lms is not None else np.zeros((0, 3), np.float32)
         recs[f"s{s}_roi"] = np.asarray(view_rect.rect.as_tuple(), np.float32) if view_rect is not None else np.zeros(4, np.float32)
     np.savez_compressed(os.path.join(out, "s_face_pipeline.npz"), seeds=np.asarray(seeds), **recs)
+    # --- full-range detector + FaceMeshV2 on the reference's fixtures -------------------
+    fdet = Detector(FullRangeNetwork())
+    fdets = fdet.detect(Image(full))
+    e2 = Estimator(FaceMeshV2()).estimate(cimg.as_view())
+    np.savez_compressed(os.path.join(out, "sad_linus_widen.npz"),
+                        image_sha=np.frombuffer(__import__("hashlib").sha256(full.tobytes()).digest(), np.uint8),
+                        crop_sha=np.frombuffer(__import__("hashlib").sha256(crop.tobytes()).digest(), np.uint8),
+                        full_range_scores=fdet.last_raw[1], full_range_detections=dets_array(fdets),
+                        v2_positions=e2.positions.copy(), v2_flag=np.float32(e2.face_flag),
+                        v2_tongue_out=np.float32(e2.tongue_out))
     for f in sorted(os.listdir(out)):
         print(f, os.path.getsize(os.path.join(out, f)))
 

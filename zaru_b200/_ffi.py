@@ -77,6 +77,13 @@ SIGNATURES = {
     "zb_estimator_estimate": (i32, [P, P, P, P, i32, P, P]),
     "zb_face_pipeline_create": (i32, [P, P, P, PP]),
     "zb_face_pipeline_destroy": (None, [P]),
+    "zb_tracker_create": (i32, [P, P, i32, f32, f32, i32, PP]),
+    "zb_tracker_destroy": (None, [P]),
+    "zb_tracker_set_loss_threshold": (i32, [P, f32]),
+    "zb_tracker_set_roi_padding": (i32, [P, f32]),
+    "zb_tracker_set_roi": (i32, [P, P, P, i32]),
+    "zb_tracker_roi": (i32, [P, P, P]),
+    "zb_tracker_track": (i32, [P, P, i32, P, P, P, P, P]),
     "zb_face_pipeline_set_threshold": (i32, [P, f32, f32, i32]),
     "zb_face_pipeline_num_landmarks": (i32, [P]),
     "zb_face_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),

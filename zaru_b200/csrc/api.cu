@@ -889,6 +889,18 @@ struct zb_estimator {
     PinBuf h_stage;
 };
 
+struct zb_tracker {
+    zb_ctx *ctx;
+    zb_net *net;
+    zb_estimator_kind kind;
+    float lo, hi;
+    int streams = 0, num_landmarks = 0;
+    float loss_thresh = 0.5f, roi_padding = 0.3f;   // LandmarkTracker::DEFAULT_* (landmark.rs:370-372)
+    Workspace ws;
+    DevBuf d_state, d_views, d_fit, d_view_rects, d_updated, d_lm, d_scalars, d_tracked, d_ids, d_set;
+    PinBuf h_stage;
+};
+
 struct zb_face_pipeline {
     zb_ctx *ctx;
     zb_net *det_net, *lm_net;
@@ -1200,6 +1212,159 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
         tm.stop();
         copy_out(out_landmarks, e->d_lm.p, sizeof(float) * 3 * (size_t)L * n, s);
         copy_out(out_scalars, e->d_scalars.p, sizeof(float) * 2 * n, s);
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        return ZB_OK;
+    });
+}
+
+// ---- LandmarkTracker, batched over streams -----------------------------------------------------------------
+zb_status zb_tracker_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, float lo, float hi, int32_t streams,
+                            zb_tracker **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
+        if (streams <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "streams must be positive");
+        if (!(hi > lo)) return fail(ZB_ERR_INVALID_ARGUMENT, "ColorMapper range must satisfy end > start");
+        if (kind != ZB_EST_FACE_MESH_V1 && kind != ZB_EST_FACE_MESH_V2)
+            return fail(ZB_ERR_INVALID_ARGUMENT, "LandmarkTracker needs an estimate with Confidence + angle_radians (face mesh)");
+        try {
+            check_estimator_net(net, kind);
+        } catch (const std::runtime_error &e) {
+            return fail(ZB_ERR_BAD_SHAPE, e.what());
+        }
+        CU(cudaSetDevice(ctx->device));
+        auto t = std::make_unique<zb_tracker>();
+        t->ctx = ctx, t->net = net, t->kind = kind, t->lo = lo, t->hi = hi, t->streams = streams;
+        t->num_landmarks = estimator_landmarks(kind);
+        t->d_state.reserve(sizeof(TrackState) * streams);
+        CU(cudaMemsetAsync(t->d_state.p, 0, sizeof(TrackState) * streams, ctx->stream));   // every RoI = None
+        CU(cudaStreamSynchronize(ctx->stream));
+        *out = t.release();
+        return ZB_OK;
+    });
+}
+
+void zb_tracker_destroy(zb_tracker *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    delete t;
+}
+
+zb_status zb_tracker_set_loss_threshold(zb_tracker *t, float v) {
+    if (!t) return fail(ZB_ERR_INVALID_ARGUMENT, "tracker is NULL");
+    t->loss_thresh = v;
+    return ZB_OK;
+}
+
+zb_status zb_tracker_set_roi_padding(zb_tracker *t, float v) {
+    if (!t) return fail(ZB_ERR_INVALID_ARGUMENT, "tracker is NULL");
+    if (!(v >= 0.0f)) return fail(ZB_ERR_INVALID_ARGUMENT, "padding must be >= 0");   // assert!(padding >= 0.0)
+    t->roi_padding = v;
+    return ZB_OK;
+}
+
+zb_status zb_tracker_set_roi(zb_tracker *t, const int32_t *ids, const zb_view *rois, int32_t k) {
+    return guarded([&]() -> zb_status {
+        if (!t || (!ids && k > 0)) return fail(ZB_ERR_INVALID_ARGUMENT, "tracker/stream_ids is NULL");
+        if (k < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "k is negative");
+        if (k == 0) return ZB_OK;
+        for (int i = 0; i < k; i++)
+            if (ids[i] < 0 || ids[i] >= t->streams) return fail(ZB_ERR_INVALID_ARGUMENT, "stream id out of range");
+        zb_ctx *ctx = t->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        t->h_stage.reserve((sizeof(int) + sizeof(ViewHost)) * (size_t)k);
+        ViewHost *hr = t->h_stage.as<ViewHost>();
+        int *hi_ = reinterpret_cast<int *>(hr + k);
+        for (int i = 0; i < k; i++) {
+            hi_[i] = ids[i];
+            if (rois) hr[i] = ViewHost{ids[i], rois[i].cx, rois[i].cy, rois[i].w, rois[i].h, rois[i].radians};
+        }
+        t->d_ids.reserve(sizeof(int) * k);
+        t->d_set.reserve(sizeof(ViewHost) * k);
+        CU(cudaMemcpyAsync(t->d_ids.p, hi_, sizeof(int) * k, cudaMemcpyHostToDevice, s));
+        if (rois) CU(cudaMemcpyAsync(t->d_set.p, hr, sizeof(ViewHost) * k, cudaMemcpyHostToDevice, s));
+        launch_tracker_set_roi(t->d_state.as<TrackState>(), t->d_ids.as<int>(), rois ? t->d_set.as<ViewHost>() : nullptr, k, s);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        return ZB_OK;
+    });
+}
+
+zb_status zb_tracker_roi(zb_tracker *t, zb_view *rois, uint8_t *has_roi) {
+    return guarded([&]() -> zb_status {
+        if (!t) return fail(ZB_ERR_INVALID_ARGUMENT, "tracker is NULL");
+        CU(cudaSetDevice(t->ctx->device));
+        std::vector<TrackState> st(t->streams);
+        CU(cudaMemcpyAsync(st.data(), t->d_state.p, sizeof(TrackState) * t->streams, cudaMemcpyDeviceToHost, t->ctx->stream));
+        CU(cudaStreamSynchronize(t->ctx->stream));
+        for (int i = 0; i < t->streams; i++) {
+            if (rois) rois[i] = zb_view{i, st[i].cx, st[i].cy, st[i].w, st[i].h, st[i].rad};
+            if (has_roi) has_roi[i] = st[i].has ? 1 : 0;
+        }
+        return ZB_OK;
+    });
+}
+
+zb_status zb_tracker_track(zb_tracker *t, const zb_frames *frames, int32_t n, float *out_landmarks, float *out_confidence,
+                           zb_view *out_view_rects, zb_view *out_updated_rois, uint8_t *out_tracked) {
+    return guarded([&]() -> zb_status {
+        if (!t) return fail(ZB_ERR_INVALID_ARGUMENT, "tracker is NULL");
+        check_frames(frames, nullptr, n);
+        if (n != t->streams) return fail(ZB_ERR_INVALID_ARGUMENT, "n must equal the tracker's stream count");
+        zb_ctx *ctx = t->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const Plan &pl = t->net->plan;
+        const int chunk = std::min(net_chunk(t->net), n);
+        const int L = t->num_landmarks;
+        t->ws.ensure(t->net, chunk, n);
+        t->d_views.reserve(sizeof(ViewDev) * n);
+        t->d_fit.reserve(4 * sizeof(float) * n);
+        t->d_view_rects.reserve(sizeof(ViewHost) * n);
+        t->d_updated.reserve(sizeof(ViewHost) * n);
+        t->d_lm.reserve(sizeof(float) * 3 * (size_t)L * n);
+        t->d_scalars.reserve(sizeof(float) * 2 * n);
+        t->d_tracked.reserve(n);
+        LandmarkParams lp{};
+        lp.kind = (int)t->kind;
+        lp.num_landmarks = L;
+        lp.net_w = pl.in_w;
+        lp.net_h = pl.in_h;
+        lp.track_transform = 1;
+        Timer tm(ctx, s);
+        prof_launch(ctx, s, "tracker_prepare", 64.0 * n, 0, [&] {
+            launch_tracker_prepare(frames->f, t->d_state.as<TrackState>(), 0, n, pl.in_w, pl.in_h, t->d_views.as<ViewDev>(),
+                                   t->d_fit.as<float>(), t->d_view_rects.as<ViewHost>(), s);
+        });
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int nc = std::min(chunk, n - c0);
+            const StemInput si{&frames->f, t->d_views.as<ViewDev>() + c0, t->lo, t->hi};
+            run_ops(t->net, t->ws, c0, nc, 0, s, &si);
+        }
+        run_ops(t->net, t->ws, 0, n, 1, s);
+        const int s0 = (int)pl.outputs[0].per_image, s1 = (int)pl.outputs[1].per_image;
+        const int s2 = pl.outputs.size() > 2 ? (int)pl.outputs[2].per_image : 0;
+        prof_launch(ctx, s, "landmarks", 24.0 * L * n, 0, [&] {
+            launch_landmarks(t->ws.outs[0].as<float>(), s0, t->ws.outs[1].as<float>(), s1,
+                             s2 ? t->ws.outs[2].as<float>() : nullptr, s2, t->d_fit.as<float>(), t->d_views.as<ViewDev>(),
+                             t->d_view_rects.as<ViewHost>(), n, lp, t->d_lm.as<float>(), t->d_scalars.as<float>(), s);
+        });
+        prof_launch(ctx, s, "tracker_update", 12.0 * L * n, 0, [&] {
+            // LandmarkIdx::LeftEyeOuterCorner = 33, RightEyeOuterCorner = 263 (mediapipe.rs:535, :540; V1 and V2)
+            launch_tracker_update(t->d_state.as<TrackState>(), t->ws.outs[0].as<float>(), s0, t->d_fit.as<float>(),
+                                  t->d_lm.as<float>(), t->d_scalars.as<float>(), n, L, t->loss_thresh, t->roi_padding, 33, 263,
+                                  t->d_updated.as<ViewHost>(), t->d_tracked.as<unsigned char>(), s);
+        });
+        CU(cudaGetLastError());
+        tm.stop();
+        copy_out(out_landmarks, t->d_lm.p, sizeof(float) * 3 * (size_t)L * n, s);
+        if (out_confidence)
+            CU(cudaMemcpy2DAsync(out_confidence, sizeof(float), t->d_scalars.p, 2 * sizeof(float), sizeof(float), n,
+                                 is_device_ptr(out_confidence) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        copy_out(out_view_rects, t->d_view_rects.p, sizeof(ViewHost) * n, s);
+        copy_out(out_updated_rois, t->d_updated.p, sizeof(ViewHost) * n, s);
+        copy_out(out_tracked, t->d_tracked.p, (size_t)n, s);
         CU(cudaStreamSynchronize(s));
         tm.finish();
         return ZB_OK;

@@ -138,6 +138,25 @@ void launch_landmarks(const float *out0, int s0, const float *out1, int s1, cons
                       const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
                       const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s);
 
+// ---- LandmarkTracker on the device (landmark.rs:361-502), one state record per stream ---------------------
+struct TrackState {            // LandmarkTracker::roi: Option<RotatedRect>
+    float cx, cy, w, h, rad;
+    int has;                   // 0 = None (never seeded, or tracking lost)
+};
+// roi.map(grow_to_fit_aspect) -> full_image.view(view_rect) -> Estimator view fit, for every stream with an RoI
+// (stream i reads frame first_frame + i); streams without an RoI get an invalid view.
+void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int first_frame, int n, int net_w, int net_h,
+                            ViewDev *out_views, float *out_fit, ViewHost *out_view_rects, cudaStream_t s);
+// confidence check, angle = roi.rad + estimate.angle_radians(), RotatedRect::bounding over the mapped landmarks,
+// roi = updated.grow_rel(padding).  out0: raw landmark tensor (view-space eye corners give angle_radians);
+// landmarks: positions already mapped to image coordinates; scalars[2*i] = confidence.
+void launch_tracker_update(TrackState *state, const float *out0, int s0, const float *fit, const float *landmarks,
+                           const float *scalars, int n, int num_landmarks, float loss_thresh, float roi_padding,
+                           int left_eye_idx, int right_eye_idx, ViewHost *out_updated, unsigned char *out_tracked,
+                           cudaStream_t s);
+// roi[ids[k]] = rois[k] (radians kept), or None when rois == nullptr
+void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s);
+
 extern long long g_launch_count;   // total kernel launches issued by this library (process-wide)
 
 }  // namespace zb

@@ -682,7 +682,162 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
     o[0] = x, o[1] = y, o[2] = z;
 }
 
+// ------------------------------------------------------------------------------------------------
+// LandmarkTracker::track_impl (landmark.rs:463-501), device resident.
+// cos/sin of a device-computed angle: evaluated in f64 and rounded once (glibc cosf/sinf are correctly rounded in
+// practice, CUDA's are not), the same convention as exp/atan2 above.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cos_sin_ref(float rad, float &c, float &s) {
+    if (rad == 0.0f) {
+        c = 1.0f, s = 0.0f;
+    } else {
+        c = (float)cos((double)rad), s = (float)sin((double)rad);
+    }
+}
+
+__global__ void __launch_bounds__(128) tracker_prepare_kernel(const FramesDev f, const TrackState *__restrict__ state,
+                                                              int first_frame, int n, int net_w, int net_h,
+                                                              ViewDev *__restrict__ out_views, float *__restrict__ out_fit,
+                                                              ViewHost *__restrict__ out_rects) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrackState st = state[i];
+    ViewDev v;
+    v.frame = first_frame + i;
+    v.flip_x = 0;
+    v.valid = st.has != 0;
+    v.cx = v.cy = 0.f, v.w = v.h = 1.f, v.cosr = 1.f, v.sinr = 0.f;
+    float fit0 = 1.f, fit1 = 0.f, fit2 = 0.f;
+    ViewHost vr;
+    vr.frame = first_frame + i;
+    vr.cx = vr.cy = vr.w = vr.h = 0.f, vr.radians = 0.f;
+    if (st.has) {
+        const float aspect = aspect_as_f32((unsigned)net_w, (unsigned)net_h);
+        // let view_rect = roi.map(|rect| rect.grow_to_fit_aspect(self.aspect_ratio));   (landmark.rs:465)
+        RectF roi;
+        roi.cx = st.cx, roi.cy = st.cy, roi.w = st.w, roi.h = st.h;
+        const RectF view_rect = grow_to_fit_aspect(roi, aspect);
+        vr.cx = view_rect.cx, vr.cy = view_rect.cy, vr.w = view_rect.w, vr.h = view_rect.h, vr.radians = st.rad;
+        float c, s;
+        cos_sin_ref(st.rad, c, s);
+        // full_image.view(view_rect)   (landmark.rs:466; parent rotation 0, so the summed angle is roi's)
+        const RRectF full = full_view(f.width, f.height);
+        const RRectF v1 = view_compose(full, view_rect, st.rad, c, s);
+        // Estimator::estimate_impl: rect = view.rect().grow_to_fit_aspect(..); view = image.view(rect)  (:320-323)
+        const RectF r1 = rect_from_top_left(0.0f, 0.0f, v1.r.w, v1.r.h);
+        const RectF r2 = grow_to_fit_aspect(r1, aspect);
+        const RRectF v2 = view_compose(v1, r2, 0.0f, c, s);
+        v.cx = v2.r.cx, v.cy = v2.r.cy, v.w = v2.r.w, v.h = v2.r.h, v.cosr = c, v.sinr = s;
+        fit0 = r2.w / (float)net_w;
+        fit1 = rect_x(r2);
+        fit2 = rect_y(r2);
+    }
+    out_views[i] = v;
+    out_fit[i * 4 + 0] = fit0, out_fit[i * 4 + 1] = fit1, out_fit[i * 4 + 2] = fit2, out_fit[i * 4 + 3] = 0.f;
+    out_rects[i] = vr;
+}
+
+// One CTA per stream.
+__global__ void __launch_bounds__(128) tracker_update_kernel(TrackState *__restrict__ state, const float *__restrict__ out0,
+                                                             int s0, const float *__restrict__ fit,
+                                                             const float *__restrict__ landmarks,
+                                                             const float *__restrict__ scalars, int num_landmarks,
+                                                             float loss_thresh, float roi_padding, int le_idx, int re_idx,
+                                                             ViewHost *__restrict__ out_updated,
+                                                             unsigned char *__restrict__ out_tracked) {
+    const int i = blockIdx.x, tid = threadIdx.x;
+    __shared__ float s_red[4][4];
+    const TrackState st = state[i];
+    ViewHost up;
+    up.frame = i;
+    up.cx = up.cy = up.w = up.h = up.radians = 0.f;
+    // `let roi = self.roi?;` and `if estimate.confidence() < self.loss_thresh { self.roi = None; return None; }`
+    const bool lost = !st.has || scalars[i * 2] < loss_thresh;
+    if (lost) {
+        if (tid == 0) {
+            state[i].has = 0;
+            out_updated[i] = up;
+            out_tracked[i] = 0;
+        }
+        return;
+    }
+    // estimate.angle_radians(): eye outer corners in VIEW coordinates (positions are mapped to the image afterwards)
+    const float scale = fit[i * 4 + 0], tlx = fit[i * 4 + 1], tly = fit[i * 4 + 2];
+    const float *o = out0 + (long long)i * s0;
+    const float lx = o[3 * le_idx] * scale + tlx, ly = o[3 * le_idx + 1] * scale + tly;
+    const float rx = o[3 * re_idx] * scale + tlx, ry = o[3 * re_idx + 1] * scale + tly;
+    const float angle = st.rad + signed_angle_to(rx - lx, ry - ly, 1.0f, 0.0f);
+    // RotatedRect::bounding(angle, points)  (rect.rs:287-325): cw = rotation_clockwise(angle) = ccw(-angle)
+    float c, s;
+    cos_sin_ref(-angle, c, s);
+    float mnx = 3.402823466e+38f, mny = 3.402823466e+38f, mxx = -3.402823466e+38f, mxy = -3.402823466e+38f;
+    const float *lm = landmarks + (long long)i * num_landmarks * 3;
+    for (int l = tid; l < num_landmarks; l += blockDim.x) {
+        float px, py;
+        rot_ccw_apply(c, s, lm[3 * l], lm[3 * l + 1], px, py);
+        mnx = fminf(mnx, px), mny = fminf(mny, py), mxx = fmaxf(mxx, px), mxy = fmaxf(mxy, py);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+    }
+    if ((tid & 31) == 0) s_red[tid >> 5][0] = mnx, s_red[tid >> 5][1] = mny, s_red[tid >> 5][2] = mxx, s_red[tid >> 5][3] = mxy;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+            mnx = fminf(mnx, s_red[w][0]), mny = fminf(mny, s_red[w][1]);
+            mxx = fmaxf(mxx, s_red[w][2]), mxy = fmaxf(mxy, s_red[w][3]);
+        }
+        const float ccx = (mnx + mxx) * 0.5f, ccy = (mny + mxy) * 0.5f;     // centre in the rotated frame
+        float c2, s2, ox, oy;
+        cos_sin_ref(angle, c2, s2);
+        rot_ccw_apply(c2, s2, ccx, ccy, ox, oy);                               // center.rotate_counterclockwise(angle)
+        up.cx = ox, up.cy = oy, up.w = mxx - mnx, up.h = mxy - mny, up.radians = angle;
+        out_updated[i] = up;
+        out_tracked[i] = 1;
+        RectF r;
+        r.cx = ox, r.cy = oy, r.w = up.w, r.h = up.h;
+        r = grow_rel(r, roi_padding);                                          // self.roi = updated.grow_rel(padding)
+        TrackState ns;
+        ns.cx = r.cx, ns.cy = r.cy, ns.w = r.w, ns.h = r.h, ns.rad = angle, ns.has = 1;
+        state[i] = ns;
+    }
+}
+
+__global__ void tracker_set_roi_kernel(TrackState *__restrict__ state, const int *__restrict__ ids,
+                                       const ViewHost *__restrict__ rois, int k) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    TrackState st;
+    st.cx = st.cy = st.w = st.h = st.rad = 0.f, st.has = 0;
+    if (rois) st.cx = rois[j].cx, st.cy = rois[j].cy, st.w = rois[j].w, st.h = rois[j].h, st.rad = rois[j].radians, st.has = 1;
+    state[ids[j]] = st;
+}
+
 }  // namespace
+
+void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int first_frame, int n, int net_w, int net_h,
+                            ViewDev *out_views, float *out_fit, ViewHost *out_view_rects, cudaStream_t s) {
+    g_launch_count++;
+    tracker_prepare_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, state, first_frame, n, net_w, net_h, out_views, out_fit,
+                                                           out_view_rects);
+}
+
+void launch_tracker_update(TrackState *state, const float *out0, int s0, const float *fit, const float *landmarks,
+                           const float *scalars, int n, int num_landmarks, float loss_thresh, float roi_padding,
+                           int left_eye_idx, int right_eye_idx, ViewHost *out_updated, unsigned char *out_tracked,
+                           cudaStream_t s) {
+    g_launch_count++;
+    tracker_update_kernel<<<n, 128, 0, s>>>(state, out0, s0, fit, landmarks, scalars, num_landmarks, loss_thresh,
+                                            roi_padding, left_eye_idx, right_eye_idx, out_updated, out_tracked);
+}
+
+void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s) {
+    g_launch_count++;
+    tracker_set_roi_kernel<<<(k + 127) / 128, 128, 0, s>>>(state, ids, rois, k);
+}
 
 void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
                    SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s, int round_f16) {

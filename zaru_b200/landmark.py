@@ -160,3 +160,98 @@ class Estimator:
                 self._h = None
         except Exception:
             pass
+
+
+class TrackingResult:
+    """landmark.rs:504-533 `TrackingResult`, for one stream."""
+
+    def __init__(self, view_rect, estimate, updated_roi):
+        self._view_rect, self._estimate, self._updated_roi = view_rect, estimate, updated_roi
+
+    def view_rect(self):
+        return self._view_rect          # (cx, cy, w, h, radians)
+
+    def estimate(self):
+        return self._estimate
+
+    def updated_roi(self):
+        return self._updated_roi        # (cx, cy, w, h, radians), before padding
+
+
+class LandmarkTracker:
+    """`LandmarkTracker` (landmark.rs:361-502) for `streams` independent streams at once; the RoIs live on the
+    device.  `track(batch)` runs one reference `track()` step per stream (stream i <- frame i of the batch) and
+    returns a list with `None` where the reference would (no RoI, or confidence below the loss threshold)."""
+    DEFAULT_LOSS_THRESHOLD = 0.5
+    DEFAULT_ROI_PADDING = 0.3
+
+    def __init__(self, network: Network, streams: int = 1):
+        self.network = network
+        self._cnn = network.cnn()
+        self._n = int(streams)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_tracker_create(context(), self._cnn.nn._h, network.kind, network.color_range[0],
+                                                network.color_range[1], self._n, C.byref(h)))
+        self._h = h
+        self._L = network.result.NUM_LANDMARKS
+        self._bufs = (np.empty((self._n, self._L, 3), np.float32), np.empty(self._n, np.float32),
+                      (_ffi.zb_view * self._n)(), (_ffi.zb_view * self._n)(), np.empty(self._n, np.uint8))
+
+    def streams(self):
+        return self._n
+
+    def set_loss_threshold(self, threshold):
+        _ffi.check(_ffi.lib().zb_tracker_set_loss_threshold(self._h, float(threshold)))
+
+    def set_roi_padding(self, padding):
+        _ffi.check(_ffi.lib().zb_tracker_set_roi_padding(self._h, float(padding)))
+
+    def set_roi(self, roi, stream: int = 0):
+        """`set_roi(roi)`: roi = (cx, cy, w, h[, radians]) or an object with .as_zb_view(); used as-is."""
+        self.set_rois([stream], [roi])
+
+    def set_rois(self, streams, rois):
+        k = len(streams)
+        ids = (C.c_int32 * k)(*[int(s) for s in streams])
+        arr = None
+        if rois is not None:
+            arr = (_ffi.zb_view * k)()
+            for j, r in enumerate(rois):
+                t = tuple(float(x) for x in r)
+                arr[j] = _ffi.zb_view(int(streams[j]), t[0], t[1], t[2], t[3], t[4] if len(t) > 4 else 0.0)
+        _ffi.check(_ffi.lib().zb_tracker_set_roi(self._h, ids, arr, k))
+
+    def clear_rois(self, streams):
+        self.set_rois(streams, None)
+
+    def rois(self):
+        """[(cx, cy, w, h, radians) or None] per stream (`LandmarkTracker::roi`)."""
+        arr, has = (_ffi.zb_view * self._n)(), (C.c_uint8 * self._n)()
+        _ffi.check(_ffi.lib().zb_tracker_roi(self._h, arr, has))
+        return [(arr[i].cx, arr[i].cy, arr[i].w, arr[i].h, arr[i].radians) if has[i] else None for i in range(self._n)]
+
+    def track_raw(self, batch):
+        lm, conf, vr, up, tracked = self._bufs
+        _ffi.check(_ffi.lib().zb_tracker_track(self._h, batch._h, self._n, lm.ctypes.data, conf.ctypes.data, vr, up,
+                                               tracked.ctypes.data))
+        return lm, conf, vr, up, tracked
+
+    def track(self, batch):
+        lm, conf, vr, up, tracked = self.track_raw(batch)
+        out = []
+        for i in range(self._n):
+            if not tracked[i]:
+                out.append(None)
+                continue
+            est = self.network.result(lm[i].copy(), np.array([conf[i], 0.0], np.float32))
+            out.append(TrackingResult((vr[i].cx, vr[i].cy, vr[i].w, vr[i].h, vr[i].radians), est,
+                                      (up[i].cx, up[i].cy, up[i].w, up[i].h, up[i].radians)))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ffi.lib().zb_tracker_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -11,8 +11,8 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi, context
-from .detection import Detection, Detections, ShortRangeNetwork
-from .landmark import FaceMeshV1
+from .detection import Detection, Detections, Detector, ShortRangeNetwork
+from .landmark import FaceMeshV1, LandmarkTracker
 
 
 class FacePipelineResult:
@@ -66,3 +66,45 @@ class FacePipeline:
                 self._h = None
         except Exception:
             pass
+
+
+class FaceStreamTracker:
+    """The reference's steady-state loop (crates/zaru/examples/facemesh.rs:36-60) over many camera streams:
+    every step `tracker.track(frame)`; only where that returns None the detector runs on that stream's frame and
+    the best detection (`max_by_key(TotalF32(confidence))`, last maximum) seeds `tracker.set_roi(bounding_rect)`,
+    to be tracked from the NEXT frame on.  Detection therefore costs nothing while tracking holds."""
+
+    def __init__(self, streams: int, detector_network=None, landmark_network=None, capacity: int = 16):
+        self.detector = Detector(detector_network or ShortRangeNetwork(), capacity=capacity)
+        self.tracker = LandmarkTracker(landmark_network or FaceMeshV1(), streams)
+        self._n = streams
+
+    def step(self, batch):
+        """Returns (tracking results [n] with None where lost, {stream: Detections} for re-detected streams)."""
+        results = self.tracker.track(batch)
+        lost = [i for i, r in enumerate(results) if r is None]
+        redetected = {}
+        if lost:
+            res = batch.resolution()
+            w, h = float(res.width()), float(res.height())
+            views = [_ffi.zb_view(i, w * 0.5, h * 0.5, w, h, 0.0) for i in lost]   # the whole frame of each lost stream
+            dets = self.detector.detect_views(batch, views)
+            ids, rois = [], []
+            for i, ds in zip(lost, dets):
+                redetected[i] = ds
+                best = None
+                for d in ds:   # max_by_key: the LAST maximum in iteration order
+                    if best is None or _total_key(d.confidence()) >= _total_key(best.confidence()):
+                        best = d
+                if best is not None:
+                    r = best.bounding_rect()
+                    ids.append(i)
+                    rois.append((r.center()[0], r.center()[1], r.width(), r.height(), 0.0))
+            if ids:
+                self.tracker.set_rois(ids, rois)
+        return results, redetected
+
+
+def _total_key(x):
+    b = int(np.float32(x).view(np.int32))
+    return b ^ 0x7FFFFFFF if b < 0 else b
