@@ -202,6 +202,8 @@ def run_gpu(args):
     zaru_b200.context(local)
     res = Resolution(FRAME_W, FRAME_H)
     batch_n = args.batch
+    if args.streams:   # config 5: S concurrent camera streams sharded round-robin over the GPUs, one frame each per step
+        batch_n = len(shard.streams_for_rank(args.streams, world, rank))
 
     # --- inputs: `unique` distinct S-face frames per rank, tiled to the batch, resident in HBM -----------
     t0 = time.perf_counter()
@@ -293,6 +295,33 @@ def run_gpu(args):
     clock_info = clocks.stop() if rank == 0 else None
     d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
 
+    # --- steady state of the reference's loop (examples/facemesh.rs): every stream holds its RoI, so a step is
+    # LandmarkTracker::track only (rotated-view sampling + face mesh + RoI update on device); the detector idles.
+    steady = None
+    if rank == 0 and not args.no_steady_state:
+        try:
+            from zaru_b200.pipeline import FaceStreamTracker
+            sn = min(batch_n, 1024)
+            loop = FaceStreamTracker(sn, capacity=args.cap)
+            sb = batch if sn == batch_n else ImageBatch.alias_device(res, d_frames.data_ptr(), sn, keepalive=d_frames)
+            loop.step(sb)                                  # all lost: detect + seed
+            held = sum(r is not None for r in loop.step(sb)[0])
+            for _ in range(args.warmup):
+                loop.tracker.track_raw(sb)
+            zaru_b200.sync()
+            zaru_b200.timer_start()
+            for _ in range(args.steps):
+                tr = loop.tracker.track_raw(sb)
+            st_ms = zaru_b200.timer_stop_ms()
+            steady = {"value": sn * args.steps / (st_ms / 1000.0), "unit": UNIT, "streams": sn,
+                      "streams_tracked": int(tr[4].sum()), "streams_tracked_after_seed": int(held),
+                      "ms_per_step": st_ms / args.steps,
+                      "what": "LandmarkTracker::track on every stream (RoIs resident on the device), detector idle; "
+                              "device time, frames resident in HBM"}
+            del loop
+        except Exception as ex:
+            log(f"[rank 0] steady-state tracker measurement skipped: {ex}")
+
     # --- per-kernel CUDA-event profile of one step (roofline block) -------------------------------------
     prof = None
     if rank == 0:
@@ -339,7 +368,9 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark",
+        "config": {"workload": ("config5: %d concurrent 1080p camera streams sharded over %d GPU(s), one frame per stream per "
+                                "step through the full face pipeline" % (args.streams, world)) if args.streams else
+                               "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark",
                    "batch_per_gpu": batch_n, "frame": "1920x1080 RGBA8", "distinct_frames": args.unique,
                    "l2_policy": f"inputs larger than L2 ({batch_n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
                    "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "1024")), "frames_with_face": n_with_face,
@@ -360,6 +391,8 @@ def run_gpu(args):
         "kernels": kernels,
         "clocks": clock_info,
     }
+    if steady is not None:
+        line["steady_state_tracking"] = steady
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_budget)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -381,6 +414,9 @@ def main():
     ap.add_argument("--cap", type=int, default=16)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-steady-state", action="store_true")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="config 5: total concurrent camera streams, sharded over the GPUs (overrides --batch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "zaru_b200" else args.warmup
 

@@ -229,6 +229,30 @@ zb_status zb_tracker_track(zb_tracker *t, const zb_frames *frames, int32_t n, fl
                            float *out_confidence, zb_view *out_view_rects, zb_view *out_updated_rois,
                            uint8_t *out_tracked);
 
+/* ---- LandmarkFilter (landmark.rs:147-202; filter/{ema,one_euro,alpha_beta}.rs) -----------------
+ * Per-coordinate smoothing of the landmark positions in NETWORK coordinates, applied inside the
+ * estimate step before the remap (landmark.rs:330-333).  One filter state per (batch slot or
+ * stream, landmark, coordinate), kept on the device; `zb_*_set_filter` resets it.
+ *   ZB_FILTER_EMA        p0 = alpha in [0,1]
+ *   ZB_FILTER_ONE_EURO   p0 = min_cutoff > 0, p1 = beta >= 0, p2 = d_cutoff (1.0 in OneEuroFilter::new)
+ *   ZB_FILTER_ALPHA_BETA p0 = alpha, p1 = beta, both in [0,1]
+ * Time-based filters use `elapsed_seconds` (the reference's TimedFilterAdapter reads a wall clock;
+ * here the caller states the frame interval).                                                   */
+typedef enum zb_filter_kind {
+    ZB_FILTER_NONE = 0,
+    ZB_FILTER_EMA = 1,
+    ZB_FILTER_ONE_EURO = 2,
+    ZB_FILTER_ALPHA_BETA = 3
+} zb_filter_kind;
+zb_status zb_estimator_set_filter(zb_estimator *e, zb_filter_kind kind, float p0, float p1, float p2,
+                                  float elapsed_seconds);
+zb_status zb_tracker_set_filter(zb_tracker *t, zb_filter_kind kind, float p0, float p1, float p2,
+                                float elapsed_seconds);
+/* values[i] = filter(state[i], values[i]) for `count` independent scalars; state is [count][3]
+ * floats (has, x, dx|v), zero-initialised = Default.  Host pointers, both updated in place.      */
+zb_status zb_filter_apply(zb_ctx *ctx, zb_filter_kind kind, float p0, float p1, float p2, float elapsed_seconds,
+                          float *state, float *values, int64_t count);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 /* JSON description of the lowered plan (fused op list, tensor layouts) of a loaded network and a
  * pointer to its packed host-side weight blob; tests replay the plan on the CPU to validate the

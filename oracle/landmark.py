@@ -169,16 +169,21 @@ class HandLiteNetwork(LandmarkNetwork):
 
 
 class Estimator:
-    """landmark.rs:256-349 (filter = identity, the default :152-158)."""
+    """landmark.rs:256-349."""
 
     def __init__(self, network: LandmarkNetwork, backend=None):
         self.network = network
         self.estimate_ = network.new_estimate()
         self.backend = backend
         self.last_raw = None
+        self.filter = None          # LandmarkFilter::default(): no filtering (landmark.rs:152-158)
 
     def input_resolution(self):
         return self.network.cnn().input_resolution()
+
+    def set_filter(self, landmark_filter):
+        """landmark.rs:293-302; an oracle.filter.LandmarkFilter."""
+        self.filter = landmark_filter
 
     def estimate(self, image, outputs=None):
         view0 = image.as_view()
@@ -190,6 +195,8 @@ class Estimator:
             outputs = cnn.estimate(view, self.backend)
         self.last_raw = outputs
         self.network.extract(outputs, self.estimate_)
+        if self.filter is not None:     # in network coordinates, before the remap (landmark.rs:330-333)
+            self.filter.filter(self.estimate_.positions)
         scale = rect.w / f32(res.width)
         pos = self.estimate_.positions
         pos *= scale                       # x, y AND z are scaled (landmark.rs:336-339)

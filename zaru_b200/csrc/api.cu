@@ -426,6 +426,19 @@ void check_frames(const zb_frames *frames, const zb_view *views, int n) {
 }
 
 // copy results to the caller (host or device pointer)
+// Device state of a LandmarkFilter for `slots` batch slots: created zeroed (= every coordinate's State::default())
+// on first use and whenever the slot count changes.  Returns nullptr when no filter is set.
+const FilterDev *filter_for(FilterDev &f, DevBuf &buf, int &slots, int n, int L, cudaStream_t s) {
+    if (f.kind == FILTER_NONE) return nullptr;
+    if (slots != n) {
+        buf.reserve(sizeof(float) * 9 * (size_t)L * n);
+        CU(cudaMemsetAsync(buf.p, 0, sizeof(float) * 9 * (size_t)L * n, s));
+        slots = n;
+    }
+    f.state = buf.as<float>();
+    return &f;
+}
+
 void copy_out(void *dst, const void *src_dev, size_t bytes, cudaStream_t s) {
     if (!dst || !bytes) return;
     CU(cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -885,8 +898,10 @@ struct zb_estimator {
     float lo, hi;
     int num_landmarks;
     Workspace ws;
-    DevBuf d_views, d_fit, d_lm, d_scalars;
+    DevBuf d_views, d_fit, d_lm, d_scalars, d_filter;
     PinBuf h_stage;
+    FilterDev filter{};          // LandmarkFilter (default: none); state slots = views of the batch
+    int filter_slots = 0;
 };
 
 struct zb_tracker {
@@ -897,8 +912,10 @@ struct zb_tracker {
     int streams = 0, num_landmarks = 0;
     float loss_thresh = 0.5f, roi_padding = 0.3f;   // LandmarkTracker::DEFAULT_* (landmark.rs:370-372)
     Workspace ws;
-    DevBuf d_state, d_views, d_fit, d_view_rects, d_updated, d_lm, d_scalars, d_tracked, d_ids, d_set;
+    DevBuf d_state, d_views, d_fit, d_view_rects, d_updated, d_lm, d_scalars, d_tracked, d_ids, d_set, d_filter;
     PinBuf h_stage;
+    FilterDev filter{};          // LandmarkFilter of the inner Estimator (default: none); one state set per stream
+    int filter_slots = 0;
 };
 
 struct zb_face_pipeline {
@@ -1206,7 +1223,8 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
             const int s2 = pl.outputs.size() > 2 ? (int)pl.outputs[2].per_image : 0;
             launch_landmarks(e->ws.outs[0].as<float>(), s0, e->ws.outs[1].as<float>(), s1,
                              s2 ? e->ws.outs[2].as<float>() : nullptr, s2, e->d_fit.as<float>(),
-                             e->d_views.as<ViewDev>(), nullptr, n, lp, e->d_lm.as<float>(), e->d_scalars.as<float>(), s);
+                             e->d_views.as<ViewDev>(), nullptr, n, lp, e->d_lm.as<float>(), e->d_scalars.as<float>(), s,
+                             filter_for(e->filter, e->d_filter, e->filter_slots, n, L, s));
         }
         CU(cudaGetLastError());
         tm.stop();
@@ -1348,7 +1366,8 @@ zb_status zb_tracker_track(zb_tracker *t, const zb_frames *frames, int32_t n, fl
         prof_launch(ctx, s, "landmarks", 24.0 * L * n, 0, [&] {
             launch_landmarks(t->ws.outs[0].as<float>(), s0, t->ws.outs[1].as<float>(), s1,
                              s2 ? t->ws.outs[2].as<float>() : nullptr, s2, t->d_fit.as<float>(), t->d_views.as<ViewDev>(),
-                             t->d_view_rects.as<ViewHost>(), n, lp, t->d_lm.as<float>(), t->d_scalars.as<float>(), s);
+                             t->d_view_rects.as<ViewHost>(), n, lp, t->d_lm.as<float>(), t->d_scalars.as<float>(), s,
+                             filter_for(t->filter, t->d_filter, t->filter_slots, n, L, s));
         });
         prof_launch(ctx, s, "tracker_update", 12.0 * L * n, 0, [&] {
             // LandmarkIdx::LeftEyeOuterCorner = 33, RightEyeOuterCorner = 263 (mediapipe.rs:535, :540; V1 and V2)
@@ -1367,6 +1386,68 @@ zb_status zb_tracker_track(zb_tracker *t, const zb_frames *frames, int32_t n, fl
         copy_out(out_tracked, t->d_tracked.p, (size_t)n, s);
         CU(cudaStreamSynchronize(s));
         tm.finish();
+        return ZB_OK;
+    });
+}
+
+// ---- LandmarkFilter ----------------------------------------------------------------------------------------
+namespace {
+zb_status check_filter(zb_filter_kind kind, float p0, float p1, float p2, float elapsed) {
+    (void)p2;
+    if (kind == ZB_FILTER_NONE) return ZB_OK;
+    if (kind == ZB_FILTER_EMA) {
+        if (!(p0 >= 0.0f && p0 <= 1.0f)) return fail(ZB_ERR_INVALID_ARGUMENT, "Ema: alpha must be in [0, 1]");   // ema.rs:18
+        return ZB_OK;
+    }
+    if (!(elapsed > 0.0f)) return fail(ZB_ERR_INVALID_ARGUMENT, "time-based filter: elapsed_seconds must be positive");
+    if (kind == ZB_FILTER_ONE_EURO) {
+        if (!(p0 > 0.0f) || !(p1 >= 0.0f)) return fail(ZB_ERR_INVALID_ARGUMENT, "OneEuroFilter: min_cutoff > 0 and beta >= 0");
+        return ZB_OK;
+    }
+    if (kind == ZB_FILTER_ALPHA_BETA) {
+        if (!(p0 >= 0.0f && p0 <= 1.0f) || !(p1 >= 0.0f && p1 <= 1.0f))
+            return fail(ZB_ERR_INVALID_ARGUMENT, "AlphaBetaFilter: alpha and beta must be in [0, 1]");
+        return ZB_OK;
+    }
+    return fail(ZB_ERR_INVALID_ARGUMENT, "unknown filter kind");
+}
+}  // namespace
+
+zb_status zb_estimator_set_filter(zb_estimator *e, zb_filter_kind kind, float p0, float p1, float p2, float elapsed) {
+    if (!e) return fail(ZB_ERR_INVALID_ARGUMENT, "estimator is NULL");
+    if (zb_status st = check_filter(kind, p0, p1, p2, elapsed)) return st;
+    e->filter = FilterDev{(int)kind, p0, p1, p2, elapsed, nullptr};
+    e->filter_slots = 0;        // state is (re)created zeroed at the next estimate
+    return ZB_OK;
+}
+
+zb_status zb_tracker_set_filter(zb_tracker *t, zb_filter_kind kind, float p0, float p1, float p2, float elapsed) {
+    if (!t) return fail(ZB_ERR_INVALID_ARGUMENT, "tracker is NULL");
+    if (zb_status st = check_filter(kind, p0, p1, p2, elapsed)) return st;
+    t->filter = FilterDev{(int)kind, p0, p1, p2, elapsed, nullptr};
+    t->filter_slots = 0;
+    return ZB_OK;
+}
+
+zb_status zb_filter_apply(zb_ctx *ctx, zb_filter_kind kind, float p0, float p1, float p2, float elapsed, float *state,
+                          float *values, int64_t count) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !state || !values) return fail(ZB_ERR_INVALID_ARGUMENT, "NULL argument");
+        if (count < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "count is negative");
+        if (zb_status st = check_filter(kind, p0, p1, p2, elapsed)) return st;
+        if (count == 0) return ZB_OK;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        DevBuf ds, dv;
+        ds.reserve(sizeof(float) * 3 * (size_t)count);
+        dv.reserve(sizeof(float) * (size_t)count);
+        CU(cudaMemcpyAsync(ds.p, state, sizeof(float) * 3 * (size_t)count, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dv.p, values, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, s));
+        launch_filter_apply(FilterDev{(int)kind, p0, p1, p2, elapsed, ds.as<float>()}, dv.as<float>(), count, s);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(state, ds.p, sizeof(float) * 3 * (size_t)count, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(values, dv.p, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
         return ZB_OK;
     });
 }

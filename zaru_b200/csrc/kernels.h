@@ -127,6 +127,18 @@ void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, 
                      int net_w, int net_h, ViewDev *out_views, float *out_fit, ViewHost *out_view_rects,
                      cudaStream_t s);
 
+// LandmarkFilter (landmark.rs:147-202) over zaru::filter (filter/{ema,one_euro,alpha_beta}.rs): one state triple
+// per (slot, landmark, coordinate), applied in NETWORK coordinates before the remap (landmark.rs:330-333).
+enum FilterKind { FILTER_NONE = 0, FILTER_EMA = 1, FILTER_ONE_EURO = 2, FILTER_ALPHA_BETA = 3 };
+struct FilterDev {
+    int kind;                  // FilterKind
+    float p0, p1, p2;          // EMA: alpha | 1-euro: min_cutoff, beta, d_cutoff | alpha-beta: alpha, beta
+    float elapsed;             // seconds since the previous sample (time-based filters)
+    float *state;              // [slots][num_landmarks][3 coords][3]: (has, x|last, dx|v); nullptr = no filtering
+};
+// values[i] = filter(state[i], values[i]) for `count` independent scalars (test hook + standalone use)
+void launch_filter_apply(const FilterDev &f, float *values, long long count, cudaStream_t s);
+
 struct LandmarkParams {
     int kind;                  // zb_estimator_kind
     int num_landmarks;
@@ -136,7 +148,8 @@ struct LandmarkParams {
 // out0/out1/out2: raw network outputs (per-image strides s0,s1,s2)
 void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
                       const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
-                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s);
+                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s,
+                      const FilterDev *filter = nullptr);
 
 // ---- LandmarkTracker on the device (landmark.rs:361-502), one state record per stream ---------------------
 struct TrackState {            // LandmarkTracker::roi: Option<RotatedRect>

@@ -626,6 +626,55 @@ __global__ void __launch_bounds__(128) face_roi_kernel(const FramesDev f, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// zaru::filter, one scalar: st = (has, x|last, dx|v).  f32 operation order of the reference; this TU has FMA
+// contraction off, so results are bit-identical to the scalar Rust code.
+__device__ __forceinline__ float smoothing_factor(float t_e, float cutoff) {      // one_euro.rs:90-93
+    const float r = 2.0f * 3.14159265358979323846f * cutoff * t_e;
+    return r / (r + 1.0f);
+}
+__device__ __forceinline__ float filter_scalar(const FilterDev &f, float *st, float x) {
+    if (f.kind == FILTER_EMA) {                                                    // ema.rs:29-42
+        if (st[0] != 0.0f) {
+            const float avg = f.p0 * x + (1.0f - f.p0) * st[1];
+            st[1] = avg;
+            return avg;
+        }
+        st[0] = 1.0f, st[1] = x;
+        return x;
+    }
+    if (f.kind == FILTER_ONE_EURO) {                                               // one_euro.rs:63-87
+        if (st[0] == 0.0f) {
+            st[0] = 1.0f, st[1] = x, st[2] = 0.0f;
+            return x;
+        }
+        const float a_d = smoothing_factor(f.elapsed, f.p2);
+        const float dx = (x - st[1]) / f.elapsed;
+        const float dx_hat = a_d * dx + (1.0f - a_d) * st[2];
+        const float cutoff = f.p0 + f.p1 * fabsf(dx_hat);
+        const float a = smoothing_factor(f.elapsed, cutoff);
+        const float x_hat = a * x + (1.0f - a) * st[1];
+        st[1] = x_hat, st[2] = dx_hat;
+        return x_hat;
+    }
+    if (f.kind == FILTER_ALPHA_BETA) {                                             // alpha_beta.rs:31-49
+        if (st[0] == 0.0f) {
+            st[0] = 1.0f, st[1] = x;
+            return x;
+        }
+        const float prediction = st[1] + st[2] * f.elapsed;
+        const float residual = x - prediction;
+        st[1] = prediction + f.p0 * residual;
+        st[2] = st[2] + f.p1 * residual / f.elapsed;
+        return st[1];
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(256) filter_apply_kernel(const FilterDev f, float *__restrict__ values, long long count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) values[i] = filter_scalar(f, f.state + 3 * i, values[i]);
+}
+
 __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict__ out0, int s0,
                                                         const float *__restrict__ out1, int s1,
                                                         const float *__restrict__ out2, int s2,
@@ -633,7 +682,7 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
                                                         const ViewDev *__restrict__ views,
                                                         const ViewHost *__restrict__ view_rects, int n,
                                                         const LandmarkParams p, float *__restrict__ landmarks,
-                                                        float *__restrict__ scalars) {
+                                                        float *__restrict__ scalars, const FilterDev flt) {
     const int img = blockIdx.y;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     const int valid = views ? views[img].valid : 1;
@@ -656,6 +705,17 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
         src = out0 + (long long)img * s0 + 3 * l;
     }
     float x = src[0], y = src[1], z = src[2];
+    if (flt.state && flt.kind != FILTER_NONE && valid) {
+        // self.filter.filter(self.estimate.landmarks_mut()) in network coordinates (landmark.rs:330-333)
+        float *st = flt.state + ((long long)img * p.num_landmarks + l) * 9;
+        x = filter_scalar(flt, st, x);
+        y = filter_scalar(flt, st + 3, y);
+        z = filter_scalar(flt, st + 6, z);
+        // the estimate now holds the filtered positions: later readers of the raw tensor (the tracker's
+        // angle_radians on the eye corners) must see them too
+        float *w = const_cast<float *>(src);
+        w[0] = x, w[1] = y, w[2] = z;
+    }
     if (views && views[img].flip_x) {
         // EyeLandmarks::flip_horizontal_in_place (eye.rs:121-125) in network-input coordinates
         const float half = (float)p.net_w / 2.0f;
@@ -896,11 +956,17 @@ void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, 
 
 void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
                       const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
-                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s) {
+                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s, const FilterDev *filter) {
     g_launch_count++;
     dim3 grid((p.num_landmarks + 127) / 128, n);
+    FilterDev none{};
     landmarks_kernel<<<grid, 128, 0, s>>>(out0, s0, out1, s1, out2, s2, fit, views, view_rects, n, p, landmarks,
-                                          scalars);
+                                          scalars, filter ? *filter : none);
+}
+
+void launch_filter_apply(const FilterDev &f, float *values, long long count, cudaStream_t s) {
+    g_launch_count++;
+    filter_apply_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(f, values, count);
 }
 
 }  // namespace zb

@@ -136,6 +136,10 @@ class Estimator:
     def input_resolution(self):
         return self._cnn.input_resolution()
 
+    def set_filter(self, landmark_filter):
+        """`Estimator::set_filter` (landmark.rs:293-302); a `zaru_b200.filter.LandmarkFilter`.  Resets the state."""
+        _ffi.check(_ffi.lib().zb_estimator_set_filter(self._h, *landmark_filter.args()))
+
     def estimate(self, image):
         """`Estimator::estimate(&image)` (landmark.rs:310)."""
         view = image.as_view()
@@ -205,6 +209,10 @@ class LandmarkTracker:
 
     def set_roi_padding(self, padding):
         _ffi.check(_ffi.lib().zb_tracker_set_roi_padding(self._h, float(padding)))
+
+    def set_filter(self, landmark_filter):
+        """`tracker.estimator_mut().set_filter(..)`: one filter state set per stream, on the device."""
+        _ffi.check(_ffi.lib().zb_tracker_set_filter(self._h, *landmark_filter.args()))
 
     def set_roi(self, roi, stream: int = 0):
         """`set_roi(roi)`: roi = (cx, cy, w, h[, radians]) or an object with .as_zb_view(); used as-is."""
