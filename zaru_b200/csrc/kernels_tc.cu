@@ -439,13 +439,25 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
         const int oy0 = tile_y * TH, ox0 = tile_x * TW;
         const float *in_img = p.in + (long long)img * p.in_img_stride;
         float *dst = s_in0 + buf * IN_TILE;
-        for (int e = tid; e < IH * IW * CQ; e += NT) {
-            const int q = e % CQ, pix = e / CQ;
-            const int ty = pix / IW, tx = pix - ty * IW;
-            const int iy = oy0 - 1 + ty, ix = ox0 - 1 + tx;
-            const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-            cp_async16(dst + pix * PS + (SWZ ? (q ^ (pix & 7)) : q) * 4, ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img,
-                       ok ? 16 : 0);
+        // row by row with the per-thread (column, quad) arithmetic hoisted out of the row loop (the per-chunk
+        // divisions were a third of the kernel's instructions)
+        constexpr int ROW_CHUNKS = IW * CQ, CPT = (ROW_CHUNKS + NT - 1) / NT;
+#pragma unroll
+        for (int u = 0; u < CPT; u++) {
+            const int c = tid + u * NT;
+            if (c < ROW_CHUNKS) {
+                const int tx = c / CQ, q = c - tx * CQ;
+                const int ix = ox0 - 1 + tx;
+                const bool col_ok = ix >= 0 && ix < p.W;
+                const float *src = in_img + ((long long)(oy0 - 1) * p.W + ix) * CS + q * 4;
+#pragma unroll 2
+                for (int ty = 0; ty < IH; ty++) {
+                    const int iy = oy0 - 1 + ty, pix = ty * IW + tx;
+                    const bool ok = col_ok && iy >= 0 && iy < p.H;
+                    cp_async16(dst + pix * PS + (SWZ ? (q ^ (pix & 7)) : q) * 4, ok ? src : in_img, ok ? 16 : 0);
+                    src += (long long)p.W * CS;
+                }
+            }
         }
     };
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "conv_common.cuh"
 #include "kernels.h"
@@ -47,13 +48,26 @@ __global__ void __launch_bounds__(TW *TH) dwpw_thin_kernel(const ConvDev p, int 
 
     // --- stage input halo tile + weights with cp.async (LDGSTS): every copy of the CTA is in flight at once
     // instead of one dependent LDG->STS round trip per loop iteration; out-of-image pixels are zero-filled.
-    for (int e = tid; e < IH * IW * CQ; e += NT) {
-        const int q = e % CQ, pix = e / CQ;
-        const int ty = pix / IW, tx = pix - ty * IW;
-        const int iy = iy_org + ty, ix = ix_org + tx;
-        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        const float *src = ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img;
-        cp_async16(s_in + pix * PS + q * 4, src, ok ? 16 : 0);
+    // row by row, per-thread (column, quad) arithmetic hoisted out of the row loop
+    constexpr int ROW_CHUNKS = IW * CQ, CPT = (ROW_CHUNKS + NT - 1) / NT;
+#pragma unroll
+    for (int u = 0; u < CPT; u++) {
+        const int c = tid + u * NT;
+        if (c < ROW_CHUNKS) {
+            const int tx = c / CQ, q = c - tx * CQ;
+            const int ix = ix_org + tx;
+            const bool col_ok = ix >= 0 && ix < p.W;
+            float *dst = s_in + tx * PS + q * 4;
+            const float *src = in_img + ((long long)iy_org * p.W + ix) * CS + q * 4;
+#pragma unroll 2
+            for (int ty = 0; ty < IH; ty++) {
+                const int iy = iy_org + ty;
+                const bool ok = col_ok && iy >= 0 && iy < p.H;
+                cp_async16(dst, ok ? src : in_img, ok ? 16 : 0);
+                dst += IW * PS;
+                src += (long long)p.W * CS;
+            }
+        }
     }
     for (int e = tid; e < 9 * CS / 4; e += NT) cp_async16(s_dww + e * 4, p.dw_w + e * 4, 16);
     for (int e = tid; e < CS / 4; e += NT) cp_async16(s_dwb + e * 4, p.dw_b + e * 4, 16);
@@ -188,14 +202,29 @@ __global__ void __launch_bounds__(32 * WARPS) dwpw_strip_kernel(const ConvDev p,
     const int iy_org = oy0 * S - p.pt, ix_org = ox0 * S - p.pl;
     const float *in_img = p.in + (long long)img * p.in_img_stride;
 
-    for (int e = tid; e < IH * IW * CQ; e += NT) {
-        const int q = e % CQ, pix = e / CQ;
-        const int ty = pix / IW, tx = pix - ty * IW;
-        const int iy = iy_org + ty, ix = ix_org + tx;
-        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        const float *src = ok ? in_img + ((long long)iy * p.W + ix) * CS + q * 4 : in_img;
-        const int slot = S == 1 ? (ty * PW + tx) : ((ty * 2 + (tx & 1)) * PW + (tx >> 1));
-        cp_async16(s_in + slot * PS + q * 4, src, ok ? 16 : 0);
+    // Halo fill, row by row: a thread's (column, channel quad) pairs are fixed, so the index arithmetic (the
+    // divisions cost a quarter of the kernel's instructions when done per 16-byte chunk) is hoisted out of the row loop.
+    constexpr int ROW_CHUNKS = IW * CQ;                // 16-byte chunks per staged input row
+    constexpr int CPT = (ROW_CHUNKS + NT - 1) / NT;    // chunks per thread per row
+#pragma unroll
+    for (int u = 0; u < CPT; u++) {
+        const int c = tid + u * NT;
+        if (c < ROW_CHUNKS) {
+            const int tx = c / CQ, q = c - tx * CQ;
+            const int ix = ix_org + tx;
+            const bool col_ok = ix >= 0 && ix < p.W;
+            const int slot = S == 1 ? tx : ((tx & 1) * PW + (tx >> 1));
+            float *dst = s_in + slot * PS + q * 4;
+            const float *src = in_img + ((long long)iy_org * p.W + ix) * CS + q * 4;
+#pragma unroll 2
+            for (int ty = 0; ty < IH; ty++) {
+                const int iy = iy_org + ty;
+                const bool ok = col_ok && iy >= 0 && iy < p.H;
+                cp_async16(dst, ok ? src : in_img, ok ? 16 : 0);
+                dst += PLANES * PW * PS;
+                src += (long long)p.W * CS;
+            }
+        }
     }
     for (int e = tid; e < 9 * CQ; e += NT) cp_async16(s_dww + e * 4, p.dw_w + e * 4, 16);
     for (int e = tid; e < CQ; e += NT) cp_async16(s_dwb + e * 4, p.dw_b + e * 4, 16);
@@ -232,6 +261,7 @@ __global__ void __launch_bounds__(32 * WARPS) dwpw_strip_kernel(const ConvDev p,
         for (int i = 0; i < PXV; i++) acc[i][j / 2] = make_float2(bv.x, bv.y), acc[i][j / 2 + 1] = make_float2(bv.z, bv.w);
     }
 
+    const bool has_mid = p.act_mid.kind != ACT_NONE;
 #pragma unroll 1
     for (int q = 0; q < CQ; q++) {
         float4 w9[9];
@@ -256,8 +286,10 @@ __global__ void __launch_bounds__(32 * WARPS) dwpw_strip_kernel(const ConvDev p,
                 }
             }
         }
+        if (has_mid) {
 #pragma unroll
-        for (int i = 0; i < PXV; i++) act4(v[i], p.act_mid, q * 4);
+            for (int i = 0; i < PXV; i++) act4(v[i], p.act_mid, q * 4);
+        }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
             const float *wrow = s_pw + (q * 4 + kk) * NP;
@@ -275,48 +307,62 @@ __global__ void __launch_bounds__(32 * WARPS) dwpw_strip_kernel(const ConvDev p,
 
     const EpiDev &e = p.epi;
     const bool res_smem = e.res == p.in;
+    // MODE 0: generic epilogue.  MODE 1 / 2: the Blaze block (no act1, residual = this block's input taken from the
+    // staged tile, then ReLU / PReLU, every channel group stored) with all the uniform branches resolved at compile
+    // time - they were ~18 % of the kernel's instructions.
+    auto epilogue = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-    for (int i = 0; i < PXV; i++) {
-        const int oy = oy0 + ty0 + i;
-        if (oy >= p.Ho) break;
-        float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+        for (int i = 0; i < PXV; i++) {
+            const int oy = oy0 + ty0 + i;
+            if (oy >= p.Ho) break;
+            float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
 #pragma unroll
-        for (int j = 0; j < NP; j += 4) {
-            if (j >= p.Nstore) break;
-            float v4[4] = {acc[i][j / 2].x, acc[i][j / 2].y, acc[i][j / 2 + 1].x, acc[i][j / 2 + 1].y};
-            act4(v4, e.act1, j);
-            if (e.res) {
-                float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (res_smem) {
-                    if (j < CS) {
-                        if (!e.res_pool) {
-                            rr = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl) + j);
-                        } else {
-                            const float4 a0 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl) + j);
-                            const float4 a1 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl + 1) + j);
-                            const float4 a2 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt + 1, p.pl) + j);
-                            const float4 a3 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt + 1, p.pl + 1) + j);
-                            rr = make_float4(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)), fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)),
-                                             fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z)), fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w)));
+            for (int j = 0; j < NP; j += 4) {
+                if (MODE == 0 && j >= p.Nstore) break;
+                float v4[4] = {acc[i][j / 2].x, acc[i][j / 2].y, acc[i][j / 2 + 1].x, acc[i][j / 2 + 1].y};
+                if (MODE == 0) act4(v4, e.act1, j);
+                if (MODE != 0 || e.res) {
+                    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE != 0 || res_smem) {
+                        if (j < CS) {
+                            if (!e.res_pool) {
+                                rr = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl) + j);
+                            } else {
+                                const float4 a0 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl) + j);
+                                const float4 a1 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt, p.pl + 1) + j);
+                                const float4 a2 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt + 1, p.pl) + j);
+                                const float4 a3 = *reinterpret_cast<const float4 *>(tap(i * S + p.pt + 1, p.pl + 1) + j);
+                                rr = make_float4(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)), fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)),
+                                                 fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z)), fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w)));
+                            }
                         }
+                    } else {
+                        rr = residual4_at(e, img, oy, ox, j);
                     }
-                } else {
-                    rr = residual4_at(e, img, oy, ox, j);
+                    v4[0] += rr.x, v4[1] += rr.y, v4[2] += rr.z, v4[3] += rr.w;
                 }
-                v4[0] += rr.x, v4[1] += rr.y, v4[2] += rr.z, v4[3] += rr.w;
+                if (MODE == 2 || (MODE == 0 && e.act2.kind == ACT_PRELU)) {
+                    const float4 sl = *reinterpret_cast<const float4 *>(s_sl + j);
+                    v4[0] = v4[0] < 0.f ? v4[0] * sl.x : v4[0];
+                    v4[1] = v4[1] < 0.f ? v4[1] * sl.y : v4[1];
+                    v4[2] = v4[2] < 0.f ? v4[2] * sl.z : v4[2];
+                    v4[3] = v4[3] < 0.f ? v4[3] * sl.w : v4[3];
+                } else if (MODE == 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) v4[c] = fmaxf(v4[c], 0.0f);
+                } else {
+                    act4(v4, e.act2, j);
+                }
+                *reinterpret_cast<float4 *>(orow + j) = make_float4(v4[0], v4[1], v4[2], v4[3]);
             }
-            if (e.act2.kind == ACT_PRELU) {
-                const float4 sl = *reinterpret_cast<const float4 *>(s_sl + j);
-                v4[0] = v4[0] < 0.f ? v4[0] * sl.x : v4[0];
-                v4[1] = v4[1] < 0.f ? v4[1] * sl.y : v4[1];
-                v4[2] = v4[2] < 0.f ? v4[2] * sl.z : v4[2];
-                v4[3] = v4[3] < 0.f ? v4[3] * sl.w : v4[3];
-            } else {
-                act4(v4, e.act2, j);
-            }
-            *reinterpret_cast<float4 *>(orow + j) = make_float4(v4[0], v4[1], v4[2], v4[3]);
         }
-    }
+    };
+    const bool blaze = e.act1.kind == ACT_NONE && e.res && res_smem && p.Nstore >= NP &&
+                       (e.act2.kind == ACT_RELU || e.act2.kind == ACT_PRELU);
+    if (!blaze) epilogue(std::integral_constant<int, 0>{});
+    else if (e.act2.kind == ACT_RELU) epilogue(std::integral_constant<int, 1>{});
+    else epilogue(std::integral_constant<int, 2>{});
 }
 
 template <int CS, int S, int NP, int PXV, int TW, int WARPS>
