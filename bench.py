@@ -29,8 +29,14 @@ ALG_MFLOP_PER_FRAME = 131.48
 # `ncu --set full` captures (profiles/README.md); keyed by profile class, value = (bytes, algorithmic bytes of
 # that same launch) so the ratio can be applied to the live per-launch algorithmic bytes.
 NCU_TRAFFIC = {
-    # dwpw_thin_kernel<16,1,16> on the 1024 x 96x96x16 block: 604.46 MB read + 555.97 MB written
-    "dwpw_thin": (604.462592e6 + 555.972096e6, 2 * 1024 * 96 * 96 * 16 * 4.0),
+    # dwpw_strip_kernel<24,1,24,2,32,4> on the 1024 x 64x64x24 block: 402.73 MB read + 351.54 MB written
+    "dwpw_thin": (402.734592e6 + 351.541760e6, 2 * 1024 * 64 * 64 * 24 * 4.0),
+    # dwpw_tc_kernel<3,1> on the 1024 x 24x24x64 block (part of the input is still L2-resident from the previous layer)
+    "dwpw_tc<tcgen05>": (153.274624e6 + 107.766528e6, 2 * 1024 * 24 * 24 * 64 * 4.0),
+    # dwpw_ttc_kernel<32,8,1,16> on the 1024 x 48x48x32 block
+    "dwpw_ttc<tcgen05>": (302.045184e6 + 253.759488e6, 2 * 1024 * 48 * 48 * 32 * 4.0),
+    # stem_kernel<5,24,2>: 128x128 sampled texels (32 B sectors of 1080p frames) + the 64x64x24 stem output
+    "stem(+sample)": (566.482688e6 + 358.369792e6, 1024 * (128 * 128 * 4.0 + 64 * 64 * 24 * 4.0)),
 }
 METRIC = "frames/sec face detect+landmark (1080p)"
 UNIT = "frames/s"

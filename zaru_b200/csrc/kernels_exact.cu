@@ -268,11 +268,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
     if (ox >= p.Wo) return;
     const int act = p.epi.act1.kind;
     for (int n0 = 0; n0 < p.Nstore; n0 += NP) {
-        float acc[PPT][NP];
+        // accumulators as float2 pairs: packed FFMA2 (two fused multiply-adds per issued instruction, each lane
+        // rounds exactly like fmaf) halves the FMA issue slots of this FMA-bound kernel
+        float2 acc[PPT][NP / 2];
 #pragma unroll
         for (int i = 0; i < PPT; i++)
 #pragma unroll
-            for (int j = 0; j < NP; j++) acc[i][j] = s_b[n0 + j];
+            for (int j = 0; j < NP; j += 2) acc[i][j / 2] = make_float2(s_b[n0 + j], s_b[n0 + j + 1]);
 #pragma unroll
         for (int t = 0; t < KS * KS; t++) {
             float xs[PPT][3];
@@ -288,10 +290,9 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
                     const float4 wv = *reinterpret_cast<const float4 *>(s_w + (t * 4 + ci) * NSP + n0 + j);
 #pragma unroll
                     for (int i = 0; i < PPT; i++) {       // each weight quad feeds PPT pixels
-                        acc[i][j] = fmaf(xs[i][ci], wv.x, acc[i][j]);
-                        acc[i][j + 1] = fmaf(xs[i][ci], wv.y, acc[i][j + 1]);
-                        acc[i][j + 2] = fmaf(xs[i][ci], wv.z, acc[i][j + 2]);
-                        acc[i][j + 3] = fmaf(xs[i][ci], wv.w, acc[i][j + 3]);
+                        const float2 aa = make_float2(xs[i][ci], xs[i][ci]);
+                        acc[i][j / 2] = __ffma2_rn(aa, make_float2(wv.x, wv.y), acc[i][j / 2]);
+                        acc[i][j / 2 + 1] = __ffma2_rn(aa, make_float2(wv.z, wv.w), acc[i][j / 2 + 1]);
                     }
                 }
             }
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const FramesDev f, const View
             for (int j = 0; j < NP; j += 4) {
                 const int n = n0 + j;
                 if (n >= p.Nstore) break;
-                float v[4] = {acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]};
+                float v[4] = {acc[i][j / 2].x, acc[i][j / 2].y, acc[i][j / 2 + 1].x, acc[i][j / 2 + 1].y};
                 if (act == ACT_RELU) {
 #pragma unroll
                     for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], 0.0f);
