@@ -209,8 +209,10 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
  *   lost if confidence < loss threshold (RoI cleared) -> landmarks mapped to frame coordinates ->
  *   updated_roi = RotatedRect::bounding(roi.rad + estimate.angle_radians(), landmarks) ->
  *   roi = updated_roi.grow_rel(roi_padding).
- * Only face-mesh estimators (ZB_EST_FACE_MESH_V1 / _V2) implement Confidence + angle_radians in the
- * reference and are accepted here.  Streams without an RoI report tracked = 0 (track() -> None).   */
+ * Accepted estimators are those whose estimate implements Confidence + angle_radians in the reference:
+ * ZB_EST_FACE_MESH_V1 / _V2 (mediapipe.rs:146-160, :259-272) and ZB_EST_HAND (hand/landmark.rs:68-78,
+ * :137-153: confidence = presence, angle from wrist / middle-finger MCP), as HandTracker uses it
+ * (hand/tracking.rs:157-163).  Streams without an RoI report tracked = 0 (track() -> None).   */
 typedef struct zb_tracker zb_tracker;
 zb_status zb_tracker_create(zb_ctx *ctx, zb_net *landmark_net, zb_estimator_kind kind, float map_lo, float map_hi,
                             int32_t streams, zb_tracker **out);

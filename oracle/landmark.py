@@ -150,6 +150,14 @@ class HandLandmarks(Estimate):
     def confidence(self):
         return self.presence
 
+    def rotation_radians(self):
+        """hand/landmark.rs:68-78: (wrist - middle_finger_mcp).signed_angle_to(Y); Wrist = 0, MiddleFingerMcp = 9."""
+        finger, wrist = self.positions[9], self.positions[0]
+        return signed_angle_to(wrist[0] - finger[0], wrist[1] - finger[1], 0.0, 1.0)
+
+    def angle_radians(self):
+        return self.rotation_radians()
+
 
 class HandLiteNetwork(LandmarkNetwork):
     """hand/landmark.rs:248-322."""

@@ -126,3 +126,40 @@ def test_tracker_loss_seed_and_batch_semantics(zb):
     for i in held:
         if r3[i] is not None:   # same frame again: the RoI converges instead of drifting
             assert np.abs(np.asarray(r3[i].updated_roi()[:2]) - np.asarray(r2[i].updated_roi()[:2])).max() <= 0.1 * r2[i].updated_roi()[2]
+
+
+def test_hand_tracker_step_matches_oracle(zb, sad_linus_full):
+    """`LandmarkTracker<hand::landmark::LandmarkResult>` as `HandTracker` builds it (hand/tracking.rs:157-163:
+    RoI = RotatedRect(palm.bounding_rect().grow_rel(1.5), palm.angle()), padding 0.4).  The reference ships no hand
+    fixture, so the step arithmetic (rotated view, presence gate, wrist / middle-MCP angle, bounding, grow_rel) is
+    compared on the face fixture with the gate opened; what the hand network sees there is irrelevant to parity."""
+    from oracle.landmark import Estimator as OEst, HandLiteNetwork as OHand, LandmarkTracker as OTracker
+    from zaru_b200.image import Image
+    from zaru_b200.landmark import HandLiteNetwork, LandmarkTracker
+    otr = OTracker(OEst(OHand()))
+    otr.loss_thresh = np.float32(-1e9)
+    otr.set_roi_padding(0.4)
+    trk = LandmarkTracker(HandLiteNetwork(), streams=1)
+    trk.set_loss_threshold(-1e9)
+    trk.set_roi_padding(0.4)
+    img = Image(sad_linus_full)
+    batch, _ = img.device()
+    from oracle.geometry import Rect as ORect, RotatedRect as ORR
+    otr.set_roi(ORR(ORect.from_center(700.0, 400.0, 420.0, 420.0), np.float32(0.3)))
+    for t in range(3):
+        roi = otr.roi
+        trk.set_roi((roi.rect.cx, roi.rect.cy, roi.rect.w, roi.rect.h, roi.radians))
+        want = otr.track(_oimg(sad_linus_full))
+        got = trk.track(batch)[0]
+        assert want is not None and got is not None
+        view_rect, est, updated = want
+        scale = float(view_rect.rect.w) / 224.0
+        lim = TOL * 224 * scale
+        assert abs(float(got.estimate().presence()) - float(est.presence)) <= 2e-3
+        assert np.abs(got.estimate().landmarks().positions() - est.positions).max() <= lim, t
+        up = got.updated_roi()
+        span = float(np.hypot(*(est.positions[0, :2] - est.positions[9, :2])))
+        assert abs(up[4] - float(updated.radians)) <= 1e-3 + 2 * lim / max(span, 1.0)
+        assert np.abs(np.asarray(up[:4]) - np.asarray(updated.rect.as_tuple(), np.float32)).max() <= 4 * lim + 1e-3 * float(updated.rect.w)
+        st = trk.rois()[0]
+        assert abs(st[2] - up[2] * 1.8) <= 1e-3 * up[2]      # grow_rel(0.4): w + 0.4 w + 0.4 w

@@ -1243,8 +1243,8 @@ zb_status zb_tracker_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, fl
         if (!ctx || !net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
         if (streams <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "streams must be positive");
         if (!(hi > lo)) return fail(ZB_ERR_INVALID_ARGUMENT, "ColorMapper range must satisfy end > start");
-        if (kind != ZB_EST_FACE_MESH_V1 && kind != ZB_EST_FACE_MESH_V2)
-            return fail(ZB_ERR_INVALID_ARGUMENT, "LandmarkTracker needs an estimate with Confidence + angle_radians (face mesh)");
+        if (kind != ZB_EST_FACE_MESH_V1 && kind != ZB_EST_FACE_MESH_V2 && kind != ZB_EST_HAND)
+            return fail(ZB_ERR_INVALID_ARGUMENT, "LandmarkTracker needs an estimate with Confidence + angle_radians (face mesh, hand)");
         try {
             check_estimator_net(net, kind);
         } catch (const std::runtime_error &e) {
@@ -1370,9 +1370,12 @@ zb_status zb_tracker_track(zb_tracker *t, const zb_frames *frames, int32_t n, fl
                              filter_for(t->filter, t->d_filter, t->filter_slots, n, L, s));
         });
         prof_launch(ctx, s, "tracker_update", 12.0 * L * n, 0, [&] {
-            // LandmarkIdx::LeftEyeOuterCorner = 33, RightEyeOuterCorner = 263 (mediapipe.rs:535, :540; V1 and V2)
+            // face: LandmarkIdx::LeftEyeOuterCorner = 33 -> RightEyeOuterCorner = 263 against X (mediapipe.rs:146-160,
+            // :535, :540; V1 and V2); hand: MiddleFingerMcp = 9 -> Wrist = 0 against Y (hand/landmark.rs:68-78)
+            const bool hand = t->kind == ZB_EST_HAND;
             launch_tracker_update(t->d_state.as<TrackState>(), t->ws.outs[0].as<float>(), s0, t->d_fit.as<float>(),
-                                  t->d_lm.as<float>(), t->d_scalars.as<float>(), n, L, t->loss_thresh, t->roi_padding, 33, 263,
+                                  t->d_lm.as<float>(), t->d_scalars.as<float>(), n, L, t->loss_thresh, t->roi_padding,
+                                  hand ? 9 : 33, hand ? 0 : 263, hand ? 0.0f : 1.0f, hand ? 1.0f : 0.0f,
                                   t->d_updated.as<ViewHost>(), t->d_tracked.as<unsigned char>(), s);
         });
         CU(cudaGetLastError());

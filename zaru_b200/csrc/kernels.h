@@ -165,8 +165,8 @@ void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int fir
 // landmarks: positions already mapped to image coordinates; scalars[2*i] = confidence.
 void launch_tracker_update(TrackState *state, const float *out0, int s0, const float *fit, const float *landmarks,
                            const float *scalars, int n, int num_landmarks, float loss_thresh, float roi_padding,
-                           int left_eye_idx, int right_eye_idx, ViewHost *out_updated, unsigned char *out_tracked,
-                           cudaStream_t s);
+                           int idx_from, int idx_to, float axis_x, float axis_y, ViewHost *out_updated,
+                           unsigned char *out_tracked, cudaStream_t s);   // angle_radians = (P[to] - P[from]).signed_angle_to(axis)
 // roi[ids[k]] = rois[k] (radians kept), or None when rois == nullptr
 void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s);
 

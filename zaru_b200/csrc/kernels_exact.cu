@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(128) tracker_update_kernel(TrackState *__restr
                                                              const float *__restrict__ landmarks,
                                                              const float *__restrict__ scalars, int num_landmarks,
                                                              float loss_thresh, float roi_padding, int le_idx, int re_idx,
+                                                             float axis_x, float axis_y,
                                                              ViewHost *__restrict__ out_updated,
                                                              unsigned char *__restrict__ out_tracked) {
     const int i = blockIdx.x, tid = threadIdx.x;
@@ -822,12 +823,14 @@ __global__ void __launch_bounds__(128) tracker_update_kernel(TrackState *__restr
         }
         return;
     }
-    // estimate.angle_radians(): eye outer corners in VIEW coordinates (positions are mapped to the image afterwards)
+    // estimate.angle_radians() in VIEW coordinates (positions are mapped to the image afterwards):
+    //   face mesh: (right_eye_outer - left_eye_outer).signed_angle_to(X)        (mediapipe.rs:146-160)
+    //   hand:      (wrist - middle_finger_mcp).signed_angle_to(Y)              (hand/landmark.rs:68-78)
     const float scale = fit[i * 4 + 0], tlx = fit[i * 4 + 1], tly = fit[i * 4 + 2];
     const float *o = out0 + (long long)i * s0;
     const float lx = o[3 * le_idx] * scale + tlx, ly = o[3 * le_idx + 1] * scale + tly;
     const float rx = o[3 * re_idx] * scale + tlx, ry = o[3 * re_idx + 1] * scale + tly;
-    const float angle = st.rad + signed_angle_to(rx - lx, ry - ly, 1.0f, 0.0f);
+    const float angle = st.rad + signed_angle_to(rx - lx, ry - ly, axis_x, axis_y);
     // RotatedRect::bounding(angle, points)  (rect.rs:287-325): cw = rotation_clockwise(angle) = ccw(-angle)
     float c, s;
     cos_sin_ref(-angle, c, s);
@@ -888,11 +891,11 @@ void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int fir
 
 void launch_tracker_update(TrackState *state, const float *out0, int s0, const float *fit, const float *landmarks,
                            const float *scalars, int n, int num_landmarks, float loss_thresh, float roi_padding,
-                           int left_eye_idx, int right_eye_idx, ViewHost *out_updated, unsigned char *out_tracked,
-                           cudaStream_t s) {
+                           int idx_from, int idx_to, float axis_x, float axis_y, ViewHost *out_updated,
+                           unsigned char *out_tracked, cudaStream_t s) {
     g_launch_count++;
     tracker_update_kernel<<<n, 128, 0, s>>>(state, out0, s0, fit, landmarks, scalars, num_landmarks, loss_thresh,
-                                            roi_padding, left_eye_idx, right_eye_idx, out_updated, out_tracked);
+                                            roi_padding, idx_from, idx_to, axis_x, axis_y, out_updated, out_tracked);
 }
 
 void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s) {
