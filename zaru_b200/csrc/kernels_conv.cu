@@ -161,6 +161,22 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
     // --- epilogue ------------------------------------------------------------------------------------
     const EpiDev &e = p.epi;
     const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0);
+    // residual of the whole micro-tile first: TM * TN / 4 independent 128-bit loads in flight instead of one
+    // dependent load in front of every `v += residual` (the same stall ncu showed in the tcgen05 kernel's epilogue)
+    const bool res_vec = e.res && (e.res_Cs % 4) == 0;
+    float4 rpre[TM][TN / 4];
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        const int m = m0 + ty * TM + i;
+        const int img = m / HoWo;
+        const int r = m - img * HoWo;
+        const int oy = r / p.Wo, ox = r - oy * p.Wo;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const int n = n0 + tx * TN + j;
+            rpre[i][j / 4] = (res_vec && m < p.M && n < p.Nstore) ? residual4_at(e, img, oy, ox, n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < TM; i++) {
         const int m = m0 + ty * TM + i;
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_gemm_kernel(const 
             act4(v, e.act1, n);
             if (e.res) {
                 if ((e.res_Cs % 4) == 0) {
-                    const float4 rr = residual4_at(e, img, oy, ox, n);
+                    const float4 rr = rpre[i][j / 4];
                     v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
                 } else {
 #pragma unroll
