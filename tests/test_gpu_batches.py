@@ -137,3 +137,34 @@ def test_config1_single_frame_detector(sad_linus_full):
     odet.detect(OImage(sad_linus_full))
     assert np.abs(scores - odet.last_raw[1]).max() < 2e-3
     assert np.abs(boxes - odet.last_raw[0]).max() < TOL * 128
+
+
+def test_config4_batch_1024_matches_small_batches():
+    """BASELINE config 4 at its full size: the bench batch (1024 frames = 32 distinct, tiled) selects other kernels than
+    small batches do (tcgen05 blocks need >= 600 CTAs), so every frame of the big batch must reproduce what the same
+    frame gives in a batch of 32 - and the very FIRST pass must already be right (a launch that needed the
+    shared-memory opt-in once failed on the first pass only)."""
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in range(32)])
+    big = np.concatenate([uniq] * 32)
+    pipe = FacePipeline()
+    res_big = pipe.run(ImageBatch.from_rgba8(Resolution(1920, 1080), big))          # first pass of this process at 1024
+    res_small = FacePipeline().run(ImageBatch.from_rgba8(Resolution(1920, 1080), uniq))
+    faces = 0
+    for i in range(1024):
+        j = i % 32
+        a, b = res_big.detections[i], res_small.detections[j]
+        assert len(a) == len(b), (i, len(a), len(b))
+        for x, y in zip(a, b):
+            assert x.anchor == y.anchor
+            assert np.abs(x.as_vector() - y.as_vector()).max() <= 0.05, i          # frame pixels (1e-3 normalised = 1.9 px)
+        if len(a):
+            faces += 1
+            assert abs(res_big.face_flags[i] - res_small.face_flags[j]) <= 1e-3
+            assert np.abs(res_big.landmarks[i] - res_small.landmarks[j]).max() <= 0.05, i
+        else:
+            assert res_big.face_flags[i] == -1.0
+    assert faces >= 512

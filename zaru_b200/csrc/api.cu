@@ -149,6 +149,13 @@ template <class F>
 void prof_launch(zb_ctx *ctx, cudaStream_t s, const char *cls, double bytes, double flops, F &&f) {
     if (!ctx->prof_on) {
         f();
+        // ZB_DEBUG_LAUNCH=1: attribute a failing launch to its layer instead of the end-of-stage check
+        static const bool debug = getenv("ZB_DEBUG_LAUNCH") && atoi(getenv("ZB_DEBUG_LAUNCH")) != 0;
+        if (debug) {
+            cudaError_t err = cudaGetLastError();
+            if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+            if (err != cudaSuccess) throw std::runtime_error(std::string("launch '") + cls + "' failed: " + cudaGetErrorString(err));
+        }
         return;
     }
     cudaEvent_t a = ctx->prof_event(), b = ctx->prof_event();
@@ -332,8 +339,10 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     p.act_mid = act_dev(op.act_mid, W);
                     // kernel choice for fused blocks: tcgen05 (3xTF32) for the wide ones, SIMT thin/tile otherwise
                     // (measured: the tcgen05 kernel has the higher per-CTA latency, so it needs >= ~2 waves of CTAs)
+                    // (stride-2 blocks the SIMT thin kernel covers stay there: 0.175 vs 0.218 ms on 32x32x42 -> 16x16x48)
                     const bool use_tc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_tc_supported(p, op.NP) &&
-                                        p.K >= ctx->tc_min_k && p.M >= ctx->tc_min_ctas * 128;
+                                        p.K >= ctx->tc_min_k && p.M >= ctx->tc_min_ctas * 128 &&
+                                        !(p.sh == 2 && dwpw_thin_supported(p));
                     const bool use_ttc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_ttc_supported(p, op.NP);
                     if (use_ttc) {
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_ttc<tcgen05>", bytes, flops,

@@ -331,7 +331,7 @@ bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float h
     const size_t smem = sizeof(float) * ((size_t)IH * IW * 4 + (size_t)KS * KS * 4 * NSP + 2 * NSP + IW + IH);
     auto kern = stem_kernel<KS, NP, PPT>;
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
             return false;
@@ -943,7 +943,7 @@ void launch_decode_nms(const float *boxes, const float *scores, const float *fit
     g_launch_count++;
     const size_t smem = (size_t)p.num_anchors * (sizeof(float4) + sizeof(float) + 4 * sizeof(int));
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
         cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }

@@ -372,7 +372,7 @@ bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
     const size_t smem = sizeof(float) * ((size_t)IH * S * PW * (CS + 4) + 10 * CS + (size_t)CS * NP + 2 * NP);
     auto kern = dwpw_strip_kernel<CS, S, NP, PXV, TW, WARPS>;
     static bool configured = false;
-    if (smem > 48 * 1024 && !configured) {
+    if (smem > 40 * 1024 && !configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
             return false;
@@ -418,7 +418,7 @@ bool launch_thin_cfg(const ConvDev &p, cudaStream_t s) {
     if (smem > 200 * 1024) return false;
     auto kern = dwpw_thin_kernel<CS, S, NP, TW, TH>;
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
             return false;
