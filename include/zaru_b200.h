@@ -132,6 +132,16 @@ zb_status zb_frames_alias(zb_ctx *ctx, const uint8_t *rgba_device, int32_t width
 zb_status zb_frames_update(zb_frames *frames, const uint8_t *rgba_host, int32_t first, int32_t count);
 void zb_frames_destroy(zb_frames *frames);
 
+/* `ImageView::to_image` (image/mod.rs:314-325) for n views of one size: out_rgba = RGBA8 [n][out_h][out_w][4] with
+ * out_w = ceil(view width), out_h = ceil(view height) (the caller rounds, like the reference); view pixel (x, y) is
+ * `ImageView::get(x, y)`: nearest texel through the rotated view, Color::NONE (0,0,0,0) outside the image.
+ * Bit-exact.  out_rgba: host_or_device.                                                            */
+zb_status zb_view_to_image(zb_ctx *ctx, const zb_frames *frames, const zb_view *views, int32_t n, int32_t out_w,
+                           int32_t out_h, uint8_t *out_rgba);
+/* `Image::clear(color)` (image/mod.rs:171-173) for frames [first, first + count) of an UPLOADED batch (aliased
+ * memory belongs to the caller and is rejected).  rgba = {r, g, b, a}.                              */
+zb_status zb_frames_clear(zb_frames *frames, int32_t first, int32_t count, const uint8_t rgba[4]);
+
 /* ---- Cnn image->tensor (crates/zaru/src/nn/mod.rs:46-126, :146-167) ------------------------ */
 /* The `image_map` closure + `sample` + `ColorMapper::linear(lo..=hi)` for n views:
  * out = f32 [n,3,out_h,out_w] (ZB_NCHW) or [n,out_h,out_w,3] (ZB_NHWC); host_or_device.

@@ -147,6 +147,15 @@ class ImageView {
         const float w = rect.rect().width(), h = rect.rect().height();
         return ImageView(image_, RotatedRect(Rect::from_top_left(cx - w * 0.5f, cy - h * 0.5f, w, h), radians));
     }
+    // `to_image` (image/mod.rs:314-325): the view's pixels as RGBA8 [ceil(h)][ceil(w)][4], sampled on the device
+    std::vector<uint8_t> to_rgba8(Resolution *out_res = nullptr) const {
+        const Resolution r{(uint32_t)std::ceil(rect().width()), (uint32_t)std::ceil(rect().height())};
+        std::vector<uint8_t> px((size_t)r.w * r.h * 4);
+        zb_view v = to_zb_view();
+        check(zb_view_to_image(context(), image_.batch()->handle(), &v, 1, (int32_t)r.w, (int32_t)r.h, px.data()));
+        if (out_res) *out_res = r;
+        return px;
+    }
     const RotatedRect &view_rect() const { return data_; }                           // ViewData::rect, root-image coordinates
     const Image &image() const { return image_; }
     zb_view to_zb_view() const { return data_.to_zb_view(image_.frame()); }

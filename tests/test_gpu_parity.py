@@ -427,3 +427,33 @@ def test_fused_sampling_is_bit_identical_to_sample_then_forward(zb, sad_linus_fu
         fit = v.view(v.rect().grow_to_fit_aspect(AspectRatio.SQUARE))
         boxes, scores = cnn.nn.estimate(cnn.tensor(fit))
         assert np.array_equal(raw_b, boxes) and np.array_equal(raw_s, scores)
+
+
+# ------------------------------------------------------------------------------------------------
+# ImageView::to_image and Image::clear on the device
+# ------------------------------------------------------------------------------------------------
+def test_view_to_image_bit_exact_and_clear(zb, sad_linus_full):
+    """`ImageView::to_image` (image/mod.rs:314-325) is the sampler without the resampling step: bit-exact against the
+    oracle for plain, oversized, fractional-size and rotated views (the reference's own pixel-level view tests,
+    image/tests.rs:71-139, pin the oracle)."""
+    from oracle.geometry import Rect as ORect, RotatedRect as ORR
+    from zaru_b200.image import Image, ImageBatch
+    from zaru_b200.rect import Rect, RotatedRect, Resolution
+    img, oimg = Image(sad_linus_full), _oimg(sad_linus_full)
+    for (cx, cy, w, h, rad) in [(640, 360, 1280, 720, 0.0), (300, 200, 101.5, 57.25, 0.0), (-20, 700, 200, 150, 0.0),
+                                (700, 400, 333, 222, 0.4), (640, 360, 900, 900, -1.2), (100.25, 99.75, 64, 64, 3.0)]:
+        got = img.view(RotatedRect(Rect.from_center(cx, cy, w, h), rad)).to_image()
+        want = oimg.view(ORR(ORect.from_center(cx, cy, w, h), rad)).to_image()
+        assert got.width() == want.width() and got.height() == want.height()
+        assert np.array_equal(got._pixels, want.buf), (cx, cy, w, h, rad)
+    # a view of a view composes like the reference (ViewData::view)
+    got = img.view(RotatedRect(Rect.from_center(700, 400, 500, 400), 0.3)).view(Rect.from_center(250, 200, 120, 80)).to_image()
+    want = oimg.view(ORR(ORect.from_center(700, 400, 500, 400), 0.3)).view(ORect.from_center(250, 200, 120, 80)).to_image()
+    assert np.array_equal(got._pixels, want.buf)
+    # Image::clear
+    frames = np.stack([sad_linus_full, sad_linus_full])
+    batch = ImageBatch.from_rgba8(Resolution(1280, 720), frames)
+    batch.clear((10, 20, 30, 255), first=1, count=1)
+    a = batch.frame(0).as_view().to_image()._pixels
+    b = batch.frame(1).as_view().to_image()._pixels
+    assert np.array_equal(a, sad_linus_full) and (b == np.array([10, 20, 30, 255], np.uint8)).all()

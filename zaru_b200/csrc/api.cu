@@ -848,6 +848,53 @@ void zb_frames_destroy(zb_frames *fr) {
 }
 
 // ---- preprocess --------------------------------------------------------------------------------------
+zb_status zb_view_to_image(zb_ctx *ctx, const zb_frames *frames, const zb_view *views, int32_t n, int32_t out_w, int32_t out_h,
+                           uint8_t *out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/out is NULL");
+        if (out_w <= 0 || out_h <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "output size must be positive");
+        check_frames(frames, views, n);
+        if (n == 0) return ZB_OK;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        std::vector<ViewDev> hv(n);
+        for (int i = 0; i < n; i++)
+            hv[i] = view_dev(views ? rrect_from_view(views[i]) : full_view(frames->f.width, frames->f.height), views ? views[i].frame : i, 0);
+        DevBuf dv, dout;
+        dv.reserve(sizeof(ViewDev) * n);
+        CU(cudaMemcpyAsync(dv.p, hv.data(), sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+        const size_t bytes = (size_t)n * out_w * out_h * 4;
+        uint8_t *d_out = out;
+        const bool dev = is_device_ptr(out);
+        if (!dev) {
+            dout.reserve(bytes);
+            d_out = dout.as<uint8_t>();
+        }
+        launch_view_to_image(frames->f, dv.as<ViewDev>(), n, out_w, out_h, d_out, s);
+        CU(cudaGetLastError());
+        if (!dev) CU(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return ZB_OK;
+    });
+}
+
+zb_status zb_frames_clear(zb_frames *frames, int32_t first, int32_t count, const uint8_t rgba[4]) {
+    return guarded([&]() -> zb_status {
+        if (!frames || !rgba) return fail(ZB_ERR_INVALID_ARGUMENT, "frames/rgba is NULL");
+        if (!frames->owned) return fail(ZB_ERR_INVALID_ARGUMENT, "aliased frames belong to the caller and cannot be cleared");
+        if (first < 0 || count < 0 || first + count > frames->f.n) return fail(ZB_ERR_INVALID_ARGUMENT, "frame range out of bounds");
+        if (count == 0) return ZB_OK;
+        zb_ctx *ctx = frames->ctx;
+        CU(cudaSetDevice(ctx->device));
+        const unsigned c = (unsigned)rgba[0] | ((unsigned)rgba[1] << 8) | ((unsigned)rgba[2] << 16) | ((unsigned)rgba[3] << 24);
+        launch_frames_clear(const_cast<uint8_t *>(frames->f.base), frames->f.frame_stride, frames->f.row_stride, frames->f.width,
+                            frames->f.height, first, count, c, ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        return ZB_OK;
+    });
+}
+
 zb_status zb_preprocess(zb_ctx *ctx, const zb_frames *frames, const zb_view *views, int32_t n, int32_t out_w,
                         int32_t out_h, float lo, float hi, zb_tensor_layout layout, float *out) {
     return guarded([&]() -> zb_status {

@@ -97,6 +97,12 @@ enum SampleLayout { SAMPLE_NCHW = 0, SAMPLE_NHWC3 = 1, SAMPLE_NHWC4 = 2 };
 void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
                    SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s, int round_f16 = 0);
 
+// ImageView::to_image (image/mod.rs:314-325): view pixel (x, y) -> RGBA8 [n][out_h][out_w][4]; Color::NONE outside.
+void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint8_t *out, cudaStream_t s);
+// Image::clear (image/mod.rs:171-173) for frames [first, first + count)
+void launch_frames_clear(uint8_t *base, long long frame_stride, long long row_stride, int width, int height, int first,
+                         int count, unsigned rgba, cudaStream_t s);
+
 // Fused sampling + stem conv (views != nullptr) or stem conv on an NHWC4 tensor (views == nullptr).
 bool stem_supported(const ConvDev &p);
 bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s,

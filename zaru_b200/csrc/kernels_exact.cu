@@ -101,6 +101,41 @@ __device__ __forceinline__ float4 sample_pixel(const FramesDev &f, const ViewDev
     return color_map(rgba, lo, adjust, f16);
 }
 
+// ImageView::get for every pixel of the view (no resampling: view pixel (x, y) -> image_coord -> texel or NONE)
+__global__ void __launch_bounds__(128) view_to_image_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
+                                                            int out_h, unsigned *__restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, img = blockIdx.z;
+    if (x >= out_w) return;
+    const ViewDev v = views[img];
+    unsigned rgba = 0u;                                  // Color::NONE
+    if (v.valid) {
+        RRectF rr;
+        rr.r.cx = v.cx, rr.r.cy = v.cy, rr.r.w = v.w, rr.r.h = v.h;
+        rr.c = v.cosr, rr.s = v.sinr, rr.rad = 0.f;
+        float px, py;
+        transform_out(rr, (float)x + 0.5f, (float)y + 0.5f, px, py);
+        const float fx = roundf(px - 0.5f), fy = roundf(py - 0.5f);
+        const bool reject = fx < 0.0f || fy < 0.0f || ceilf(fx) >= 4294967296.0f || ceilf(fy) >= 4294967296.0f;
+        if (!reject) {
+            const unsigned ix = (fx == fx) ? (unsigned)fx : 0u, iy = (fy == fy) ? (unsigned)fy : 0u;
+            if (ix < (unsigned)f.width && iy < (unsigned)f.height)
+                rgba = __ldg(reinterpret_cast<const unsigned *>(f.base + (long long)v.frame * f.frame_stride +
+                                                                (long long)iy * f.row_stride + (long long)ix * 4));
+        }
+    }
+    out[((long long)img * out_h + y) * out_w + x] = rgba;
+}
+
+__global__ void __launch_bounds__(256) frames_clear_kernel(uint8_t *base, long long frame_stride, long long row_stride, int width,
+                                                           int height, int first, unsigned rgba) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= width) return;
+    *reinterpret_cast<unsigned *>(base + (long long)(first + blockIdx.z) * frame_stride + (long long)blockIdx.y * row_stride +
+                                  (long long)x * 4) = rgba;
+    (void)height;
+}
+
 __global__ void __launch_bounds__(256) sample_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
                                                      int out_h, float lo, float hi, int layout,
                                                      float *__restrict__ out, long long out_img_stride, int f16) {
@@ -881,6 +916,17 @@ __global__ void tracker_set_roi_kernel(TrackState *__restrict__ state, const int
 }
 
 }  // namespace
+
+void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint8_t *out, cudaStream_t s) {
+    g_launch_count++;
+    view_to_image_kernel<<<dim3((out_w + 127) / 128, out_h, n), 128, 0, s>>>(f, views, out_w, out_h, reinterpret_cast<unsigned *>(out));
+}
+
+void launch_frames_clear(uint8_t *base, long long frame_stride, long long row_stride, int width, int height, int first,
+                         int count, unsigned rgba, cudaStream_t s) {
+    g_launch_count++;
+    frames_clear_kernel<<<dim3((width + 255) / 256, height, count), 256, 0, s>>>(base, frame_stride, row_stride, width, height, first, rgba);
+}
 
 void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int first_frame, int n, int net_w, int net_h,
                             ViewDev *out_views, float *out_fit, ViewHost *out_view_rects, cudaStream_t s) {

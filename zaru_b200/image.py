@@ -54,6 +54,11 @@ class ImageBatch:
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         _ffi.check(_ffi.lib().zb_frames_update(self._h, frames.ctypes.data, first, frames.shape[0]))
 
+    def clear(self, color=(0, 0, 0, 0), first: int = 0, count: int = None):
+        """`Image::clear(color)` (image/mod.rs:171-173) on frames [first, first + count) of an uploaded batch."""
+        c = (C.c_uint8 * 4)(*[int(v) for v in color])
+        _ffi.check(_ffi.lib().zb_frames_clear(self._h, first, self._n - first if count is None else count, c))
+
     def __len__(self):
         return self._n
 
@@ -149,6 +154,19 @@ class ImageView:
 
     def as_view(self) -> "ImageView":
         return self
+
+    def to_image(self) -> "Image":
+        """`ImageView::to_image` (image/mod.rs:314-325): the view's pixels (nearest texel through the rotation,
+        Color::NONE outside the image) as a new Image of size ceil(width) x ceil(height); sampled on the device."""
+        import math
+        r = self.rect()
+        w, h = int(math.ceil(float(r.width()))), int(math.ceil(float(r.height())))
+        batch, idx = self._image.device()
+        out = np.empty((h, w, 4), np.uint8)
+        view = (_ffi.zb_view * 1)(self.to_zb_view(idx))
+        from . import context
+        _ffi.check(_ffi.lib().zb_view_to_image(context(), batch._h, view, 1, w, h, out.ctypes.data))
+        return Image(out)
 
     def image(self) -> Image:
         return self._image
