@@ -385,11 +385,16 @@ bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
     return true;
 }
 
-// Envelope of the strip kernel: Cs_in 16 or 24, all output channels in one register pass (PXV * Ns <= 64).
+// Envelope of the strip kernel: Cs_in 8, 16 or 24, all output channels in one register pass (PXV * Ns <= 64).
 bool launch_dwpw_strip(const ConvDev &p, cudaStream_t s) {
     static const bool disabled = getenv("ZB_NO_STRIP") && atoi(getenv("ZB_NO_STRIP")) != 0;
     if (disabled || p.Ns > 32) return false;
     const bool wide = p.Wo % 32 == 0 || p.Wo > 64;       // 32-pixel-wide tiles unless that wastes half a tile
+    if (p.Cs_in == 8) {   // FaceMeshV2 / full-range BlazeFace first blocks (128x128x8 -> 16, 96x96x8 -> 32)
+        if (p.sh != 1) return false;
+        if (p.Ns <= 16) return wide ? launch_strip_cfg<8, 1, 16, 4, 32, 4>(p, s) : launch_strip_cfg<8, 1, 16, 4, 16, 2>(p, s);
+        return wide ? launch_strip_cfg<8, 1, 32, 2, 32, 4>(p, s) : launch_strip_cfg<8, 1, 32, 2, 16, 2>(p, s);
+    }
     if (p.Cs_in == 16) {
         if (p.sh == 1) {
             if (p.Ns <= 16) return wide ? launch_strip_cfg<16, 1, 16, 4, 32, 4>(p, s) : launch_strip_cfg<16, 1, 16, 4, 16, 2>(p, s);
@@ -450,6 +455,7 @@ bool dwpw_thin_supported(const ConvDev &p) {
     if (p.sh == 2 && !(p.pt == 0 && p.pl == 0)) return false;
     if (p.epi.res && p.epi.res == p.in && p.epi.res_Cs != p.Cs_in) return false;
     if (p.M % (p.Ho * p.Wo)) return false;
+    if (p.Cs_in == 8) return p.sh == 1 && p.Ns <= 32;   // strip kernel only
     return p.Cs_in == 16 || p.Cs_in == 24 || p.Cs_in == 32 || p.Cs_in == 40 || p.Cs_in == 48;
 }
 
