@@ -39,6 +39,7 @@ NCU_TRAFFIC = {
     "stem(+sample)": (566.482688e6 + 358.369792e6, 1024 * (128 * 128 * 4.0 + 64 * 64 * 24 * 4.0)),
 }
 METRIC = "frames/sec face detect+landmark (1080p)"
+WORKLOAD = "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark"
 UNIT = "frames/s"
 
 
@@ -165,8 +166,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config4: full face pipeline on synthetic 1080p frames (CPU reference arm, bounded sample)",
-                       "frames_per_step": per_worker * cores},
+            # same workload string as the GPU arm; the CPU arm runs a bounded sample of it per step
+            "config": {"workload": WORKLOAD, "frame": "1920x1080 RGBA8", "frames_per_step": per_worker * cores,
+                       "note": "CPU reference arm: bounded sample of the same workload on the host cores"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -376,7 +378,7 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": ("config5: %d concurrent 1080p camera streams sharded over %d GPU(s), one frame per stream per "
                                 "step through the full face pipeline" % (args.streams, world)) if args.streams else
-                               "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark",
+                               WORKLOAD,
                    "batch_per_gpu": batch_n, "frame": "1920x1080 RGBA8", "distinct_frames": args.unique,
                    "l2_policy": f"inputs larger than L2 ({batch_n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
                    "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "1024")), "frames_with_face": n_with_face,
