@@ -163,3 +163,35 @@ def test_hand_tracker_step_matches_oracle(zb, sad_linus_full):
         assert np.abs(np.asarray(up[:4]) - np.asarray(updated.rect.as_tuple(), np.float32)).max() <= 4 * lim + 1e-3 * float(updated.rect.w)
         st = trk.rois()[0]
         assert abs(st[2] - up[2] * 1.8) <= 1e-3 * up[2]      # grow_rel(0.4): w + 0.4 w + 0.4 w
+
+
+def test_widened_entry_points_reject_bad_arguments(zb, sad_linus_full):
+    """Error behaviour of the rank 2/4 entry points: a status + message, never an abort (SURVEY 8b 'Errors')."""
+    import ctypes as C
+    from zaru_b200 import _ffi, context
+    from zaru_b200.image import Image, ImageBatch
+    from zaru_b200.landmark import EyeNetwork, FaceMeshV1, LandmarkTracker
+    from zaru_b200.rect import Resolution
+    lib = _ffi.lib()
+    trk = LandmarkTracker(FaceMeshV1(), streams=2)
+    img = Image(sad_linus_full)
+    batch1, _ = img.device()
+    with pytest.raises(_ffi.ZaruError) as e:          # one frame for a two-stream tracker
+        trk.track(batch1)
+    assert e.value.status == _ffi.ZB_ERR_INVALID_ARGUMENT
+    with pytest.raises(_ffi.ZaruError):               # stream id out of range
+        trk.set_rois([2], [(10.0, 10.0, 5.0, 5.0, 0.0)])
+    with pytest.raises(_ffi.ZaruError):               # the eye network has no Confidence / angle: not trackable
+        LandmarkTracker(EyeNetwork(), streams=1)
+    with pytest.raises(_ffi.ZaruError):               # zero streams
+        LandmarkTracker(FaceMeshV1(), streams=0)
+    # to_image with a non-positive size, clear on memory the library does not own
+    out = np.zeros((4, 4, 4), np.uint8)
+    view = (_ffi.zb_view * 1)(_ffi.zb_view(0, 2.0, 2.0, 4.0, 4.0, 0.0))
+    assert lib.zb_view_to_image(context(), batch1._h, view, 1, 0, 4, out.ctypes.data) == _ffi.ZB_ERR_INVALID_ARGUMENT
+    import torch
+    dev = torch.zeros((1, 8, 8, 4), dtype=torch.uint8, device="cuda")
+    alias = ImageBatch.alias_device(Resolution(8, 8), dev.data_ptr(), 1, keepalive=dev)
+    with pytest.raises(_ffi.ZaruError):
+        alias.clear((1, 2, 3, 4))
+    assert b"cannot be cleared" in lib.zb_last_error()
