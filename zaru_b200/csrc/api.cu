@@ -471,7 +471,7 @@ extern "C" {
 
 const char *zb_last_error(void) { return t_last_error.c_str(); }
 
-const char *zb_version(void) { return "zaru_b200 0.1 (sm_100a, f32 SIMT conv-gemm + fused dw/pw blocks)"; }
+const char *zb_version(void) { return "zaru_b200 0.1 (sm_100a, f32: fused dw/pw blocks on SIMT strips + tcgen05 3xTF32, exact sampling/decode/NMS)"; }
 
 zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
     return guarded([&]() -> zb_status {
