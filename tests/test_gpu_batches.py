@@ -168,3 +168,41 @@ def test_config4_batch_1024_matches_small_batches():
         else:
             assert res_big.face_flags[i] == -1.0
     assert faces >= 512
+
+
+@pytest.mark.parametrize("n", [8, 96, 300])
+def test_pinned_host_frames_gather_pipeline_matches_resident_frames(n):
+    """Zero-copy ingest (`zb_frames_alias` on PINNED HOST memory): the pipeline gathers the sampled texels across PCIe
+    into staging images on a second stream and samples those through identity views - bit-identical sampling by
+    construction - while other chunks compute.  Results must equal the device-resident path (identical sets, same
+    numbers up to the kernel selection that depends on the chunk size), for ragged chunk counts too; with the
+    staging path disabled (ZB_NO_GATHER is read once per process, so the old path is covered by n < 8) nothing changes."""
+    import torch
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in range(12)])
+    frames = np.concatenate([uniq] * ((n + 11) // 12))[:n]
+    host = torch.from_numpy(frames).pin_memory()
+    res = Resolution(1920, 1080)
+    pinned = ImageBatch.alias_pinned_host(res, host.data_ptr(), n, keepalive=host)
+    resident = ImageBatch.from_rgba8(res, frames)
+    pipe = FacePipeline()
+    a = pipe.run(pinned)
+    b = pipe.run(resident)
+    a2 = pipe.run(pinned)                       # staging buffers / events are reused
+    faces = 0
+    for i in range(n):
+        assert len(a.detections[i]) == len(b.detections[i]) == len(a2.detections[i]), i
+        for x, y in zip(a.detections[i], b.detections[i]):
+            assert x.anchor == y.anchor
+            assert np.abs(x.as_vector() - y.as_vector()).max() <= 0.05, i
+        if len(a.detections[i]):
+            faces += 1
+            assert abs(a.face_flags[i] - b.face_flags[i]) <= 1e-3
+            assert np.abs(a.landmarks[i] - b.landmarks[i]).max() <= 0.05, i
+            assert np.array_equal(a.landmarks[i], a2.landmarks[i])
+        else:
+            assert a.face_flags[i] == -1.0 and b.face_flags[i] == -1.0
+    assert faces >= n // 3

@@ -985,6 +985,10 @@ struct zb_face_pipeline {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf d_views, d_fit, d_dets, d_counts, d_lm_views, d_lm_fit, d_rois, d_lm, d_scalars;
+    // pinned-host frames: texel staging images + identity views for the gather-pipelined path
+    DevBuf d_stage_det, d_stage_lm, d_id_det, d_id_lm;
+    std::vector<cudaEvent_t> ev_chunk;   // 3 events per chunk: gather-1 done, detector done, gather-2 done
+    int id_n = 0;
     PinBuf h_stage, h_counts;
     int cap = 0;
 };
@@ -1540,6 +1544,7 @@ void zb_face_pipeline_destroy(zb_face_pipeline *p) {
     if (p->stream2) cudaStreamSynchronize(p->stream2), cudaStreamDestroy(p->stream2);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
+    for (cudaEvent_t e : p->ev_chunk) cudaEventDestroy(e);
     delete p;
 }
 
@@ -1618,8 +1623,100 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             CU(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
         }
         const int s0 = (int)lpl.outputs[0].per_image, s1 = (int)lpl.outputs[1].per_image;
+        // ---- frames in pinned host memory: gather-pipelined path ------------------------------------------------
+        // The sampler reads ~50 K scattered texels per frame across PCIe.  Fused into the stem kernels those reads
+        // hold every SM hostage for ~2x the compute time of the whole step.  Instead a small-grid gather kernel on a
+        // second stream copies exactly those texels into HBM staging images (bit-identical sampling by construction,
+        // see launch_gather_texels) while the compute stream works on other chunks:
+        //   G:  g1(0) g1(1) g2(0) g1(2) g2(1) ...        (PCIe)      C:  D(0) D(1) L(0) D(2) L(1) ...   (SMs)
+        static const bool gather_env = !(getenv("ZB_NO_GATHER") && atoi(getenv("ZB_NO_GATHER")) != 0);
+        const bool gather = gather_env && frames->host_mapped && n >= 8 && !ctx->prof_on && !two_streams;
+        if (gather) {
+            static const int gchunk_env = getenv("ZB_GATHER_CHUNK") ? atoi(getenv("ZB_GATHER_CHUNK")) : 0;
+            static const int gctas_env = getenv("ZB_GATHER_CTAS") ? atoi(getenv("ZB_GATHER_CTAS")) : 0;
+            // measured (1024 frames): 2 chunks 21.5 ms, 4 chunks 23.4 ms, 8 chunks 25.9 ms, fused-in-stem 22.8 ms -
+            // small chunks cost more compute efficiency than the extra overlap returns; PCIe moves ~0.85 MB per
+            // frame (64 B per scattered texel), i.e. ~20 ms per 1024 frames whatever the schedule
+            const int gchunk = std::min(chunk, gchunk_env > 0 ? gchunk_env : std::max(8, (n + 1) / 2));
+            const int K = (n + gchunk - 1) / gchunk;
+            const int gctas = gctas_env > 0 ? gctas_env : 148;
+            if (!p->stream2) {
+                CU(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+            }
+            while ((int)p->ev_chunk.size() < 3 * K) {
+                cudaEvent_t e;
+                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                p->ev_chunk.push_back(e);
+            }
+            const int dw = dpl.in_w, dh = dpl.in_h, lw = lpl.in_w, lh = lpl.in_h;
+            p->d_stage_det.reserve(sizeof(uint32_t) * (size_t)n * dw * dh);
+            p->d_stage_lm.reserve(sizeof(uint32_t) * (size_t)n * lw * lh);
+            if (p->id_n != n) {   // identity views over the staging images (frame i of the staging batch = frame i)
+                std::vector<ViewDev> idv(2 * (size_t)n);
+                for (int i = 0; i < n; i++) {
+                    idv[i] = view_dev(full_view(dw, dh), i, 0);
+                    idv[n + i] = view_dev(full_view(lw, lh), i, 0);
+                }
+                p->d_id_det.reserve(sizeof(ViewDev) * n);
+                p->d_id_lm.reserve(sizeof(ViewDev) * n);
+                CU(cudaMemcpyAsync(p->d_id_det.p, idv.data(), sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+                CU(cudaMemcpyAsync(p->d_id_lm.p, idv.data() + n, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
+                CU(cudaStreamSynchronize(s));   // idv is a local vector
+                p->id_n = n;
+            }
+            FramesDev fdet{p->d_stage_det.as<uint8_t>(), dw, dh, (long long)dw * 4, (long long)dw * dh * 4, n};
+            FramesDev flm{p->d_stage_lm.as<uint8_t>(), lw, lh, (long long)lw * 4, (long long)lw * lh * 4, n};
+            cudaStream_t g = p->stream2;
+            Workspace &wd = p->ws_det[0], &wl = p->ws_lm[0];
+            CU(cudaEventRecord(p->ev_fork, s));                  // view / fit uploads above are on s
+            CU(cudaStreamWaitEvent(g, p->ev_fork, 0));
+            auto ev = [&](int kk, int which) { return p->ev_chunk[3 * kk + which]; };
+            auto gather2 = [&](int kk) {
+                const int c0 = kk * gchunk, nc = std::min(gchunk, n - c0);
+                CU(cudaStreamWaitEvent(g, ev(kk, 1), 0));        // RoIs of chunk kk exist
+                launch_gather_texels(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lw, lh,
+                                     p->d_stage_lm.as<uint32_t>() + (size_t)c0 * lw * lh, gctas, g);
+                CU(cudaEventRecord(ev(kk, 2), g));
+            };
+            auto landmarks = [&](int kk) {
+                const int c0 = kk * gchunk, nc = std::min(gchunk, n - c0);
+                CU(cudaStreamWaitEvent(s, ev(kk, 2), 0));
+                const StemInput sl{&flm, p->d_id_lm.as<ViewDev>() + c0, -1.0f, 1.0f};
+                run_ops(p->lm_net, wl, c0, nc, 0, s, &sl);
+                run_ops(p->lm_net, wl, c0, nc, 1, s);
+                const int s2 = p->lm_kind == ZB_EST_FACE_MESH_V2 ? (int)lpl.outputs[2].per_image : 0;
+                launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
+                                 s2 ? wl.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2, p->d_lm_fit.as<float>() + 4 * c0,
+                                 p->d_lm_views.as<ViewDev>() + c0, p->d_rois.as<ViewHost>() + c0, nc, lp,
+                                 p->d_lm.as<float>() + (size_t)c0 * L * 3, p->d_scalars.as<float>() + 2 * c0, s);
+            };
+            for (int kk = 0; kk < K; kk++) {
+                const int c0 = kk * gchunk, nc = std::min(gchunk, n - c0);
+                launch_gather_texels(frames->f, p->d_views.as<ViewDev>() + c0, nc, dw, dh,
+                                     p->d_stage_det.as<uint32_t>() + (size_t)c0 * dw * dh, gctas, g);
+                CU(cudaEventRecord(ev(kk, 0), g));
+                if (kk >= 1) gather2(kk - 1);
+                CU(cudaStreamWaitEvent(s, ev(kk, 0), 0));
+                const StemInput sd{&fdet, p->d_id_det.as<ViewDev>() + c0, -1.0f, 1.0f};
+                run_ops(p->det_net, wd, c0, nc, 0, s, &sd);
+                run_ops(p->det_net, wd, c0, nc, 1, s);
+                launch_decode_nms(wd.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
+                                  wd.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image, p->d_fit.as<float>() + 4 * c0, nc, dp,
+                                  p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, s);
+                launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0, nc, lw, lh,
+                                p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0, p->d_rois.as<ViewHost>() + c0, s);
+                CU(cudaEventRecord(ev(kk, 1), s));
+                if (kk >= 1) landmarks(kk - 1);
+            }
+            gather2(K - 1);
+            landmarks(K - 1);
+            CU(cudaEventRecord(p->ev_join, g));
+            CU(cudaStreamWaitEvent(s, p->ev_join, 0));
+        }
         int k = 0;
-        for (int c0 = 0; c0 < n; c0 += chunk, k++) {
+        for (int c0 = gather ? n : 0; c0 < n; c0 += chunk, k++) {
             const int nc = std::min(chunk, n - c0);
             const int j = k % ns;
             cudaStream_t cs = j == 0 ? s : p->stream2;

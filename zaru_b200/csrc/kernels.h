@@ -97,6 +97,14 @@ enum SampleLayout { SAMPLE_NCHW = 0, SAMPLE_NHWC3 = 1, SAMPLE_NHWC4 = 2 };
 void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, float lo, float hi,
                    SampleLayout layout, float *out, long long out_img_stride, cudaStream_t s, int round_f16 = 0);
 
+// Zero-copy ingest, decoupled: copy exactly the texels the nearest-neighbour sampler would read (same bit-exact
+// address computation) from frames in pinned HOST memory into a compact RGBA8 staging image [n][out_h][out_w] in HBM
+// (0 = Color::NONE where the sampler reads nothing).  Sampling that staging image through an identity view is then
+// bit-identical to sampling the frame, so the PCIe-latency-bound part runs as a small-grid kernel on its own stream
+// while other chunks compute.
+void launch_gather_texels(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint32_t *out, int max_ctas,
+                          cudaStream_t s);
+
 // ImageView::to_image (image/mod.rs:314-325): view pixel (x, y) -> RGBA8 [n][out_h][out_w][4]; Color::NONE outside.
 void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint8_t *out, cudaStream_t s);
 // Image::clear (image/mod.rs:171-173) for frames [first, first + count)

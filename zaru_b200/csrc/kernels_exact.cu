@@ -101,6 +101,35 @@ __device__ __forceinline__ float4 sample_pixel(const FramesDev &f, const ViewDev
     return color_map(rgba, lo, adjust, f16);
 }
 
+// Persistent small grid: each thread keeps 4 independent host-memory reads in flight per iteration.
+__global__ void __launch_bounds__(256) gather_texels_kernel(const FramesDev f, const ViewDev *__restrict__ views, int n,
+                                                            int out_w, int out_h, unsigned *__restrict__ out) {
+    const long long per = (long long)out_w * out_h, total = per * n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        const unsigned *addr[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = i0 + u * stride;
+            addr[u] = nullptr;
+            if (i < total) {
+                const int img = (int)(i / per);
+                const int r = (int)(i - (long long)img * per);
+                const int y = r / out_w, x = r - y * out_w;
+                addr[u] = sample_address(f, views[img], x, y, out_w, out_h);
+            }
+        }
+        unsigned v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = addr[u] ? __ldg(addr[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = i0 + u * stride;
+            if (i < total) out[i] = v[u];
+        }
+    }
+}
+
 // ImageView::get for every pixel of the view (no resampling: view pixel (x, y) -> image_coord -> texel or NONE)
 __global__ void __launch_bounds__(128) view_to_image_kernel(const FramesDev f, const ViewDev *__restrict__ views, int out_w,
                                                             int out_h, unsigned *__restrict__ out) {
@@ -916,6 +945,15 @@ __global__ void tracker_set_roi_kernel(TrackState *__restrict__ state, const int
 }
 
 }  // namespace
+
+void launch_gather_texels(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint32_t *out, int max_ctas,
+                          cudaStream_t s) {
+    g_launch_count++;
+    const long long total = (long long)n * out_w * out_h;
+    long long ctas = (total + 4 * 256 - 1) / (4 * 256);
+    if (ctas > max_ctas) ctas = max_ctas;
+    gather_texels_kernel<<<(unsigned)ctas, 256, 0, s>>>(f, views, n, out_w, out_h, out);
+}
 
 void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint8_t *out, cudaStream_t s) {
     g_launch_count++;
