@@ -1637,8 +1637,34 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             // measured (1024 frames): 2 chunks 21.5 ms, 4 chunks 23.4 ms, 8 chunks 25.9 ms, fused-in-stem 22.8 ms -
             // small chunks cost more compute efficiency than the extra overlap returns; PCIe moves ~0.85 MB per
             // frame (64 B per scattered texel), i.e. ~20 ms per 1024 frames whatever the schedule
-            const int gchunk = std::min(chunk, gchunk_env > 0 ? gchunk_env : std::max(8, (n + 1) / 2));
-            const int K = (n + gchunk - 1) / gchunk;
+            // chunk boundaries: equal chunks of ZB_GATHER_CHUNK frames, or (default) the weights of ZB_GATHER_SPLIT -
+            // a small first chunk lets compute start early, a small last chunk shortens the tail that cannot overlap
+            std::vector<int> bounds{0};
+            if (gchunk_env > 0) {
+                for (int c = std::min(chunk, gchunk_env); bounds.back() < n; bounds.push_back(std::min(n, bounds.back() + c))) {}
+            } else {
+                static const std::string split_env = getenv("ZB_GATHER_SPLIT") ? getenv("ZB_GATHER_SPLIT") : "1,1";
+                std::vector<int> wts;
+                for (size_t i = 0; i < split_env.size();) {
+                    size_t j = split_env.find(',', i);
+                    if (j == std::string::npos) j = split_env.size();
+                    const int w = atoi(split_env.substr(i, j - i).c_str());
+                    if (w > 0) wts.push_back(w);
+                    i = j + 1;
+                }
+                if (wts.empty()) wts = {1, 1};
+                int total_w = 0;
+                for (int w : wts) total_w += w;
+                int acc_w = 0;
+                for (size_t i = 0; i < wts.size(); i++) {
+                    acc_w += wts[i];
+                    int b = i + 1 == wts.size() ? n : std::min(n, (int)((long long)n * acc_w / total_w));
+                    b = std::min(b, bounds.back() + chunk);            // never beyond the workspace capacity
+                    if (b > bounds.back()) bounds.push_back(b);
+                }
+                while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + chunk));
+            }
+            const int K = (int)bounds.size() - 1;
             const int gctas = gctas_env > 0 ? gctas_env : 148;
             if (!p->stream2) {
                 CU(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
@@ -1674,14 +1700,14 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             CU(cudaStreamWaitEvent(g, p->ev_fork, 0));
             auto ev = [&](int kk, int which) { return p->ev_chunk[3 * kk + which]; };
             auto gather2 = [&](int kk) {
-                const int c0 = kk * gchunk, nc = std::min(gchunk, n - c0);
+                const int c0 = bounds[kk], nc = bounds[kk + 1] - c0;
                 CU(cudaStreamWaitEvent(g, ev(kk, 1), 0));        // RoIs of chunk kk exist
                 launch_gather_texels(frames->f, p->d_lm_views.as<ViewDev>() + c0, nc, lw, lh,
                                      p->d_stage_lm.as<uint32_t>() + (size_t)c0 * lw * lh, gctas, g);
                 CU(cudaEventRecord(ev(kk, 2), g));
             };
             auto landmarks = [&](int kk) {
-                const int c0 = kk * gchunk, nc = std::min(gchunk, n - c0);
+                const int c0 = bounds[kk], nc = bounds[kk + 1] - c0;
                 CU(cudaStreamWaitEvent(s, ev(kk, 2), 0));
                 const StemInput sl{&flm, p->d_id_lm.as<ViewDev>() + c0, -1.0f, 1.0f};
                 run_ops(p->lm_net, wl, c0, nc, 0, s, &sl);
@@ -1693,7 +1719,7 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                                  p->d_lm.as<float>() + (size_t)c0 * L * 3, p->d_scalars.as<float>() + 2 * c0, s);
             };
             for (int kk = 0; kk < K; kk++) {
-                const int c0 = kk * gchunk, nc = std::min(gchunk, n - c0);
+                const int c0 = bounds[kk], nc = bounds[kk + 1] - c0;
                 launch_gather_texels(frames->f, p->d_views.as<ViewDev>() + c0, nc, dw, dh,
                                      p->d_stage_det.as<uint32_t>() + (size_t)c0 * dw * dh, gctas, g);
                 CU(cudaEventRecord(ev(kk, 0), g));
