@@ -206,3 +206,37 @@ def test_pinned_host_frames_gather_pipeline_matches_resident_frames(n):
         else:
             assert a.face_flags[i] == -1.0 and b.face_flags[i] == -1.0
     assert faces >= n // 3
+
+
+@pytest.mark.parametrize("name,lo,size,big", [("face_detection_short_range", -1.0, 128, 1100), ("face_landmark", -1.0, 192, 700),
+                                              ("iris_landmark", -1.0, 64, 1500), ("palm_detection_lite", 0.0, 192, 420),
+                                              ("hand_landmark_lite", 0.0, 224, 420), ("face_detection_full_range", -1.0, 192, 420),
+                                              ("face_landmarks_detector", -1.0, 256, 300)])
+def test_every_network_large_batch_equals_small_batch(assets_dir, name, lo, size, big):
+    """Kernel selection depends on the launch size (tcgen05 blocks from ~600 CTAs, strip / tile kernels by map size,
+    per-batch stage for the deep layers): a LARGE batch of every network must reproduce, image by image, what the same
+    images give in a batch of 6 - and the oracle on one of them.  Ragged batch sizes on purpose."""
+    import os
+    from oracle import nn as onn
+    from zaru_b200.nn import NeuralNetwork
+    path = os.path.join(assets_dir, "onnx", name + ".onnx")
+    net = NeuralNetwork.from_path(path)
+    rng = np.random.default_rng(11)
+    base = rng.uniform(lo, 1.0, size=(6, 3, size // 8, size // 8)).astype(np.float32)
+    six = np.repeat(np.repeat(base, 8, axis=2), 8, axis=3)
+    six += rng.uniform(-0.02, 0.02, size=six.shape).astype(np.float32)
+    six = np.clip(six, lo, 1.0)
+    x = np.concatenate([six] * ((big + 5) // 6))[:big]
+    got_big = net.estimate(x)
+    got_small = net.estimate(six)
+    want = onn.NeuralNetwork(path, backend="cv2").estimate(six[:1])
+    for k, (gb, gs) in enumerate(zip(got_big, got_small)):
+        scale = max(1.0, float(np.abs(gs).max()))
+        f16 = name == "face_landmarks_detector"
+        tol = (2e-3 if f16 else 2e-4) * scale      # f16-output model: one f16 step of the largest value
+        for i in range(big):
+            assert np.abs(gb[i] - gs[i % 6]).max() <= tol, (name, k, i, float(np.abs(gb[i] - gs[i % 6]).max()), scale)
+        lim = max(1e-3 * size, 5e-3) if gs.shape[-1] > 2 else 5e-3
+        if f16:
+            lim += 0.125
+        assert np.abs(gs[:1] - want[k]).max() <= lim, (name, k)
