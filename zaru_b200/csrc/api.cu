@@ -127,7 +127,9 @@ struct zb_ctx {
     // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
     int tc_mode = 1;                     // ZB_TC: 0 = SIMT only, 1 = tcgen05 3xTF32 for fused blocks with K >= tc_min_k
     int tc_min_k = 48;                   // ZB_TC_MIN_K
-    int tc_min_ctas = 600;               // ZB_TC_MIN_CTAS
+    int tc_min_ctas = 500;               // ZB_TC_MIN_CTAS: stride-1 blocks (8x8x96 at batch 1024 = 512 CTAs: 0.23 vs 0.42 ms on the GEMM tile)
+    int tc_min_ctas_s2 = 1 << 20;        // ZB_TC_MIN_CTAS_S2: stride-2 blocks stay on the GEMM tile (their tcgen05 producer has no
+                                         // window reuse: 0.189 vs 0.220 ms on 24x24x64 -> 12x12x128, 0.175 vs 0.218 ms on 32x32x42 -> 16x16x48)
     bool prof_on = false;
     bool prof_detail = false;            // ZB_PROF_DETAIL=1: one profile row per layer instead of per kernel class
     std::vector<ProfRec> prof;
@@ -341,7 +343,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     // (measured: the tcgen05 kernel has the higher per-CTA latency, so it needs >= ~2 waves of CTAs)
                     // (stride-2 blocks the SIMT thin kernel covers stay there: 0.175 vs 0.218 ms on 32x32x42 -> 16x16x48)
                     const bool use_tc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_tc_supported(p, op.NP) &&
-                                        p.K >= ctx->tc_min_k && p.M >= ctx->tc_min_ctas * 128 &&
+                                        p.K >= ctx->tc_min_k && p.M >= (p.sh == 2 ? ctx->tc_min_ctas_s2 : ctx->tc_min_ctas) * 128 &&
                                         !(p.sh == 2 && dwpw_thin_supported(p));
                     const bool use_ttc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_ttc_supported(p, op.NP);
                     if (use_ttc) {
@@ -497,6 +499,7 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         if (const char *c = getenv("ZB_TC")) ctx->tc_mode = atoi(c);
         if (const char *c = getenv("ZB_TC_MIN_K")) ctx->tc_min_k = atoi(c);
         if (const char *c = getenv("ZB_TC_MIN_CTAS")) ctx->tc_min_ctas = atoi(c);
+        if (const char *c = getenv("ZB_TC_MIN_CTAS_S2")) ctx->tc_min_ctas_s2 = atoi(c);
         if (const char *c = getenv("ZB_CHUNK")) {
             int v = atoi(c);
             if (v > 0) ctx->default_chunk = v;
