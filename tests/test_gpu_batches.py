@@ -240,3 +240,45 @@ def test_every_network_large_batch_equals_small_batch(assets_dir, name, lo, size
         if f16:
             lim += 0.125
         assert np.abs(gs[:1] - want[k]).max() <= lim, (name, k)
+
+
+def test_small_batch_cuda_graph_replay_is_invisible():
+    """Small batches are launch-bound (49 launches per pass), so the pipeline replays a captured CUDA graph from the
+    third identical call on (first call: plain launches, second: capture).  Results must be bit-identical across the
+    three modes, a changed threshold or another batch must not replay a stale graph, and the frames' CURRENT content
+    is what gets processed (the graph bakes in addresses, not pixels)."""
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    n = 20
+    frames = np.stack([synth.s_face_frame(1000 + s, allow_empty=False)[0] for s in range(n)])
+    res = Resolution(1920, 1080)
+    batch = ImageBatch.from_rgba8(res, frames)
+    pipe = FacePipeline()
+    runs = [pipe.run(batch) for _ in range(4)]            # plain, capture, replay, replay
+    for r in runs[1:]:
+        assert np.array_equal(r.landmarks, runs[0].landmarks) and np.array_equal(r.face_flags, runs[0].face_flags)
+        assert [len(d) for d in r.detections] == [len(d) for d in runs[0].detections]
+    assert sum(len(d) > 0 for d in runs[0].detections) >= n // 2
+    # new pixels behind the same handle: the replayed graph must see them
+    batch.update(frames[::-1].copy())
+    flipped = pipe.run(batch)
+    assert np.array_equal(flipped.landmarks[0], runs[0].landmarks[n - 1])
+    assert np.array_equal(flipped.landmarks[n - 1], runs[0].landmarks[0])
+    batch.update(frames)
+    # a changed threshold must not replay the old graph
+    pipe.set_threshold(0.999, 0.3)
+    strict = pipe.run(batch)
+    assert sum(len(d) for d in strict.detections) < sum(len(d) for d in runs[0].detections)
+    pipe.set_threshold(0.5, 0.3)
+    again = [pipe.run(batch) for _ in range(3)]
+    for r in again:
+        assert np.array_equal(r.landmarks, runs[0].landmarks)
+    # another batch in between (different addresses): never a stale replay
+    other = ImageBatch.from_rgba8(res, frames[:7])
+    o1 = pipe.run(other)
+    b1 = pipe.run(batch)
+    o2 = pipe.run(other)
+    assert np.array_equal(o1.landmarks, o2.landmarks) and np.array_equal(o1.landmarks, runs[0].landmarks[:7])
+    assert np.array_equal(b1.landmarks, runs[0].landmarks)

@@ -992,6 +992,10 @@ struct zb_face_pipeline {
     DevBuf d_stage_det, d_stage_lm, d_id_det, d_id_lm;
     std::vector<cudaEvent_t> ev_chunk;   // 3 events per chunk: gather-1 done, detector done, gather-2 done
     int id_n = 0;
+    // CUDA graph of one pipeline pass (small batches are launch-bound: 49 launches per pass): captured the second
+    // time the same configuration (frames, n, buffers, thresholds) is seen, replayed afterwards
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key = 0, pending_key = 0;
     PinBuf h_stage, h_counts;
     int cap = 0;
 };
@@ -1548,6 +1552,7 @@ void zb_face_pipeline_destroy(zb_face_pipeline *p) {
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (cudaEvent_t e : p->ev_chunk) cudaEventDestroy(e);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     delete p;
 }
 
@@ -1744,8 +1749,56 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             CU(cudaEventRecord(p->ev_join, g));
             CU(cudaStreamWaitEvent(s, p->ev_join, 0));
         }
+        // ---- small batches: replay a captured CUDA graph of the pass -------------------------------------------
+        static const bool graph_env = !(getenv("ZB_NO_GRAPH") && atoi(getenv("ZB_NO_GRAPH")) != 0);
+        static const int graph_max_n = getenv("ZB_GRAPH_MAX_N") ? atoi(getenv("ZB_GRAPH_MAX_N")) : 512;
+        const bool use_graph = graph_env && !gather && !two_streams && !ctx->prof_on && n <= graph_max_n;
+        uint64_t key = 0;
+        bool capturing = false, replayed = false;
+        struct CaptureGuard {            // an exception while capturing must not leave the stream in capture mode
+            cudaStream_t st;
+            bool *active;
+            ~CaptureGuard() {
+                if (*active) {
+                    cudaGraph_t g = nullptr;
+                    cudaStreamEndCapture(st, &g);
+                    if (g) cudaGraphDestroy(g);
+                    cudaGetLastError();
+                }
+            }
+        } capture_guard{s, &capturing};
+        if (use_graph) {
+            // everything the captured launches bake in: addresses, sizes, thresholds
+            uint64_t h = 1469598103934665603ull;
+            auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+            const Workspace &wd = p->ws_det[0], &wl = p->ws_lm[0];
+            const void *ptrs[] = {frames->f.base, p->d_views.p, p->d_fit.p, p->d_dets.p, p->d_counts.p, p->d_lm_views.p, p->d_lm_fit.p,
+                                  p->d_rois.p, p->d_lm.p, p->d_scalars.p, wd.arena.p, wd.arena1.p, wl.arena.p, wl.arena1.p};
+            for (const void *q : ptrs) mix((uint64_t)(uintptr_t)q);
+            for (const auto &o : wd.outs) mix((uint64_t)(uintptr_t)o.p);
+            for (const auto &o : wl.outs) mix((uint64_t)(uintptr_t)o.p);
+            const uint64_t vals[] = {(uint64_t)n, (uint64_t)cap, (uint64_t)chunk, (uint64_t)wd.cap, (uint64_t)wd.out_images, (uint64_t)wl.cap,
+                                     (uint64_t)wl.out_images, (uint64_t)frames->f.width, (uint64_t)frames->f.height,
+                                     (uint64_t)frames->f.row_stride, (uint64_t)frames->f.frame_stride, (uint64_t)p->mode,
+                                     (uint64_t)p->det_kind, (uint64_t)p->lm_kind};
+            for (uint64_t v : vals) mix(v);
+            uint32_t tb, ib;
+            memcpy(&tb, &p->thresh, 4), memcpy(&ib, &p->iou, 4);
+            mix(tb), mix(ib);
+            key = h | 1;
+            if (p->graph_exec && p->graph_key == key) {
+                CU(cudaGraphLaunch(p->graph_exec, s));
+                replayed = true;
+            } else if (p->pending_key == key) {           // second sighting: every lazy initialisation has happened
+                if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec), p->graph_exec = nullptr;
+                CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                capturing = true;
+            } else {
+                p->pending_key = key;
+            }
+        }
         int k = 0;
-        for (int c0 = gather ? n : 0; c0 < n; c0 += chunk, k++) {
+        for (int c0 = (gather || replayed) ? n : 0; c0 < n; c0 += chunk, k++) {
             const int nc = std::min(chunk, n - c0);
             const int j = k % ns;
             cudaStream_t cs = j == 0 ? s : p->stream2;
@@ -1780,6 +1833,19 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         if (two_streams) {
             CU(cudaEventRecord(p->ev_join, p->stream2));
             CU(cudaStreamWaitEvent(s, p->ev_join, 0));
+        }
+        if (capturing) {
+            cudaGraph_t graph = nullptr;
+            capturing = false;
+            CU(cudaStreamEndCapture(s, &graph));
+            cudaError_t ge = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ge != cudaSuccess) {
+                p->graph_exec = nullptr;
+                throw std::runtime_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ge));
+            }
+            p->graph_key = key;
+            CU(cudaGraphLaunch(p->graph_exec, s));
         }
         CU(cudaGetLastError());
         tm.stop();
