@@ -457,3 +457,41 @@ def test_view_to_image_bit_exact_and_clear(zb, sad_linus_full):
     a = batch.frame(0).as_view().to_image()._pixels
     b = batch.frame(1).as_view().to_image()._pixels
     assert np.array_equal(a, sad_linus_full) and (b == np.array([10, 20, 30, 255], np.uint8)).all()
+
+
+def test_empty_and_degenerate_inputs(zb, sad_linus_full):
+    """Edge cases of the boundary: zero views / frames are a no-op, a view entirely outside the image samples
+    Color::NONE everywhere (tensor == lo, like the reference's out-of-bounds reads), a 1x1 image works, NaN view
+    parameters do not crash (Rust: NaN casts to 0), and wrong frame indices are rejected."""
+    from zaru_b200 import _ffi, context
+    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200.image import Image
+    from zaru_b200.landmark import Estimator, FaceMeshV1
+    from zaru_b200.rect import Rect, RotatedRect
+    lib = _ffi.lib()
+    img = Image(sad_linus_full)
+    batch, _ = img.device()
+    det, est = Detector(ShortRangeNetwork()), Estimator(FaceMeshV1())
+    assert det.detect_views(batch, []) == []
+    assert est.estimate_views(batch, []) == []
+    out = np.full((1, 3, 16, 16), 7.0, np.float32)
+    assert lib.zb_preprocess(context(), batch._h, None, 0, 16, 16, -1.0, 1.0, _ffi.ZB_NCHW, out.ctypes.data) == 0
+    assert (out == 7.0).all()
+    # a view far outside the image: every sample is Color::NONE -> colour-mapped 0 = lo
+    far = img.view(RotatedRect(Rect.from_center(-5000.0, -5000.0, 300.0, 300.0), 0.3))
+    t = det._cnn.tensor(far)
+    assert (t == -1.0).all()
+    assert len(det.detect(far)) == 0
+    # 1x1 image
+    one = Image(np.array([[[10, 20, 30, 255]]], np.uint8))
+    t1 = det._cnn.tensor(one.as_view())
+    assert np.isfinite(t1).all() and t1.shape == (1, 3, 128, 128)
+    assert len(det.detect(one)) == 0
+    # NaN view: no crash, a tensor comes back
+    nan_view = (_ffi.zb_view * 1)(_ffi.zb_view(0, float("nan"), 100.0, 50.0, 50.0, 0.0))
+    out = np.empty((1, 3, 8, 8), np.float32)
+    assert lib.zb_preprocess(context(), batch._h, nan_view, 1, 8, 8, 0.0, 1.0, _ffi.ZB_NCHW, out.ctypes.data) == 0
+    assert np.isfinite(out).all()
+    # frame index out of range
+    bad = (_ffi.zb_view * 1)(_ffi.zb_view(3, 10.0, 10.0, 5.0, 5.0, 0.0))
+    assert lib.zb_preprocess(context(), batch._h, bad, 1, 8, 8, 0.0, 1.0, _ffi.ZB_NCHW, out.ctypes.data) == _ffi.ZB_ERR_INVALID_ARGUMENT

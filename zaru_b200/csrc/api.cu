@@ -901,7 +901,7 @@ zb_status zb_frames_clear(zb_frames *frames, int32_t first, int32_t count, const
 zb_status zb_preprocess(zb_ctx *ctx, const zb_frames *frames, const zb_view *views, int32_t n, int32_t out_w,
                         int32_t out_h, float lo, float hi, zb_tensor_layout layout, float *out) {
     return guarded([&]() -> zb_status {
-        if (!ctx || !views || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/views/out is NULL");
+        if (!ctx || !out || (!views && n != 0)) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/views/out is NULL");
         if (out_w <= 0 || out_h <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, "bad output resolution");
         if (!(hi > lo)) return fail(ZB_ERR_INVALID_ARGUMENT, "ColorMapper range must satisfy end > start");
         check_frames(frames, views, n);
