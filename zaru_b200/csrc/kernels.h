@@ -62,6 +62,7 @@ void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out,
 // FLOAT16-output networks: round every element to f16 (nearest even) and widen back, in place
 void launch_round_f16(float *data, long long count, cudaStream_t s);
 
+bool launch_pw_thin(const ConvDev &p, cudaStream_t s);   // kernels_thin.cu: thin 1x1 convs (few channels, large maps); false = not taken
 bool dwpw_thin_supported(const ConvDev &p);   // kernels_thin.cu: would launch_conv(CONV_DWPW) take the thin kernel?
 
 // ---- tensor-core path: kernels_tc.cu ------------------------------------------------------------

@@ -387,6 +387,7 @@ inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total +
 void launch_conv(const ConvDev &p, ConvMode mode, cudaStream_t s) {
     g_launch_count++;
     if (mode == CONV_DWPW && launch_dwpw_thin(p, s)) return;
+    if (mode == CONV_PW && launch_pw_thin(p, s)) return;
     if (p.Ns <= 16) launch_conv_tile<256, 16, 4, 4>(p, mode, s);
     else if (p.Ns <= 32) launch_conv_tile<128, 32, 4, 4>(p, mode, s);
     else if (p.Ns <= 64) launch_conv_tile<128, 64, 8, 4>(p, mode, s);

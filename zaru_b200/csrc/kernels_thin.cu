@@ -453,6 +453,101 @@ bool launch_thin_cs(const ConvDev &p, cudaStream_t s) {
     return p.Ns <= 16 ? launch_thin_cfg<CS, 2, 16>(p, s) : launch_thin_cfg<CS, 2, 32>(p, s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Thin pointwise conv (1x1, stride 1) for few channels on large maps - the projection convs of inverted-residual
+// blocks (FaceMeshV2: 128x128x16 -> 8, 64x64x32 -> 16): one thread = PX pixels (128 pixels apart, so a warp's loads
+// are contiguous), the K x N weights are read from shared memory as broadcasts once per PX pixels, packed FFMA2.
+// The GEMM tile spends 0.47 ms on 512 x 128x128x16 -> 8 (memory floor 0.12 ms): K = 16 is one half-empty k-step.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int NP, int PX>
+__global__ void __launch_bounds__(128) pw_thin_kernel(const ConvDev p) {
+    __shared__ __align__(16) float s_w[CIN * NP];
+    __shared__ __align__(16) float s_b[NP], s_s1[NP], s_s2[NP];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < CIN * NP; e += 128) {
+        const int k = e / NP, n = e - k * NP;
+        s_w[e] = n < p.Ns ? __ldg(p.w + (long long)k * p.Ns + n) : 0.f;
+    }
+    const EpiDev &e = p.epi;
+    for (int n = tid; n < NP; n += 128) {
+        s_b[n] = n < p.Ns ? __ldg(e.bias + n) : 0.f;
+        s_s1[n] = (e.act1.kind == ACT_PRELU && n < p.Ns) ? __ldg(e.act1.slope + n) : 0.f;
+        s_s2[n] = (e.act2.kind == ACT_PRELU && n < p.Ns) ? __ldg(e.act2.slope + n) : 0.f;
+    }
+    __syncthreads();
+    const long long m0 = (long long)blockIdx.x * (128 * PX) + tid;
+    const int HoWo = p.Ho * p.Wo;
+    float4 x[PX][CIN / 4];
+#pragma unroll
+    for (int i = 0; i < PX; i++) {
+        const long long m = m0 + 128 * i;
+        if (m < p.M) {
+            const int img = (int)(m / HoWo);
+            const float *src = p.in + (long long)img * p.in_img_stride + (m - (long long)img * HoWo) * CIN;
+#pragma unroll
+            for (int q = 0; q < CIN / 4; q++) x[i][q] = ldg4(src + q * 4);
+        } else {
+#pragma unroll
+            for (int q = 0; q < CIN / 4; q++) x[i][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    float2 acc[PX][NP / 2];
+#pragma unroll
+    for (int j = 0; j < NP; j += 2)
+#pragma unroll
+        for (int i = 0; i < PX; i++) acc[i][j / 2] = make_float2(s_b[j], s_b[j + 1]);
+#pragma unroll
+    for (int k = 0; k < CIN; k++) {
+#pragma unroll
+        for (int j = 0; j < NP; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(s_w + k * NP + j);
+#pragma unroll
+            for (int i = 0; i < PX; i++) {
+                const float4 xq = x[i][k / 4];
+                const float a = (k & 3) == 0 ? xq.x : (k & 3) == 1 ? xq.y : (k & 3) == 2 ? xq.z : xq.w;
+                fma4s(acc[i][j / 2], acc[i][j / 2 + 1], a, wv);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PX; i++) {
+        const long long m = m0 + 128 * i;
+        if (m >= p.M) continue;
+        const int img = (int)(m / HoWo);
+        const int r = (int)(m - (long long)img * HoWo);
+        const int oy = r / p.Wo, ox = r - oy * p.Wo;
+        float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
+#pragma unroll
+        for (int j = 0; j < NP; j += 4) {
+            if (j >= p.Nstore) break;
+            float v[4] = {acc[i][j / 2].x, acc[i][j / 2].y, acc[i][j / 2 + 1].x, acc[i][j / 2 + 1].y};
+            if (e.act1.kind == ACT_PRELU) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[c] = v[c] < 0.f ? v[c] * s_s1[j + c] : v[c];
+            } else {
+                act4(v, e.act1, j);
+            }
+            if (e.res) {
+                const float4 rr = residual4_at(e, img, oy, ox, j);
+                v[0] += rr.x, v[1] += rr.y, v[2] += rr.z, v[3] += rr.w;
+            }
+            if (e.act2.kind == ACT_PRELU) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[c] = v[c] < 0.f ? v[c] * s_s2[j + c] : v[c];
+            } else {
+                act4(v, e.act2, j);
+            }
+            *reinterpret_cast<float4 *>(orow + j) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+template <int CIN, int NP, int PX>
+bool launch_pw_thin_cfg(const ConvDev &p, cudaStream_t s) {
+    pw_thin_kernel<CIN, NP, PX><<<(unsigned)((p.M + 128 * PX - 1) / (128 * PX)), 128, 0, s>>>(p);
+    return true;
+}
+
 }  // namespace
 
 // Returns false when the layer is outside the thin kernel's envelope (the GEMM-tile kernel handles it).
@@ -483,5 +578,25 @@ bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
     }
 }
 
+
+// Pointwise convs the thin kernel takes from the GEMM tile: 1x1 stride 1, Cs_in 16 or 32, N <= 32, maps >= 32x32,
+// 4-aligned stores, residual (if any) vectorisable.
+bool launch_pw_thin(const ConvDev &p, cudaStream_t s) {
+    static const bool disabled = getenv("ZB_NO_PW_THIN") && atoi(getenv("ZB_NO_PW_THIN")) != 0;
+    if (disabled) return false;
+    if (p.kh != 1 || p.kw != 1 || p.sh != 1 || p.sw != 1 || p.pt != 0 || p.pl != 0) return false;
+    if (p.K != p.Cs_in || (p.Cs_in != 16 && p.Cs_in != 32) || p.Ns > 32 || p.Ns % 4 || p.Nstore % 4 || p.out_pix_stride % 4) return false;
+    if (p.Ho * p.Wo < 1024 || p.M % (p.Ho * p.Wo)) return false;
+    if (p.epi.res && (p.epi.res_Cs % 4)) return false;
+    const int np = p.Ns <= 8 ? 8 : p.Ns <= 16 ? 16 : 32;
+    if (p.Cs_in == 16) {
+        if (np == 8) return launch_pw_thin_cfg<16, 8, 4>(p, s);
+        if (np == 16) return launch_pw_thin_cfg<16, 16, 4>(p, s);
+        return launch_pw_thin_cfg<16, 32, 2>(p, s);
+    }
+    if (np == 8) return launch_pw_thin_cfg<32, 8, 2>(p, s);
+    if (np == 16) return launch_pw_thin_cfg<32, 16, 2>(p, s);
+    return launch_pw_thin_cfg<32, 32, 2>(p, s);
+}
 
 }  // namespace zb
