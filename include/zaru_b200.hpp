@@ -463,4 +463,51 @@ class LandmarkTracker {
 };
 
 }  // namespace landmark
+
+// The fused per-frame face pipeline (examples/facemesh.rs:36-55 + one LandmarkTracker::track step on the same frame):
+// detect -> best detection -> RoI -> face mesh, all on the device, for every frame of a batch.
+class FacePipeline {
+   public:
+    struct Result {
+        std::vector<std::vector<detection::Detection>> detections;   // frame coordinates
+        std::vector<float> landmarks;                                 // [n][L][3], frame coordinates
+        std::vector<float> face_flags;                                // [n]; -1 where no face was detected
+        std::vector<RotatedRect> rois;                                // view_rect used for the mesh
+        int32_t num_landmarks = 0;
+    };
+    FacePipeline(const detection::Network &det, const landmark::Network &lm, const std::string &model_dir, int32_t capacity = 16)
+        : det_(nn::NeuralNetwork::from_path(model_dir + "/" + det.onnx)), lm_(nn::NeuralNetwork::from_path(model_dir + "/" + lm.onnx)),
+          cap_(capacity) {
+        check(zb_face_pipeline_create(context(), det_->handle(), lm_->handle(), &h_));
+        L_ = zb_face_pipeline_num_landmarks(h_);
+    }
+    ~FacePipeline() { zb_face_pipeline_destroy(h_); }
+    FacePipeline(const FacePipeline &) = delete;
+    void set_threshold(float det_thresh, float iou_thresh, detection::NmsMode mode = detection::NmsMode::Average) {
+        check(zb_face_pipeline_set_threshold(h_, det_thresh, iou_thresh, (zb_nms_mode)mode));
+    }
+    Result run(const ImageBatch &batch) {
+        const int32_t n = batch.len();
+        std::vector<zb_detection> dets((size_t)n * cap_);
+        std::vector<int32_t> counts(n);
+        std::vector<zb_view> rois(n);
+        Result r;
+        r.num_landmarks = L_;
+        r.landmarks.resize((size_t)n * L_ * 3);
+        r.face_flags.resize(n);
+        check(zb_face_pipeline_run(h_, batch.handle(), n, dets.data(), counts.data(), cap_, r.landmarks.data(), r.face_flags.data(), rois.data()));
+        r.detections.resize(n);
+        for (int32_t i = 0; i < n; i++) {
+            for (int32_t k = 0; k < counts[i] && k < cap_; k++) r.detections[i].emplace_back(dets[(size_t)i * cap_ + k]);
+            r.rois.push_back(RotatedRect::from_zb_view(rois[i]));
+        }
+        return r;
+    }
+
+   private:
+    std::shared_ptr<nn::NeuralNetwork> det_, lm_;
+    int32_t cap_, L_ = 0;
+    zb_face_pipeline *h_ = nullptr;
+};
+
 }  // namespace zaru

@@ -45,6 +45,9 @@ int main(int argc, char **argv) {
         double tsum = 0;
         for (float v : tensor) tsum += v;
 
+        FacePipeline pipe(detection::ShortRangeNetwork(), landmark::FaceMeshV1(), models);
+        auto pr = pipe.run(*full.batch());
+
         bool threw = false;
         try {
             trk.set_roi_padding(-1.0f);
@@ -63,6 +66,8 @@ int main(int argc, char **argv) {
                     none_before ? "true" : "false", tr ? "true" : "false", tr ? tr->estimate.confidence : 0.f, tr ? tr->updated_roi.rect().r.cx : 0.f,
                     tr ? tr->updated_roi.rect().r.cy : 0.f, tr ? tr->updated_roi.rect().width() : 0.f, tr ? tr->updated_roi.rect().height() : 0.f,
                     tr ? tr->updated_roi.radians : 0.f);
+        std::printf(" \"pipe_dets\": %zu, \"pipe_flag\": %.9g, \"pipe_lm0\": [%.9g, %.9g, %.9g], \"pipe_L\": %d,\n", pr.detections[0].size(),
+                    pr.face_flags[0], pr.landmarks[0], pr.landmarks[1], pr.landmarks[2], pr.num_landmarks);
         std::printf(" \"tensor_len\": %zu, \"tensor_sum\": %.9g, \"padding_rejected\": %s}\n", tensor.size(), tsum, threw ? "true" : "false");
         return 0;
     } catch (const std::exception &ex) {

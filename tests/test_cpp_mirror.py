@@ -73,3 +73,8 @@ def test_cpp_mirror_matches_python_mirror_and_reference_assertions(tmp_path, ass
     t = trk.track(batch)[0]
     assert t is not None and np.allclose(got["updated"], t.updated_roi(), rtol=0, atol=1e-3)
     assert got["tensor_len"] == 3 * 128 * 128
+    from zaru_b200.pipeline import FacePipeline
+    pr = FacePipeline().run(batch)
+    assert got["pipe_dets"] == len(pr.detections[0]) and got["pipe_L"] == 468
+    assert abs(got["pipe_flag"] - float(pr.face_flags[0])) <= 1e-6
+    assert np.allclose(got["pipe_lm0"], pr.landmarks[0, 0], rtol=0, atol=1e-3)
