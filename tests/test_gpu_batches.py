@@ -141,7 +141,7 @@ def test_config1_single_frame_detector(sad_linus_full):
 
 def test_config4_batch_1024_matches_small_batches():
     """BASELINE config 4 at its full size: the bench batch (1024 frames = 32 distinct, tiled) selects other kernels than
-    small batches do (tcgen05 blocks need >= 600 CTAs), so every frame of the big batch must reproduce what the same
+    small batches do (tcgen05 blocks need >= 500 CTAs), so every frame of the big batch must reproduce what the same
     frame gives in a batch of 32 - and the very FIRST pass must already be right (a launch that needed the
     shared-memory opt-in once failed on the first pass only)."""
     from zaru_b200 import synth
@@ -213,7 +213,7 @@ def test_pinned_host_frames_gather_pipeline_matches_resident_frames(n):
                                               ("hand_landmark_lite", 0.0, 224, 420), ("face_detection_full_range", -1.0, 192, 420),
                                               ("face_landmarks_detector", -1.0, 256, 300)])
 def test_every_network_large_batch_equals_small_batch(assets_dir, name, lo, size, big):
-    """Kernel selection depends on the launch size (tcgen05 blocks from ~600 CTAs, strip / tile kernels by map size,
+    """Kernel selection depends on the launch size (tcgen05 blocks from ~500 CTAs, strip / tile kernels by map size,
     per-batch stage for the deep layers): a LARGE batch of every network must reproduce, image by image, what the same
     images give in a batch of 6 - and the oracle on one of them.  Ragged batch sizes on purpose."""
     import os
