@@ -131,9 +131,21 @@ def cpu_baseline_single(budget_s=15.0):
     while time.perf_counter() - t0 < budget_s:
         n += _cpu_worker_run(4)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port", "cpu_model": cpu_model(),
             "sample": f"{n} 1080p S-face frames in {dt:.1f} s: oracle (numpy restatement + cv2.dnn, 1 thread) of "
                       "sample->BlazeFace->NMS->crop->face mesh; ort/tract cannot be built here"}
+
+
+def cpu_model() -> str:
+    """CPU model string of the box (SURVEY 8d asks for it next to the core count)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def run_reference(args):
@@ -169,7 +181,7 @@ def run_reference(args):
             # same workload string as the GPU arm; the CPU arm runs a bounded sample of it per step
             "config": {"workload": WORKLOAD, "frame": "1920x1080 RGBA8", "frames_per_step": per_worker * cores,
                        "note": "CPU reference arm: bounded sample of the same workload on the host cores"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(), "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
