@@ -282,3 +282,43 @@ def test_small_batch_cuda_graph_replay_is_invisible():
     o2 = pipe.run(other)
     assert np.array_equal(o1.landmarks, o2.landmarks) and np.array_equal(o1.landmarks, runs[0].landmarks[:7])
     assert np.array_equal(b1.landmarks, runs[0].landmarks)
+
+
+def test_two_host_threads_two_contexts(assets_dir):
+    """SURVEY 8b 'Threading': one `zb_ctx` (stream + workspace) per host thread, networks loaded per context; two threads
+    running forward passes concurrently on the same GPU must each get exactly what a serial run gives."""
+    import ctypes as C
+    import os
+    import threading
+    from zaru_b200 import _ffi
+    lib = _ffi.lib()
+    raw = open(os.path.join(assets_dir, "onnx", "face_detection_short_range.onnx"), "rb").read()
+    rng = np.random.default_rng(21)
+    inputs = [rng.uniform(-1, 1, size=(24, 3, 128, 128)).astype(np.float32) for _ in range(2)]
+
+    def run(x, iters, out):
+        ctx, net = C.c_void_p(), C.c_void_p()
+        _ffi.check(lib.zb_ctx_create(0, C.byref(ctx)))
+        buf = (C.c_char * len(raw)).from_buffer_copy(raw)
+        _ffi.check(lib.zb_net_load(ctx, buf, len(raw), C.byref(net)))
+        boxes = np.empty((x.shape[0], 896, 16), np.float32)
+        scores = np.empty((x.shape[0], 896, 1), np.float32)
+        ptrs = (C.c_void_p * 2)(boxes.ctypes.data, scores.ctypes.data)
+        for _ in range(iters):
+            _ffi.check(lib.zb_net_estimate(net, x.ctypes.data, x.shape[0], ptrs))
+        out.append((boxes.copy(), scores.copy()))
+        lib.zb_net_destroy(net)
+        lib.zb_ctx_destroy(ctx)
+
+    serial = [[], []]
+    for i in range(2):
+        run(inputs[i], 1, serial[i])
+    conc = [[], []]
+    threads = [threading.Thread(target=run, args=(inputs[i], 25, conc[i])) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(2):
+        assert len(conc[i]) == 1, "a worker thread raised"
+        assert np.array_equal(conc[i][0][0], serial[i][0][0]) and np.array_equal(conc[i][0][1], serial[i][0][1])
