@@ -256,7 +256,14 @@ def test_small_batch_cuda_graph_replay_is_invisible():
     res = Resolution(1920, 1080)
     batch = ImageBatch.from_rgba8(res, frames)
     pipe = FacePipeline()
-    runs = [pipe.run(batch) for _ in range(4)]            # plain, capture, replay, replay
+    import zaru_b200
+    counts = []
+    runs = []
+    for _ in range(4):                                    # plain, capture, replay, replay
+        c0 = zaru_b200.launch_count()
+        runs.append(pipe.run(batch))
+        counts.append(zaru_b200.launch_count() - c0)
+    assert counts[0] > 40 and len(set(counts)) == 1, counts   # replayed launches are counted like issued ones
     for r in runs[1:]:
         assert np.array_equal(r.landmarks, runs[0].landmarks) and np.array_equal(r.face_flags, runs[0].face_flags)
         assert [len(d) for d in r.detections] == [len(d) for d in runs[0].detections]

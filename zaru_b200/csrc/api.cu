@@ -996,6 +996,7 @@ struct zb_face_pipeline {
     // time the same configuration (frames, n, buffers, thresholds) is seen, replayed afterwards
     cudaGraphExec_t graph_exec = nullptr;
     uint64_t graph_key = 0, pending_key = 0;
+    long long graph_launches = 0, capture_base = 0;   // kernels inside the captured pass (zb_launch_count stays truthful)
     PinBuf h_stage, h_counts;
     int cap = 0;
 };
@@ -1788,11 +1789,13 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             key = h | 1;
             if (p->graph_exec && p->graph_key == key) {
                 CU(cudaGraphLaunch(p->graph_exec, s));
+                g_launch_count += p->graph_launches;
                 replayed = true;
             } else if (p->pending_key == key) {           // second sighting: every lazy initialisation has happened
                 if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec), p->graph_exec = nullptr;
                 CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
                 capturing = true;
+                p->capture_base = g_launch_count;
             } else {
                 p->pending_key = key;
             }
@@ -1845,6 +1848,7 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                 throw std::runtime_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ge));
             }
             p->graph_key = key;
+            p->graph_launches = g_launch_count - p->capture_base;
             CU(cudaGraphLaunch(p->graph_exec, s));
         }
         CU(cudaGetLastError());

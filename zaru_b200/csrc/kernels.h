@@ -2,6 +2,8 @@
 // kernels_exact.cu).  Plain structs, no CUDA types beyond cudaStream_t.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include "plan.h"
@@ -185,6 +187,6 @@ void launch_tracker_update(TrackState *state, const float *out0, int s0, const f
 // roi[ids[k]] = rois[k] (radians kept), or None when rois == nullptr
 void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s);
 
-extern long long g_launch_count;   // total kernel launches issued by this library (process-wide)
+extern std::atomic<long long> g_launch_count;   // total kernel launches issued by this library (process-wide)
 
 }  // namespace zb

@@ -22,7 +22,7 @@
 
 namespace zb {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s);   // kernels_thin.cu
 
