@@ -80,6 +80,29 @@ def main():
                         full_range_scores=fdet.last_raw[1], full_range_detections=dets_array(fdets),
                         v2_positions=e2.positions.copy(), v2_flag=np.float32(e2.face_flag),
                         v2_tongue_out=np.float32(e2.tongue_out))
+    # --- LandmarkTracker steps (free-running oracle) + filter sequences ----------------------
+    from oracle import filter as ofilter
+    from oracle.landmark import LandmarkTracker
+    base = synth.s_face_frame(500, allow_empty=False)[0]
+    seq = [np.roll(np.roll(base, 6 * t, axis=1), 3 * t, axis=0) for t in range(4)]
+    trk = LandmarkTracker(Estimator(FaceMeshV1()))
+    trk.set_roi(Detector(ShortRangeNetwork()).detect(Image(seq[0]))[0].rect)
+    rec = {"frame_sha": np.frombuffer(__import__("hashlib").sha256(base.tobytes()).digest(), np.uint8)}
+    for t, fr in enumerate(seq):
+        roi = trk.roi
+        rec[f"t{t}_roi_in"] = np.asarray([roi.rect.cx, roi.rect.cy, roi.rect.w, roi.rect.h, roi.radians], np.float32)
+        view_rect, est, updated = trk.track(Image(fr))
+        rec[f"t{t}_view_rect"] = np.asarray([*view_rect.rect.as_tuple(), view_rect.radians], np.float32)
+        rec[f"t{t}_conf"] = np.float32(est.face_flag)
+        rec[f"t{t}_positions"] = est.positions.copy()
+        rec[f"t{t}_updated"] = np.asarray([*updated.rect.as_tuple(), updated.radians], np.float32)
+    rng = np.random.default_rng(3)
+    xs = (rng.uniform(-200, 200, 64).astype(np.float32)[None, :] + np.arange(10, dtype=np.float32)[:, None] * rng.uniform(-3, 3, 64).astype(np.float32)[None, :])
+    for name, flt in (("ema", ofilter.Ema(0.3)), ("one_euro", ofilter.OneEuroFilter(1.5, 0.05, 0.8)), ("alpha_beta", ofilter.AlphaBetaFilter(0.6, 0.2))):
+        sts = [flt.new_state() for _ in range(64)]
+        rec[f"filter_{name}"] = np.array([[flt.filter(sts[i], xs[t, i], 1.0 / 30.0) for i in range(64)] for t in range(10)], np.float32)
+    rec["filter_inputs"] = xs.astype(np.float32)
+    np.savez_compressed(os.path.join(out, "tracker_filter.npz"), **rec)
     for f in sorted(os.listdir(out)):
         print(f, os.path.getsize(os.path.join(out, f)))
 
