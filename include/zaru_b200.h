@@ -212,6 +212,20 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                                zb_detection *out_dets, int32_t *out_counts, int32_t cap,
                                float *out_landmarks, float *out_flags, zb_view *out_rois);
 
+/* ---- palm detection + hand landmarks, fused (BASELINE config 3) ------------------------------
+ * The same device-resident two-stage machinery with the hand crop rule of HandTracker
+ * (hand/tracking.rs:136, :159): detect palms on each whole frame (palm_detection_lite, ColorMapper 0..=1) ->
+ * highest-confidence palm -> RoI = RotatedRect(bounding_rect.grow_rel(1.5), det.angle()) -> one
+ * LandmarkTracker::track step (rotated view, hand_landmark_lite) -> 21 landmarks in frame coordinates.
+ * out_scalars [n][2] = {presence, raw handedness} (hand/landmark.rs:298-322; -1 / 0 where no palm was found).  */
+typedef zb_face_pipeline zb_hand_pipeline;
+zb_status zb_hand_pipeline_create(zb_ctx *ctx, zb_net *palm_net, zb_net *hand_landmark_net, zb_hand_pipeline **out);
+void zb_hand_pipeline_destroy(zb_hand_pipeline *p);
+zb_status zb_hand_pipeline_set_threshold(zb_hand_pipeline *p, float det_thresh, float iou_thresh, zb_nms_mode mode);
+zb_status zb_hand_pipeline_run(zb_hand_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
+                               int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_scalars,
+                               zb_view *out_rois);
+
 /* ---- LandmarkTracker (landmark.rs:361-502), batched over independent streams ------------------
  * One tracker owns `streams` RoI slots that live on the device.  zb_tracker_track runs ONE
  * `LandmarkTracker::track` step for every stream (stream i reads frame i of `frames`):

@@ -329,3 +329,54 @@ def test_two_host_threads_two_contexts(assets_dir):
     for i in range(2):
         assert len(conc[i]) == 1, "a worker thread raised"
         assert np.array_equal(conc[i][0][0], serial[i][0][0]) and np.array_equal(conc[i][0][1], serial[i][0][1])
+
+
+def test_config3_fused_hand_pipeline_matches_oracle(sad_linus_full):
+    """BASELINE config 3 as ONE device-resident call (`zb_hand_pipeline_run`): palm detector -> best palm ->
+    RotatedRect(bounding_rect.grow_rel(1.5), det.angle()) (hand/tracking.rs:136, :159) -> one LandmarkTracker::track
+    step of the hand landmark network.  The reference has no hand fixture, so the palm threshold is lowered until the
+    face images yield candidates; what matters is that both sides make the same candidates, the same rotated RoI and
+    the same landmarks."""
+    from oracle.detection import Detector as ODetector, PalmLiteNetwork as OPalm
+    from oracle.geometry import RotatedRect as ORR
+    from oracle.landmark import Estimator as OEst, HandLiteNetwork as OHand, LandmarkTracker as OTracker
+    from oracle.image import Image as OImage
+    from tests.oracle_pipeline import _total_key
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import HandPipeline
+    from zaru_b200.rect import Resolution
+    frames = np.stack([synth.s_face_frame(1000 + s, allow_empty=False)[0] for s in (0, 3, 5, 8)])
+    pipe = HandPipeline(capacity=64)
+    pipe.set_threshold(0.1, 0.3)
+    res = pipe.run(ImageBatch.from_rgba8(Resolution(1920, 1080), frames))
+    odet = ODetector(OPalm())
+    odet.thresh = np.float32(0.1)
+    checked = 0
+    for i in range(len(frames)):
+        oimg = OImage(frames[i])
+        dets = odet.detect(oimg)
+        if float(np.abs(odet.last_raw[1] - np.log(0.1 / 0.9)).min()) < 1e-2:
+            continue                                       # a logit next to the threshold: set identity not required
+        assert len(res.detections[i]) == len(dets), i
+        if not dets:
+            assert res.presence[i] == -1.0
+            continue
+        for g, w in zip(res.detections[i], dets):
+            assert g.anchor == w.anchor
+            assert np.abs(g.as_vector()[2:] - w.as_vector()[2:]).max() <= TOL * 192 * 10.0
+        best = None
+        for d in dets:
+            if best is None or _total_key(d.confidence) >= _total_key(best.confidence):
+                best = d
+        trk = OTracker(OEst(OHand()))
+        trk.loss_thresh = np.float32(-1e9)
+        trk.set_roi(ORR(best.rect.grow_rel(1.5), best.angle))
+        view_rect, est, _ = trk.track(oimg)
+        assert np.allclose(res.rois[i, :4], np.asarray(view_rect.rect.as_tuple(), np.float32), atol=TOL * 192 * 10.0 * 2.5)
+        assert abs(res.rois[i, 4] - float(view_rect.radians)) <= 2e-3
+        scale = float(view_rect.rect.w) / 224.0
+        assert abs(float(res.presence[i]) - float(est.presence)) <= 5e-3
+        assert np.abs(res.landmarks[i] - est.positions).max() <= TOL * 224 * scale + 12.0 * TOL * 192, i
+        checked += 1
+    assert checked >= 2

@@ -37,3 +37,19 @@ for dname, dnet in (("short_range", ShortRangeNetwork), ("full_range", FullRange
         print(json.dumps({"detector": dname, "mesh": lname, "batch": n, "frames_per_s": n * steps / (ms / 1000.0),
                           "ms_per_step": ms / steps, "frames_with_face": int((out[3] >= 0).sum())}), flush=True)
         del pipe
+
+# BASELINE config 3 as one fused call: palm detector + hand landmarks (threshold lowered: the frames hold no hands)
+from zaru_b200.pipeline import HandPipeline  # noqa: E402
+
+hp = HandPipeline(capacity=64)
+hp.set_threshold(0.1, 0.3)
+m = min(n, 256)
+hb = ImageBatch.from_rgba8(Resolution(1920, 1080), frames[:m])
+for _ in range(3):
+    r = hp.run(hb)
+ms = 0.0
+for _ in range(5):
+    r = hp.run(hb)                       # run() also builds Python objects: take the device time of each call
+    ms += zaru_b200.last_device_ms()
+print(json.dumps({"detector": "palm_lite", "mesh": "hand_landmark_lite", "batch": m, "frames_per_s": m * 5 / (ms / 1000.0),
+                  "ms_per_step": ms / 5, "frames_with_candidate": int((r.presence >= 0).sum())}), flush=True)

@@ -89,6 +89,10 @@ SIGNATURES = {
     "zb_filter_apply": (i32, [P, i32, f32, f32, f32, f32, P, P, i64]),
     "zb_view_to_image": (i32, [P, P, P, i32, i32, i32, P]),
     "zb_frames_clear": (i32, [P, i32, i32, P]),
+    "zb_hand_pipeline_create": (i32, [P, P, P, PP]),
+    "zb_hand_pipeline_destroy": (None, [P]),
+    "zb_hand_pipeline_set_threshold": (i32, [P, f32, f32, i32]),
+    "zb_hand_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),
     "zb_face_pipeline_set_threshold": (i32, [P, f32, f32, i32]),
     "zb_face_pipeline_num_landmarks": (i32, [P]),
     "zb_face_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),

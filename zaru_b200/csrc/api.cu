@@ -1529,10 +1529,12 @@ zb_status zb_face_pipeline_create(zb_ctx *ctx, zb_net *det_net, zb_net *lm_net, 
         if (!ctx || !det_net || !lm_net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
         // detector / mesh generation is recognised by the output shapes: short range (896 anchors) or full range
         // (2304), FaceMeshV1 (468 points) or FaceMeshV2 (478 points + tongueOut)
-        const zb_detector_kind dk = det_net->plan.outputs.size() >= 2 && det_net->plan.outputs[1].per_image == 2304
-                                        ? ZB_DET_FACE_FULL_RANGE : ZB_DET_FACE_SHORT_RANGE;
-        const zb_estimator_kind lk = !lm_net->plan.outputs.empty() && lm_net->plan.outputs[0].per_image == 1434
-                                         ? ZB_EST_FACE_MESH_V2 : ZB_EST_FACE_MESH_V1;
+        const int64_t anchors = det_net->plan.outputs.size() >= 2 ? det_net->plan.outputs[1].per_image : 0;
+        const int64_t lm0 = !lm_net->plan.outputs.empty() ? lm_net->plan.outputs[0].per_image : 0;
+        const zb_detector_kind dk = anchors == 2304 ? ZB_DET_FACE_FULL_RANGE : anchors == 2016 ? ZB_DET_PALM : ZB_DET_FACE_SHORT_RANGE;
+        const zb_estimator_kind lk = lm0 == 1434 ? ZB_EST_FACE_MESH_V2 : lm0 == 63 ? ZB_EST_HAND : ZB_EST_FACE_MESH_V1;
+        if ((dk == ZB_DET_PALM) != (lk == ZB_EST_HAND))
+            return fail(ZB_ERR_BAD_SHAPE, "a palm detector pairs with the hand landmark network, a face detector with a face mesh");
         try {
             check_detector_net(det_net, dk);
             check_estimator_net(lm_net, lk);
@@ -1577,6 +1579,11 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         CU(cudaSetDevice(ctx->device));
         cudaStream_t s = ctx->stream;
         const Plan &dpl = p->det_net->plan, &lpl = p->lm_net->plan;
+        // hand pipeline (palm detector + hand landmarks): ColorMapper 0..=1 (hand/detection.rs:61, hand/landmark.rs:261),
+        // RoI = RotatedRect(bounding_rect.grow_rel(1.5), det.angle()) (hand/tracking.rs:136, :159); face: -1..=1, plain RoI
+        const bool hand = p->lm_kind == ZB_EST_HAND;
+        const float map_lo = hand ? 0.0f : -1.0f, roi_grow = hand ? 1.5f : 0.0f;
+        const int roi_use_angle = hand ? 1 : 0;
         // Frames in pinned host memory are sampled across PCIe: split the batch into >= 4 chunks and alternate
         // them between two streams so one chunk's (PCIe-latency-bound) sampling overlaps the other's compute.
         static const bool two_stream_env = getenv("ZB_TWO_STREAMS") && atoi(getenv("ZB_TWO_STREAMS")) != 0;   // measured: no gain, PCIe-bound
@@ -1718,10 +1725,10 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             auto landmarks = [&](int kk) {
                 const int c0 = bounds[kk], nc = bounds[kk + 1] - c0;
                 CU(cudaStreamWaitEvent(s, ev(kk, 2), 0));
-                const StemInput sl{&flm, p->d_id_lm.as<ViewDev>() + c0, -1.0f, 1.0f};
+                const StemInput sl{&flm, p->d_id_lm.as<ViewDev>() + c0, map_lo, 1.0f};
                 run_ops(p->lm_net, wl, c0, nc, 0, s, &sl);
                 run_ops(p->lm_net, wl, c0, nc, 1, s);
-                const int s2 = p->lm_kind == ZB_EST_FACE_MESH_V2 ? (int)lpl.outputs[2].per_image : 0;
+                const int s2 = (p->lm_kind == ZB_EST_FACE_MESH_V2 || p->lm_kind == ZB_EST_HAND) ? (int)lpl.outputs[2].per_image : 0;
                 launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
                                  s2 ? wl.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2, p->d_lm_fit.as<float>() + 4 * c0,
                                  p->d_lm_views.as<ViewDev>() + c0, p->d_rois.as<ViewHost>() + c0, nc, lp,
@@ -1734,14 +1741,15 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                 CU(cudaEventRecord(ev(kk, 0), g));
                 if (kk >= 1) gather2(kk - 1);
                 CU(cudaStreamWaitEvent(s, ev(kk, 0), 0));
-                const StemInput sd{&fdet, p->d_id_det.as<ViewDev>() + c0, -1.0f, 1.0f};
+                const StemInput sd{&fdet, p->d_id_det.as<ViewDev>() + c0, map_lo, 1.0f};
                 run_ops(p->det_net, wd, c0, nc, 0, s, &sd);
                 run_ops(p->det_net, wd, c0, nc, 1, s);
                 launch_decode_nms(wd.outs[0].as<float>() + (size_t)c0 * dpl.outputs[0].per_image,
                                   wd.outs[1].as<float>() + (size_t)c0 * dpl.outputs[1].per_image, p->d_fit.as<float>() + 4 * c0, nc, dp,
                                   p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, s);
                 launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0, nc, lw, lh,
-                                p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0, p->d_rois.as<ViewHost>() + c0, s);
+                                p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0, p->d_rois.as<ViewHost>() + c0, s,
+                                roi_grow, roi_use_angle);
                 CU(cudaEventRecord(ev(kk, 1), s));
                 if (kk >= 1) landmarks(kk - 1);
             }
@@ -1807,7 +1815,7 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             cudaStream_t cs = j == 0 ? s : p->stream2;
             Workspace &wd = p->ws_det[j], &wl = p->ws_lm[j];
             // detector: (fused) sampling + stage 0 + stage 1, decode/NMS, RoI -> landmark view (all on device)
-            const StemInput sd{&frames->f, p->d_views.as<ViewDev>() + c0, -1.0f, 1.0f};
+            const StemInput sd{&frames->f, p->d_views.as<ViewDev>() + c0, map_lo, 1.0f};
             run_ops(p->det_net, wd, c0, nc, 0, cs, &sd);
             run_ops(p->det_net, wd, c0, nc, 1, cs);
             prof_launch(ctx, cs, "decode_nms", 4.0 * nc * dp.num_anchors * (dp.num_params + 1), 0, [&] {
@@ -1819,14 +1827,14 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
             prof_launch(ctx, cs, "face_roi", 128.0 * nc, 0, [&] {
                 launch_face_roi(frames->f, p->d_dets.as<DetDev>() + (size_t)c0 * cap, p->d_counts.as<int>() + c0, cap, c0, nc,
                                 lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0,
-                                p->d_rois.as<ViewHost>() + c0, cs);
+                                p->d_rois.as<ViewHost>() + c0, cs, roi_grow, roi_use_angle);
             });
             // landmarks
-            const StemInput sl{&frames->f, p->d_lm_views.as<ViewDev>() + c0, -1.0f, 1.0f};
+            const StemInput sl{&frames->f, p->d_lm_views.as<ViewDev>() + c0, map_lo, 1.0f};
             run_ops(p->lm_net, wl, c0, nc, 0, cs, &sl);
             run_ops(p->lm_net, wl, c0, nc, 1, cs);
             prof_launch(ctx, cs, "landmarks", 8.0 * nc * (3 * L + 1), 0, [&] {
-                const int s2 = p->lm_kind == ZB_EST_FACE_MESH_V2 ? (int)lpl.outputs[2].per_image : 0;
+                const int s2 = (p->lm_kind == ZB_EST_FACE_MESH_V2 || p->lm_kind == ZB_EST_HAND) ? (int)lpl.outputs[2].per_image : 0;
                 launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
                                  s2 ? wl.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2, p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
                                  p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
@@ -1871,6 +1879,35 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                 return fail(ZB_ERR_CAPACITY, "frame " + std::to_string(i) + " produced " + std::to_string(hc[i]) +
                                                  " detections; capacity is " + std::to_string(cap));
         return ZB_OK;
+    });
+}
+
+// ---- palm detector + hand landmarks (BASELINE config 3): the same fused machinery, hand crop rule --------------------
+zb_status zb_hand_pipeline_create(zb_ctx *ctx, zb_net *palm_net, zb_net *hand_net, zb_hand_pipeline **out) {
+    zb_status st = zb_face_pipeline_create(ctx, palm_net, hand_net, out);
+    if (st == ZB_OK && (*out)->lm_kind != ZB_EST_HAND) {
+        zb_face_pipeline_destroy(*out);
+        *out = nullptr;
+        return fail(ZB_ERR_BAD_SHAPE, "zb_hand_pipeline_create needs the palm detector and the hand landmark network");
+    }
+    return st;
+}
+
+void zb_hand_pipeline_destroy(zb_hand_pipeline *p) { zb_face_pipeline_destroy(p); }
+
+zb_status zb_hand_pipeline_set_threshold(zb_hand_pipeline *p, float det_thresh, float iou_thresh, zb_nms_mode mode) {
+    return zb_face_pipeline_set_threshold(p, det_thresh, iou_thresh, mode);
+}
+
+zb_status zb_hand_pipeline_run(zb_hand_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
+                               int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_scalars, zb_view *out_rois) {
+    const zb_status st = zb_face_pipeline_run(p, frames, n, out_dets, out_counts, cap, out_landmarks, nullptr, out_rois);
+    if ((st != ZB_OK && st != ZB_ERR_CAPACITY) || !out_scalars || n == 0) return st;
+    return guarded([&]() -> zb_status {
+        cudaStream_t s = p->ctx->stream;
+        copy_out(out_scalars, p->d_scalars.p, sizeof(float) * 2 * (size_t)n, s);
+        CU(cudaStreamSynchronize(s));
+        return st;
     });
 }
 

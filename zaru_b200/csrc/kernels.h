@@ -142,7 +142,7 @@ void launch_decode_nms(const float *boxes, const float *scores, const float *fit
 // Face pipeline glue: best detection -> RoI -> tracker view (landmark.rs:465-466) composed with the full frame.
 void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, int cap, int first_frame, int n,
                      int net_w, int net_h, ViewDev *out_views, float *out_fit, ViewHost *out_view_rects,
-                     cudaStream_t s);
+                     cudaStream_t s, float grow_rel_amount = 0.0f, int use_angle = 0);   // hand RoI: grow_rel(1.5) + detection angle (hand/tracking.rs:136, :159)
 
 // LandmarkFilter (landmark.rs:147-202) over zaru::filter (filter/{ema,one_euro,alpha_beta}.rs): one state triple
 // per (slot, landmark, coordinate), applied in NETWORK coordinates before the remap (landmark.rs:330-333).

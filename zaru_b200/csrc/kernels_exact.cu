@@ -640,10 +640,12 @@ __global__ void __launch_bounds__(256) decode_nms_kernel(const float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cos_sin_ref(float rad, float &c, float &s);
 __global__ void __launch_bounds__(128) face_roi_kernel(const FramesDev f, const DetDev *__restrict__ dets,
                                                        const int *__restrict__ counts, int cap, int first_frame,
                                                        int n, int net_w, int net_h, ViewDev *__restrict__ out_views,
-                                                       float *__restrict__ out_fit, ViewHost *__restrict__ out_rects) {
+                                                       float *__restrict__ out_fit, ViewHost *__restrict__ out_rects,
+                                                       float grow, int use_angle) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cnt = min(counts[i], cap);
@@ -671,16 +673,21 @@ __global__ void __launch_bounds__(128) face_roi_kernel(const FramesDev f, const 
         // tracker.set_roi(detection.bounding_rect()); view_rect = roi.map(grow_to_fit_aspect)  (landmark.rs:465)
         RectF roi;
         roi.cx = d[best].cx, roi.cy = d[best].cy, roi.w = d[best].w, roi.h = d[best].h;
+        // hand: RotatedRect::new(det.bounding_rect().grow_rel(1.5), det.angle())   (hand/tracking.rs:136, :159)
+        if (grow != 0.0f) roi = grow_rel(roi, grow);
+        const float rad = use_angle ? d[best].angle : 0.0f;
+        float c, s;
+        cos_sin_ref(rad, c, s);                  // rotation 0 -> cos 1, sin 0 exactly
         const RectF view_rect = grow_to_fit_aspect(roi, aspect);
-        vr.cx = view_rect.cx, vr.cy = view_rect.cy, vr.w = view_rect.w, vr.h = view_rect.h;
-        // full_image.view(view_rect)   (landmark.rs:466; rotation 0 -> cos 1, sin 0 exactly)
+        vr.cx = view_rect.cx, vr.cy = view_rect.cy, vr.w = view_rect.w, vr.h = view_rect.h, vr.radians = rad;
+        // full_image.view(view_rect)   (landmark.rs:466)
         const RRectF full = full_view(f.width, f.height);
-        const RRectF v1 = view_compose(full, view_rect, 0.0f, 1.0f, 0.0f);
+        const RRectF v1 = view_compose(full, view_rect, rad, c, s);
         // Estimator::estimate_impl: rect = view.rect().grow_to_fit_aspect(..); view = image.view(rect)  (:320-323)
         const RectF r1 = rect_from_top_left(0.0f, 0.0f, v1.r.w, v1.r.h);
         const RectF r2 = grow_to_fit_aspect(r1, aspect);
-        const RRectF v2 = view_compose(v1, r2, 0.0f, 1.0f, 0.0f);
-        v.cx = v2.r.cx, v.cy = v2.r.cy, v.w = v2.r.w, v.h = v2.r.h;
+        const RRectF v2 = view_compose(v1, r2, 0.0f, c, s);
+        v.cx = v2.r.cx, v.cy = v2.r.cy, v.w = v2.r.w, v.h = v2.r.h, v.cosr = c, v.sinr = s;
         fit0 = r2.w / (float)net_w;   // scale = rect.width() / input_res.width()   (:336)
         fit1 = rect_x(r2);
         fit2 = rect_y(r2);
@@ -758,7 +765,10 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
             a = valid ? sigmoid_ref(out1[(long long)img * s1]) : -1.0f;
             b = out2[(long long)img * s2];
         }
-        if (p.kind == 2) a = out1[(long long)img * s1], b = out2[(long long)img * s2]; // hand/landmark.rs:310-311
+        if (p.kind == 2) {                                                             // hand/landmark.rs:310-311
+            a = valid ? out1[(long long)img * s1] : -1.0f;
+            b = valid ? out2[(long long)img * s2] : 0.0f;
+        }
         scalars[img * 2 + 0] = a, scalars[img * 2 + 1] = b;
     }
     if (l >= p.num_landmarks) return;
@@ -1036,10 +1046,10 @@ void launch_decode_nms(const float *boxes, const float *scores, const float *fit
 
 void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, int cap, int first_frame, int n,
                      int net_w, int net_h, ViewDev *out_views, float *out_fit, ViewHost *out_view_rects,
-                     cudaStream_t s) {
+                     cudaStream_t s, float grow_rel_amount, int use_angle) {
     g_launch_count++;
     face_roi_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, dets, counts, cap, first_frame, n, net_w, net_h, out_views,
-                                                    out_fit, out_view_rects);
+                                                    out_fit, out_view_rects, grow_rel_amount, use_angle);
 }
 
 void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,

@@ -108,3 +108,51 @@ class FaceStreamTracker:
 def _total_key(x):
     b = int(np.float32(x).view(np.int32))
     return b ^ 0x7FFFFFFF if b < 0 else b
+
+
+class HandPipelineResult:
+    def __init__(self, detections, landmarks, presence, handedness, rois):
+        self.detections = detections      # list[Detections] of palms, frame coordinates
+        self.landmarks = landmarks        # [n,21,3] float32, frame coordinates
+        self.presence = presence          # [n] hand presence (-1 where no palm was detected)
+        self.raw_handedness = handedness  # [n]
+        self.rois = rois                  # [n,5]: view_rect (cx, cy, w, h, radians) used for the landmark network
+
+
+class HandPipeline:
+    """Palm detection + hand landmarks on device (BASELINE config 3): per frame the best palm seeds
+    `RotatedRect(bounding_rect.grow_rel(1.5), det.angle())` (hand/tracking.rs:136, :159) and one
+    `LandmarkTracker::track` step of the hand landmark network runs on that rotated view."""
+
+    def __init__(self, capacity: int = 16):
+        from .detection import PalmLiteNetwork
+        from .landmark import HandLiteNetwork
+        self._det = PalmLiteNetwork().cnn()
+        self._lm = HandLiteNetwork().cnn()
+        self._cap = capacity
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_hand_pipeline_create(context(), self._det.nn._h, self._lm.nn._h, C.byref(h)))
+        self._h = h
+
+    def set_threshold(self, det_thresh=0.5, iou_thresh=0.3, mode=_ffi.ZB_NMS_AVERAGE):
+        _ffi.check(_ffi.lib().zb_hand_pipeline_set_threshold(self._h, det_thresh, iou_thresh, mode))
+
+    def run(self, batch, n=None) -> HandPipelineResult:
+        n = len(batch) if n is None else n
+        dets = (_ffi.zb_detection * (n * self._cap))()
+        counts = (C.c_int32 * n)()
+        lm = np.empty((n, 21, 3), np.float32)
+        sc = np.empty((n, 2), np.float32)
+        rois = (_ffi.zb_view * n)()
+        _ffi.check(_ffi.lib().zb_hand_pipeline_run(self._h, batch._h, n, dets, counts, self._cap, lm.ctypes.data, sc.ctypes.data, rois))
+        out = [Detections(Detection(dets[i * self._cap + k]) for k in range(min(counts[i], self._cap))) for i in range(n)]
+        r = np.array([[v.cx, v.cy, v.w, v.h, v.radians] for v in rois], np.float32).reshape(n, 5)
+        return HandPipelineResult(out, lm, sc[:, 0].copy(), sc[:, 1].copy(), r)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ffi.lib().zb_hand_pipeline_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
