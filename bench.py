@@ -312,6 +312,70 @@ def run_gpu(args):
         (zc_ms_max,) = shard.max_over_ranks([zc_ms], dist, "cuda")
     except Exception as ex:   # pinned allocation of the full batch can fail on small hosts
         log(f"[rank {rank}] zero-copy e2e skipped: {ex}")
+    # --- e2e, zero-copy, T host threads: the reference's own parallelism is one Detector per thread (`&mut self`,
+    # rayon map_init); here every thread owns a zb_ctx + pipeline + its own pinned frames, so while one pipeline's
+    # texel gather keeps PCIe busy the other one computes - ingest overlaps ACROSS steps, not just within one -------
+    mt_ms_max, mt_threads = None, max(1, args.e2e_threads)
+    if zc_ms_max is not None and mt_threads > 1:
+        import threading
+        bufs = None
+        try:
+            bufs = [h_big]
+            for i in range(1, mt_threads):
+                hb = torch.empty((zc_n, FRAME_H, FRAME_W, 4), dtype=torch.uint8, pin_memory=True)
+                hb.copy_(torch.roll(h_big, shifts=7 * i, dims=0))      # same frames in another order: another buffer
+                bufs.append(hb)
+        except Exception as ex:   # noqa: BLE001 - not enough pinnable host memory
+            log(f"[rank {rank}] multi-threaded zero-copy e2e skipped: {ex}")
+            bufs = None
+        # every collective below is reached by every rank whatever happened locally
+        if shard.max_over_ranks([0.0 if bufs is not None else 1.0], dist, "cuda")[0] == 0.0:
+            ready, start, done = (threading.Barrier(mt_threads + 1) for _ in range(3))
+            errs = []
+
+            def worker(i):
+                try:
+                    zaru_b200.thread_context(local)
+                    wp = FacePipeline(capacity=args.cap)
+                    wb = ImageBatch.alias_pinned_host(res, bufs[i].data_ptr(), zc_n, keepalive=bufs[i])
+                    for _ in range(max(2, args.warmup // 2 + 1)):
+                        wp.run_raw(wb, zc_n)
+                    zaru_b200.sync()
+                    ready.wait()
+                    start.wait()
+                    for _ in range(args.steps):
+                        wp.run_raw(wb, zc_n)                           # returns with the results in host memory
+                    zaru_b200.sync()
+                    done.wait()
+                except Exception as ex:   # noqa: BLE001 - report and release the other parties
+                    errs.append(ex)
+                    for bar in (ready, start, done):
+                        bar.abort()
+
+            workers = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(mt_threads)]
+            for t in workers:
+                t.start()
+            try:
+                ready.wait()
+            except threading.BrokenBarrierError:
+                pass
+            barrier()
+            mt_ms = None
+            try:
+                start.wait()
+                m0 = time.perf_counter()
+                done.wait()
+                mt_ms = 1000.0 * (time.perf_counter() - m0)
+            except threading.BrokenBarrierError:
+                pass
+            for t in workers:
+                t.join()
+            if errs:
+                log(f"[rank {rank}] multi-threaded zero-copy e2e failed: {errs[0]}")
+                mt_ms = None
+            bad, worst = shard.max_over_ranks([1.0 if mt_ms is None else 0.0, mt_ms or 0.0], dist, "cuda")
+            mt_ms_max = worst if bad == 0.0 else None
+        bufs = None
     clock_info = clocks.stop() if rank == 0 else None
     d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
 
@@ -377,6 +441,23 @@ def run_gpu(args):
             e2e_best = dict(e2e_zc, explicit_copy=e2e_copy)
         else:
             e2e_best = dict(e2e_copy, zero_copy=e2e_zc)
+        if mt_ms_max is not None:
+            mt_value = world * mt_threads * zc_n * args.steps / (mt_ms_max / 1000.0)
+            e2e_mt = {"value": mt_value, "unit": UNIT, "h2d_bytes_per_step": mt_threads * e2e_zc["h2d_bytes_per_step"],
+                      "d2h_bytes_per_step": mt_threads * e2e_zc["d2h_bytes_per_step"], "batch_per_gpu": mt_threads * zc_n,
+                      "ms_per_step": mt_ms_max / args.steps, "host_threads": mt_threads,
+                      "note": "%d host threads per GPU, each with its own zb_ctx + zb_face_pipeline + %d frames in its own "
+                              "PINNED HOST buffer (the reference's one-Detector-per-thread model); a step = every thread "
+                              "passes its batch once (zb_frames_alias zero-copy texel gather across PCIe inside the timed "
+                              "region, results D2H into host buffers every step); one pipeline's gather overlaps the "
+                              "other's compute; wall clock between barriers around the K steps; h2d bytes = upper bound, "
+                              "one 64 B read per sampled texel" % (mt_threads, zc_n)}
+            if mt_value > e2e_best["value"]:
+                nested = {k: v for k, v in e2e_best.items() if k in ("explicit_copy", "zero_copy")}
+                single = {k: v for k, v in e2e_best.items() if k not in ("explicit_copy", "zero_copy")}
+                e2e_best = dict(e2e_mt, single_thread=single, **nested)
+            else:
+                e2e_best = dict(e2e_best, multi_thread=e2e_mt)
     peak, peak_src = peaks()
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     total_ms = sum(v["ms"] for v in prof.values())
@@ -431,6 +512,8 @@ def main():
     ap.add_argument("--impl", default="zaru_b200", choices=["zaru_b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--e2e-batch", type=int, default=256)
+    ap.add_argument("--e2e-threads", type=int, default=2,
+                    help="host threads (each with its own context + pipeline) of the multi-threaded zero-copy e2e leg; 1 = off")
     ap.add_argument("--unique", type=int, default=32)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--cap", type=int, default=16)

@@ -208,6 +208,57 @@ def test_pinned_host_frames_gather_pipeline_matches_resident_frames(n):
     assert faces >= n // 3
 
 
+def test_thread_contexts_two_pinned_host_pipelines_in_flight():
+    """`zaru_b200.thread_context()`: the reference's one-Detector-per-thread model (`&mut self`; rayon map_init,
+    eval_face_recognition.rs:67-70).  Two host threads, each with its own zb_ctx + networks + face pipeline + pinned
+    host frames, run concurrently on one GPU (one pipeline's PCIe texel gather overlaps the other's compute - the
+    bench's multi-threaded e2e leg); every thread must get exactly what the main thread's context gives serially."""
+    import threading
+    import torch
+    import zaru_b200
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    n = 40
+    uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in range(10)])
+    res = Resolution(1920, 1080)
+    hosts = [torch.from_numpy(np.concatenate([np.roll(uniq, k, axis=0)] * 4)).pin_memory() for k in (0, 3)]
+    main_ctx = zaru_b200.context_key()
+    serial = [FacePipeline().run(ImageBatch.alias_pinned_host(res, h.data_ptr(), n, keepalive=h)) for h in hosts]
+    out, errs, keys = [None, None], [], [None, None]
+    gate = threading.Barrier(2)
+
+    def work(i):
+        try:
+            zaru_b200.thread_context()
+            keys[i] = zaru_b200.context_key()
+            pipe = FacePipeline()
+            batch = ImageBatch.alias_pinned_host(res, hosts[i].data_ptr(), n, keepalive=hosts[i])
+            gate.wait()
+            for _ in range(6):
+                out[i] = pipe.run(batch)
+            zaru_b200.sync()
+        except Exception as ex:   # noqa: BLE001
+            errs.append(ex)
+            gate.abort()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    assert len({main_ctx, keys[0], keys[1]}) == 3          # three distinct contexts
+    assert zaru_b200.context_key() == main_ctx             # the main thread keeps the process-wide one
+    for i in range(2):
+        assert [len(d) for d in out[i].detections] == [len(d) for d in serial[i].detections]
+        assert np.array_equal(out[i].landmarks, serial[i].landmarks)
+        assert np.array_equal(out[i].face_flags, serial[i].face_flags)
+        assert np.array_equal(out[i].rois, serial[i].rois)
+    assert sum(len(d) > 0 for d in serial[0].detections) >= n // 3
+
+
 @pytest.mark.parametrize("name,lo,size,big", [("face_detection_short_range", -1.0, 128, 1100), ("face_landmark", -1.0, 192, 700),
                                               ("iris_landmark", -1.0, 64, 1500), ("palm_detection_lite", 0.0, 192, 420),
                                               ("hand_landmark_lite", 0.0, 224, 420), ("face_detection_full_range", -1.0, 192, 420),

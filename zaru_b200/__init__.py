@@ -8,24 +8,52 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 from . import _ffi
 from ._ffi import ZaruError, load_library  # noqa: F401
 
 _ctx = None
+_tls = threading.local()
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def context(device: int | None = None):
     """The process-wide `zb_ctx` (one per GPU; LOCAL_RANK picks the device under torchrun)."""
     global _ctx
+    own = getattr(_tls, "ctx", None)
+    if own is not None:
+        return own
     if _ctx is None:
         if device is None:
-            device = int(os.environ.get("ZARU_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            device = _default_device()
         h = C.c_void_p()
         _ffi.check(_ffi.lib().zb_ctx_create(device, C.byref(h)))
         _ctx = h
     return _ctx
+
+
+def _default_device() -> int:
+    return int(os.environ.get("ZARU_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def thread_context(device: int | None = None):
+    """Give the CALLING thread its own `zb_ctx` (stream + event pool) on the GPU; everything this thread creates
+    afterwards (networks, detectors, pipelines, frame batches) lives on it.  This is the reference's threading model
+    (SURVEY 8b): `Detector::detect` takes `&mut self`, so parallel callers hold one detector per thread (rayon
+    `map_init`, eval_face_recognition.rs:67-70) - here two threads on one GPU let one pipeline's PCIe ingest overlap
+    the other's compute.  Idempotent per thread."""
+    own = getattr(_tls, "ctx", None)
+    if own is None:
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_ctx_create(_default_device() if device is None else device, C.byref(h)))
+        _tls.ctx = own = h
+    return own
+
+
+def context_key() -> int:
+    """Identity of the calling thread's context (network caches are per context)."""
+    return int(context().value or 0)
 
 
 def model_dir() -> str:

@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _ffi, context, model_path
+from . import _ffi, context, context_key, model_path
 from .nn import Cnn, CnnInputShape, ColorMapper, NeuralNetwork
 from .rect import Rect
 
@@ -92,7 +92,7 @@ class Network:
     _cnn_cache = {}
 
     def cnn(self) -> Cnn:
-        key = (type(self).__name__, model_path(self.onnx))
+        key = (type(self).__name__, model_path(self.onnx), context_key())
         if key not in Network._cnn_cache:
             Network._cnn_cache[key] = Cnn(NeuralNetwork.from_path(model_path(self.onnx)), CnnInputShape.NCHW,
                                           ColorMapper.linear(*self.color_range))
