@@ -510,4 +510,50 @@ class FacePipeline {
     zb_face_pipeline *h_ = nullptr;
 };
 
+// Palm detection + hand landmarks on device (BASELINE config 3): per frame the best palm seeds
+// RotatedRect(bounding_rect.grow_rel(1.5), det.angle()) (hand/tracking.rs:136, :159) and one LandmarkTracker::track
+// step of the hand landmark network runs on that rotated view.
+class HandPipeline {
+   public:
+    struct Result {
+        std::vector<std::vector<detection::Detection>> detections;   // palms, frame coordinates
+        std::vector<float> landmarks;                                 // [n][21][3], frame coordinates
+        std::vector<float> presence, raw_handedness;                  // [n]; presence -1 where no palm was detected
+        std::vector<RotatedRect> rois;                                // rotated view_rect used for the landmark network
+    };
+    explicit HandPipeline(const std::string &model_dir, int32_t capacity = 16)
+        : det_(nn::NeuralNetwork::from_path(model_dir + "/" + detection::PalmLiteNetwork().onnx)),
+          lm_(nn::NeuralNetwork::from_path(model_dir + "/" + landmark::HandLiteNetwork().onnx)), cap_(capacity) {
+        check(zb_hand_pipeline_create(context(), det_->handle(), lm_->handle(), &h_));
+    }
+    ~HandPipeline() { zb_hand_pipeline_destroy(h_); }
+    HandPipeline(const HandPipeline &) = delete;
+    void set_threshold(float det_thresh, float iou_thresh, detection::NmsMode mode = detection::NmsMode::Average) {
+        check(zb_hand_pipeline_set_threshold(h_, det_thresh, iou_thresh, (zb_nms_mode)mode));
+    }
+    Result run(const ImageBatch &batch) {
+        const int32_t n = batch.len();
+        std::vector<zb_detection> dets((size_t)n * cap_);
+        std::vector<int32_t> counts(n);
+        std::vector<zb_view> rois(n);
+        std::vector<float> scalars((size_t)n * 2);
+        Result r;
+        r.landmarks.resize((size_t)n * 21 * 3);
+        check(zb_hand_pipeline_run(h_, batch.handle(), n, dets.data(), counts.data(), cap_, r.landmarks.data(), scalars.data(), rois.data()));
+        r.detections.resize(n);
+        for (int32_t i = 0; i < n; i++) {
+            for (int32_t k = 0; k < counts[i] && k < cap_; k++) r.detections[i].emplace_back(dets[(size_t)i * cap_ + k]);
+            r.rois.push_back(RotatedRect::from_zb_view(rois[i]));
+            r.presence.push_back(scalars[2 * (size_t)i]);
+            r.raw_handedness.push_back(scalars[2 * (size_t)i + 1]);
+        }
+        return r;
+    }
+
+   private:
+    std::shared_ptr<nn::NeuralNetwork> det_, lm_;
+    int32_t cap_;
+    zb_hand_pipeline *h_ = nullptr;
+};
+
 }  // namespace zaru

@@ -48,6 +48,12 @@ int main(int argc, char **argv) {
         FacePipeline pipe(detection::ShortRangeNetwork(), landmark::FaceMeshV1(), models);
         auto pr = pipe.run(*full.batch());
 
+        // BASELINE config 3 through the mirror: the reference has no hand fixture, so the palm threshold is lowered
+        // until the face image yields candidates (same trick as the oracle parity test)
+        HandPipeline hands(models);
+        hands.set_threshold(0.1f, 0.3f);
+        auto hr = hands.run(*full.batch());
+
         bool threw = false;
         try {
             trk.set_roi_padding(-1.0f);
@@ -68,6 +74,9 @@ int main(int argc, char **argv) {
                     tr ? tr->updated_roi.radians : 0.f);
         std::printf(" \"pipe_dets\": %zu, \"pipe_flag\": %.9g, \"pipe_lm0\": [%.9g, %.9g, %.9g], \"pipe_L\": %d,\n", pr.detections[0].size(),
                     pr.face_flags[0], pr.landmarks[0], pr.landmarks[1], pr.landmarks[2], pr.num_landmarks);
+        std::printf(" \"hand_dets\": %zu, \"hand_presence\": %.9g, \"hand_lm0\": [%.9g, %.9g, %.9g], \"hand_roi\": [%.9g, %.9g, %.9g, %.9g, %.9g],\n",
+                    hr.detections[0].size(), hr.presence[0], hr.landmarks[0], hr.landmarks[1], hr.landmarks[2], hr.rois[0].rect().r.cx,
+                    hr.rois[0].rect().r.cy, hr.rois[0].rect().width(), hr.rois[0].rect().height(), hr.rois[0].radians);
         std::printf(" \"tensor_len\": %zu, \"tensor_sum\": %.9g, \"padding_rejected\": %s}\n", tensor.size(), tsum, threw ? "true" : "false");
         return 0;
     } catch (const std::exception &ex) {

@@ -78,3 +78,11 @@ def test_cpp_mirror_matches_python_mirror_and_reference_assertions(tmp_path, ass
     assert got["pipe_dets"] == len(pr.detections[0]) and got["pipe_L"] == 468
     assert abs(got["pipe_flag"] - float(pr.face_flags[0])) <= 1e-6
     assert np.allclose(got["pipe_lm0"], pr.landmarks[0, 0], rtol=0, atol=1e-3)
+    from zaru_b200.pipeline import HandPipeline
+    hp = HandPipeline()
+    hp.set_threshold(0.1, 0.3)
+    hr = hp.run(batch)
+    assert got["hand_dets"] == len(hr.detections[0]) >= 1
+    assert abs(got["hand_presence"] - float(hr.presence[0])) <= 1e-6
+    assert np.allclose(got["hand_lm0"], hr.landmarks[0, 0], rtol=0, atol=1e-3)
+    assert np.allclose(got["hand_roi"], hr.rois[0], rtol=0, atol=1e-3)
