@@ -191,6 +191,25 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def pinned_frames(torch, n):
+    """[n,1080,1920,4] uint8 host tensor, page-locked by cudaHostRegister at its exact size.  (torch's pinned-memory
+    allocator rounds every block up to a power of two: the 8.49 GB of a 1024-frame batch would pin 16 GB per buffer,
+    per rank.)  Registered mapped + portable, so `zb_frames_alias` can hand the same pointer to the sampler."""
+    nbytes = n * FRAME_BYTES
+    raw = torch.empty(nbytes + 4096, dtype=torch.uint8)
+    off = (-raw.data_ptr()) % 4096
+    t = raw[off:off + nbytes].view(n, FRAME_H, FRAME_W, 4)
+    rc = int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 1 | 2))
+    if rc != 0:
+        raise RuntimeError(f"cudaHostRegister of {nbytes / 1e9:.2f} GB failed (cudaError {rc})")
+    return t
+
+
+def unpin_frames(torch, t):
+    if t is not None:
+        torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -273,7 +292,7 @@ def run_gpu(args):
 
     # --- end to end through the public API with HOST frames (`e2e`) -------------------------------------
     e2e_n = min(args.e2e_batch, batch_n)
-    h_frames = torch.empty((e2e_n, FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory()
+    h_frames = pinned_frames(torch, e2e_n)
     h_frames.copy_(d_frames[:e2e_n])
     e2e_batch = ImageBatch.from_rgba8(res, h_frames.numpy())
     h_ptr = h_frames.numpy()
@@ -296,7 +315,7 @@ def run_gpu(args):
     zc_ms_max = None
     try:
         reps = (zc_n + e2e_n - 1) // e2e_n
-        h_big = torch.empty((zc_n, FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory()
+        h_big = pinned_frames(torch, zc_n)
         for r in range(reps):
             lo_i, hi_i = r * e2e_n, min(zc_n, (r + 1) * e2e_n)
             h_big[lo_i:hi_i].copy_(h_frames[:hi_i - lo_i])
@@ -322,7 +341,7 @@ def run_gpu(args):
         try:
             bufs = [h_big]
             for i in range(1, mt_threads):
-                hb = torch.empty((zc_n, FRAME_H, FRAME_W, 4), dtype=torch.uint8, pin_memory=True)
+                hb = pinned_frames(torch, zc_n)
                 hb.copy_(torch.roll(h_big, shifts=7 * i, dims=0))      # same frames in another order: another buffer
                 bufs.append(hb)
         except Exception as ex:   # noqa: BLE001 - not enough pinnable host memory
@@ -375,6 +394,10 @@ def run_gpu(args):
                 mt_ms = None
             bad, worst = shard.max_over_ranks([1.0 if mt_ms is None else 0.0, mt_ms or 0.0], dist, "cuda")
             mt_ms_max = worst if bad == 0.0 else None
+        if bufs is not None:
+            zaru_b200.sync()
+            for hb in bufs[1:]:
+                unpin_frames(torch, hb)
         bufs = None
     clock_info = clocks.stop() if rank == 0 else None
     d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
