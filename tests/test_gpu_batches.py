@@ -259,6 +259,41 @@ def test_thread_contexts_two_pinned_host_pipelines_in_flight():
     assert sum(len(d) > 0 for d in serial[0].detections) >= n // 3
 
 
+def test_two_gpus_in_one_process():
+    """One process, one `zb_ctx` per GPU ('per GPU one host thread, one context, weights replicated').  The
+    dynamic shared-memory opt-in of the big-tile kernels is per device: after device 0 has configured them, device 1
+    must still launch them (regression: the opt-in cache used to be per process).  Needs two GPUs."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import zaru_b200
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    frames = np.stack([synth.s_face_frame(1000 + s)[0] for s in range(24)])
+    res = Resolution(1920, 1080)
+    first = FacePipeline().run(ImageBatch.from_rgba8(res, frames))          # the process-wide context (device 0)
+    out, errs = [], []
+
+    def other_gpu():
+        try:
+            zaru_b200.thread_context(1)
+            out.append(FacePipeline().run(ImageBatch.from_rgba8(res, frames)))
+            zaru_b200.sync()
+        except Exception as ex:   # noqa: BLE001
+            errs.append(ex)
+
+    t = threading.Thread(target=other_gpu)
+    t.start()
+    t.join()
+    assert not errs, errs
+    assert [len(d) for d in out[0].detections] == [len(d) for d in first.detections]
+    assert np.array_equal(out[0].landmarks, first.landmarks) and np.array_equal(out[0].face_flags, first.face_flags)
+    assert sum(len(d) > 0 for d in first.detections) >= 8
+
+
 @pytest.mark.parametrize("name,lo,size,big", [("face_detection_short_range", -1.0, 128, 1100), ("face_landmark", -1.0, 192, 700),
                                               ("iris_landmark", -1.0, 64, 1500), ("palm_detection_lite", 0.0, 192, 420),
                                               ("hand_landmark_lite", 0.0, 224, 420), ("face_detection_full_range", -1.0, 192, 420),

@@ -9,6 +9,26 @@
 #include "plan.h"
 
 namespace zb {
+// Dynamic shared memory above the 48 KB default needs cudaFuncSetAttribute once per kernel AND PER DEVICE: one process may
+// hold contexts on several GPUs (one zb_ctx per GPU), so the "already configured" cache is indexed by the current
+// device.  Thread-safe: concurrent first launches at worst repeat an idempotent attribute call.
+struct SmemOptIn {
+    std::atomic<size_t> bytes[64];   // static storage: zero-initialised
+    template <class Kernel>
+    bool ensure(Kernel kern, size_t smem) {
+        if (smem <= 40 * 1024) return true;   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError(), false;
+        std::atomic<size_t> &have = bytes[dev & 63];
+        if (smem <= have.load(std::memory_order_relaxed)) return true;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cudaGetLastError(), false;
+        have.store(smem, std::memory_order_relaxed);
+        return true;
+    }
+};
+}  // namespace zb
+
+namespace zb {
 
 struct ActDev {
     int kind;

@@ -394,14 +394,8 @@ bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float h
     const int NSP = (p.Ns + NP - 1) / NP * NP;
     const size_t smem = sizeof(float) * ((size_t)IH * IW * 4 + (size_t)KS * KS * 4 * NSP + 2 * NSP + IW + IH);
     auto kern = stem_kernel<KS, NP, PPT>;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     kern<<<(unsigned)(tiles_x * tiles_y * images), 256, smem, s>>>(f, views, lo, hi, p, tiles_x, tiles_y, NSP, f16);
@@ -1036,11 +1030,8 @@ void launch_decode_nms(const float *boxes, const float *scores, const float *fit
                        DetDev *out, int *out_counts, cudaStream_t s) {
     g_launch_count++;
     const size_t smem = (size_t)p.num_anchors * (sizeof(float4) + sizeof(float) + 4 * sizeof(int));
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
-        cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    opt_in.ensure(decode_nms_kernel, smem);   // a failure surfaces as the launch error
     decode_nms_kernel<<<n, 256, smem, s>>>(boxes, scores, fit, p, out, out_counts);
 }
 

@@ -647,14 +647,8 @@ template <int CS, int TH, int NBUF, int TW>
 bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
     const size_t smem = ttc_smem<CS, TH, NBUF, TW>(NP);
     auto kern = dwpw_ttc_kernel<CS, TH, NBUF, TW>;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     const int total = tiles_x * tiles_y * images;
@@ -742,14 +736,8 @@ bool launch_dwpw_tc_ks(const ConvDev &p, const float *w_hi, const float *w_lo, i
     const size_t smem = dwpw_tc_smem(KC, NP);
     if (smem > 220 * 1024) return false;
     auto kern = dwpw_tc_kernel<KS, STRIP>;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, smem)) return false;
     kern<<<(unsigned)((p.M + TC_M - 1) / TC_M), 256, smem, s>>>(p, w_hi, w_lo, NP, KC, Kpad);
     return true;
 }
@@ -800,11 +788,8 @@ bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int
 // D[128,N] = A[128,K] * B[N,K]^T on tcgen05 (nsplit 1: raw TF32, 3: 3xTF32).  Device pointers.
 bool launch_tc_mma_rate(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps, int ctas, long long *cycles_dev, cudaStream_t s) {
     if (N % 8 || N < 8 || N > 256 || iters < 1 || ksteps < 1 || (ksteps & (ksteps - 1)) || N * ksteps > 512) return false;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024) != cudaSuccess) return false;
-        configured = true;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(tc_mma_rate_kernel, 48 * 1024)) return false;
     g_launch_count++;
     tc_mma_rate_kernel<<<ctas, 128, 48 * 1024, s>>>(N, lbo_a, sbo_a, a_off, iters, ksteps, cycles_dev);
     return true;
@@ -814,14 +799,8 @@ bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K,
     if (N % 16 || N < 16 || N > 256 || K % 8 || K < 8) return false;
     const size_t smem = sizeof(float) * 2 * ((size_t)K * TC_M + (size_t)K * N) + 1024;
     if (smem > 220 * 1024) return false;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
-        if (cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(tc_gemm_test_kernel, smem)) return false;
     g_launch_count++;
     tc_gemm_test_kernel<<<1, 128, smem, s>>>(A, B, D, N, K, nsplit);
     return true;

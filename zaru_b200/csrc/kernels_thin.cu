@@ -382,14 +382,8 @@ bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
     constexpr int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3, PW = S == 1 ? IW : TW + 1;
     const size_t smem = sizeof(float) * ((size_t)IH * S * PW * (CS + 4) + 10 * CS + (size_t)CS * NP + 2 * NP);
     auto kern = dwpw_strip_kernel<CS, S, NP, PXV, TW, WARPS>;
-    static bool configured = false;
-    if (smem > 40 * 1024 && !configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        configured = true;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     kern<<<dim3(tiles_x, tiles_y, images), 32 * WARPS, smem, s>>>(p, tiles_x, tiles_y);
@@ -433,14 +427,8 @@ bool launch_thin_cfg(const ConvDev &p, cudaStream_t s) {
     const size_t smem = sizeof(float) * ((size_t)IH * IW * (CS + 4) + 9 * CS + CS + (size_t)CS * NSP + 2 * NSP);
     if (smem > 200 * 1024) return false;
     auto kern = dwpw_thin_kernel<CS, S, NP, TW, TH>;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {   // 40 KB: leaves room for the static __shared__ variables under the 48 KB default
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     kern<<<(unsigned)(tiles_x * tiles_y * images), TW * TH, smem, s>>>(p, tiles_x, tiles_y, NSP);
