@@ -203,6 +203,12 @@ void zb_face_pipeline_destroy(zb_face_pipeline *p);
 zb_status zb_face_pipeline_set_threshold(zb_face_pipeline *p, float det_thresh, float iou_thresh,
                                          zb_nms_mode mode);
 int32_t zb_face_pipeline_num_landmarks(const zb_face_pipeline *p);
+/* By default the landmark network runs only on the frames in which the detector found something - the reference's
+ * loop calls its estimator only then (examples/facemesh.rs:49-55) - through an ordered compaction on the device (one
+ * 4-byte count read back per chunk; batches small enough to be replayed as a CUDA graph always run densely).
+ * dense != 0 runs it over every frame; the results are the same either way (frames without a detection report
+ * flag -1 and zero landmarks).                                                                    */
+zb_status zb_face_pipeline_set_dense(zb_face_pipeline *p, int32_t dense);
 /* The detector may be the short- or the full-range BlazeFace and the mesh FaceMeshV1 (L = 468) or FaceMeshV2
  * (L = 478), recognised by their output shapes; zb_face_pipeline_num_landmarks returns L.
  * out_dets [n][cap], out_counts [n], out_landmarks [n][L][3], out_flags [n] (sigmoid

@@ -208,6 +208,50 @@ def test_pinned_host_frames_gather_pipeline_matches_resident_frames(n):
     assert faces >= n // 3
 
 
+def test_landmark_stage_only_on_frames_with_a_detection():
+    """Above the CUDA-graph batch limit the pipeline compacts the frames in which the detector found a face and runs the
+    landmark network on those only (the reference's loop calls its estimator only then, examples/facemesh.rs:49-55).
+    `set_dense(True)` forces the network over every frame: same detections, same flags (-1 and zero landmarks where
+    nothing was detected), landmarks equal up to the batch-size-dependent kernel selection; fewer launches' worth of
+    work is visible in the device time.  Also with NO face in any frame (count 0: the landmark network is skipped)."""
+    import zaru_b200
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FacePipeline
+    from zaru_b200.rect import Resolution
+    uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in range(20)])
+    n = 530                                                   # > 512: not replayed as a graph
+    frames = np.concatenate([uniq] * ((n + 19) // 20))[:n]
+    res = Resolution(1920, 1080)
+    batch = ImageBatch.from_rgba8(res, frames)
+    pipe = FacePipeline()
+    a = pipe.run(batch)
+    ms_compact = zaru_b200.last_device_ms()
+    pipe.set_dense(True)
+    b = pipe.run(batch)
+    ms_dense = zaru_b200.last_device_ms()
+    pipe.set_dense(False)
+    a2 = pipe.run(batch)
+    with_face = a.face_flags >= 0
+    assert 0.3 * n < with_face.sum() < 0.9 * n                # the set has both kinds of frames
+    assert np.array_equal(with_face, b.face_flags >= 0)
+    assert [len(d) for d in a.detections] == [len(d) for d in b.detections]
+    assert np.array_equal(with_face, np.array([len(d) > 0 for d in a.detections]))
+    assert np.all(a.landmarks[~with_face] == 0) and np.all(b.landmarks[~with_face] == 0)
+    assert np.all(a.face_flags[~with_face] == -1.0) and np.all(b.face_flags[~with_face] == -1.0)
+    assert np.abs(a.face_flags[with_face] - b.face_flags[with_face]).max() <= 1e-3
+    assert np.abs(a.landmarks[with_face] - b.landmarks[with_face]).max() <= 0.05
+    assert np.array_equal(a.rois, b.rois)
+    assert np.array_equal(a.landmarks, a2.landmarks) and np.array_equal(a.face_flags, a2.face_flags)
+    assert ms_compact < ms_dense
+    # frames repeat with period 20: frame i and i + 20 must agree exactly although they sit in different compact slots
+    assert np.array_equal(a.landmarks[:20], a.landmarks[500:520])
+    noise = np.random.default_rng(3).integers(0, 256, size=(1, 1080, 1920, 4), dtype=np.uint8)
+    empty = ImageBatch.from_rgba8(res, np.concatenate([noise] * 520))
+    e = pipe.run(empty)
+    assert all(len(d) == 0 for d in e.detections) and np.all(e.face_flags == -1.0) and np.all(e.landmarks == 0)
+
+
 def test_thread_contexts_two_pinned_host_pipelines_in_flight():
     """`zaru_b200.thread_context()`: the reference's one-Detector-per-thread model (`&mut self`; rayon map_init,
     eval_face_recognition.rs:67-70).  Two host threads, each with its own zb_ctx + networks + face pipeline + pinned

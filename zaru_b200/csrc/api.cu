@@ -997,7 +997,11 @@ struct zb_face_pipeline {
     cudaGraphExec_t graph_exec = nullptr;
     uint64_t graph_key = 0, pending_key = 0;
     long long graph_launches = 0, capture_base = 0;   // kernels inside the captured pass (zb_launch_count stays truthful)
-    PinBuf h_stage, h_counts;
+    PinBuf h_stage, h_counts, h_nvalid;
+    // landmark stage on the frames WITH a detection only (ordered compaction on the device, see compact_views_kernel);
+    // dense = 1 forces the landmark network over every frame (results for frames without a detection are identical)
+    DevBuf d_lm_views_c, d_sel, d_nvalid;
+    int dense = 0;
     int cap = 0;
 };
 
@@ -1567,6 +1571,12 @@ zb_status zb_face_pipeline_set_threshold(zb_face_pipeline *p, float t, float iou
 
 int32_t zb_face_pipeline_num_landmarks(const zb_face_pipeline *p) { return p ? estimator_landmarks(p->lm_kind) : 0; }
 
+zb_status zb_face_pipeline_set_dense(zb_face_pipeline *p, int32_t dense) {
+    if (!p) return fail(ZB_ERR_INVALID_ARGUMENT, "pipeline is NULL");
+    p->dense = dense != 0;
+    return ZB_OK;
+}
+
 zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
                                int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_flags,
                                zb_view *out_rois) {
@@ -1808,6 +1818,14 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                 p->pending_key = key;
             }
         }
+        static const bool compact_env = !(getenv("ZB_NO_COMPACT") && atoi(getenv("ZB_NO_COMPACT")) != 0);
+        const bool compact = compact_env && !p->dense && !use_graph && !two_streams && !gather;
+        if (compact) {
+            p->d_lm_views_c.reserve(sizeof(ViewDev) * n);
+            p->d_sel.reserve(sizeof(int) * n);
+            p->d_nvalid.reserve(sizeof(int));
+            p->h_nvalid.reserve(sizeof(int));
+        }
         int k = 0;
         for (int c0 = (gather || replayed) ? n : 0; c0 < n; c0 += chunk, k++) {
             const int nc = std::min(chunk, n - c0);
@@ -1829,17 +1847,37 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
                                 lpl.in_w, lpl.in_h, p->d_lm_views.as<ViewDev>() + c0, p->d_lm_fit.as<float>() + 4 * c0,
                                 p->d_rois.as<ViewHost>() + c0, cs, roi_grow, roi_use_angle);
             });
-            // landmarks
-            const StemInput sl{&frames->f, p->d_lm_views.as<ViewDev>() + c0, map_lo, 1.0f};
-            run_ops(p->lm_net, wl, c0, nc, 0, cs, &sl);
-            run_ops(p->lm_net, wl, c0, nc, 1, cs);
-            prof_launch(ctx, cs, "landmarks", 8.0 * nc * (3 * L + 1), 0, [&] {
-                const int s2 = (p->lm_kind == ZB_EST_FACE_MESH_V2 || p->lm_kind == ZB_EST_HAND) ? (int)lpl.outputs[2].per_image : 0;
-                launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
-                                 s2 ? wl.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2, p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
-                                 p->d_rois.as<ViewHost>() + c0, nc, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
-                                 p->d_scalars.as<float>() + 2 * c0, cs);
-            });
+            // landmarks: only for the frames of this chunk that have a detection (the reference calls its estimator only
+            // when the detector found something, examples/facemesh.rs:49-55).  The count comes back to the host once per
+            // chunk; not inside a captured graph (sizes are baked in there) - small batches run the network densely.
+            int n_lm = nc;
+            const ViewDev *lm_views = p->d_lm_views.as<ViewDev>() + c0;
+            const int *sel = nullptr;
+            if (compact) {
+                prof_launch(ctx, cs, "compact", (double)nc * (sizeof(ViewDev) + 12), 0, [&] {
+                    launch_compact_views(p->d_lm_views.as<ViewDev>() + c0, nc, p->d_lm_views_c.as<ViewDev>() + c0,
+                                         p->d_sel.as<int>() + c0, p->d_nvalid.as<int>(), p->d_scalars.as<float>() + 2 * c0, cs);
+                });
+                CU(cudaMemsetAsync(p->d_lm.as<float>() + (size_t)c0 * L * 3, 0, sizeof(float) * 3 * (size_t)L * nc, cs));
+                CU(cudaMemcpyAsync(p->h_nvalid.p, p->d_nvalid.p, sizeof(int), cudaMemcpyDeviceToHost, cs));
+                CU(cudaStreamSynchronize(cs));
+                n_lm = *p->h_nvalid.as<int>();
+                if (n_lm < 0 || n_lm > nc) throw std::runtime_error("compaction returned an impossible count");
+                lm_views = p->d_lm_views_c.as<ViewDev>() + c0;
+                sel = p->d_sel.as<int>() + c0;
+            }
+            if (n_lm > 0) {
+                const StemInput sl{&frames->f, lm_views, map_lo, 1.0f};
+                run_ops(p->lm_net, wl, c0, n_lm, 0, cs, &sl);
+                run_ops(p->lm_net, wl, c0, n_lm, 1, cs);
+                prof_launch(ctx, cs, "landmarks", 8.0 * n_lm * (3 * L + 1), 0, [&] {
+                    const int s2 = (p->lm_kind == ZB_EST_FACE_MESH_V2 || p->lm_kind == ZB_EST_HAND) ? (int)lpl.outputs[2].per_image : 0;
+                    launch_landmarks(wl.outs[0].as<float>() + (size_t)c0 * s0, s0, wl.outs[1].as<float>() + (size_t)c0 * s1, s1,
+                                     s2 ? wl.outs[2].as<float>() + (size_t)c0 * s2 : nullptr, s2, p->d_lm_fit.as<float>() + 4 * c0, p->d_lm_views.as<ViewDev>() + c0,
+                                     p->d_rois.as<ViewHost>() + c0, n_lm, lp, p->d_lm.as<float>() + (size_t)c0 * L * 3,
+                                     p->d_scalars.as<float>() + 2 * c0, cs, nullptr, sel);
+                });
+            }
         }
         if (two_streams) {
             CU(cudaEventRecord(p->ev_join, p->stream2));

@@ -186,7 +186,10 @@ struct LandmarkParams {
 void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
                       const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
                       const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s,
-                      const FilterDev *filter = nullptr);
+                      const FilterDev *filter = nullptr, const int *sel = nullptr);
+// Ordered compaction of the frames with a valid RoI view (see compact_views_kernel); `sel` != nullptr in
+// launch_landmarks maps network output row j back to frame sel[j].
+void launch_compact_views(const ViewDev *views, int n, ViewDev *out_views, int *sel, int *count, float *scalars, cudaStream_t s);
 
 // ---- LandmarkTracker on the device (landmark.rs:361-502), one state record per stream ---------------------
 struct TrackState {            // LandmarkTracker::roi: Option<RotatedRect>

@@ -741,6 +741,45 @@ __global__ void __launch_bounds__(256) filter_apply_kernel(const FilterDev f, fl
     if (i < count) values[i] = filter_scalar(f, f.state + 3 * i, values[i]);
 }
 
+// Frames whose RoI view is valid (a face / palm was detected), in frame order: sel[j] = frame, out_views[j] = its view,
+// *count = how many.  The landmark network then runs on `count` images instead of all n - the reference only calls its
+// estimator when the detector found something (examples/facemesh.rs:49-55).  Frames without a detection get their
+// result scalars here (flag / presence -1, second scalar 0); their landmark rows are zero-filled by the caller.
+__global__ void __launch_bounds__(1024) compact_views_kernel(const ViewDev *__restrict__ views, int n, ViewDev *__restrict__ out_views,
+                                                             int *__restrict__ sel, int *__restrict__ count,
+                                                             float *__restrict__ scalars) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const bool v = i < n && views[i].valid;
+        const unsigned m = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) warp_sums[w] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int k = 0; k < w; k++) off += warp_sums[k];
+        if (v) {
+            const int j = off + __popc(m & ((1u << lane) - 1u));
+            sel[j] = i;
+            out_views[j] = views[i];
+        } else if (i < n && scalars) {
+            scalars[2 * i + 0] = -1.0f;
+            scalars[2 * i + 1] = 0.0f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int k = 0; k < 32; k++) t += warp_sums[k];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
 __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict__ out0, int s0,
                                                         const float *__restrict__ out1, int s1,
                                                         const float *__restrict__ out2, int s2,
@@ -748,10 +787,19 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
                                                         const ViewDev *__restrict__ views,
                                                         const ViewHost *__restrict__ view_rects, int n,
                                                         const LandmarkParams p, float *__restrict__ landmarks,
-                                                        float *__restrict__ scalars, const FilterDev flt) {
-    const int img = blockIdx.y;
+                                                        float *__restrict__ scalars, const FilterDev flt,
+                                                        const int *__restrict__ sel) {
+    // `sel` (compacted pipeline): network output row blockIdx.y belongs to frame sel[blockIdx.y]; the raw tensors are
+    // indexed by the row, everything per frame (fit, views, view rects, filter state, results) by the frame
+    const int img = sel ? sel[blockIdx.y] : (int)blockIdx.y;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     const int valid = views ? views[img].valid : 1;
+    if (sel) {
+        const long long row = blockIdx.y;
+        out0 += (row - img) * s0;
+        if (out1) out1 += (row - img) * s1;
+        if (out2) out2 += (row - img) * s2;
+    }
     if (l == 0 && scalars) {
         float a = 0.f, b = 0.f;
         if (p.kind == 0) a = valid ? sigmoid_ref(out1[(long long)img * s1]) : -1.0f;  // mediapipe.rs:60
@@ -1045,12 +1093,18 @@ void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, 
 
 void launch_landmarks(const float *out0, int s0, const float *out1, int s1, const float *out2, int s2,
                       const float *fit, const ViewDev *views, const ViewHost *view_rects, int n,
-                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s, const FilterDev *filter) {
+                      const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s, const FilterDev *filter,
+                      const int *sel) {
     g_launch_count++;
     dim3 grid((p.num_landmarks + 127) / 128, n);
     FilterDev none{};
     landmarks_kernel<<<grid, 128, 0, s>>>(out0, s0, out1, s1, out2, s2, fit, views, view_rects, n, p, landmarks,
-                                          scalars, filter ? *filter : none);
+                                          scalars, filter ? *filter : none, sel);
+}
+
+void launch_compact_views(const ViewDev *views, int n, ViewDev *out_views, int *sel, int *count, float *scalars, cudaStream_t s) {
+    g_launch_count++;
+    compact_views_kernel<<<1, 1024, 0, s>>>(views, n, out_views, sel, count, scalars);
 }
 
 void launch_filter_apply(const FilterDev &f, float *values, long long count, cudaStream_t s) {

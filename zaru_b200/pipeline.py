@@ -37,6 +37,10 @@ class FacePipeline:
     def set_threshold(self, det_thresh=0.5, iou_thresh=0.3, mode=_ffi.ZB_NMS_AVERAGE):
         _ffi.check(_ffi.lib().zb_face_pipeline_set_threshold(self._h, det_thresh, iou_thresh, mode))
 
+    def set_dense(self, dense: bool):
+        """dense=True: run the landmark network over every frame instead of only those with a detection (same results)."""
+        _ffi.check(_ffi.lib().zb_face_pipeline_set_dense(self._h, 1 if dense else 0))
+
     def _buffers(self, n):
         if self._bufs is None or self._bufs[0] != n:
             self._bufs = (n, (_ffi.zb_detection * (n * self._cap))(), (C.c_int32 * n)(),
