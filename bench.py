@@ -251,6 +251,11 @@ def run_gpu(args):
     # independent streams shard round-robin over the GPUs (stream s -> rank s % world); every rank owns
     # `unique` distinct synthetic streams and no data-path collective is needed
     my_streams = shard.streams_for_rank(args.unique * world, world, rank)
+    if not args.streams:
+        # weak scaling = the same work on every GPU: the landmark stage runs only on frames with a detection, so ranks
+        # with different synthetic frames would do different amounts of work (measured at N = 2 with per-rank frame
+        # sets: 6.2 ms per step on one rank, 7.0-7.4 ms on the other) - every rank gets the same `unique` frames
+        my_streams = list(range(args.unique))
     uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in my_streams])
     d_uniq = torch.from_numpy(uniq).cuda()
     idx = torch.arange(batch_n, device="cuda") % args.unique
@@ -304,6 +309,8 @@ def run_gpu(args):
     pipe.set_dense(False)
     barrier()
     (dense_ms_max,) = shard.max_over_ranks([dense_ms], dist, "cuda")
+    log(f"[rank {rank}] device ms per step: {dev_ms / args.steps:.3f} (wall {wall_ms / args.steps:.3f}), "
+        f"all frames landmarked {dense_ms / args.steps:.3f}")
 
     # --- end to end through the public API with HOST frames (`e2e`) -------------------------------------
     e2e_n = min(args.e2e_batch, batch_n)
@@ -515,6 +522,8 @@ def run_gpu(args):
                                 "step through the full face pipeline" % (args.streams, world)) if args.streams else
                                WORKLOAD,
                    "batch_per_gpu": batch_n, "frame": "1920x1080 RGBA8", "distinct_frames": args.unique,
+                   "frames_per_rank": ("sharded camera streams (stream s -> rank s % N)" if args.streams else
+                                       "the same distinct frames on every rank (equal work per GPU)"),
                    "l2_policy": f"inputs larger than L2 ({batch_n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
                    "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "1024")), "frames_with_face": n_with_face,
                    "landmark_policy": "face mesh runs on the frames in which BlazeFace found a face (device-side compaction), as "
