@@ -228,6 +228,7 @@ typedef zb_face_pipeline zb_hand_pipeline;
 zb_status zb_hand_pipeline_create(zb_ctx *ctx, zb_net *palm_net, zb_net *hand_landmark_net, zb_hand_pipeline **out);
 void zb_hand_pipeline_destroy(zb_hand_pipeline *p);
 zb_status zb_hand_pipeline_set_threshold(zb_hand_pipeline *p, float det_thresh, float iou_thresh, zb_nms_mode mode);
+zb_status zb_hand_pipeline_set_dense(zb_hand_pipeline *p, int32_t dense);   /* see zb_face_pipeline_set_dense */
 zb_status zb_hand_pipeline_run(zb_hand_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
                                int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_scalars,
                                zb_view *out_rois);

@@ -532,6 +532,7 @@ class HandPipeline {
     void set_threshold(float det_thresh, float iou_thresh, detection::NmsMode mode = detection::NmsMode::Average) {
         check(zb_hand_pipeline_set_threshold(h_, det_thresh, iou_thresh, (zb_nms_mode)mode));
     }
+    void set_dense(bool dense) { check(zb_hand_pipeline_set_dense(h_, dense ? 1 : 0)); }   // landmark network over every frame
     Result run(const ImageBatch &batch) {
         const int32_t n = batch.len();
         std::vector<zb_detection> dets((size_t)n * cap_);

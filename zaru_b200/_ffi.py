@@ -95,6 +95,7 @@ SIGNATURES = {
     "zb_hand_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),
     "zb_face_pipeline_set_threshold": (i32, [P, f32, f32, i32]),
     "zb_face_pipeline_set_dense": (i32, [P, i32]),
+    "zb_hand_pipeline_set_dense": (i32, [P, i32]),
     "zb_face_pipeline_num_landmarks": (i32, [P]),
     "zb_face_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),
     "zb_net_plan_json": (i32, [P, C.c_char_p, sz, C.POINTER(sz)]),

@@ -1937,6 +1937,8 @@ zb_status zb_hand_pipeline_set_threshold(zb_hand_pipeline *p, float det_thresh, 
     return zb_face_pipeline_set_threshold(p, det_thresh, iou_thresh, mode);
 }
 
+zb_status zb_hand_pipeline_set_dense(zb_hand_pipeline *p, int32_t dense) { return zb_face_pipeline_set_dense(p, dense); }
+
 zb_status zb_hand_pipeline_run(zb_hand_pipeline *p, const zb_frames *frames, int32_t n, zb_detection *out_dets,
                                int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_scalars, zb_view *out_rois) {
     const zb_status st = zb_face_pipeline_run(p, frames, n, out_dets, out_counts, cap, out_landmarks, nullptr, out_rois);

@@ -141,6 +141,10 @@ class HandPipeline:
     def set_threshold(self, det_thresh=0.5, iou_thresh=0.3, mode=_ffi.ZB_NMS_AVERAGE):
         _ffi.check(_ffi.lib().zb_hand_pipeline_set_threshold(self._h, det_thresh, iou_thresh, mode))
 
+    def set_dense(self, dense: bool):
+        """dense=True: run the hand landmark network over every frame instead of only those with a palm (same results)."""
+        _ffi.check(_ffi.lib().zb_hand_pipeline_set_dense(self._h, 1 if dense else 0))
+
     def run(self, batch, n=None) -> HandPipelineResult:
         n = len(batch) if n is None else n
         dets = (_ffi.zb_detection * (n * self._cap))()
