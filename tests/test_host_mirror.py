@@ -43,3 +43,32 @@ def test_view_composition_matches_oracle():
         assert float(r.rotation_radians()) == float(o.data.rect_.radians)
     assert Resolution(1920, 1080).aspect_ratio() == AspectRatio(16, 9)
     assert img.as_view().view_rect() == RotatedRect(Rect.from_top_left(0, 0, 1280, 720), 0.0)
+
+
+def test_thread_context_and_pipeline_switches_exist_and_fail_loudly_without_a_gpu():
+    """Host API added for the multi-threaded ingest and the detection-gated landmark stage: present in the mirror, and
+    - like everything else - an error, not a CPU fallback, when there is no CUDA device."""
+    import threading
+
+    import pytest
+    import torch
+
+    import zaru_b200
+    from zaru_b200 import ZaruError
+    from zaru_b200.pipeline import FacePipeline, HandPipeline
+    assert callable(zaru_b200.thread_context) and callable(zaru_b200.context_key)
+    assert callable(FacePipeline.set_dense) and callable(HandPipeline.set_dense)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    seen = []
+
+    def worker():
+        try:
+            zaru_b200.thread_context()
+        except ZaruError as ex:
+            seen.append(str(ex))
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert seen and "no CPU fallback" in seen[0]
