@@ -203,12 +203,19 @@ def pinned_frames(torch, n):
     t = raw[off:off + nbytes].view(n, FRAME_H, FRAME_W, 4)
     rc = int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 1 | 2))
     if rc != 0:
+        if n <= 256:   # small buffer: let torch's pinned allocator have it (rounded up, but only a few GB)
+            return torch.empty((n, FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory()
         raise RuntimeError(f"cudaHostRegister of {nbytes / 1e9:.2f} GB failed (cudaError {rc})")
+    _registered.add(t.data_ptr())
     return t
 
 
+_registered = set()
+
+
 def unpin_frames(torch, t):
-    if t is not None:
+    if t is not None and t.data_ptr() in _registered:
+        _registered.discard(t.data_ptr())
         torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
 
 
