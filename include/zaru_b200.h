@@ -158,6 +158,10 @@ void zb_detector_destroy(zb_detector *det);
 zb_status zb_detector_set_threshold(zb_detector *det, float thresh);              /* :188-191 */
 zb_status zb_detector_set_nms(zb_detector *det, float iou_thresh, zb_nms_mode m); /* :197-200 */
 zb_status zb_detector_input_resolution(const zb_detector *det, int32_t *w, int32_t *h);
+/* `Detector::timers()` (detection.rs:155-157, :272-275): {t_infer, t_extract, t_nms} of the LAST detect / extract
+ * call in ms of device time (CUDA events; the fused decode+NMS kernel's time is apportioned by the per-image phase
+ * durations it sums).  The reference's `Timer` (timer.rs:16-97) averages over calls; the mirrors do that on top.   */
+zb_status zb_detector_timers(const zb_detector *det, float out_ms[3]);
 /* `Detector::detect(&image)` for n views at once (views == NULL: every whole frame):
  * aspect-fit view -> tensor -> CNN -> sigmoid/threshold/decode -> NMS -> map back to the
  * coordinate system of each given view (detection.rs:216-270).
@@ -182,6 +186,9 @@ zb_status zb_estimator_create(zb_ctx *ctx, zb_net *net, zb_estimator_kind kind, 
 void zb_estimator_destroy(zb_estimator *est);
 int32_t zb_estimator_num_landmarks(const zb_estimator *est);
 zb_status zb_estimator_input_resolution(const zb_estimator *est, int32_t *w, int32_t *h);
+/* `Estimator::timers()` (landmark.rs:259-261, :288-291): {t_infer, t_extract, t_filter} of the LAST estimate call
+ * (device ms).  The LandmarkFilter runs inside the extract kernel, so t_filter reads 0.                          */
+zb_status zb_estimator_timers(const zb_estimator *est, float out_ms[3]);
 /* `Estimator::estimate(&view)` for n views: landmarks [n][L][3] in the coordinate system of
  * each given view (x,y,z scaled; x,y offset: landmark.rs:336-345); scalars [n][2]:
  *   face: {sigmoid(face_flag), 0}; eye: {0,0}; hand: {presence, raw_handedness}.
@@ -217,6 +224,27 @@ zb_status zb_face_pipeline_set_dense(zb_face_pipeline *p, int32_t dense);
 zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int32_t n,
                                zb_detection *out_dets, int32_t *out_counts, int32_t cap,
                                float *out_landmarks, float *out_flags, zb_view *out_rois);
+
+/* ---- face mesh -> eye crops -> iris landmarks, fused (BASELINE config 2) ---------------------
+ * The reference has no in-tree composition of the iris stage; this is the one its helpers spell out:
+ *   face_rois[i] (a detector crop; NULL = every whole frame) -> tracker.set_roi(roi) + one LandmarkTracker::track
+ *   step (landmark.rs:456-501): face-mesh landmarks in frame coordinates + sigmoid(face_flag);
+ *   eyes = LandmarkResultV1::left_eye() / right_eye() (mediapipe.rs:163-192: RotatedRect::bounding(rotation_radians(),
+ *   [bottom, corner, corner, top])), each grown by RotatedRect::grow_rel(eye margin, default 0);
+ *   EyeNetwork via `Estimator::estimate(&image.view(eye))` (landmark.rs:314-348, eye.rs:30-65), the right eye with the
+ *   sampled tensor mirrored and x un-mirrored (eye.rs:24-28, :121-125; same rule as zb_estimator_estimate's flip_x);
+ *   eye landmarks mapped through eye.transform_out into frame coordinates.
+ * Outputs (host_or_device, any may be NULL): out_face_landmarks [n][L][3], out_face_flags [n], out_face_view_rects [n],
+ * out_eye_rois [2n] (left eye of face i at 2i, right eye at 2i + 1; after the margin), out_eye_landmarks [2n][76][3]
+ * (5 iris points, then 71 contour points).                                                                        */
+typedef struct zb_face_iris_pipeline zb_face_iris_pipeline;
+zb_status zb_face_iris_pipeline_create(zb_ctx *ctx, zb_net *face_mesh_net, zb_net *iris_net, zb_face_iris_pipeline **out);
+void zb_face_iris_pipeline_destroy(zb_face_iris_pipeline *p);
+zb_status zb_face_iris_pipeline_set_eye_margin(zb_face_iris_pipeline *p, float grow_rel_amount);
+int32_t zb_face_iris_pipeline_num_landmarks(const zb_face_iris_pipeline *p);
+zb_status zb_face_iris_pipeline_run(zb_face_iris_pipeline *p, const zb_frames *frames, const zb_view *face_rois, int32_t n,
+                                    float *out_face_landmarks, float *out_face_flags, zb_view *out_face_view_rects,
+                                    zb_view *out_eye_rois, float *out_eye_landmarks);
 
 /* ---- palm detection + hand landmarks, fused (BASELINE config 3) ------------------------------
  * The same device-resident two-stage machinery with the hand crop rule of HandTracker

@@ -98,6 +98,12 @@ class FaceLandmarksV2(Estimate):
     def angle_radians(self):
         return self.rotation_radians()
 
+    # mediapipe.rs:315-344: the same four LandmarkIdx entries per eye as V1
+    left_eye = FaceLandmarks.left_eye
+    right_eye = FaceLandmarks.right_eye
+    LEFT_EYE_INNER, LEFT_EYE_TOP, LEFT_EYE_BOTTOM = 133, 159, 145
+    RIGHT_EYE_INNER, RIGHT_EYE_TOP, RIGHT_EYE_BOTTOM = 362, 386, 374
+
 
 class FaceMeshV2(LandmarkNetwork):
     """mediapipe.rs:81-115 (f16 model: input rounded to f16, outputs widened from f16 by NeuralNetwork.estimate)."""
@@ -193,18 +199,26 @@ class Estimator:
         """landmark.rs:293-302; an oracle.filter.LandmarkFilter."""
         self.filter = landmark_filter
 
-    def estimate(self, image, outputs=None):
+    def estimate(self, image, outputs=None, flip_x=False):
+        """flip_x (the build's right-eye rule, face/eye.rs:24-28 + :121-125; DESIGN.md "crop rules"): the sampled tensor
+        is mirrored left-right and the estimate is flipped back with flip_horizontal_in_place(input_resolution)
+        before the remap."""
         view0 = image.as_view()
         cnn = self.network.cnn()
         res = cnn.input_resolution()
         rect = view0.rect().grow_to_fit_aspect(res.aspect_ratio())
         view = view0.view(rect)
         if outputs is None:
-            outputs = cnn.estimate(view, self.backend)
+            if flip_x:
+                outputs = cnn.nn.estimate(np.ascontiguousarray(cnn.tensor(view.as_view())[:, :, :, ::-1]), self.backend)
+            else:
+                outputs = cnn.estimate(view, self.backend)
         self.last_raw = outputs
         self.network.extract(outputs, self.estimate_)
         if self.filter is not None:     # in network coordinates, before the remap (landmark.rs:330-333)
             self.filter.filter(self.estimate_.positions)
+        if flip_x:
+            self.estimate_.flip_horizontal_in_place(res.width)
         scale = rect.w / f32(res.width)
         pos = self.estimate_.positions
         pos *= scale                       # x, y AND z are scaled (landmark.rs:336-339)

@@ -4,7 +4,8 @@ import numpy as np
 
 from oracle.detection import Detector, ShortRangeNetwork
 from oracle.image import Image
-from oracle.landmark import Estimator, FaceMeshV1, LandmarkTracker
+from oracle.geometry import RotatedRect
+from oracle.landmark import Estimator, EyeNetwork, FaceMeshV1, LandmarkTracker
 
 
 def _total_key(x):
@@ -29,3 +30,28 @@ def face_pipeline(frame_rgba: np.ndarray, backend="cv2"):
     tracker.set_roi(best.rect)
     view_rect, est, _ = tracker.track(img)
     return dets, est.positions.copy(), est.face_flag, view_rect, raw
+
+
+def face_iris_pipeline(frame_rgba: np.ndarray, roi, eye_margin=0.0, backend="cv2", mesh_network=None):
+    """BASELINE config 2 (what `zb_face_iris_pipeline_run` claims to do), composed from the reference's pieces:
+    tracker.set_roi(roi) + one `LandmarkTracker::track` step (landmark.rs:456-501) -> `left_eye()` / `right_eye()`
+    (mediapipe.rs:163-192), each `grow_rel(eye_margin)` -> `Estimator::estimate(&image.view(eye))` with EyeNetwork
+    (the right eye mirrored, eye.rs:24-28, :121-125) -> `eye.transform_out` into frame coordinates.
+    roi = (cx, cy, w, h, radians).  Returns (face positions [L,3], face_flag, view_rect, [left, right] eye
+    RotatedRects, eye positions [2,76,3])."""
+    from oracle.geometry import Rect
+    img = Image(frame_rgba)
+    tracker = LandmarkTracker(Estimator(mesh_network or FaceMeshV1(), backend=backend))
+    tracker.loss_thresh = np.float32(-1.0)
+    tracker.set_roi(RotatedRect(Rect.from_center(*[np.float32(v) for v in roi[:4]]), np.float32(roi[4])))
+    view_rect, est, _ = tracker.track(img)
+    face = est.positions.copy()
+    eyes, eye_pos = [], np.zeros((2, 76, 3), np.float32)
+    for side, rect in enumerate((est.left_eye(), est.right_eye())):
+        rect = rect.grow_rel(eye_margin) if eye_margin else rect
+        eyes.append(rect)
+        e = Estimator(EyeNetwork(), backend=backend).estimate(img.view(rect), flip_x=(side == 1))
+        for k, p in enumerate(e.positions):
+            ox, oy = rect.transform_out((p[0], p[1]))
+            eye_pos[side, k] = (ox, oy, p[2])
+    return face, est.face_flag, view_rect, eyes, eye_pos

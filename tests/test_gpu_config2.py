@@ -1,0 +1,152 @@
+"""BASELINE.json config 2 on the device: face mesh (192x192) on detector crops -> `left_eye()` / `right_eye()`
+(mediapipe.rs:163-192) -> iris network (64x64) on the two eye crops, the right one mirrored (eye.rs:24-28, :121-125),
+through `zb_face_iris_pipeline_run`, against the oracle composition (tests/oracle_pipeline.face_iris_pipeline) and the
+committed golden vectors; at the full batch of 256 crops through batch invariance and permutation equivariance.
+Also `Detector::timers()` / `Estimator::timers()` (detection.rs:272-275, landmark.rs:288-291)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import zaru_b200
+    zaru_b200.load_library()
+    zaru_b200.context()
+    return zaru_b200
+
+
+def _check_against(res, i, face, flag, view_rect5, eyes5, eye_pos, face_scale, name=""):
+    """Tolerances (north_star): 1e-3 of the network input size, mapped to frame pixels by the crop scale."""
+    assert abs(float(res.face_flags[i]) - float(flag)) <= TOL, name
+    assert np.abs(res.face_view_rects[i] - view_rect5).max() <= 1e-3, name
+    assert np.abs(res.face_landmarks[i] - face).max() <= TOL * 192 * face_scale, name
+    # eye rectangles are functions of 4 mesh landmarks each: same budget as the landmarks they come from (x2: a size
+    # is a difference of two positions); rotation within 1e-3 rad
+    assert np.abs(res.eye_rois[i][:, :4] - eyes5[:, :4]).max() <= 2 * TOL * 192 * face_scale, name
+    assert np.abs(res.eye_rois[i][:, 4] - eyes5[:, 4]).max() <= 1e-3, name
+    for side in range(2):
+        eye_scale = max(float(eyes5[side, 2]), float(eyes5[side, 3])) / 64.0
+        # the eye crop itself moves with the mesh landmarks (by up to the budget above); the iris network's own
+        # budget comes on top
+        budget = TOL * 64 * eye_scale + 2 * TOL * 192 * face_scale
+        assert np.abs(res.eye_landmarks[i, side] - eye_pos[side]).max() <= budget, (name, side)
+
+
+def test_face_iris_pipeline_matches_golden_vectors(zb, sad_linus_full, sad_linus_cropped):
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FaceIrisPipeline
+    from zaru_b200.rect import Resolution
+    g = np.load(os.path.join(GOLD, "face_iris.npz"))
+    for name in g["cases"]:
+        img = sad_linus_full if name.startswith("full") else sad_linus_cropped
+        h, w = img.shape[:2]
+        batch = ImageBatch.from_rgba8(Resolution(w, h), img[None])
+        roi = g[f"{name}_roi"]
+        pipe = FaceIrisPipeline(eye_margin=float(g[f"{name}_margin"]))
+        res = pipe.run(batch, [(0, *[float(v) for v in roi])])
+        _check_against(res, 0, g[f"{name}_face"], g[f"{name}_flag"], g[f"{name}_view_rect"], g[f"{name}_eyes"],
+                       g[f"{name}_eye_positions"], float(g[f"{name}_view_rect"][2]) / 192.0, name)
+        # the host accessor (LandmarkResultV1::left_eye / right_eye on the returned landmarks) is the device's eye RoI
+        from zaru_b200.landmark import LandmarkResultV1
+        r = LandmarkResultV1(res.face_landmarks[0], np.array([res.face_flags[0], 0], np.float32))
+        for side, rr in enumerate((r.left_eye(), r.right_eye())):
+            rr = rr.grow_rel(float(g[f"{name}_margin"])) if float(g[f"{name}_margin"]) else rr
+            got = np.array([*rr.center(), *rr.rect().size(), rr.rotation_radians()], np.float32)
+            assert np.abs(got - res.eye_rois[0, side]).max() <= 1e-3, (name, side)
+
+
+def test_face_iris_pipeline_matches_oracle_on_synthetic_frames(zb):
+    """S-crop: face RoIs = the oracle detector's detections on S-face frames, incl. rotated crops."""
+    from oracle.detection import Detector as ODet, ShortRangeNetwork as ONet
+    from oracle.image import Image as OImage
+    from tests.oracle_pipeline import face_iris_pipeline
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FaceIrisPipeline
+    from zaru_b200.rect import Resolution
+    frames = np.stack([synth.s_face_frame(s, allow_empty=False)[0] for s in (7, 501, 502)])
+    batch = ImageBatch.from_rgba8(Resolution(1920, 1080), frames)
+    rois = []
+    rng = np.random.default_rng(11)
+    for i, fr in enumerate(frames):
+        for d in ODet(ONet()).detect(OImage(fr))[:2]:
+            r = d.rect
+            rois.append((i, float(r.cx), float(r.cy), float(r.w), float(r.h), float(rng.choice([0.0, rng.uniform(-0.3, 0.3)]))))
+    assert len(rois) >= 3
+    for margin in (0.0, 0.5):
+        pipe = FaceIrisPipeline(eye_margin=margin)
+        res = pipe.run(batch, rois)
+        for i, roi in enumerate(rois):
+            face, flag, view_rect, eyes, eye_pos = face_iris_pipeline(frames[roi[0]], roi[1:], eye_margin=margin)
+            vr5 = np.asarray([*view_rect.rect.as_tuple(), view_rect.radians], np.float32)
+            eyes5 = np.asarray([[*e.rect.as_tuple(), e.radians] for e in eyes], np.float32)
+            _check_against(res, i, face, flag, vr5, eyes5, eye_pos, float(vr5[2]) / 192.0, f"roi {i} margin {margin}")
+
+
+def test_config2_batch256_invariance_and_permutation(zb):
+    """The full config-2 batch: 256 face crops (512 eye crops) in one call == the same crops run alone / permuted."""
+    from zaru_b200 import synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FaceIrisPipeline
+    from zaru_b200.rect import Resolution
+    frames = np.stack([synth.s_face_frame(500 + i, allow_empty=False)[0] for i in range(8)])
+    batch = ImageBatch.from_rgba8(Resolution(1920, 1080), frames)
+    rng = np.random.default_rng(4)
+    rois = []
+    for i in range(256):
+        w = float(rng.uniform(150, 600))
+        rois.append((i % 8, float(rng.uniform(300, 1600)), float(rng.uniform(250, 850)), w, w * float(rng.uniform(0.85, 1.2)),
+                     float(rng.choice([0.0, rng.uniform(-0.4, 0.4)]))))
+    pipe = FaceIrisPipeline(eye_margin=0.5)
+    big = pipe.run(batch, rois)
+    assert big.eye_landmarks.shape == (256, 2, 76, 3) and np.isfinite(big.eye_landmarks).all()
+    for i in (0, 3, 100, 255):
+        one = pipe.run(batch, [rois[i]])
+        scale = max(rois[i][3], rois[i][4]) / 192.0
+        assert np.abs(one.face_landmarks[0] - big.face_landmarks[i]).max() <= 2e-2 * max(1.0, scale), i
+        assert np.abs(one.eye_rois[0] - big.eye_rois[i]).max() <= 4e-2 * max(1.0, scale), i
+        assert np.abs(one.eye_landmarks[0] - big.eye_landmarks[i]).max() <= 8e-2 * max(1.0, scale), i
+    perm = rng.permutation(256)
+    shuf = pipe.run(batch, [rois[j] for j in perm])
+    for k in (0, 9, 200):
+        assert np.array_equal(shuf.face_landmarks[k], big.face_landmarks[perm[k]])
+        assert np.array_equal(shuf.eye_landmarks[k], big.eye_landmarks[perm[k]])
+    # whole-frame default (face_rois = NULL) runs and is well formed
+    whole = pipe.run(batch)
+    assert whole.face_landmarks.shape == (8, 468, 3)
+
+
+def test_detector_and_estimator_timers(zb, sad_linus_full, sad_linus_cropped):
+    """`Detector::timers()` = infer / extract / nms, `Estimator::timers()` = infer / extract / filter, fed with device
+    time: positive after a call, inference dominates, `Display` resets (timer.rs:76-88)."""
+    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200.image import Image
+    from zaru_b200.landmark import Estimator, FaceMeshV1
+    det = Detector(ShortRangeNetwork())
+    for _ in range(3):
+        det.detect(Image(sad_linus_full))
+    names, vals = [], []
+    for t in det.timers():
+        s = str(t)
+        names.append(s.split(":")[0])
+        assert s.split(": ")[1].startswith("3x")
+        vals.append(float(s.split("x")[1][:-2]))
+    assert names == ["infer", "extract", "nms"]
+    assert vals[0] > 0.0 and vals[0] > vals[1] and vals[0] > vals[2]
+    assert [str(t).split(": ")[1] for t in det.timers()] == ["0x0.0ms"] * 3
+    est = Estimator(FaceMeshV1())
+    est.estimate(Image(sad_linus_cropped))
+    out = [str(t) for t in est.timers()]
+    assert [o.split(":")[0] for o in out] == ["infer", "extract", "filter"] and out[0].split(": ")[1].startswith("1x")
+    # raw device milliseconds behind the mirrors
+    import ctypes as C
+    from zaru_b200 import _ffi
+    ms = (C.c_float * 3)()
+    _ffi.check(_ffi.lib().zb_detector_timers(det._h, ms))
+    assert ms[0] > 0 and ms[1] > 0 and ms[2] > 0

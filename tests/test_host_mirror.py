@@ -72,3 +72,55 @@ def test_thread_context_and_pipeline_switches_exist_and_fail_loudly_without_a_gp
     t.start()
     t.join()
     assert seen and "no CPU fallback" in seen[0]
+
+
+def test_rotated_rect_bounding_reference_kats_and_oracle_agreement():
+    """Port of rect.rs:661-708 (`test_rotated_rect_bounding`) for the host mirror, plus bit-equality with the oracle's
+    restatement on random inputs."""
+    tau = np.float32(2 * math.pi)
+    assert RotatedRect.bounding(0.0, []) is None
+    assert RotatedRect.bounding(0.0, [(0, 0), (1, 1)]) == RotatedRect(Rect.from_top_left(0, 0, 1, 1), 0.0)
+    assert RotatedRect.bounding(0.0, [(0, 0), (10, 0)]) == RotatedRect(Rect.from_top_left(0, 0, 10, 0), 0.0)
+    for rad in (tau / np.float32(2), tau / np.float32(4)):
+        r = RotatedRect.bounding(rad, [(0, 0), (1, 1)])
+        want = Rect.from_top_left(0, 0, 1, 1)
+        assert np.allclose(_t(r.rect()), _t(want), atol=1e-6) and r.rotation_radians() == rad
+    assert np.allclose(_t(RotatedRect.bounding(tau / np.float32(4), [(0, 0), (9, 9)]).rect()), _t(Rect.from_top_left(0, 0, 9, 9)), atol=1e-5)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        pts = rng.uniform(-300, 2000, (int(rng.integers(1, 9)), 2)).astype(np.float32)
+        rad = np.float32(rng.uniform(-math.pi, math.pi))
+        a, b = RotatedRect.bounding(rad, pts), og.RotatedRect.bounding(rad, pts)
+        assert _t(a.rect()) == tuple(float(v) for v in b.rect.as_tuple())
+        assert float(a.rotation_radians()) == float(b.radians)
+
+
+def test_face_mesh_result_eye_rects_match_oracle():
+    """`LandmarkResultV1::rotation_radians / left_eye / right_eye` (mediapipe.rs:146-192) and the V2 twins (:315-344,
+    :407-421): the host mirror's accessors against the oracle's, bit for bit."""
+    from oracle.landmark import FaceLandmarks, FaceLandmarksV2
+    from zaru_b200.landmark import LandmarkResultV1, LandmarkResultV2
+    rng = np.random.default_rng(6)
+    for cls, ocls, n in ((LandmarkResultV1, FaceLandmarks, 468), (LandmarkResultV2, FaceLandmarksV2, 478)):
+        for _ in range(20):
+            pos = rng.uniform(0, 1080, (n, 3)).astype(np.float32)
+            m = cls(pos.copy(), np.array([0.9, 0.0], np.float32))
+            o = ocls()
+            o.positions[:] = pos
+            assert float(m.rotation_radians()) == float(o.rotation_radians())
+            for got, want in ((m.left_eye(), o.left_eye()), (m.right_eye(), o.right_eye())):
+                assert _t(got.rect()) == tuple(float(v) for v in want.rect.as_tuple())
+                assert float(got.rotation_radians()) == float(want.radians)
+
+
+def test_timer_mirror_averages_and_resets_like_the_reference():
+    """timer.rs:16-97: EMA with alpha 0.3 over the recorded durations, count, `Display` prints and resets."""
+    from zaru_b200.timer import Timer
+    t = Timer("infer")
+    t.record(0.010)
+    t.record(0.020)
+    want = np.float32(0.3) * np.float32(0.020) + (np.float32(1.0) - np.float32(0.3)) * np.float32(0.010)
+    assert str(t) == f"infer: 2x{float(want) * 1000.0:.1f}ms"
+    assert str(t) == "infer: 0x0.0ms"
+    t.record(0.004)
+    assert str(t) == "infer: 1x4.0ms"

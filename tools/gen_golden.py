@@ -26,12 +26,39 @@ def dets_array(dets):
         if dets else np.zeros((0, 19), np.float32)
 
 
+def gen_face_iris(out, full, crop):
+    """BASELINE config 2: face mesh -> left_eye()/right_eye() -> iris network (tests/oracle_pipeline.face_iris_pipeline)
+    on the reference's two fixture images; the RoI on sad_linus.jpg is the oracle detector's best detection."""
+    from tests.oracle_pipeline import face_iris_pipeline
+    sha = lambda a: np.frombuffer(__import__("hashlib").sha256(a.tobytes()).digest(), np.uint8)
+    rec = {"crop_sha": sha(crop), "full_sha": sha(full)}
+    h, w = crop.shape[:2]
+    d = Detector(ShortRangeNetwork()).detect(Image(full))[0].rect
+    cases = [("crop_upright", crop, (w / 2, h / 2, w, h, 0.0), 0.0),
+             ("crop_rot_p10_m05", crop, (w / 2, h / 2, w, h, float(np.radians(f32(10.0)))), 0.5),
+             ("crop_rot_m10_m025", crop, (w / 2, h / 2, w, h, float(np.radians(f32(-10.0)))), 0.25),
+             ("full_det_m05", full, (float(d.cx), float(d.cy), float(d.w), float(d.h), 0.0), 0.5)]
+    for name, img, roi, margin in cases:
+        face, flag, view_rect, eyes, eye_pos = face_iris_pipeline(img, roi, eye_margin=margin)
+        rec[f"{name}_roi"] = np.asarray(roi, np.float32)
+        rec[f"{name}_margin"] = np.float32(margin)
+        rec[f"{name}_face"] = face
+        rec[f"{name}_flag"] = np.float32(flag)
+        rec[f"{name}_view_rect"] = np.asarray([*view_rect.rect.as_tuple(), view_rect.radians], np.float32)
+        rec[f"{name}_eyes"] = np.asarray([[*e.rect.as_tuple(), e.radians] for e in eyes], np.float32)
+        rec[f"{name}_eye_positions"] = eye_pos
+    np.savez_compressed(os.path.join(out, "face_iris.npz"), cases=np.asarray([c[0] for c in cases]), **rec)
+
+
 def main():
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     assets = synth.assets_dir()
     full = synth.load_image_rgba(os.path.join(assets, "img", "sad_linus.jpg"))
     crop = synth.load_image_rgba(os.path.join(assets, "img", "sad_linus_cropped.jpg"))
+    if "face_iris" in sys.argv[1:]:          # only the config-2 vectors (the other files stay byte-identical)
+        gen_face_iris(out, full, crop)
+        return
 
     # --- detects_face fixture ---------------------------------------------------------------------
     det = Detector(ShortRangeNetwork())
@@ -103,6 +130,7 @@ def main():
         rec[f"filter_{name}"] = np.array([[flt.filter(sts[i], xs[t, i], 1.0 / 30.0) for i in range(64)] for t in range(10)], np.float32)
     rec["filter_inputs"] = xs.astype(np.float32)
     np.savez_compressed(os.path.join(out, "tracker_filter.npz"), **rec)
+    gen_face_iris(out, full, crop)
     for f in sorted(os.listdir(out)):
         print(f, os.path.getsize(os.path.join(out, f)))
 

@@ -98,6 +98,13 @@ SIGNATURES = {
     "zb_hand_pipeline_set_dense": (i32, [P, i32]),
     "zb_face_pipeline_num_landmarks": (i32, [P]),
     "zb_face_pipeline_run": (i32, [P, P, i32, P, P, i32, P, P, P]),
+    "zb_detector_timers": (i32, [P, C.POINTER(f32)]),
+    "zb_estimator_timers": (i32, [P, C.POINTER(f32)]),
+    "zb_face_iris_pipeline_create": (i32, [P, P, P, PP]),
+    "zb_face_iris_pipeline_destroy": (None, [P]),
+    "zb_face_iris_pipeline_set_eye_margin": (i32, [P, f32]),
+    "zb_face_iris_pipeline_num_landmarks": (i32, [P]),
+    "zb_face_iris_pipeline_run": (i32, [P, P, P, i32, P, P, P, P, P]),
     "zb_net_plan_json": (i32, [P, C.c_char_p, sz, C.POINTER(sz)]),
     "zb_net_weights": (i32, [P, C.POINTER(C.POINTER(C.c_float)), C.POINTER(sz)]),
     "zb_plan_from_onnx": (i32, [P, sz, i32, C.c_char_p, sz, C.POINTER(sz), P, sz, C.POINTER(sz)]),

@@ -428,6 +428,7 @@ void fit_view(const RRectF &base, int net_w, int net_h, RRectF &sampled, float f
 void check_frames(const zb_frames *frames, const zb_view *views, int n) {
     if (!frames) throw std::runtime_error("frames is NULL");
     if (n < 0) throw std::runtime_error("negative batch size");
+    if (n > 65535) throw std::runtime_error("batch of " + std::to_string(n) + " views exceeds 65535 per call (one grid dimension); split the batch");
     if (!views && n > frames->f.n) throw std::runtime_error("n exceeds the number of frames in the batch");
     if (views)
         for (int i = 0; i < n; i++)
@@ -946,8 +947,14 @@ struct zb_detector {
     float iou = 0.3f;           // NonMaxSuppression::DEFAULT_IOU_THRESH (nms.rs:28)
     int mode = ZB_NMS_AVERAGE;  // nms.rs:39
     Workspace ws;
-    DevBuf d_views, d_fit, d_dets, d_counts;
-    PinBuf h_stage, h_counts;
+    DevBuf d_views, d_fit, d_dets, d_counts, d_phase;
+    PinBuf h_stage, h_counts, h_phase;
+    cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // Detector::timers(): start | infer done | extract+nms done
+    float t_ms[3] = {0.f, 0.f, 0.f};                     // infer, extract, nms of the last detect / extract call
+    ~zb_detector() {
+        for (cudaEvent_t e : ev_t)
+            if (e) cudaEventDestroy(e);
+    }
 };
 
 struct zb_estimator {
@@ -961,6 +968,12 @@ struct zb_estimator {
     PinBuf h_stage;
     FilterDev filter{};          // LandmarkFilter (default: none); state slots = views of the batch
     int filter_slots = 0;
+    cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};   // Estimator::timers(): start | infer done | extract(+filter) done
+    float t_ms[3] = {0.f, 0.f, 0.f};                     // infer, extract, filter (fused into extract: 0)
+    ~zb_estimator() {
+        for (cudaEvent_t e : ev_t)
+            if (e) cudaEventDestroy(e);
+    }
 };
 
 struct zb_tracker {
@@ -1054,6 +1067,19 @@ void check_estimator_net(const zb_net *net, zb_estimator_kind kind) {
     if (!ok) throw std::runtime_error("bad shape: landmark network outputs do not match the estimator kind");
 }
 
+void ensure_events(cudaEvent_t (&ev)[3]) {
+    for (cudaEvent_t &e : ev)
+        if (!e) CU(cudaEventCreate(&e));
+}
+
+// t_extract / t_nms: the decode+NMS kernel's event time apportioned by the per-CTA phase durations it summed
+void split_post_ms(float post_ms, const unsigned long long *phase, float &extract_ms, float &nms_ms) {
+    const double a = (double)phase[0], b = (double)phase[1];
+    const double f = a + b > 0.0 ? a / (a + b) : 0.5;
+    extract_ms = (float)(post_ms * f);
+    nms_ms = (float)(post_ms * (1.0 - f));
+}
+
 }  // namespace
 
 extern "C" {
@@ -1100,6 +1126,14 @@ zb_status zb_detector_input_resolution(const zb_detector *d, int32_t *w, int32_t
     return ZB_OK;
 }
 
+// `Detector::timers()` (detection.rs:272-275): t_infer, t_extract, t_nms of the LAST detect / extract call, in ms of
+// device time (the reference's Timer keeps an EMA over calls; the mirrors do that on top of these numbers).
+zb_status zb_detector_timers(const zb_detector *d, float out_ms[3]) {
+    if (!d || !out_ms) return fail(ZB_ERR_INVALID_ARGUMENT, "detector/out_ms is NULL");
+    for (int i = 0; i < 3; i++) out_ms[i] = d->t_ms[i];
+    return ZB_OK;
+}
+
 zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_view *views, int32_t n,
                              zb_detection *out_dets, int32_t *out_counts, int32_t cap, float *raw_boxes,
                              float *raw_scores) {
@@ -1131,17 +1165,27 @@ zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_v
         d->h_counts.reserve(sizeof(int) * n);
         CU(cudaMemcpyAsync(d->d_views.p, hv, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(d->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
-        const DecodeParams dp = decode_params(d->kind, pl, d->thresh, d->iou, d->mode, cap);
+        DecodeParams dp = decode_params(d->kind, pl, d->thresh, d->iou, d->mode, cap);
+        ensure_events(d->ev_t);
+        d->d_phase.reserve(2 * sizeof(unsigned long long));
+        d->h_phase.reserve(2 * sizeof(unsigned long long));
+        CU(cudaMemsetAsync(d->d_phase.p, 0, 2 * sizeof(unsigned long long), s));
+        CU(cudaMemsetAsync(d->d_dets.p, 0, sizeof(DetDev) * (size_t)n * cap, s));   // slots >= count read as zero
+        dp.phase_ns = d->d_phase.as<unsigned long long>();
         Timer tm(ctx, s);
+        CU(cudaEventRecord(d->ev_t[0], s));
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
             const StemInput si{&frames->f, d->d_views.as<ViewDev>() + c0, d->lo, d->hi};
             run_ops(d->net, d->ws, c0, nc, 0, s, &si);
         }
         run_ops(d->net, d->ws, 0, n, 1, s);
+        CU(cudaEventRecord(d->ev_t[1], s));
         launch_decode_nms(d->ws.outs[0].as<float>(), d->ws.outs[1].as<float>(), d->d_fit.as<float>(), n, dp,
                           d->d_dets.as<DetDev>(), d->d_counts.as<int>(), s);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(d->ev_t[2], s));
+        CU(cudaMemcpyAsync(d->h_phase.p, d->d_phase.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         tm.stop();
         copy_out(out_dets, d->d_dets.p, sizeof(DetDev) * (size_t)n * cap, s);
         copy_out(out_counts, d->d_counts.p, sizeof(int) * n, s);
@@ -1150,6 +1194,12 @@ zb_status zb_detector_detect(zb_detector *d, const zb_frames *frames, const zb_v
         CU(cudaMemcpyAsync(d->h_counts.p, d->d_counts.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         tm.finish();
+        {
+            float post = 0.f;
+            CU(cudaEventElapsedTime(&d->t_ms[0], d->ev_t[0], d->ev_t[1]));
+            CU(cudaEventElapsedTime(&post, d->ev_t[1], d->ev_t[2]));
+            split_post_ms(post, d->h_phase.as<unsigned long long>(), d->t_ms[1], d->t_ms[2]);
+        }
         const int *hc = d->h_counts.as<int>();
         for (int i = 0; i < n; i++)
             if (hc[i] > cap)
@@ -1198,15 +1248,31 @@ zb_status zb_detector_extract(zb_detector *d, const float *raw_boxes, const floa
         d->d_counts.reserve(sizeof(int) * n);
         d->h_counts.reserve(sizeof(int) * n);
         CU(cudaMemcpyAsync(d->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        ensure_events(d->ev_t);
+        d->d_phase.reserve(2 * sizeof(unsigned long long));
+        d->h_phase.reserve(2 * sizeof(unsigned long long));
+        CU(cudaMemsetAsync(d->d_phase.p, 0, 2 * sizeof(unsigned long long), s));
+        CU(cudaMemsetAsync(d->d_dets.p, 0, sizeof(DetDev) * (size_t)n * cap, s));
+        DecodeParams dpt = dp;
+        dpt.phase_ns = d->d_phase.as<unsigned long long>();
         Timer tm(ctx, s);
-        launch_decode_nms(pb, ps, d->d_fit.as<float>(), n, dp, d->d_dets.as<DetDev>(), d->d_counts.as<int>(), s);
+        CU(cudaEventRecord(d->ev_t[1], s));
+        launch_decode_nms(pb, ps, d->d_fit.as<float>(), n, dpt, d->d_dets.as<DetDev>(), d->d_counts.as<int>(), s);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(d->ev_t[2], s));
+        CU(cudaMemcpyAsync(d->h_phase.p, d->d_phase.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         tm.stop();
         copy_out(out_dets, d->d_dets.p, sizeof(DetDev) * (size_t)n * cap, s);
         copy_out(out_counts, d->d_counts.p, sizeof(int) * n, s);
         CU(cudaMemcpyAsync(d->h_counts.p, d->d_counts.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         tm.finish();
+        {
+            float post = 0.f;
+            CU(cudaEventElapsedTime(&post, d->ev_t[1], d->ev_t[2]));
+            d->t_ms[0] = 0.f;   // no inference in extract-only calls
+            split_post_ms(post, d->h_phase.as<unsigned long long>(), d->t_ms[1], d->t_ms[2]);
+        }
         const int *hc = d->h_counts.as<int>();
         for (int i = 0; i < n; i++)
             if (hc[i] > cap)
@@ -1249,6 +1315,14 @@ zb_status zb_estimator_input_resolution(const zb_estimator *e, int32_t *w, int32
     return ZB_OK;
 }
 
+// `Estimator::timers()` (landmark.rs:288-291): t_infer, t_extract, t_filter of the LAST estimate call (device ms).
+// The filter is applied inside the extract kernel here, so t_filter reads 0 and t_extract includes it.
+zb_status zb_estimator_timers(const zb_estimator *e, float out_ms[3]) {
+    if (!e || !out_ms) return fail(ZB_ERR_INVALID_ARGUMENT, "estimator/out_ms is NULL");
+    for (int i = 0; i < 3; i++) out_ms[i] = e->t_ms[i];
+    return ZB_OK;
+}
+
 zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const zb_view *views, const uint8_t *flip_x,
                                 int32_t n, float *out_landmarks, float *out_scalars) {
     return guarded([&]() -> zb_status {
@@ -1283,13 +1357,16 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
         lp.net_w = pl.in_w;
         lp.net_h = pl.in_h;
         lp.track_transform = 0;
+        ensure_events(e->ev_t);
         Timer tm(ctx, s);
+        CU(cudaEventRecord(e->ev_t[0], s));
         for (int c0 = 0; c0 < n; c0 += chunk) {
             const int nc = std::min(chunk, n - c0);
             const StemInput si{&frames->f, e->d_views.as<ViewDev>() + c0, e->lo, e->hi};
             run_ops(e->net, e->ws, c0, nc, 0, s, &si);
         }
         run_ops(e->net, e->ws, 0, n, 1, s);
+        CU(cudaEventRecord(e->ev_t[1], s));
         {
             const int s0 = (int)pl.outputs[0].per_image, s1 = (int)pl.outputs[1].per_image;
             const int s2 = pl.outputs.size() > 2 ? (int)pl.outputs[2].per_image : 0;
@@ -1299,11 +1376,15 @@ zb_status zb_estimator_estimate(zb_estimator *e, const zb_frames *frames, const 
                              filter_for(e->filter, e->d_filter, e->filter_slots, n, L, s));
         }
         CU(cudaGetLastError());
+        CU(cudaEventRecord(e->ev_t[2], s));
         tm.stop();
         copy_out(out_landmarks, e->d_lm.p, sizeof(float) * 3 * (size_t)L * n, s);
         copy_out(out_scalars, e->d_scalars.p, sizeof(float) * 2 * n, s);
         CU(cudaStreamSynchronize(s));
         tm.finish();
+        CU(cudaEventElapsedTime(&e->t_ms[0], e->ev_t[0], e->ev_t[1]));
+        CU(cudaEventElapsedTime(&e->t_ms[1], e->ev_t[1], e->ev_t[2]));
+        e->t_ms[2] = 0.f;   // the LandmarkFilter runs inside the extract kernel (landmarks_kernel)
         return ZB_OK;
     });
 }
@@ -1636,6 +1717,7 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         p->h_counts.reserve(sizeof(int) * n);
         CU(cudaMemcpyAsync(p->d_views.p, hv, sizeof(ViewDev) * n, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(p->d_fit.p, hfit, 4 * sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(p->d_dets.p, 0, sizeof(DetDev) * (size_t)n * cap, s));   // slots >= count read as zero
         const DecodeParams dp = decode_params(p->det_kind, dpl, p->thresh, p->iou, p->mode, cap);
         LandmarkParams lp{};
         lp.kind = p->lm_kind;
@@ -1920,6 +2002,150 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
     });
 }
 
+// ---- face mesh -> eye RoIs -> iris landmarks (BASELINE config 2), all on the device -----------------------------------
+struct zb_face_iris_pipeline {
+    zb_ctx *ctx = nullptr;
+    zb_net *mesh_net = nullptr, *iris_net = nullptr;
+    zb_estimator_kind mesh_kind = ZB_EST_FACE_MESH_V1;
+    float eye_margin = 0.0f;             // RotatedRect::grow_rel applied to left_eye() / right_eye() before the crop
+    Workspace ws_mesh, ws_iris;
+    DevBuf d_rois, d_views, d_fit, d_view_rects, d_lm, d_scalars;
+    DevBuf d_eye_views, d_eye_fit, d_eye_rects, d_eye_lm, d_eye_scalars;
+    PinBuf h_stage;
+};
+
+zb_status zb_face_iris_pipeline_create(zb_ctx *ctx, zb_net *mesh_net, zb_net *iris_net, zb_face_iris_pipeline **out) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !mesh_net || !iris_net || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/net/out is NULL");
+        const int64_t lm0 = !mesh_net->plan.outputs.empty() ? mesh_net->plan.outputs[0].per_image : 0;
+        const zb_estimator_kind mk = lm0 == 1434 ? ZB_EST_FACE_MESH_V2 : ZB_EST_FACE_MESH_V1;
+        try {
+            check_estimator_net(mesh_net, mk);
+            check_estimator_net(iris_net, ZB_EST_EYE);
+        } catch (const std::runtime_error &e) {
+            return fail(ZB_ERR_BAD_SHAPE, e.what());
+        }
+        auto p = std::make_unique<zb_face_iris_pipeline>();
+        p->ctx = ctx, p->mesh_net = mesh_net, p->iris_net = iris_net, p->mesh_kind = mk;
+        *out = p.release();
+        return ZB_OK;
+    });
+}
+
+void zb_face_iris_pipeline_destroy(zb_face_iris_pipeline *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    delete p;
+}
+
+zb_status zb_face_iris_pipeline_set_eye_margin(zb_face_iris_pipeline *p, float grow_rel_amount) {
+    if (!p) return fail(ZB_ERR_INVALID_ARGUMENT, "pipeline is NULL");
+    if (!(grow_rel_amount >= 0.0f)) return fail(ZB_ERR_INVALID_ARGUMENT, "eye margin must be >= 0");
+    p->eye_margin = grow_rel_amount;
+    return ZB_OK;
+}
+
+int32_t zb_face_iris_pipeline_num_landmarks(const zb_face_iris_pipeline *p) { return p ? estimator_landmarks(p->mesh_kind) : 0; }
+
+zb_status zb_face_iris_pipeline_run(zb_face_iris_pipeline *p, const zb_frames *frames, const zb_view *face_rois, int32_t n,
+                                    float *out_face_landmarks, float *out_face_flags, zb_view *out_face_view_rects,
+                                    zb_view *out_eye_rois, float *out_eye_landmarks) {
+    return guarded([&]() -> zb_status {
+        if (!p) return fail(ZB_ERR_INVALID_ARGUMENT, "pipeline is NULL");
+        check_frames(frames, face_rois, n);
+        if (n > 32767) return fail(ZB_ERR_INVALID_ARGUMENT, "at most 32767 faces per call (two eye views each)");
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = p->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const Plan &mpl = p->mesh_net->plan, &ipl = p->iris_net->plan;
+        const int L = estimator_landmarks(p->mesh_kind), LE = estimator_landmarks(ZB_EST_EYE);
+        const int ne = 2 * n;
+        const int mchunk = std::min(net_chunk(p->mesh_net), n), ichunk = std::min(net_chunk(p->iris_net), ne);
+        p->ws_mesh.ensure(p->mesh_net, mchunk, n);
+        p->ws_iris.ensure(p->iris_net, ichunk, ne);
+        // face RoIs as given (NULL: every whole frame), used like LandmarkTracker::set_roi + one track step
+        p->h_stage.reserve(sizeof(ViewHost) * (size_t)n);
+        ViewHost *hr = p->h_stage.as<ViewHost>();
+        for (int i = 0; i < n; i++) {
+            if (face_rois)
+                hr[i] = ViewHost{face_rois[i].frame, face_rois[i].cx, face_rois[i].cy, face_rois[i].w, face_rois[i].h, face_rois[i].radians};
+            else
+                hr[i] = ViewHost{i, (float)frames->f.width * 0.5f, (float)frames->f.height * 0.5f, (float)frames->f.width,
+                                 (float)frames->f.height, 0.0f};
+        }
+        p->d_rois.reserve(sizeof(ViewHost) * n);
+        p->d_views.reserve(sizeof(ViewDev) * n);
+        p->d_fit.reserve(4 * sizeof(float) * n);
+        p->d_view_rects.reserve(sizeof(ViewHost) * n);
+        p->d_lm.reserve(sizeof(float) * 3 * (size_t)L * n);
+        p->d_scalars.reserve(sizeof(float) * 2 * n);
+        p->d_eye_views.reserve(sizeof(ViewDev) * ne);
+        p->d_eye_fit.reserve(4 * sizeof(float) * ne);
+        p->d_eye_rects.reserve(sizeof(ViewHost) * ne);
+        p->d_eye_lm.reserve(sizeof(float) * 3 * (size_t)LE * ne);
+        p->d_eye_scalars.reserve(sizeof(float) * 2 * ne);
+        CU(cudaMemcpyAsync(p->d_rois.p, hr, sizeof(ViewHost) * n, cudaMemcpyHostToDevice, s));
+        Timer tm(ctx, s);
+        // 1. face mesh on every RoI: view_rect = roi.map(grow_to_fit_aspect), landmarks mapped to frame coordinates
+        prof_launch(ctx, s, "rois_prepare", 64.0 * n, 0, [&] {
+            launch_rois_prepare(frames->f, p->d_rois.as<ViewHost>(), n, mpl.in_w, mpl.in_h, p->d_views.as<ViewDev>(),
+                                p->d_fit.as<float>(), p->d_view_rects.as<ViewHost>(), s);
+        });
+        for (int c0 = 0; c0 < n; c0 += mchunk) {
+            const int nc = std::min(mchunk, n - c0);
+            const StemInput si{&frames->f, p->d_views.as<ViewDev>() + c0, -1.0f, 1.0f};   // mediapipe.rs:53
+            run_ops(p->mesh_net, p->ws_mesh, c0, nc, 0, s, &si);
+        }
+        run_ops(p->mesh_net, p->ws_mesh, 0, n, 1, s);
+        {
+            LandmarkParams lp{};
+            lp.kind = (int)p->mesh_kind, lp.num_landmarks = L, lp.net_w = mpl.in_w, lp.net_h = mpl.in_h, lp.track_transform = 1;
+            const int s0 = (int)mpl.outputs[0].per_image, s1 = (int)mpl.outputs[1].per_image;
+            const int s2 = p->mesh_kind == ZB_EST_FACE_MESH_V2 ? (int)mpl.outputs[2].per_image : 0;
+            prof_launch(ctx, s, "landmarks", 8.0 * n * (3 * L + 1), 0, [&] {
+                launch_landmarks(p->ws_mesh.outs[0].as<float>(), s0, p->ws_mesh.outs[1].as<float>(), s1,
+                                 s2 ? p->ws_mesh.outs[2].as<float>() : nullptr, s2, p->d_fit.as<float>(), p->d_views.as<ViewDev>(),
+                                 p->d_view_rects.as<ViewHost>(), n, lp, p->d_lm.as<float>(), p->d_scalars.as<float>(), s);
+            });
+        }
+        // 2. left_eye() / right_eye() -> two eye views per face (right eye mirrored)
+        prof_launch(ctx, s, "eye_rois", 160.0 * n, 0, [&] {
+            launch_eye_rois(frames->f, p->d_lm.as<float>(), p->d_views.as<ViewDev>(), n, L, ipl.in_w, ipl.in_h, p->eye_margin,
+                            p->d_eye_views.as<ViewDev>(), p->d_eye_fit.as<float>(), p->d_eye_rects.as<ViewHost>(), s);
+        });
+        // 3. iris network on the 2n eye crops; landmarks through eye_rect.transform_out into frame coordinates
+        for (int c0 = 0; c0 < ne; c0 += ichunk) {
+            const int nc = std::min(ichunk, ne - c0);
+            const StemInput si{&frames->f, p->d_eye_views.as<ViewDev>() + c0, -1.0f, 1.0f};   // eye.rs:41
+            run_ops(p->iris_net, p->ws_iris, c0, nc, 0, s, &si);
+        }
+        run_ops(p->iris_net, p->ws_iris, 0, ne, 1, s);
+        {
+            LandmarkParams lp{};
+            lp.kind = (int)ZB_EST_EYE, lp.num_landmarks = LE, lp.net_w = ipl.in_w, lp.net_h = ipl.in_h, lp.track_transform = 1;
+            const int s0 = (int)ipl.outputs[0].per_image, s1 = (int)ipl.outputs[1].per_image;
+            prof_launch(ctx, s, "landmarks", 8.0 * ne * 3 * LE, 0, [&] {
+                launch_landmarks(p->ws_iris.outs[0].as<float>(), s0, p->ws_iris.outs[1].as<float>(), s1, nullptr, 0,
+                                 p->d_eye_fit.as<float>(), p->d_eye_views.as<ViewDev>(), p->d_eye_rects.as<ViewHost>(), ne, lp,
+                                 p->d_eye_lm.as<float>(), p->d_eye_scalars.as<float>(), s);
+            });
+        }
+        CU(cudaGetLastError());
+        tm.stop();
+        copy_out(out_face_landmarks, p->d_lm.p, sizeof(float) * 3 * (size_t)L * n, s);
+        if (out_face_flags)
+            CU(cudaMemcpy2DAsync(out_face_flags, sizeof(float), p->d_scalars.p, 2 * sizeof(float), sizeof(float), n,
+                                 is_device_ptr(out_face_flags) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        copy_out(out_face_view_rects, p->d_view_rects.p, sizeof(ViewHost) * n, s);
+        copy_out(out_eye_rois, p->d_eye_rects.p, sizeof(ViewHost) * ne, s);
+        copy_out(out_eye_landmarks, p->d_eye_lm.p, sizeof(float) * 3 * (size_t)LE * ne, s);
+        CU(cudaStreamSynchronize(s));
+        tm.finish();
+        return ZB_OK;
+    });
+}
+
 // ---- palm detector + hand landmarks (BASELINE config 3): the same fused machinery, hand crop rule --------------------
 zb_status zb_hand_pipeline_create(zb_ctx *ctx, zb_net *palm_net, zb_net *hand_net, zb_hand_pipeline **out) {
     zb_status st = zb_face_pipeline_create(ctx, palm_net, hand_net, out);
@@ -1943,12 +2169,16 @@ zb_status zb_hand_pipeline_run(zb_hand_pipeline *p, const zb_frames *frames, int
                                int32_t *out_counts, int32_t cap, float *out_landmarks, float *out_scalars, zb_view *out_rois) {
     const zb_status st = zb_face_pipeline_run(p, frames, n, out_dets, out_counts, cap, out_landmarks, nullptr, out_rois);
     if ((st != ZB_OK && st != ZB_ERR_CAPACITY) || !out_scalars || n == 0) return st;
-    return guarded([&]() -> zb_status {
+    const std::string first_error = t_last_error;   // guarded() clears it; a capacity message must survive the copy below
+    const zb_status st2 = guarded([&]() -> zb_status {
         cudaStream_t s = p->ctx->stream;
         copy_out(out_scalars, p->d_scalars.p, sizeof(float) * 2 * (size_t)n, s);
         CU(cudaStreamSynchronize(s));
-        return st;
+        return ZB_OK;
     });
+    if (st2 != ZB_OK) return st2;
+    t_last_error = first_error;
+    return st;
 }
 
 }  // extern "C"

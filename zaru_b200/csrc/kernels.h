@@ -154,6 +154,7 @@ struct DecodeParams {
     float thresh, iou_thresh;
     int nms_mode;              // 0 remove, 1 average
     int cap;
+    unsigned long long *phase_ns;   // optional [2]: summed per-CTA extract / nms phase durations (Detector::timers split)
 };
 // one CTA per image: sigmoid/threshold/decode -> NMS -> remap (fit: scale, tl.x, tl.y)
 void launch_decode_nms(const float *boxes, const float *scores, const float *fit, int n, const DecodeParams &p,
@@ -200,6 +201,14 @@ struct TrackState {            // LandmarkTracker::roi: Option<RotatedRect>
 // (stream i reads frame first_frame + i); streams without an RoI get an invalid view.
 void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int first_frame, int n, int net_w, int net_h,
                             ViewDev *out_views, float *out_fit, ViewHost *out_view_rects, cudaStream_t s);
+// The same step for caller-supplied RoIs (rois[i].frame names the frame).
+void launch_rois_prepare(const FramesDev &f, const ViewHost *rois, int n, int net_w, int net_h, ViewDev *out_views, float *out_fit,
+                         ViewHost *out_view_rects, cudaStream_t s);
+// LandmarkResultV1::left_eye() / right_eye() (mediapipe.rs:146-192) from face-mesh landmarks in frame coordinates:
+// eye views 2i (left) and 2i + 1 (right, flip_x) for `estimator.estimate(&image.view(eye.grow_rel(margin)))`; out_rects =
+// the (grown) eye RotatedRects whose transform_out maps the eye landmarks back to the frame.
+void launch_eye_rois(const FramesDev &f, const float *landmarks, const ViewDev *face_views, int n, int num_landmarks, int net_w,
+                     int net_h, float margin, ViewDev *out_views, float *out_fit, ViewHost *out_rects, cudaStream_t s);
 // confidence check, angle = roi.rad + estimate.angle_radians(), RotatedRect::bounding over the mapped landmarks,
 // roi = updated.grow_rel(padding).  out0: raw landmark tensor (view-space eye corners give angle_radians);
 // landmarks: positions already mapped to image coordinates; scalars[2*i] = confidence.

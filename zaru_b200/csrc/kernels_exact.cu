@@ -514,6 +514,10 @@ __global__ void __launch_bounds__(256) decode_nms_kernel(const float *__restrict
     const float *bx = boxes + (long long)img * A * p.num_params;
     const float *sc = scores + (long long)img * A;
     const int tid = threadIdx.x, T = blockDim.x;
+    // Detector::timers() split (detection.rs:155-157, :231-243): when asked for, the CTA's extract / nms phase durations
+    // are summed (ns) so the host can apportion the kernel's event time between t_extract and t_nms
+    unsigned long long t_start = 0, t_mid = 0;
+    if (p.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
     // 1. sigmoid + threshold, compact in anchor order  (face/detection.rs:109-113: `if conf < thresh {continue}`)
     int n = 0;
@@ -536,6 +540,7 @@ __global__ void __launch_bounds__(256) decode_nms_kernel(const float *__restrict
         n += tot;
     }
     __syncthreads();
+    if (p.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_mid));
 
     // 2. stable ascending rank sort by TotalF32(confidence)  (nms.rs:66; tie order fixed as stable)
     for (int c = tid; c < n; c += T) {
@@ -631,6 +636,12 @@ __global__ void __launch_bounds__(256) decode_nms_kernel(const float *__restrict
         __syncthreads();
     }
     if (tid == 0) out_counts[img] = n_out;
+    if (p.phase_ns && tid == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        atomicAdd(p.phase_ns, t_mid - t_start);
+        atomicAdd(p.phase_ns + 1, t_end - t_mid);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -791,11 +802,14 @@ __global__ void __launch_bounds__(128) landmarks_kernel(const float *__restrict_
                                                         const int *__restrict__ sel) {
     // `sel` (compacted pipeline): network output row blockIdx.y belongs to frame sel[blockIdx.y]; the raw tensors are
     // indexed by the row, everything per frame (fit, views, view rects, filter state, results) by the frame
-    const int img = sel ? sel[blockIdx.y] : (int)blockIdx.y;
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    // (the batch index lives on grid.x: grid.y is limited to 65535)
+    const int bpi = (p.num_landmarks + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int brow = (int)(blockIdx.x / bpi);
+    const int img = sel ? sel[brow] : brow;
+    const int l = (int)(blockIdx.x - (unsigned)brow * bpi) * blockDim.x + threadIdx.x;
     const int valid = views ? views[img].valid : 1;
     if (sel) {
-        const long long row = blockIdx.y;
+        const long long row = brow;
         out0 += (row - img) * s0;
         if (out1) out1 += (row - img) * s1;
         if (out2) out2 += (row - img) * s2;
@@ -872,6 +886,32 @@ __device__ __forceinline__ void cos_sin_ref(float rad, float &c, float &s) {
     }
 }
 
+// roi -> (optional) grow_to_fit_aspect -> full_image.view(rect) -> Estimator view fit.  pre_fit = 1 is the tracker's
+// `view_rect = roi.map(grow_to_fit_aspect)` (landmark.rs:465); pre_fit = 0 is `estimator.estimate(&image.view(roi))`.
+__device__ __forceinline__ void roi_to_view(const FramesDev &f, int frame, RectF roi, float rad, int pre_fit, int net_w, int net_h,
+                                            ViewDev &v, float &fit0, float &fit1, float &fit2, ViewHost &vr) {
+    const float aspect = aspect_as_f32((unsigned)net_w, (unsigned)net_h);
+    // let view_rect = roi.map(|rect| rect.grow_to_fit_aspect(self.aspect_ratio));   (landmark.rs:465)
+    const RectF view_rect = pre_fit ? grow_to_fit_aspect(roi, aspect) : roi;
+    vr.frame = frame;
+    vr.cx = view_rect.cx, vr.cy = view_rect.cy, vr.w = view_rect.w, vr.h = view_rect.h, vr.radians = rad;
+    float c, s;
+    cos_sin_ref(rad, c, s);
+    // full_image.view(view_rect)   (landmark.rs:466; parent rotation 0, so the summed angle is roi's)
+    const RRectF full = full_view(f.width, f.height);
+    const RRectF v1 = view_compose(full, view_rect, rad, c, s);
+    // Estimator::estimate_impl: rect = view.rect().grow_to_fit_aspect(..); view = image.view(rect)  (:320-323)
+    const RectF r1 = rect_from_top_left(0.0f, 0.0f, v1.r.w, v1.r.h);
+    const RectF r2 = grow_to_fit_aspect(r1, aspect);
+    const RRectF v2 = view_compose(v1, r2, 0.0f, c, s);
+    v.frame = frame;
+    v.valid = 1;
+    v.cx = v2.r.cx, v.cy = v2.r.cy, v.w = v2.r.w, v.h = v2.r.h, v.cosr = c, v.sinr = s;
+    fit0 = r2.w / (float)net_w;
+    fit1 = rect_x(r2);
+    fit2 = rect_y(r2);
+}
+
 __global__ void __launch_bounds__(128) tracker_prepare_kernel(const FramesDev f, const TrackState *__restrict__ state,
                                                               int first_frame, int n, int net_w, int net_h,
                                                               ViewDev *__restrict__ out_views, float *__restrict__ out_fit,
@@ -882,36 +922,94 @@ __global__ void __launch_bounds__(128) tracker_prepare_kernel(const FramesDev f,
     ViewDev v;
     v.frame = first_frame + i;
     v.flip_x = 0;
-    v.valid = st.has != 0;
+    v.valid = 0;
     v.cx = v.cy = 0.f, v.w = v.h = 1.f, v.cosr = 1.f, v.sinr = 0.f;
     float fit0 = 1.f, fit1 = 0.f, fit2 = 0.f;
     ViewHost vr;
     vr.frame = first_frame + i;
     vr.cx = vr.cy = vr.w = vr.h = 0.f, vr.radians = 0.f;
     if (st.has) {
-        const float aspect = aspect_as_f32((unsigned)net_w, (unsigned)net_h);
-        // let view_rect = roi.map(|rect| rect.grow_to_fit_aspect(self.aspect_ratio));   (landmark.rs:465)
         RectF roi;
         roi.cx = st.cx, roi.cy = st.cy, roi.w = st.w, roi.h = st.h;
-        const RectF view_rect = grow_to_fit_aspect(roi, aspect);
-        vr.cx = view_rect.cx, vr.cy = view_rect.cy, vr.w = view_rect.w, vr.h = view_rect.h, vr.radians = st.rad;
-        float c, s;
-        cos_sin_ref(st.rad, c, s);
-        // full_image.view(view_rect)   (landmark.rs:466; parent rotation 0, so the summed angle is roi's)
-        const RRectF full = full_view(f.width, f.height);
-        const RRectF v1 = view_compose(full, view_rect, st.rad, c, s);
-        // Estimator::estimate_impl: rect = view.rect().grow_to_fit_aspect(..); view = image.view(rect)  (:320-323)
-        const RectF r1 = rect_from_top_left(0.0f, 0.0f, v1.r.w, v1.r.h);
-        const RectF r2 = grow_to_fit_aspect(r1, aspect);
-        const RRectF v2 = view_compose(v1, r2, 0.0f, c, s);
-        v.cx = v2.r.cx, v.cy = v2.r.cy, v.w = v2.r.w, v.h = v2.r.h, v.cosr = c, v.sinr = s;
-        fit0 = r2.w / (float)net_w;
-        fit1 = rect_x(r2);
-        fit2 = rect_y(r2);
+        roi_to_view(f, first_frame + i, roi, st.rad, 1, net_w, net_h, v, fit0, fit1, fit2, vr);
     }
     out_views[i] = v;
     out_fit[i * 4 + 0] = fit0, out_fit[i * 4 + 1] = fit1, out_fit[i * 4 + 2] = fit2, out_fit[i * 4 + 3] = 0.f;
     out_rects[i] = vr;
+}
+
+// Caller-supplied RoIs (rois[i].frame names the frame): one tracker-style step per RoI, as tracker_prepare_kernel does
+// for the RoIs it holds itself.
+__global__ void __launch_bounds__(128) rois_prepare_kernel(const FramesDev f, const ViewHost *__restrict__ rois, int n, int net_w,
+                                                           int net_h, ViewDev *__restrict__ out_views, float *__restrict__ out_fit,
+                                                           ViewHost *__restrict__ out_rects) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ViewHost r = rois[i];
+    ViewDev v;
+    v.flip_x = 0;
+    float fit0, fit1, fit2;
+    ViewHost vr;
+    RectF roi;
+    roi.cx = r.cx, roi.cy = r.cy, roi.w = r.w, roi.h = r.h;
+    roi_to_view(f, r.frame, roi, r.radians, 1, net_w, net_h, v, fit0, fit1, fit2, vr);
+    out_views[i] = v;
+    out_fit[i * 4 + 0] = fit0, out_fit[i * 4 + 1] = fit1, out_fit[i * 4 + 2] = fit2, out_fit[i * 4 + 3] = 0.f;
+    out_rects[i] = vr;
+}
+
+// LandmarkResultV1::left_eye() / right_eye() (mediapipe.rs:146-192) for face i -> eye views 2i (left) and 2i + 1 (right,
+// mirrored: eye.rs:24-28) of BASELINE config 2:
+//   rotation = (right_eye_outer - left_eye_outer).signed_angle_to(X)
+//   eye      = RotatedRect::bounding(rotation, [bottom, corner, corner, top])       (rect.rs:287-325)
+//   view     = image.view(eye.map(|r| r.grow_rel(margin)))  ->  Estimator::estimate(&view)   (landmark.rs:314-348)
+// `landmarks` are the face-mesh positions in FRAME coordinates ([n][L][3]); face_views[i] gives the frame and validity.
+__global__ void __launch_bounds__(128) eye_roi_kernel(const FramesDev f, const float *__restrict__ landmarks,
+                                                      const ViewDev *__restrict__ face_views, int n, int L, int net_w, int net_h,
+                                                      float margin, ViewDev *__restrict__ out_views, float *__restrict__ out_fit,
+                                                      ViewHost *__restrict__ out_rects) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * n) return;
+    const int i = e >> 1, right = e & 1;
+    const ViewDev fv = face_views[i];
+    ViewDev v;
+    v.frame = fv.frame;
+    v.flip_x = right;
+    v.valid = 0;
+    v.cx = v.cy = 0.f, v.w = v.h = 1.f, v.cosr = 1.f, v.sinr = 0.f;
+    float fit0 = 1.f, fit1 = 0.f, fit2 = 0.f;
+    ViewHost vr;
+    vr.frame = fv.frame;
+    vr.cx = vr.cy = vr.w = vr.h = 0.f, vr.radians = 0.f;
+    if (fv.valid) {
+        const float *lm = landmarks + (long long)i * L * 3;
+        // LandmarkIdx (mediapipe.rs:530-545)
+        const float lx = lm[3 * 33], ly = lm[3 * 33 + 1], rx = lm[3 * 263], ry = lm[3 * 263 + 1];
+        const float rot = signed_angle_to(rx - lx, ry - ly, 1.0f, 0.0f);
+        const int idx_l[4] = {145, 33, 133, 159}, idx_r[4] = {374, 362, 263, 386};
+        float c, s;
+        cos_sin_ref(-rot, c, s);                       // cw = rotation_clockwise(rot) = ccw(-rot)
+        float mnx = 3.402823466e+38f, mny = 3.402823466e+38f, mxx = -3.402823466e+38f, mxy = -3.402823466e+38f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int l = right ? idx_r[k] : idx_l[k];
+            float px, py;
+            rot_ccw_apply(c, s, lm[3 * l], lm[3 * l + 1], px, py);
+            mnx = fminf(mnx, px), mny = fminf(mny, py), mxx = fmaxf(mxx, px), mxy = fmaxf(mxy, py);
+        }
+        const float ccx = (mnx + mxx) * 0.5f, ccy = (mny + mxy) * 0.5f;
+        float c2, s2, ox, oy;
+        cos_sin_ref(rot, c2, s2);
+        rot_ccw_apply(c2, s2, ccx, ccy, ox, oy);
+        RectF roi;
+        roi.cx = ox, roi.cy = oy, roi.w = mxx - mnx, roi.h = mxy - mny;
+        if (margin != 0.0f) roi = grow_rel(roi, margin);
+        roi_to_view(f, fv.frame, roi, rot, 0, net_w, net_h, v, fit0, fit1, fit2, vr);
+        v.flip_x = right;
+    }
+    out_views[e] = v;
+    out_fit[e * 4 + 0] = fit0, out_fit[e * 4 + 1] = fit1, out_fit[e * 4 + 2] = fit2, out_fit[e * 4 + 3] = 0.f;
+    out_rects[e] = vr;
 }
 
 // One CTA per stream.
@@ -1025,6 +1123,19 @@ void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int fir
                                                            out_view_rects);
 }
 
+void launch_rois_prepare(const FramesDev &f, const ViewHost *rois, int n, int net_w, int net_h, ViewDev *out_views, float *out_fit,
+                         ViewHost *out_view_rects, cudaStream_t s) {
+    g_launch_count++;
+    rois_prepare_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, rois, n, net_w, net_h, out_views, out_fit, out_view_rects);
+}
+
+void launch_eye_rois(const FramesDev &f, const float *landmarks, const ViewDev *face_views, int n, int num_landmarks, int net_w,
+                     int net_h, float margin, ViewDev *out_views, float *out_fit, ViewHost *out_rects, cudaStream_t s) {
+    g_launch_count++;
+    eye_roi_kernel<<<(2 * n + 127) / 128, 128, 0, s>>>(f, landmarks, face_views, n, num_landmarks, net_w, net_h, margin, out_views,
+                                                       out_fit, out_rects);
+}
+
 void launch_tracker_update(TrackState *state, const float *out0, int s0, const float *fit, const float *landmarks,
                            const float *scalars, int n, int num_landmarks, float loss_thresh, float roi_padding,
                            int idx_from, int idx_to, float axis_x, float axis_y, ViewHost *out_updated,
@@ -1096,7 +1207,7 @@ void launch_landmarks(const float *out0, int s0, const float *out1, int s1, cons
                       const LandmarkParams &p, float *landmarks, float *scalars, cudaStream_t s, const FilterDev *filter,
                       const int *sel) {
     g_launch_count++;
-    dim3 grid((p.num_landmarks + 127) / 128, n);
+    dim3 grid((unsigned)((p.num_landmarks + 127) / 128) * (unsigned)n);
     FilterDev none{};
     landmarks_kernel<<<grid, 128, 0, s>>>(out0, s0, out1, s1, out2, s2, fit, views, view_rects, n, p, landmarks,
                                           scalars, filter ? *filter : none, sel);

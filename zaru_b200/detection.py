@@ -7,6 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi, context, context_key, model_path
+from .timer import Timer
 from .nn import Cnn, CnnInputShape, ColorMapper, NeuralNetwork
 from .rect import Rect
 
@@ -135,9 +136,20 @@ class Detector:
                                                  network.color_range[1], C.byref(h)))
         self._h = h
         self.last_raw = None
+        self._timers = (Timer("infer"), Timer("extract"), Timer("nms"))   # detection.rs:174-176
 
     def input_resolution(self):
         return self._cnn.input_resolution()
+
+    def timers(self):
+        """`Detector::timers()` (detection.rs:272-275): t_infer, t_extract, t_nms, fed with device time."""
+        return iter(self._timers)
+
+    def _record_timers(self):
+        ms = (C.c_float * 3)()
+        _ffi.check(_ffi.lib().zb_detector_timers(self._h, ms))
+        for t, v in zip(self._timers, ms):
+            t.record(v / 1000.0)
 
     def set_threshold(self, thresh):
         self._thresh = float(thresh)
@@ -179,6 +191,7 @@ class Detector:
         arr = (_ffi.zb_view * n)(*zviews) if zviews is not None else None
         _ffi.check(_ffi.lib().zb_detector_extract(self._h, raw_boxes.ctypes.data, raw_scores.ctypes.data, arr, n,
                                                   dets, counts, self._cap))
+        self._record_timers()
         return [Detections(Detection(dets[i * self._cap + k]) for k in range(min(counts[i], self._cap)))
                 for i in range(n)]
 
@@ -193,6 +206,7 @@ class Detector:
             raw_s = np.empty([n] + ss[1:], np.float32)
             pb, ps = raw_b.ctypes.data, raw_s.ctypes.data
         _ffi.check(_ffi.lib().zb_detector_detect(self._h, batch._h, views, n, dets, counts, self._cap, pb, ps))
+        self._record_timers()
         self.last_raw = (raw_b, raw_s)
         out = []
         for i in range(n):

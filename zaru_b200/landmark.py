@@ -8,6 +8,8 @@ import numpy as np
 
 from . import _ffi, context, context_key, model_path
 from .nn import Cnn, CnnInputShape, ColorMapper, NeuralNetwork
+from .rect import RotatedRect, signed_angle_to
+from .timer import Timer
 
 
 class Landmarks:
@@ -35,20 +37,53 @@ class Estimate:
         return self._landmarks
 
 
-class LandmarkResultV1(Estimate):
+class LandmarkIdx:
+    """mediapipe.rs:530-545."""
+    MouthLeft, MouthRight, MouthTop, MouthBottom = 78, 308, 13, 14
+    LeftEyeOuterCorner, LeftEyeInnerCorner, LeftEyeTop, LeftEyeBottom = 33, 133, 159, 145
+    RightEyeInnerCorner, RightEyeOuterCorner, RightEyeTop, RightEyeBottom = 362, 263, 386, 374
+    RightEyebrowInnerCorner, LeftEyebrowInnerCorner = 295, 65
+
+
+class _FaceMeshResult(Estimate):
+    """What LandmarkResultV1 and LandmarkResultV2 share: rotation and the eye rectangles."""
+
+    def confidence(self):
+        return np.float32(self._scalars[0])
+
+    def _xy(self, idx):
+        p = self._landmarks.positions()[idx]
+        return (p[0], p[1])
+
+    def rotation_radians(self):
+        """mediapipe.rs:146-160 / :407-421: (right_eye_outer - left_eye_outer).signed_angle_to(Vec2::X)."""
+        le, re = self._xy(LandmarkIdx.LeftEyeOuterCorner), self._xy(LandmarkIdx.RightEyeOuterCorner)
+        return signed_angle_to(re[0] - le[0], re[1] - le[1], 1.0, 0.0)
+
+    def angle_radians(self):
+        return self.rotation_radians()
+
+    def left_eye(self) -> RotatedRect:
+        """mediapipe.rs:163-176 / :315-328: a RotatedRect containing the left eye."""
+        I = LandmarkIdx
+        return RotatedRect.bounding(self.rotation_radians(), [self._xy(i) for i in (
+            I.LeftEyeBottom, I.LeftEyeOuterCorner, I.LeftEyeInnerCorner, I.LeftEyeTop)])
+
+    def right_eye(self) -> RotatedRect:
+        """mediapipe.rs:179-192 / :331-344."""
+        I = LandmarkIdx
+        return RotatedRect.bounding(self.rotation_radians(), [self._xy(i) for i in (
+            I.RightEyeBottom, I.RightEyeInnerCorner, I.RightEyeOuterCorner, I.RightEyeTop)])
+
+
+class LandmarkResultV1(_FaceMeshResult):
     """mediapipe.rs:118-192."""
     NUM_LANDMARKS = 468
 
-    def confidence(self):
-        return np.float32(self._scalars[0])
 
-
-class LandmarkResultV2(Estimate):
+class LandmarkResultV2(_FaceMeshResult):
     """mediapipe.rs `LandmarkResultV2`: 478 landmarks, face flag, tongueOut blendshape."""
     NUM_LANDMARKS = 478
-
-    def confidence(self):
-        return np.float32(self._scalars[0])
 
     def tongue_out(self):
         return np.float32(self._scalars[1])
@@ -60,6 +95,27 @@ class EyeLandmarks(Estimate):
 
     def iris_center(self):
         return self._landmarks.positions()[0]
+
+    def iris_contour(self):
+        return self._landmarks.positions()[1:5]
+
+    def eye_contour(self):
+        return self._landmarks.positions()[5:]
+
+    def iris_diameter(self):
+        """eye.rs:104-113: mean distance of the 4 contour points from the centre, times 2 (f32)."""
+        c = self.iris_center()
+        radius = np.float32(0.0)
+        for p in self.iris_contour():
+            d = c - p
+            radius = radius + np.sqrt((np.float32(0.0) + d[0] * d[0] + d[1] * d[1]) + d[2] * d[2], dtype=np.float32)
+        return radius / np.float32(4.0) * np.float32(2.0)
+
+    def flip_horizontal_in_place(self, full_res):
+        """eye.rs:121-125."""
+        half = np.float32(full_res.width()) / np.float32(2.0)
+        pos = self._landmarks.positions()
+        pos[:, 0] = -(pos[:, 0] - half) + half
 
 
 class HandLandmarkResult(Estimate):
@@ -132,9 +188,14 @@ class Estimator:
                                                   network.color_range[1], C.byref(h)))
         self._h = h
         self._L = _ffi.lib().zb_estimator_num_landmarks(h)
+        self._timers = (Timer("infer"), Timer("extract"), Timer("filter"))   # landmark.rs:270-272
 
     def input_resolution(self):
         return self._cnn.input_resolution()
+
+    def timers(self):
+        """`Estimator::timers()` (landmark.rs:288-291): t_infer, t_extract, t_filter, fed with device time."""
+        return iter(self._timers)
 
     def set_filter(self, landmark_filter):
         """`Estimator::set_filter` (landmark.rs:293-302); a `zaru_b200.filter.LandmarkFilter`.  Resets the state."""
@@ -155,6 +216,10 @@ class Estimator:
         if flip_x is not None:
             flips = (C.c_uint8 * n)(*[1 if f else 0 for f in flip_x])
         _ffi.check(_ffi.lib().zb_estimator_estimate(self._h, batch._h, arr, flips, n, lm.ctypes.data, sc.ctypes.data))
+        ms = (C.c_float * 3)()
+        _ffi.check(_ffi.lib().zb_estimator_timers(self._h, ms))
+        for t, v in zip(self._timers, ms):
+            t.record(v / 1000.0)
         return [self.network.result(lm[i], sc[i]) for i in range(n)]
 
     def __del__(self):

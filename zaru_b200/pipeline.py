@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _ffi, context
 from .detection import Detection, Detections, Detector, ShortRangeNetwork
-from .landmark import FaceMeshV1, LandmarkTracker
+from .landmark import EyeLandmarks, EyeNetwork, FaceMeshV1, LandmarkTracker
 
 
 class FacePipelineResult:
@@ -161,6 +161,76 @@ class HandPipeline:
         try:
             if self._h:
                 _ffi.lib().zb_hand_pipeline_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class FaceIrisResult:
+    def __init__(self, face_landmarks, face_flags, face_view_rects, eye_rois, eye_landmarks):
+        self.face_landmarks = face_landmarks    # [n,L,3] frame coordinates
+        self.face_flags = face_flags            # [n] sigmoid(face_flag)
+        self.face_view_rects = face_view_rects  # [n,5] (cx, cy, w, h, radians): the view the mesh ran on
+        self.eye_rois = eye_rois                # [n,2,5]: left / right eye RotatedRect after the margin
+        self.eye_landmarks = eye_landmarks      # [n,2,76,3] frame coordinates: 5 iris points, then 71 contour points
+
+    def eyes(self, i):
+        """(left, right) `EyeLandmarks` of face i."""
+        z = np.zeros(2, np.float32)
+        return EyeLandmarks(self.eye_landmarks[i, 0], z), EyeLandmarks(self.eye_landmarks[i, 1], z)
+
+
+class FaceIrisPipeline:
+    """BASELINE config 2 on the device: face mesh on each detector crop -> `left_eye()` / `right_eye()`
+    (mediapipe.rs:163-192) -> EyeNetwork on the two eye crops, the right one mirrored (eye.rs:24-28, :121-125).
+    The reference ships the pieces but no composition; include/zaru_b200.h states the rule."""
+
+    def __init__(self, mesh_network=None, eye_network=None, eye_margin: float = 0.0):
+        self._mesh = (mesh_network or FaceMeshV1()).cnn()
+        self._iris = (eye_network or EyeNetwork()).cnn()
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_face_iris_pipeline_create(context(), self._mesh.nn._h, self._iris.nn._h, C.byref(h)))
+        self._h = h
+        self._L = _ffi.lib().zb_face_iris_pipeline_num_landmarks(h)
+        self._bufs = None
+        if eye_margin:
+            self.set_eye_margin(eye_margin)
+
+    def set_eye_margin(self, amount: float):
+        _ffi.check(_ffi.lib().zb_face_iris_pipeline_set_eye_margin(self._h, float(amount)))
+
+    def _buffers(self, n):
+        if self._bufs is None or self._bufs[0] != n:
+            self._bufs = (n, np.empty((n, self._L, 3), np.float32), np.empty(n, np.float32), (_ffi.zb_view * n)(),
+                          (_ffi.zb_view * (2 * n))(), np.empty((n, 2, 76, 3), np.float32))
+        return self._bufs
+
+    def run_raw(self, batch, rois=None, n=None):
+        """rois: ctypes array of zb_view (face crops) or None for every whole frame."""
+        n = (len(batch) if rois is None else len(rois)) if n is None else n
+        _, lm, flags, vr, er, elm = self._buffers(n)
+        _ffi.check(_ffi.lib().zb_face_iris_pipeline_run(self._h, batch._h, rois, n, lm.ctypes.data, flags.ctypes.data, vr, er,
+                                                        elm.ctypes.data))
+        return lm, flags, vr, er, elm
+
+    def run(self, batch, rois=None) -> FaceIrisResult:
+        """rois: list of (frame, cx, cy, w, h[, radians]) face crops, or None for every whole frame."""
+        arr = None
+        if rois is not None:
+            arr = (_ffi.zb_view * len(rois))()
+            for j, r in enumerate(rois):
+                t = tuple(r)
+                arr[j] = _ffi.zb_view(int(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4]), float(t[5]) if len(t) > 5 else 0.0)
+        lm, flags, vr, er, elm = self.run_raw(batch, arr)
+        n = lm.shape[0]
+        v5 = lambda v: [v.cx, v.cy, v.w, v.h, v.radians]
+        return FaceIrisResult(lm.copy(), flags.copy(), np.array([v5(v) for v in vr], np.float32).reshape(n, 5),
+                              np.array([v5(v) for v in er], np.float32).reshape(n, 2, 5), elm.copy())
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ffi.lib().zb_face_iris_pipeline_destroy(self._h)
                 self._h = None
         except Exception:
             pass

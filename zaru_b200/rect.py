@@ -16,6 +16,16 @@ _f = np.float32
 _libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
 _libm.cosf.restype = _libm.sinf.restype = ctypes.c_float
 _libm.cosf.argtypes = _libm.sinf.argtypes = [ctypes.c_float]
+_libm.atan2f.restype = ctypes.c_float
+_libm.atan2f.argtypes = [ctypes.c_float, ctypes.c_float]
+
+
+def signed_angle_to(ax, ay, bx, by):
+    """`Vec2::signed_angle_to` (zaru-linalg vector.rs:568-573): -perp_dot(a, b).atan2(dot(a, b)), f32."""
+    ax, ay, bx, by = _f(ax), _f(ay), _f(bx), _f(by)
+    perp = ax * by - ay * bx
+    dot = (_f(0.0) + ax * bx) + ay * by
+    return -_f(_libm.atan2f(float(perp), float(dot)))
 
 
 def _cos_sin(radians):
@@ -121,6 +131,18 @@ class Rect:
     def move_by(self, offset):
         return Rect(self._cx + _f(offset[0]), self._cy + _f(offset[1]), self._w, self._h)
 
+    @classmethod
+    def bounding(cls, points):
+        """`Rect::bounding` (rect.rs:49-68); None for no points."""
+        pts = [(_f(p[0]), _f(p[1])) for p in points]
+        if not pts:
+            return None
+        minx, miny = pts[0]
+        maxx, maxy = pts[0]
+        for x, y in pts[1:]:
+            minx, miny, maxx, maxy = min(minx, x), min(miny, y), max(maxx, x), max(maxy, y)
+        return cls.from_top_left(minx, miny, maxx - minx, maxy - miny)
+
     def scale(self, s):
         return Rect(self._cx, self._cy, self._w * _f(s), self._h * _f(s))
 
@@ -160,6 +182,25 @@ class RotatedRect:
     @classmethod
     def of(cls, r):
         return r if isinstance(r, RotatedRect) else cls(r, 0.0)
+
+    @classmethod
+    def bounding(cls, radians, points):
+        """`RotatedRect::bounding(radians, points)` (rect.rs:287-325); None for no points."""
+        pts = [(_f(p[0]), _f(p[1])) for p in points]
+        if not pts:
+            return None
+        radians = _f(radians)
+        c, s = _cos_sin(-radians)                   # rotation_clockwise(r) = rotation_counterclockwise(-r)
+        fmax = _f(np.finfo(np.float32).max)
+        minx = miny = fmax
+        maxx = maxy = -fmax
+        for x, y in pts:
+            px, py = _rot(c, s, x, y)
+            minx, miny, maxx, maxy = min(minx, px), min(miny, py), max(maxx, px), max(maxy, py)
+        ccx, ccy = (minx + maxx) * _f(0.5), (miny + maxy) * _f(0.5)
+        c2, s2 = _cos_sin(radians)
+        cx, cy = _rot(c2, s2, ccx, ccy)             # center.rotate_counterclockwise(radians)
+        return cls(Rect.from_center(cx, cy, maxx - minx, maxy - miny), radians)
 
     def rect(self):
         return self._rect
