@@ -2,9 +2,13 @@
 """bench.py — frames/s of the full face pipeline (BlazeFace -> NMS -> crop -> face mesh) on synthetic
 1080p frames, BASELINE.json config 4: batch 1024 per GPU, frames resident in HBM.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (config 4, the headline)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+    python bench.py --config 2 ...                            # face mesh + iris on 256 detector crops
+    python bench.py --config 3 ...                            # palm detection + hand landmarks, batch 256
+    python bench.py --streams S ...                           # config 5: S camera streams sharded over the GPUs
 
+Both arms run the SAME synthetic frames (seeds 1000 .. 1000 + unique - 1) and print `frames_with_face`.
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what every field means.
 """
 from __future__ import annotations
@@ -27,22 +31,32 @@ ALG_MB_PER_FRAME = 12.82      # block-fused network traffic 12
 ALG_MB_DETECT = 4.93 + 128 * 128 * 4 / 1e6     # BlazeFace + its sampled texels: every frame
 ALG_MB_LANDMARK = 7.68 + 192 * 192 * 4 / 1e6   # face mesh + its sampled texels: frames with a detection only
 ALG_MFLOP_PER_FRAME = 131.48
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel classes, from the committed
-# `ncu --set full` captures (profiles/README.md); keyed by profile class, value = (bytes, algorithmic bytes of
-# that same launch) so the ratio can be applied to the live per-launch algorithmic bytes.
-NCU_TRAFFIC = {
-    # dwpw_strip_kernel<24,1,24,2,32,4> on the 1024 x 64x64x24 block: 402.73 MB read + 351.54 MB written
-    "dwpw_thin": (402.734592e6 + 351.541760e6, 2 * 1024 * 64 * 64 * 24 * 4.0),
-    # dwpw_tc_kernel<3,1> on the 1024 x 24x24x64 block (part of the input is still L2-resident from the previous layer)
-    "dwpw_tc<tcgen05>": (153.274624e6 + 107.766528e6, 2 * 1024 * 24 * 24 * 64 * 4.0),
-    # dwpw_ttc_kernel<32,8,1,16> on the 1024 x 48x48x32 block
-    "dwpw_ttc<tcgen05>": (302.045184e6 + 253.759488e6, 2 * 1024 * 48 * 48 * 32 * 4.0),
-    # stem_kernel<5,24,2>: 128x128 sampled texels (32 B sectors of 1080p frames) + the 64x64x24 stem output
-    "stem(+sample)": (566.482688e6 + 358.369792e6, 1024 * (128 * 128 * 4.0 + 64 * 64 * 24 * 4.0)),
-}
 METRIC = "frames/sec face detect+landmark (1080p)"
 WORKLOAD = "config4: full face pipeline on synthetic 1080p frames: sample->BlazeFace->NMS->crop->face_landmark"
 UNIT = "frames/s"
+SEED0 = 1000                  # both arms: S-face frames of seeds SEED0 .. SEED0 + unique - 1
+# SURVEY.md §8(d) per-unit algorithmic work of the other configs (block-fused traffic model, f32)
+CONFIGS = {
+    2: {"workload": "config2: face landmark (192x192 face mesh) + iris landmark (64x64) on detector crops, batch 256",
+        "metric": "faces/sec face mesh + 2x iris landmark on detector crops", "unit": "faces/s",
+        "alg_mb": 16.64 + (192 * 192 + 2 * 64 * 64) * 4 / 1e6, "alg_mflop": 284.6,
+        "model": "16.64 MB = face_landmark 7.68 + 2 x iris 4.48 (SURVEY 8d) + 0.18 MB sampled texels per face"},
+    3: {"workload": "config3: palm detection (192x192) + hand landmark (224x224) two-stage pipeline, batch 256",
+        "metric": "frames/sec palm detect + hand landmark (1080p)", "unit": "frames/s",
+        "alg_mb": 26.73 + (192 * 192 + 224 * 224) * 4 / 1e6, "alg_mflop": 857.6,
+        "model": "26.73 MB = palm_lite 21.68 + hand_lite 5.05 (SURVEY 8d) + 0.35 MB sampled texels per frame"},
+}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch measured by `ncu --set full` for named kernels, written by tools/ncu_traffic.py from a
+    capture of THIS round: {kernel function: {dram_bytes, algorithmic_bytes, source}}.  A kernel that is not in the
+    file has no measured traffic (the JSON line then carries null)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
 def log(*a):
@@ -64,12 +78,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.stamps, self.window = index, None, [], [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -78,15 +92,20 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+            self.stamps.append(time.perf_counter())
+
+    def mark(self, t0, t1):
+        """Remember the wall-clock window of the device-timed loop: samples inside it are counted separately."""
+        self.window = (t0, t1)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, inside = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for k, ln in enumerate(self.lines):
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -95,11 +114,15 @@ class ClockSampler:
                 mx.append(float(parts[2]))
             except ValueError:
                 continue
+            if self.window and k < len(self.stamps) and self.window[0] <= self.stamps[k] <= self.window[1] + 0.05:
+                inside.append(float(parts[1]))
             for name, v in zip(names, parts[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_device_loop": len(inside),
+                "sm_mhz_in_device_loop": statistics.median(inside) if inside else None, "reasons": sorted(reasons),
+                "sampled_over": "the device-timed loop and the e2e legs (nvidia-smi -lms 50)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,34 +131,69 @@ class ClockSampler:
 _worker_frames = None
 
 
-def _cpu_worker_init(seed0, count):
-    global _worker_frames
+_worker_cfg = 4
+_worker_rois = None
+
+
+def _cpu_unit(cfg, k):
+    """One unit of work of config `cfg` on the oracle port; returns 1 when the unit reached the landmark stage."""
+    from tests import oracle_pipeline as op
+    frame = _worker_frames[k % len(_worker_frames)]
+    if cfg == 4:
+        return 1 if len(op.face_pipeline(frame)[0]) > 0 else 0
+    if cfg == 3:   # dense: every frame pays for palm + hand, as SURVEY 8(d)'s unit and the device arm's headline do
+        return 1 if len(op.hand_pipeline(frame, thresh=0.1, dense=True)[0]) > 0 else 0
+    fi, roi = _worker_rois[k % len(_worker_rois)]
+    op.face_iris_pipeline(_worker_frames[fi], roi, eye_margin=0.5)
+    return 1
+
+
+def _cpu_worker_init(seeds, cfg=4):
+    """seeds: the S-face seeds this worker cycles through - the SAME set the GPU arm tiles its batch from."""
+    global _worker_frames, _worker_cfg, _worker_rois
     import cv2
-    cv2.setNumThreads(1)
+    cv2.setNumThreads(1)           # mirrors with_intra_threads(1) / with_inter_threads(1), nn/mod.rs:345-346
     from zaru_b200 import synth
-    _worker_frames = [synth.s_face_frame(seed0 + i)[0] for i in range(count)]
-    from tests.oracle_pipeline import face_pipeline
-    face_pipeline(_worker_frames[0])   # load + warm the networks
+    _worker_cfg = cfg
+    _worker_frames = [synth.s_face_frame(int(sd))[0] for sd in seeds]
+    if cfg == 2:                   # S-crop: the face RoIs are the oracle detector's detections on the same frames
+        from oracle.detection import Detector, ShortRangeNetwork
+        from oracle.image import Image
+        _worker_rois = []
+        for fi, fr in enumerate(_worker_frames):
+            for d in Detector(ShortRangeNetwork()).detect(Image(fr)):
+                r = d.rect
+                _worker_rois.append((fi, (float(r.cx), float(r.cy), float(r.w), float(r.h), 0.0)))
+        if not _worker_rois:
+            h, w = _worker_frames[0].shape[:2]
+            _worker_rois = [(0, (w / 2, h / 2, min(w, h) / 2, min(w, h) / 2, 0.0))]
+    _cpu_unit(cfg, 0)              # load + warm the networks
 
 
-def _cpu_worker_run(n):
-    from tests.oracle_pipeline import face_pipeline
-    for i in range(n):
-        face_pipeline(_worker_frames[i % len(_worker_frames)])
-    return n
+def _cpu_worker_run(first, n):
+    """Units first .. first + n - 1 of the cyclic frame sequence; returns (units, units that reached the landmark stage)."""
+    hits = 0
+    for k in range(first, first + n):
+        hits += _cpu_unit(_worker_cfg, k)
+    return n, hits
 
 
-def cpu_baseline_single(budget_s=15.0):
-    """Oracle pipeline on ONE host core over distinct S-face frames for ~budget_s seconds."""
-    _cpu_worker_init(5000, 8)
+def cpu_baseline_single(budget_s=15.0, unique=32, cfg=4, unit=UNIT):
+    """Oracle pipeline on ONE host core over the bench's own frames (in seed order) for ~budget_s seconds."""
+    seeds = list(range(SEED0, SEED0 + (unique if cfg == 4 else min(unique, 8))))
+    _cpu_worker_init(seeds, cfg)
     t0 = time.perf_counter()
-    n = 0
+    n = hits = 0
     while time.perf_counter() - t0 < budget_s:
-        n += _cpu_worker_run(4)
+        a, b = _cpu_worker_run(n, 4 if cfg == 4 else 1)
+        n, hits = n + a, hits + b
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port", "cpu_model": cpu_model(),
-            "sample": f"{n} 1080p S-face frames in {dt:.1f} s: oracle (numpy restatement + cv2.dnn, 1 thread) of "
-                      "sample->BlazeFace->NMS->crop->face mesh; ort/tract cannot be built here"}
+    what = {4: "sample->BlazeFace->NMS->crop->face mesh", 2: "face mesh -> eye crops -> 2x iris network on one detector crop",
+            3: "sample->palm detector->NMS->rotated crop->hand landmarks (threshold 0.1, hand stage on every frame)"}[cfg]
+    return {"value": n / dt, "unit": unit, "cores": 1, "kind": "port", "cpu_model": cpu_model(),
+            "frames_with_face" if cfg == 4 else "units_with_detection": hits, "frames": n,
+            "sample": f"{n} units in {dt:.1f} s over the S-face frames of seeds {seeds[0]}..{seeds[-1]} (the GPU arm's frames, "
+                      f"in order): oracle (numpy restatement + cv2.dnn, 1 thread) of {what}; ort/tract cannot be built here"}
 
 
 def cpu_model() -> str:
@@ -156,35 +214,50 @@ def run_reference(args):
         return 0
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_worker = 16
+    cfg = args.config
+    per_worker = {4: 16, 2: 8, 3: 2}[cfg]            # units per worker per step: a step stays a few seconds of CPU work
     ctx = mp.get_context("spawn")
-    pools = [ctx.Pool(1, initializer=_cpu_worker_init, initargs=(9000 + 8 * w, 8)) for w in range(cores)]
+    # every worker cycles through the GPU arm's own frames (seeds SEED0 ..), starting at a different offset, so a step
+    # covers the frame set evenly and both arms see the same fraction of frames with a face
+    uniq = args.unique if cfg == 4 else min(args.unique, 8)
+    seeds = list(range(SEED0, SEED0 + uniq))
+    pools = [ctx.Pool(1, initializer=_cpu_worker_init, initargs=(seeds, cfg)) for _ in range(cores)]
+    cursor = [0]
 
     def step():
-        rs = [p.apply_async(_cpu_worker_run, (per_worker,)) for p in pools]
-        return sum(r.get() for r in rs)
+        base = cursor[0]
+        cursor[0] += per_worker * cores
+        rs = [p.apply_async(_cpu_worker_run, (base + w * per_worker, per_worker)) for w, p in enumerate(pools)]
+        got = [r.get() for r in rs]
+        return sum(g[0] for g in got), sum(g[1] for g in got)
 
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
-    frames = 0
+    frames = hits = 0
     for _ in range(args.steps):
-        frames += step()
+        a, b = step()
+        frames, hits = frames + a, hits + b
     dt = time.perf_counter() - t0
     for p in pools:
         p.terminate()
     value = frames / dt
-    sample = (f"{per_worker * cores} 1080p S-face frames per step over {cores} worker processes "
-              "(one oracle Detector+Estimator per worker, cv2.dnn 1 thread each; mirrors rayon map_init, "
-              "eval_face_recognition.rs:67-70)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    metric, unit, workload = METRIC, UNIT, WORKLOAD
+    if cfg in CONFIGS:
+        metric, unit, workload = CONFIGS[cfg]["metric"], CONFIGS[cfg]["unit"], CONFIGS[cfg]["workload"]
+    sample = (f"{per_worker * cores} units per step over {cores} worker processes, cycling through the S-face frames of seeds "
+              f"{seeds[0]}..{seeds[-1]} = the GPU arm's frames (one oracle pipeline per worker, cv2.dnn 1 thread each; "
+              "mirrors rayon map_init, eval_face_recognition.rs:67-70)")
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             # same workload string as the GPU arm; the CPU arm runs a bounded sample of it per step
-            "config": {"workload": WORKLOAD, "frame": "1920x1080 RGBA8", "frames_per_step": per_worker * cores,
+            "config": {"workload": workload, "frame": "1920x1080 RGBA8", "frames_per_step": per_worker * cores,
+                       "distinct_frames": uniq, "frame_seeds": f"{seeds[0]}..{seeds[-1]} (same as the GPU arm)",
+                       "frames": frames, "frames_with_face": hits,
                        "note": "CPU reference arm: bounded sample of the same workload on the host cores"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(), "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "cpu_model": cpu_model(), "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
@@ -217,6 +290,186 @@ def unpin_frames(torch, t):
     if t is not None and t.data_ptr() in _registered:
         _registered.discard(t.data_ptr())
         torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+
+
+
+def roofline_block(prof, peak, peak_src):
+    """`roofline` for the dominant KERNEL FUNCTION of the profiled step (CUDA events per launch, zb_profile_*): its
+    launches' algorithmic bytes / its summed duration.  Also the per-class table with the functions inside each class."""
+    total_ms = sum(v["ms"] for v in prof.values())
+    funcs = {}
+    for cls, v in prof.items():
+        for fn, k in v.get("kernels", {cls: v}).items():
+            f = funcs.setdefault(fn, {"launches": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0, "class": cls})
+            for key in ("launches", "ms", "bytes", "flops"):
+                f[key] += k[key]
+    name, top = max(funcs.items(), key=lambda kv: kv[1]["ms"])
+    achieved = top["bytes"] / (top["ms"] / 1000.0) / 1e9
+    traffic, traffic_src = None, "no `ncu --set full` capture of this kernel from this round (profiles/ncu_traffic.json)"
+    rec = ncu_traffic().get(name)
+    if rec:   # measured DRAM bytes of the captured launch, scaled to this run's launches by algorithmic bytes
+        traffic = rec["dram_bytes"] / rec["algorithmic_bytes"] * top["bytes"] / top["launches"]
+        traffic_src = rec["source"]
+    fmt = lambda v: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
+                     "GBps": round(v["bytes"] / (v["ms"] / 1000.0) / 1e9, 1) if v["ms"] > 0 else None,
+                     "TFLOPs": round(v["flops"] / (v["ms"] / 1000.0) / 1e12, 2) if v["ms"] > 0 else None}
+    kernels = {}
+    for cls, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        kernels[cls] = fmt(v)
+        inner = v.get("kernels", {})
+        if len(inner) > 1 or (inner and next(iter(inner)) != cls):
+            kernels[cls]["functions"] = {fn: fmt(k) for fn, k in sorted(inner.items(), key=lambda kv: -kv[1]["ms"])}
+    roof = {"bound": "hbm", "kernel": name, "kernel_class": top["class"], "launches": top["launches"],
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "avg_launch_ms": top["ms"] / top["launches"], "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": top["bytes"] / top["launches"], "peak_source": peak_src,
+            "share_of_step": top["ms"] / total_ms, "tflops": top["flops"] / (top["ms"] / 1000.0) / 1e12}
+    return roof, kernels
+
+
+def run_gpu_stage(args):
+    """BASELINE configs 2 and 3 on one or more GPUs: the same contract as the headline run (device-resident `value`,
+    `e2e` with host frames copied in and results copied out every step, `roofline`, `cpu_baseline`, `clocks`)."""
+    import numpy as np
+    import torch
+
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    cfg = args.config
+    spec = CONFIGS[cfg]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import zaru_b200
+    from zaru_b200 import _ffi, shard, synth
+    from zaru_b200.image import ImageBatch
+    from zaru_b200.pipeline import FaceIrisPipeline, FacePipeline, HandPipeline
+    from zaru_b200.rect import Resolution
+
+    zaru_b200.load_library()
+    zaru_b200.context(local)
+    res = Resolution(FRAME_W, FRAME_H)
+    n = args.batch if args.batch != 1024 else 256          # BASELINE: batch 256 for configs 2 and 3
+    uniq_n = min(args.unique, n)
+    uniq = np.stack([synth.s_face_frame(SEED0 + s)[0] for s in range(uniq_n)])
+    d_uniq = torch.from_numpy(uniq).cuda()
+    d_frames = d_uniq[torch.arange(n, device="cuda") % uniq_n].contiguous()   # [n,1080,1920,4]: 2.1 GB at n = 256 (> L2)
+    del d_uniq
+    torch.cuda.synchronize()
+    batch = ImageBatch.alias_device(res, d_frames.data_ptr(), n, keepalive=d_frames)
+    h_frames = pinned_frames(torch, n)
+    h_frames.copy_(d_frames)
+    e2e_batch = ImageBatch.from_rgba8(res, h_frames.numpy())
+    h_ptr = h_frames.numpy()
+    extra = {}
+    if cfg == 2:
+        # S-crop (SURVEY 8d): the face RoIs are detector crops - this library's own BlazeFace detections on the frames
+        det = FacePipeline(capacity=args.cap)
+        d = det.run(batch, n)
+        found = [i for i in range(n) if len(d.detections[i]) > 0]
+        if not found:
+            raise RuntimeError("no face detected on the synthetic frames")
+        rois = (_ffi.zb_view * n)()
+        for k in range(n):
+            i = found[k % len(found)]
+            best = max(d.detections[i], key=lambda x: float(x.confidence())).bounding_rect()   # tracker.set_roi(bounding_rect)
+            rois[k] = _ffi.zb_view(i, float(best.center()[0]), float(best.center()[1]), float(best.width()), float(best.height()), 0.0)
+        del det
+        pipe = FaceIrisPipeline(eye_margin=0.5)
+        run = lambda bt: pipe.run_raw(bt, rois, n)
+        d2h = n * (468 * 12 + 4 + 24 + 2 * 24 + 2 * 76 * 12)
+        extra = {"face_crops": n, "eye_crops": 2 * n, "frames_with_face": len(found), "eye_margin": 0.5,
+                 "crops": "the face RoIs are this library's BlazeFace detections on the same frames (S-crop, SURVEY 8d)"}
+    else:
+        pipe = HandPipeline(capacity=args.cap)
+        pipe.set_threshold(0.1, 0.3)     # no hand fixture exists in the reference: lowered until the frames yield palms
+        pipe.set_dense(True)             # SURVEY 8d's unit: 1 palm pass + 1 hand-landmark pass per frame
+        run = lambda bt: pipe.run(bt, n)
+        d2h = n * (args.cap * 88 + 4 + 21 * 12 + 8 + 24)
+        extra = {"palm_threshold": 0.1, "hand_stage": "every frame (dense): SURVEY 8d's unit is 1 palm pass + 1 hand pass"}
+
+    def barrier():
+        zaru_b200.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        out = run(batch)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = zaru_b200.launch_count()
+    wall0 = time.perf_counter()
+    zaru_b200.timer_start()
+    for _ in range(args.steps):
+        out = run(batch)
+    dev_ms = zaru_b200.timer_stop_ms()
+    zaru_b200.sync()
+    clocks.mark(wall0, time.perf_counter())
+    launches = zaru_b200.launch_count() - launches0
+    barrier()
+    if cfg == 3:
+        extra["frames_with_palm"] = int(sum(len(x) > 0 for x in out.detections))
+    (dev_ms_max,) = shard.max_over_ranks([dev_ms], dist, "cuda")
+
+    def e2e_step():
+        e2e_batch.update(h_ptr, 0)       # host -> device copy of this step's frames (pinned memory)
+        return run(e2e_batch)            # results land in host buffers
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    zaru_b200.sync()
+    e2e_ms = 1000.0 * (time.perf_counter() - e0)
+    (e2e_ms_max,) = shard.max_over_ranks([e2e_ms], dist, "cuda")
+    clock_info = clocks.stop() if rank == 0 else None
+    prof = None
+    if rank == 0:
+        zaru_b200.profile_begin()
+        run(batch)
+        prof = zaru_b200.profile_end()
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    roof, kernels = roofline_block(prof, peak, peak_src)
+    value = world * n * args.steps / (dev_ms_max / 1000.0)
+    pipe_gbs = value / world * spec["alg_mb"] * 1e6 / 1e9
+    line = {"metric": spec["metric"], "value": value, "unit": spec["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict({"workload": spec["workload"], "batch_per_gpu": n, "frame": "1920x1080 RGBA8", "distinct_frames": uniq_n,
+                            "frame_seeds": f"{SEED0}..{SEED0 + uniq_n - 1}",
+                            "l2_policy": f"inputs larger than L2 ({n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
+                            "timing": "CUDA events on the library stream around the K steps, max over ranks"}, **extra),
+            "gpu_launches": int(launches),
+            "e2e": {"value": world * n * args.steps / (e2e_ms_max / 1000.0), "unit": spec["unit"],
+                    "h2d_bytes_per_step": n * FRAME_BYTES, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps,
+                    "note": "pinned host frames -> zb_frames_update (explicit H2D of whole frames) -> pipeline run -> results D2H"},
+            "roofline": dict(roof, pipeline={"achieved": pipe_gbs, "frac": pipe_gbs / peak, "model": spec["model"],
+                                             "tflops": value / world * spec["alg_mflop"] / 1e6}),
+            "kernels": kernels, "clocks": clock_info}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_single(args.cpu_budget, args.unique, cfg, spec["unit"])
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
 
 
 def run_gpu(args):
@@ -263,7 +516,7 @@ def run_gpu(args):
         # with different synthetic frames would do different amounts of work (measured at N = 2 with per-rank frame
         # sets: 6.2 ms per step on one rank, 7.0-7.4 ms on the other) - every rank gets the same `unique` frames
         my_streams = list(range(args.unique))
-    uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in my_streams])
+    uniq = np.stack([synth.s_face_frame(SEED0 + s)[0] for s in my_streams])
     d_uniq = torch.from_numpy(uniq).cuda()
     idx = torch.arange(batch_n, device="cuda") % args.unique
     d_frames = d_uniq[idx].contiguous()            # [batch,1080,1920,4] uint8, 8.49 GB at batch 1024 (> 126 MB L2)
@@ -299,6 +552,7 @@ def run_gpu(args):
     zaru_b200.sync()
     torch.cuda.synchronize()
     wall_ms = 1000.0 * (time.perf_counter() - wall0)
+    clocks.mark(wall0, time.perf_counter())
     launches = zaru_b200.launch_count() - launches0
     barrier()
     n_with_face = int((flags >= 0).sum())
@@ -473,6 +727,7 @@ def run_gpu(args):
         return 0
 
     value = world * batch_n * args.steps / (dev_ms_max / 1000.0)
+    dense_value = world * batch_n * args.steps / (dense_ms_max / 1000.0)
     e2e_value = world * e2e_n * args.steps / (e2e_ms_max / 1000.0)
     e2e_copy = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n * FRAME_BYTES, "d2h_bytes_per_step": d2h,
                 "batch_per_gpu": e2e_n, "ms_per_step": e2e_ms_max / args.steps,
@@ -511,13 +766,7 @@ def run_gpu(args):
             else:
                 e2e_best = dict(e2e_best, multi_thread=e2e_mt)
     peak, peak_src = peaks()
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    total_ms = sum(v["ms"] for v in prof.values())
-    achieved = top[1]["bytes"] / (top[1]["ms"] / 1000.0) / 1e9
-    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
-                   "GBps": round(v["bytes"] / (v["ms"] / 1000.0) / 1e9, 1) if v["ms"] > 0 else None,
-                   "TFLOPs": round(v["flops"] / (v["ms"] / 1000.0) / 1e12, 2) if v["ms"] > 0 else None}
-               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    roof, kernels = roofline_block(prof, peak, peak_src)
     face_frac = n_with_face / float(batch_n)
     alg_mb = ALG_MB_DETECT + face_frac * ALG_MB_LANDMARK     # landmark traffic only for the frames that reach that stage
     pipeline_gbs = value / world * alg_mb * 1e6 / 1e9
@@ -533,33 +782,33 @@ def run_gpu(args):
                                        "the same distinct frames on every rank (equal work per GPU)"),
                    "l2_policy": f"inputs larger than L2 ({batch_n * FRAME_BYTES / 1e9:.2f} GB of frames per GPU, no flush)",
                    "chunk": args.chunk or int(os.environ.get("ZB_CHUNK", "1024")), "frames_with_face": n_with_face,
+                   "frame_seeds": f"{SEED0}..{SEED0 + args.unique - 1} (the reference arm cycles through the same frames)",
+                   "headline": "`value` = the reference loop's workload on these frames (both arms skip the face mesh on frames "
+                               "without a detection, examples/facemesh.rs:49-55); `all_frames_landmarked` = SURVEY §8d's unit",
                    "landmark_policy": "face mesh runs on the frames in which BlazeFace found a face (device-side compaction), as "
                                       "the reference's loop and the CPU arm do; `all_frames_landmarked` = forced over every frame",
                    "timing": "CUDA events on the library stream around the K steps, max over ranks"},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "gpu_launches": int(launches),
-        "all_frames_landmarked": {"value": world * batch_n * args.steps / (dense_ms_max / 1000.0), "unit": UNIT,
-                                  "ms_per_step": dense_ms_max / args.steps},
+        "all_frames_landmarked": {"value": dense_value, "unit": UNIT, "ms_per_step": dense_ms_max / args.steps,
+                                  "what": "SURVEY §8d's unit of work (12.82 MB, 131.48 MFLOP per frame): the face mesh "
+                                          "forced over every frame, with or without a detection"},
         "e2e": e2e_best,
-        "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     # measured DRAM bytes per launch = this class's ncu traffic/algorithmic ratio x live algorithmic bytes
-                     "traffic": (NCU_TRAFFIC[top[0]][0] / NCU_TRAFFIC[top[0]][1] * top[1]["bytes"] / top[1]["launches"]
-                                 if top[0] in NCU_TRAFFIC else None),
-                     "algorithmic_bytes_per_launch": top[1]["bytes"] / top[1]["launches"],
-                     "peak_source": peak_src,
-                     "share_of_step": top[1]["ms"] / total_ms,
-                     "pipeline": {"achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
-                                  "model": f"{alg_mb:.2f} MB algorithmic bytes per frame = {ALG_MB_DETECT:.2f} (detector, every frame) + "
-                                           f"{face_frac:.3f} x {ALG_MB_LANDMARK:.2f} (face mesh, frames with a detection) "
-                                           f"(SURVEY §8d: {ALG_MB_PER_FRAME} when every frame has a face) x frames/s per GPU"}},
+        "roofline": dict(roof, pipeline={"achieved": pipeline_gbs, "frac": pipeline_gbs / peak,
+                                         "model": f"{alg_mb:.2f} MB algorithmic bytes per frame = {ALG_MB_DETECT:.2f} (detector, every frame) + "
+                                                  f"{face_frac:.3f} x {ALG_MB_LANDMARK:.2f} (face mesh, frames with a detection) "
+                                                  f"(SURVEY §8d: {ALG_MB_PER_FRAME} when every frame has a face) x frames/s per GPU"},
+                         pipeline_all_frames_landmarked={
+                             "achieved": dense_value / world * ALG_MB_PER_FRAME * 1e6 / 1e9,
+                             "frac": dense_value / world * ALG_MB_PER_FRAME * 1e6 / 1e9 / peak,
+                             "model": f"SURVEY §8d unit: {ALG_MB_PER_FRAME} MB per frame x `all_frames_landmarked` frames/s per GPU"}),
         "kernels": kernels,
         "clocks": clock_info,
     }
     if steady is not None:
         line["steady_state_tracking"] = steady
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_single(args.cpu_budget)
+        line["cpu_baseline"] = cpu_baseline_single(args.cpu_budget, args.unique)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
@@ -582,6 +831,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-steady-state", action="store_true")
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4],
+                    help="BASELINE.json config: 4 = full face pipeline (default, the headline), 2 = face mesh + iris on "
+                         "detector crops (batch 256), 3 = palm detection + hand landmarks (batch 256)")
     ap.add_argument("--streams", type=int, default=0,
                     help="config 5: total concurrent camera streams, sharded over the GPUs (overrides --batch)")
     args = ap.parse_args()
@@ -593,6 +845,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.config in CONFIGS:
+        return run_gpu_stage(args)
     return run_gpu(args)
 
 

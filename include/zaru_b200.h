@@ -348,6 +348,10 @@ zb_status zb_timer_stop(zb_ctx *ctx, float *ms);
  * where bytes/flops are the ALGORITHMIC work of those launches (DESIGN.md "roofline").        */
 zb_status zb_profile_begin(zb_ctx *ctx);
 zb_status zb_profile_end(zb_ctx *ctx, char *json, size_t cap, size_t *needed);
+/* per_layer != 0: one profile row per network layer ("dwpw3x3 96x96x16->96x96x16 s1 [chunk]") instead of per op
+ * class.  Either way every row lists the kernel FUNCTIONS (with template arguments) its launches went to:
+ * {row: {launches, ms, bytes, flops, kernels: {function: {launches, ms, bytes, flops}}}}.            */
+zb_status zb_profile_set_detail(zb_ctx *ctx, int32_t per_layer);
 
 #ifdef __cplusplus
 }

@@ -55,3 +55,33 @@ def face_iris_pipeline(frame_rgba: np.ndarray, roi, eye_margin=0.0, backend="cv2
             ox, oy = rect.transform_out((p[0], p[1]))
             eye_pos[side, k] = (ox, oy, p[2])
     return face, est.face_flag, view_rect, eyes, eye_pos
+
+
+def hand_pipeline(frame_rgba: np.ndarray, thresh=0.5, backend="cv2", dense=False):
+    """BASELINE config 3 (what `zb_hand_pipeline_run` claims to do): palm detector on the whole frame -> best palm ->
+    RoI = RotatedRect(bounding_rect.grow_rel(1.5), det.angle()) (hand/tracking.rs:136, :159) -> one
+    `LandmarkTracker::track` step of the hand landmark network.  dense: frames without a palm still pay for a hand
+    inference (on the centre square), like the device pipeline's dense mode - for timing only.
+    Returns (detections, positions [21,3] or None, presence or -1, view_rect or None)."""
+    from oracle.detection import PalmLiteNetwork
+    from oracle.geometry import Rect
+    from oracle.landmark import HandLiteNetwork
+    img = Image(frame_rgba)
+    det = Detector(PalmLiteNetwork(), backend=backend)
+    det.thresh = np.float32(thresh)
+    dets = det.detect(img)
+    tracker = LandmarkTracker(Estimator(HandLiteNetwork(), backend=backend))
+    tracker.loss_thresh = np.float32(-1e9)
+    if not dets:
+        if dense:
+            h, w = frame_rgba.shape[:2]
+            tracker.set_roi(RotatedRect(Rect.from_center(w / 2, h / 2, min(w, h), min(w, h)), 0.0))
+            tracker.track(img)
+        return dets, None, np.float32(-1.0), None
+    best = None
+    for d in dets:
+        if best is None or _total_key(d.confidence) >= _total_key(best.confidence):
+            best = d
+    tracker.set_roi(RotatedRect(best.rect.grow_rel(1.5), best.angle))
+    view_rect, est, _ = tracker.track(img)
+    return dets, est.positions.copy(), est.presence, view_rect

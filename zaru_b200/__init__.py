@@ -94,13 +94,18 @@ def timer_stop_ms() -> float:
     return float(ms.value)
 
 
-def profile_begin():
+def profile_begin(per_layer: bool = False):
+    """Bracket every kernel launch on this thread's context with CUDA events; per_layer: one row per network layer."""
+    _ffi.check(_ffi.lib().zb_profile_set_detail(context(), 1 if per_layer else 0))
     _ffi.check(_ffi.lib().zb_profile_begin(context()))
 
 
 def profile_end() -> dict:
-    """Stop profiling; {kernel class: {launches, ms, bytes, flops}} (CUDA events per launch)."""
+    """Stop profiling; {row: {launches, ms, bytes, flops, kernels: {function: {...}}}} (CUDA events per launch)."""
     import json
-    buf = C.create_string_buffer(1 << 16)
-    _ffi.check(_ffi.lib().zb_profile_end(context(), buf, len(buf), None))
+    need = C.c_size_t(0)
+    buf = C.create_string_buffer(1 << 18)
+    _ffi.check(_ffi.lib().zb_profile_end(context(), buf, len(buf), C.byref(need)))
+    if need.value > len(buf):
+        raise RuntimeError("profile JSON truncated")
     return json.loads(buf.value.decode())

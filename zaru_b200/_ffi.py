@@ -115,6 +115,7 @@ SIGNATURES = {
     "zb_timer_stop": (i32, [P, C.POINTER(f32)]),
     "zb_profile_begin": (i32, [P]),
     "zb_profile_end": (i32, [P, C.c_char_p, sz, C.POINTER(sz)]),
+    "zb_profile_set_detail": (i32, [P, i32]),
 }
 
 _lib = None

@@ -113,7 +113,8 @@ struct PinBuf {
 }  // namespace
 
 struct ProfRec {
-    const char *cls;
+    std::string cls;             // op class (or layer label with ZB_PROF_DETAIL)
+    const char *kernel;          // kernel function actually launched (static string; nullptr: the class name)
     cudaEvent_t a, b;
     double bytes, flops;
 };
@@ -162,9 +163,10 @@ void prof_launch(zb_ctx *ctx, cudaStream_t s, const char *cls, double bytes, dou
     }
     cudaEvent_t a = ctx->prof_event(), b = ctx->prof_event();
     CU(cudaEventRecord(a, s));
+    t_kernel_name = nullptr;
     f();
     CU(cudaEventRecord(b, s));
-    ctx->prof.push_back({cls, a, b, bytes, flops});
+    ctx->prof.push_back({cls, t_kernel_name, a, b, bytes, flops});
 }
 }  // namespace
 
@@ -602,6 +604,12 @@ zb_status zb_profile_begin(zb_ctx *ctx) {
     return ZB_OK;
 }
 
+zb_status zb_profile_set_detail(zb_ctx *ctx, int32_t per_layer) {
+    if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    ctx->prof_detail = per_layer != 0;
+    return ZB_OK;
+}
+
 zb_status zb_profile_end(zb_ctx *ctx, char *json, size_t cap, size_t *needed) {
     return guarded([&]() -> zb_status {
         if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");
@@ -609,26 +617,46 @@ zb_status zb_profile_end(zb_ctx *ctx, char *json, size_t cap, size_t *needed) {
         CU(cudaStreamSynchronize(ctx->stream));
         ctx->prof_on = false;
         struct Agg { long long launches = 0; double ms = 0, bytes = 0, flops = 0; };
-        std::vector<std::pair<std::string, Agg>> agg;
+        struct ClassAgg { Agg total; std::vector<std::pair<std::string, Agg>> kernels; };
+        std::vector<std::pair<std::string, ClassAgg>> agg;
         for (auto &r : ctx->prof) {
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, r.a, r.b));
-            Agg *a = nullptr;
+            ClassAgg *a = nullptr;
             for (auto &kv : agg)
                 if (kv.first == r.cls) a = &kv.second;
             if (!a) {
-                agg.push_back({r.cls, Agg{}});
+                agg.push_back({r.cls, ClassAgg{}});
                 a = &agg.back().second;
             }
-            a->launches++, a->ms += ms, a->bytes += r.bytes, a->flops += r.flops;
+            a->total.launches++, a->total.ms += ms, a->total.bytes += r.bytes, a->total.flops += r.flops;
+            const std::string kn = r.kernel ? r.kernel : r.cls;
+            Agg *k = nullptr;
+            for (auto &kv : a->kernels)
+                if (kv.first == kn) k = &kv.second;
+            if (!k) {
+                a->kernels.push_back({kn, Agg{}});
+                k = &a->kernels.back().second;
+            }
+            k->launches++, k->ms += ms, k->bytes += r.bytes, k->flops += r.flops;
         }
+        // {class: {launches, ms, bytes, flops, kernels: {kernel function: {launches, ms, bytes, flops}}}}
         std::string s = "{";
-        char buf[512];
-        for (size_t i = 0; i < agg.size(); i++) {
-            snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%lld,\"ms\":%.6f,\"bytes\":%.1f,\"flops\":%.1f}", i ? "," : "",
-                     agg[i].first.c_str(), agg[i].second.launches, agg[i].second.ms, agg[i].second.bytes,
-                     agg[i].second.flops);
+        char buf[768];
+        auto put = [&](const std::string &name, const Agg &g, bool close) {
+            snprintf(buf, sizeof buf, "\"%s\":{\"launches\":%lld,\"ms\":%.6f,\"bytes\":%.1f,\"flops\":%.1f%s", name.c_str(), g.launches,
+                     g.ms, g.bytes, g.flops, close ? "}" : "");
             s += buf;
+        };
+        for (size_t i = 0; i < agg.size(); i++) {
+            if (i) s += ",";
+            put(agg[i].first, agg[i].second.total, false);
+            s += ",\"kernels\":{";
+            for (size_t k = 0; k < agg[i].second.kernels.size(); k++) {
+                if (k) s += ",";
+                put(agg[i].second.kernels[k].first, agg[i].second.kernels[k].second, true);
+            }
+            s += "}}";
         }
         s += "}";
         if (needed) *needed = s.size() + 1;

@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <initializer_list>
 #include <stdint.h>
+#include <string>
 
 #include "plan.h"
 
@@ -220,5 +222,29 @@ void launch_tracker_update(TrackState *state, const float *out0, int s0, const f
 void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s);
 
 extern std::atomic<long long> g_launch_count;   // total kernel launches issued by this library (process-wide)
+
+// Name of the kernel FUNCTION (with its template arguments) the last launch_* call on this thread actually launched:
+// the per-launch profiler reports time per kernel, not only per op class (bench.py's roofline names a kernel).
+extern thread_local const char *t_kernel_name;
+inline std::string make_kernel_name(const char *base, std::initializer_list<int> targs) {
+    std::string r = base;
+    if (targs.size()) {
+        r += "<";
+        bool first = true;
+        for (int v : targs) {
+            if (!first) r += ",";
+            r += std::to_string(v);
+            first = false;
+        }
+        r += ">";
+    }
+    return r;
+}
+// one static string per call site (and per template instantiation of the enclosing launcher)
+#define ZB_KNAME(base, ...)                                                       \
+    do {                                                                          \
+        static const std::string _zb_kn = ::zb::make_kernel_name(base, {__VA_ARGS__}); \
+        ::zb::t_kernel_name = _zb_kn.c_str();                                     \
+    } while (0)
 
 }  // namespace zb

@@ -23,6 +23,7 @@
 namespace zb {
 
 std::atomic<long long> g_launch_count{0};
+thread_local const char *t_kernel_name = nullptr;
 
 bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s);   // kernels_thin.cu
 
@@ -225,11 +226,22 @@ void launch_conv_cfg(const ConvDev &p, ConvMode mode, cudaStream_t s) {
     dim3 grid((p.M + BM - 1) / BM, (p.Ns + BN - 1) / BN);
     dim3 block((BM / TM) * (BN / TN));
     switch (mode) {
-        case CONV_GATHER: conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_GATHER, 0><<<grid, block, 0, s>>>(p); break;
-        case CONV_PW: conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_PW, 0><<<grid, block, 0, s>>>(p); break;
+        case CONV_GATHER:
+            ZB_KNAME("conv_gemm_kernel", BM, BN, TM, TN, BKT, CONV_GATHER, 0);
+            conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_GATHER, 0><<<grid, block, 0, s>>>(p);
+            break;
+        case CONV_PW:
+            ZB_KNAME("conv_gemm_kernel", BM, BN, TM, TN, BKT, CONV_PW, 0);
+            conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_PW, 0><<<grid, block, 0, s>>>(p);
+            break;
         case CONV_DWPW:
-            if (p.kh == 3 && p.kw == 3) conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_DWPW, 3><<<grid, block, 0, s>>>(p);
-            else if (p.kh == 5 && p.kw == 5) conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_DWPW, 5><<<grid, block, 0, s>>>(p);
+            if (p.kh == 3 && p.kw == 3) {
+                ZB_KNAME("conv_gemm_kernel", BM, BN, TM, TN, BKT, CONV_DWPW, 3);
+                conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_DWPW, 3><<<grid, block, 0, s>>>(p);
+            } else if (p.kh == 5 && p.kw == 5) {
+                ZB_KNAME("conv_gemm_kernel", BM, BN, TM, TN, BKT, CONV_DWPW, 5);
+                conv_gemm_kernel<BM, BN, TM, TN, BKT, CONV_DWPW, 5><<<grid, block, 0, s>>>(p);
+            }
             else throw std::runtime_error("unsupported op: fused depthwise kernel other than 3x3 / 5x5");
             break;
     }
@@ -397,6 +409,7 @@ void launch_conv(const ConvDev &p, ConvMode mode, cudaStream_t s) {
 void launch_dw(const ConvDev &p, cudaStream_t s) {
     g_launch_count++;
     long long total = (long long)p.M * (p.Cs_in / 4);
+    ZB_KNAME("dw_kernel");
     dw_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
 }
 
@@ -404,6 +417,7 @@ void launch_maxpool2(const float *in, long long in_img_stride, int H, int W, int
                      long long out_img_stride, int n, cudaStream_t s) {
     g_launch_count++;
     long long total = (long long)n * ((H - 2) / 2 + 1) * ((W - 2) / 2 + 1) * (Cs / 4);
+    ZB_KNAME("maxpool2_kernel");
     maxpool2_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride, n);
 }
 
@@ -411,12 +425,14 @@ void launch_resize2x(const float *in, long long in_img_stride, int H, int W, int
                      long long out_img_stride, int n, cudaStream_t s) {
     g_launch_count++;
     long long total = (long long)n * 4 * H * W * (Cs / 4);
+    ZB_KNAME("resize2x_kernel");
     resize2x_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride, n);
 }
 
 void launch_gap(const float *in, long long in_img_stride, int H, int W, int Cs, float *out, long long out_img_stride,
                 int n, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("gap_kernel");
     gap_kernel<<<blocks_for((long long)n * Cs, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride, n);
 }
 
@@ -425,6 +441,7 @@ void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int 
                     cudaStream_t s) {
     g_launch_count++;
     long long total = (long long)n * H * W * Cs;
+    ZB_KNAME("eltwise_kernel");
     eltwise_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, in_img_stride, H, W, Cs, out, out_img_stride,
                                                           out_pix_stride, Nstore, epi, n);
 }
@@ -432,11 +449,13 @@ void launch_eltwise(const float *in, long long in_img_stride, int H, int W, int 
 void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out, long long out_img_stride,
                           cudaStream_t s, int round_f16) {
     g_launch_count++;
+    ZB_KNAME("nchw_to_nhwc4_kernel");
     nchw_to_nhwc4_kernel<<<blocks_for((long long)n * H * W, 256), 256, 0, s>>>(in_nchw, n, H, W, out, out_img_stride, round_f16);
 }
 
 void launch_round_f16(float *data, long long count, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("round_f16_kernel");
     round_f16_kernel<<<blocks_for(count, 256), 256, 0, s>>>(data, count);
 }
 

@@ -398,6 +398,7 @@ bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float h
     if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
+    ZB_KNAME("stem_kernel", KS, NP, PPT);
     kern<<<(unsigned)(tiles_x * tiles_y * images), 256, smem, s>>>(f, views, lo, hi, p, tiles_x, tiles_y, NSP, f16);
     return true;
 }
@@ -1102,23 +1103,27 @@ void launch_gather_texels(const FramesDev &f, const ViewDev *views, int n, int o
     const long long total = (long long)n * out_w * out_h;
     long long ctas = (total + 4 * 256 - 1) / (4 * 256);
     if (ctas > max_ctas) ctas = max_ctas;
+    ZB_KNAME("gather_texels_kernel");
     gather_texels_kernel<<<(unsigned)ctas, 256, 0, s>>>(f, views, n, out_w, out_h, out);
 }
 
 void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint8_t *out, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("view_to_image_kernel");
     view_to_image_kernel<<<dim3((out_w + 127) / 128, out_h, n), 128, 0, s>>>(f, views, out_w, out_h, reinterpret_cast<unsigned *>(out));
 }
 
 void launch_frames_clear(uint8_t *base, long long frame_stride, long long row_stride, int width, int height, int first,
                          int count, unsigned rgba, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("frames_clear_kernel");
     frames_clear_kernel<<<dim3((width + 255) / 256, height, count), 256, 0, s>>>(base, frame_stride, row_stride, width, height, first, rgba);
 }
 
 void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int first_frame, int n, int net_w, int net_h,
                             ViewDev *out_views, float *out_fit, ViewHost *out_view_rects, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("tracker_prepare_kernel");
     tracker_prepare_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, state, first_frame, n, net_w, net_h, out_views, out_fit,
                                                            out_view_rects);
 }
@@ -1126,12 +1131,14 @@ void launch_tracker_prepare(const FramesDev &f, const TrackState *state, int fir
 void launch_rois_prepare(const FramesDev &f, const ViewHost *rois, int n, int net_w, int net_h, ViewDev *out_views, float *out_fit,
                          ViewHost *out_view_rects, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("rois_prepare_kernel");
     rois_prepare_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, rois, n, net_w, net_h, out_views, out_fit, out_view_rects);
 }
 
 void launch_eye_rois(const FramesDev &f, const float *landmarks, const ViewDev *face_views, int n, int num_landmarks, int net_w,
                      int net_h, float margin, ViewDev *out_views, float *out_fit, ViewHost *out_rects, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("eye_roi_kernel");
     eye_roi_kernel<<<(2 * n + 127) / 128, 128, 0, s>>>(f, landmarks, face_views, n, num_landmarks, net_w, net_h, margin, out_views,
                                                        out_fit, out_rects);
 }
@@ -1141,12 +1148,14 @@ void launch_tracker_update(TrackState *state, const float *out0, int s0, const f
                            int idx_from, int idx_to, float axis_x, float axis_y, ViewHost *out_updated,
                            unsigned char *out_tracked, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("tracker_update_kernel");
     tracker_update_kernel<<<n, 128, 0, s>>>(state, out0, s0, fit, landmarks, scalars, num_landmarks, loss_thresh,
                                             roi_padding, idx_from, idx_to, axis_x, axis_y, out_updated, out_tracked);
 }
 
 void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("tracker_set_roi_kernel");
     tracker_set_roi_kernel<<<(k + 127) / 128, 128, 0, s>>>(state, ids, rois, k);
 }
 
@@ -1155,6 +1164,7 @@ void launch_sample(const FramesDev &f, const ViewDev *views, int n, int out_w, i
     g_launch_count++;
     dim3 block(128);
     dim3 grid((out_w + 127) / 128, out_h, n);
+    ZB_KNAME("sample_kernel");
     sample_kernel<<<grid, block, 0, s>>>(f, views, out_w, out_h, lo, hi, (int)layout, out, out_img_stride, round_f16);
 }
 
@@ -1191,6 +1201,7 @@ void launch_decode_nms(const float *boxes, const float *scores, const float *fit
     const size_t smem = (size_t)p.num_anchors * (sizeof(float4) + sizeof(float) + 4 * sizeof(int));
     static SmemOptIn opt_in;
     opt_in.ensure(decode_nms_kernel, smem);   // a failure surfaces as the launch error
+    ZB_KNAME("decode_nms_kernel");
     decode_nms_kernel<<<n, 256, smem, s>>>(boxes, scores, fit, p, out, out_counts);
 }
 
@@ -1198,6 +1209,7 @@ void launch_face_roi(const FramesDev &f, const DetDev *dets, const int *counts, 
                      int net_w, int net_h, ViewDev *out_views, float *out_fit, ViewHost *out_view_rects,
                      cudaStream_t s, float grow_rel_amount, int use_angle) {
     g_launch_count++;
+    ZB_KNAME("face_roi_kernel");
     face_roi_kernel<<<(n + 127) / 128, 128, 0, s>>>(f, dets, counts, cap, first_frame, n, net_w, net_h, out_views,
                                                     out_fit, out_view_rects, grow_rel_amount, use_angle);
 }
@@ -1209,17 +1221,20 @@ void launch_landmarks(const float *out0, int s0, const float *out1, int s1, cons
     g_launch_count++;
     dim3 grid((unsigned)((p.num_landmarks + 127) / 128) * (unsigned)n);
     FilterDev none{};
+    ZB_KNAME("landmarks_kernel");
     landmarks_kernel<<<grid, 128, 0, s>>>(out0, s0, out1, s1, out2, s2, fit, views, view_rects, n, p, landmarks,
                                           scalars, filter ? *filter : none, sel);
 }
 
 void launch_compact_views(const ViewDev *views, int n, ViewDev *out_views, int *sel, int *count, float *scalars, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("compact_views_kernel");
     compact_views_kernel<<<1, 1024, 0, s>>>(views, n, out_views, sel, count, scalars);
 }
 
 void launch_filter_apply(const FilterDev &f, float *values, long long count, cudaStream_t s) {
     g_launch_count++;
+    ZB_KNAME("filter_apply_kernel");
     filter_apply_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(f, values, count);
 }
 

@@ -666,6 +666,7 @@ bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     // NBUF == 2: persistent CTAs (as many as fit on the SMs) looping over tiles with the next input tile
     // prefetched; NBUF == 1: one tile per CTA (measured faster: more resident CTAs overlap the serial phases)
     static const int poll_all = getenv("ZB_TC_POLL_ALL") ? atoi(getenv("ZB_TC_POLL_ALL")) : 1;
+    ZB_KNAME("dwpw_ttc_kernel", CS, TH, NBUF, TW);
     if (NBUF == 1) {
         kern<<<dim3(tiles_x, tiles_y, images), 256, smem, s>>>(p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
     } else {
@@ -738,6 +739,7 @@ bool launch_dwpw_tc_ks(const ConvDev &p, const float *w_hi, const float *w_lo, i
     auto kern = dwpw_tc_kernel<KS, STRIP>;
     static SmemOptIn opt_in;
     if (!opt_in.ensure(kern, smem)) return false;
+    ZB_KNAME("dwpw_tc_kernel", KS, STRIP ? 1 : 0);
     kern<<<(unsigned)((p.M + TC_M - 1) / TC_M), 256, smem, s>>>(p, w_hi, w_lo, NP, KC, Kpad);
     return true;
 }

@@ -386,6 +386,7 @@ bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
     if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
+    ZB_KNAME("dwpw_strip_kernel", CS, S, NP, PXV, TW, WARPS);
     kern<<<dim3(tiles_x, tiles_y, images), 32 * WARPS, smem, s>>>(p, tiles_x, tiles_y);
     return true;
 }
@@ -431,6 +432,7 @@ bool launch_thin_cfg(const ConvDev &p, cudaStream_t s) {
     if (!opt_in.ensure(kern, smem)) return false;
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
+    ZB_KNAME("dwpw_thin_kernel", CS, S, NP, TW, TH);
     kern<<<(unsigned)(tiles_x * tiles_y * images), TW * TH, smem, s>>>(p, tiles_x, tiles_y, NSP);
     return true;
 }
@@ -532,6 +534,7 @@ __global__ void __launch_bounds__(128) pw_thin_kernel(const ConvDev p) {
 
 template <int CIN, int NP, int PX>
 bool launch_pw_thin_cfg(const ConvDev &p, cudaStream_t s) {
+    ZB_KNAME("pw_thin_kernel", CIN, NP, PX);
     pw_thin_kernel<CIN, NP, PX><<<(unsigned)((p.M + 128 * PX - 1) / (128 * PX)), 128, 0, s>>>(p);
     return true;
 }

@@ -158,6 +158,18 @@ OnnxTensor parse_tensor(const uint8_t *d, size_t n) {
     } else {
         throw std::runtime_error("onnx: unsupported initializer data type " + std::to_string(t.dtype));
     }
+    // The element count must be what `dims` says: the weight packing indexes the data by the dims, so a truncated or
+    // inconsistent tensor would be read out of bounds (the reference's `from_onnx(..).load()` returns Err for such models).
+    uint64_t count = 1;
+    for (int64_t d : t.dims) {
+        if (d < 0 || d > (int64_t)1 << 31) throw std::runtime_error("onnx: initializer '" + t.name + "' has an invalid dimension");
+        count *= (uint64_t)d;
+        if (count > (uint64_t)1 << 33) throw std::runtime_error("onnx: initializer '" + t.name + "' is implausibly large");
+    }
+    const uint64_t have = (t.dtype == 1 || t.dtype == 10) ? t.f.size() : t.i.size();
+    if (have != count)
+        throw std::runtime_error("onnx: initializer '" + t.name + "' holds " + std::to_string(have) + " elements but its dims say " +
+                                 std::to_string(count));
     return t;
 }
 

@@ -166,7 +166,14 @@ struct Lowerer {
         return a;
     }
 
+    static void need_inputs(const OnnxNode &n, size_t k) {
+        if (n.inputs.size() < k)
+            throw std::runtime_error("onnx: node '" + n.name + "' (" + n.op + ") has " + std::to_string(n.inputs.size()) +
+                                     " inputs, needs at least " + std::to_string(k));
+    }
+
     void lower_conv(const OnnxNode &n) {
+        need_inputs(n, 2);
         const OnnxTensor *w = init(n.inputs[1]);
         const OnnxTensor *b = n.inputs.size() > 2 ? init(n.inputs[2]) : nullptr;
         if (!w || w->dims.size() != 4) unsupported("Conv with non-constant / non-4D weights");
@@ -182,6 +189,12 @@ struct Lowerer {
         int sh = strides.size() > 0 ? (int)strides[0] : 1, sw = strides.size() > 1 ? (int)strides[1] : 1;
         int pt = pads.size() > 0 ? (int)pads[0] : 0, pl = pads.size() > 1 ? (int)pads[1] : 0;
         int pb = pads.size() > 2 ? (int)pads[2] : 0, pr = pads.size() > 3 ? (int)pads[3] : 0;
+        if (cout <= 0 || cin_g <= 0 || kh <= 0 || kw <= 0 || kh > 64 || kw > 64)
+            throw std::runtime_error("onnx: Conv '" + n.name + "' has an invalid weight shape");
+        if (sh <= 0 || sw <= 0 || sh > 64 || sw > 64) throw std::runtime_error("onnx: Conv '" + n.name + "' has an invalid stride");
+        if (pt < 0 || pl < 0 || pb < 0 || pr < 0 || pt > 64 || pl > 64 || pb > 64 || pr > 64)
+            throw std::runtime_error("onnx: Conv '" + n.name + "' has invalid pads");
+        if (group <= 0) throw std::runtime_error("onnx: Conv '" + n.name + "' has an invalid group");
 
         int in = materialize(n.inputs[0]);
         const TensorInfo ti = plan.tensors[in];
@@ -239,6 +252,7 @@ struct Lowerer {
     }
 
     void lower_gemm(const OnnxNode &n) {
+        need_inputs(n, 2);
         const OnnxTensor *w = init(n.inputs[1]);
         const OnnxTensor *b = n.inputs.size() > 2 ? init(n.inputs[2]) : nullptr;
         if (!w || w->dims.size() != 2) unsupported("Gemm with non-constant B");
@@ -268,6 +282,7 @@ struct Lowerer {
     }
 
     void lower_act(const OnnxNode &n) {
+        need_inputs(n, n.op == "PRelu" ? 2 : 1);
         const OnnxTensor *slope = nullptr;
         ActSpec a = make_act(n, &slope);
         int p = foldable_producer(n.inputs[0]);
@@ -320,6 +335,7 @@ struct Lowerer {
     }
 
     void lower_add(const OnnxNode &n) {
+        need_inputs(n, 2);
         for (int side = 0; side < 2; side++) {
             const std::string &a = n.inputs[side], &b = n.inputs[1 - side];
             int p = foldable_producer(a);
@@ -366,6 +382,7 @@ struct Lowerer {
         if (n.has("mode") && n.attr_s("mode") != "constant") unsupported("Pad mode " + n.attr_s("mode"));
         if (n.attr_f("value", 0.f) != 0.f) unsupported("Pad with non-zero value");
         if (pads.size() != 8) unsupported("Pad on a non-4D tensor");
+        if (pads[5] < 0 || pads[5] > 4096) throw std::runtime_error("onnx: Pad '" + n.name + "' has an invalid channel pad");
         for (int i = 0; i < 8; i++)
             if (i != 5 && pads[i] != 0) unsupported("Pad on a non-channel axis");
         const Value &src = val(n.inputs[0]);
@@ -479,7 +496,10 @@ struct Lowerer {
             if (out[i] == -1) infer = (int)i;
             else known *= out[i];
         }
-        if (infer >= 0) out[infer] = total / known;
+        if (infer >= 0) {
+            if (known <= 0) throw std::runtime_error("onnx: Reshape '" + n.name + "' cannot infer a dimension");
+            out[infer] = total / known;
+        }
         if (out.empty() || out[0] != 1) unsupported("Reshape that folds the batch dimension");
         f.shape = out;
         values[n.outputs[0]] = f;
@@ -662,7 +682,11 @@ struct Lowerer {
             const TensorInfo &to = plan.tensors[op.out];
             op.Ns = to.exact ? round_up(op.N, 4) : to.Cs;
             op.Nstore = to.exact ? op.N : to.Cs;
+            if ((op.kind == OP_CONV || op.kind == OP_DW || op.kind == OP_DWPW) && !s.w)
+                throw std::runtime_error("onnx: convolution without constant weights");
             if (op.kind == OP_CONV) {
+                const size_t want = (size_t)op.N * s.cin * (s.gemm ? 1 : op.kh * op.kw);
+                if (s.w->f.size() != want) throw std::runtime_error("onnx: Conv/Gemm weight holds the wrong number of elements");
                 op.K = op.kh * op.kw * ti.Cs;
                 std::vector<float> w((size_t)op.K * op.Ns, 0.f);
                 for (int co = 0; co < op.N; co++)
@@ -678,6 +702,9 @@ struct Lowerer {
                 op.b_off = pack_vec(s.b, op.N, op.Ns, "bias");
             } else if (op.kind == OP_DW || op.kind == OP_DWPW) {
                 int C = ti.C, Cs = ti.Cs;
+                if (s.w->f.size() != (size_t)C * op.kh * op.kw) throw std::runtime_error("onnx: depthwise weight holds the wrong number of elements");
+                if (op.kind == OP_DWPW && (!s.w2 || s.w2->f.size() != (size_t)op.N * C))
+                    throw std::runtime_error("onnx: pointwise weight holds the wrong number of elements");
                 std::vector<float> w((size_t)op.kh * op.kw * Cs, 0.f);
                 for (int c = 0; c < C; c++)
                     for (int ky = 0; ky < op.kh; ky++)
@@ -740,6 +767,8 @@ struct Lowerer {
         if (in.shape.size() != 4 || in.shape[1] != 3) unsupported("input that is not [1,3,h,w]");
         plan.input_name = in.name;
         plan.io_f16 = in.elem_type == 10;
+        if (in.shape[2] <= 0 || in.shape[3] <= 0 || in.shape[2] > 8192 || in.shape[3] > 8192)
+            throw std::runtime_error("onnx: input height/width must be in 1..8192");
         plan.in_h = (int)in.shape[2];
         plan.in_w = (int)in.shape[3];
         plan.input = new_tensor(in.name, 3, plan.in_h, plan.in_w);
@@ -752,6 +781,7 @@ struct Lowerer {
 
         for (auto &n : g.nodes) {
             if (n.outputs.empty()) continue;
+            need_inputs(n, 1);
             if (n.op == "Conv") lower_conv(n);
             else if (n.op == "Gemm") lower_gemm(n);
             else if (n.op == "Relu" || n.op == "PRelu" || n.op == "Clip" || n.op == "Sigmoid") lower_act(n);
@@ -771,6 +801,17 @@ struct Lowerer {
         return std::move(plan);
     }
 };
+
+// tensor / node names come from the model file: keep the JSON valid whatever bytes they hold
+std::string json_str(const std::string &in) {
+    std::string o;
+    for (unsigned char c : in) {
+        if (c == '"' || c == '\\') o += '\\', o += (char)c;
+        else if (c < 0x20 || c >= 0x7f) o += '?';
+        else o += (char)c;
+    }
+    return o;
+}
 
 void json_act(std::ostringstream &os, const char *key, const ActSpec &a) {
     os << "\"" << key << "\":{\"kind\":" << a.kind << ",\"lo\":" << a.lo << ",\"hi\":" << a.hi
@@ -793,7 +834,7 @@ std::string Plan::to_json() const {
        << ",\"num_weights\":" << weights.size() << ",\"tensors\":[";
     for (size_t i = 0; i < tensors.size(); i++) {
         const auto &t = tensors[i];
-        os << (i ? "," : "") << "{\"name\":\"" << t.name << "\",\"C\":" << t.C << ",\"H\":" << t.H << ",\"W\":" << t.W
+        os << (i ? "," : "") << "{\"name\":\"" << json_str(t.name) << "\",\"C\":" << t.C << ",\"H\":" << t.H << ",\"W\":" << t.W
            << ",\"Cs\":" << t.Cs << ",\"exact\":" << (t.exact ? 1 : 0) << ",\"buffer\":" << t.buffer << ",\"arena\":" << t.arena
            << ",\"offset\":" << t.offset << ",\"img_stride\":" << t.img_stride << ",\"def_op\":" << t.def_op
            << ",\"last_use\":" << t.last_use << "}";
@@ -813,11 +854,11 @@ std::string Plan::to_json() const {
         json_act(os, "act1", o.act1);
         os << ",";
         json_act(os, "act2", o.act2);
-        os << ",\"nodes\":\"" << o.src_nodes << "\"}";
+        os << ",\"nodes\":\"" << json_str(o.src_nodes) << "\"}";
     }
     os << "],\"outputs\":[";
     for (size_t i = 0; i < outputs.size(); i++) {
-        os << (i ? "," : "") << "{\"name\":\"" << outputs[i].name << "\",\"per_image\":" << outputs[i].per_image
+        os << (i ? "," : "") << "{\"name\":\"" << json_str(outputs[i].name) << "\",\"per_image\":" << outputs[i].per_image
            << ",\"shape\":[";
         for (size_t k = 0; k < outputs[i].shape.size(); k++) os << (k ? "," : "") << outputs[i].shape[k];
         os << "]}";
