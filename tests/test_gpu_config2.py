@@ -113,8 +113,11 @@ def test_config2_batch256_invariance_and_permutation(zb):
         assert np.abs(one.eye_rois[0] - big.eye_rois[i]).max() <= 4e-2 * max(1.0, scale), i
         # the eye crop is re-sampled (nearest texel) from an RoI that itself moved by the mesh landmarks' run-to-run
         # difference (FP32 tiles for a batch of one, 3xTF32 tcgen05 at 256): texels flip, the iris network sees a
-        # slightly different image - still a few 1e-3 of the 64-pixel input
-        assert np.abs(one.eye_landmarks[0] - big.eye_landmarks[i]).max() <= 2e-1 * max(1.0, scale), i
+        # slightly different image: bounded by 2 % of the eye crop (about one pixel of the 64-pixel input); the parity
+        # tests against the oracle above are the accuracy statement, this one guards the batching machinery
+        eye_size = float(big.eye_rois[i][:, 2:4].max())
+        err = float(np.abs(one.eye_landmarks[0] - big.eye_landmarks[i]).max())
+        assert err <= 2e-2 * eye_size, (i, err, eye_size)
     perm = rng.permutation(256)
     shuf = pipe.run(batch, [rois[j] for j in perm])
     for k in (0, 9, 200):
