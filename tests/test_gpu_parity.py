@@ -10,6 +10,8 @@ import os
 import numpy as np
 import pytest
 
+from tests.tolerances import assert_logits_close
+
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
@@ -116,8 +118,10 @@ def test_network_forward_matches_oracle(zb, assets_dir, name, lo, size, sad_linu
         # raw head tensors are in network-input pixel units (or logits): normalise coordinates by input size
         err = float(np.abs(g - r).max())
         noise = float(np.abs(want2[k] - r[:1]).max())   # oracle-vs-oracle floor on the fixture image
-        limit = max(TOL * size, 4 * noise) if g.shape[-1] > 2 else max(5e-3, 4 * noise)
-        assert err <= limit, (name, k, err, noise)
+        if g.shape[-1] > 2:
+            assert err <= max(TOL * size, 4 * noise), (name, k, err, noise)
+        else:       # logits / flags: 4e-3 (= 1e-3 on the score) + 2e-5 |v| for the saturated ones, above the oracle-vs-oracle floor
+            assert_logits_close(g, r, extra=4 * noise, what=(name, k, err, noise))
 
 
 def test_network_forward_chunking_is_invisible(zb, assets_dir):
@@ -247,7 +251,7 @@ def test_detector_batch_on_synthetic_1080p(zb):
     for i in range(n):
         want = odet.detect(_oimg(frames[i]))
         margin = float(np.abs(odet.last_raw[1]).min())
-        assert np.abs(raw_s[i] - odet.last_raw[1][0]).max() < 5e-3
+        assert_logits_close(raw_s[i], odet.last_raw[1][0], what=i)
         if margin < 1e-2:
             continue   # a logit within 1e-2 of the threshold: set identity is not required
         _check_dets(got[i], want, 128 * 15.0, f"frame{i}")

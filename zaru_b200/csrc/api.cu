@@ -129,6 +129,12 @@ struct zb_ctx {
     int tc_mode = 1;                     // ZB_TC: 0 = SIMT only, 1 = tcgen05 3xTF32 for fused blocks with K >= tc_min_k
     int tc_min_k = 48;                   // ZB_TC_MIN_K
     int tc_min_ctas = 500;               // ZB_TC_MIN_CTAS: stride-1 blocks (8x8x96 at batch 1024 = 512 CTAs: 0.23 vs 0.42 ms on the GEMM tile)
+    int tcb_mode = 1;                    // ZB_TCB: 1 = tile-block kernel (TMA halo staging + tcgen05) for fused blocks with K >= tcb_min_k
+    int tcb_min_k = 32;                  // ZB_TCB_MIN_K
+    int tcb_gemm_mode = 1;               // ZB_TCB_GEMM: tcgen05 GEMM kernel for plain convs (1x1, dense, 2x2 stride 2 ...)
+    int tcb_gemm_min_m = 1;              // ZB_TCB_GEMM_MIN_M: smaller launches stay on the FFMA tile
+    int tcb_over_thin = 0;               // ZB_TCB_OVER_THIN: also take the stride-2 blocks the SIMT thin kernel covers
+    int tcb_over_ttc = 0;                // ZB_TCB_OVER_TTC: also take the large-map thin blocks of the tile-tc kernel
     int tc_min_ctas_s2 = 1 << 20;        // ZB_TC_MIN_CTAS_S2: stride-2 blocks stay on the GEMM tile (their tcgen05 producer has no
                                          // window reuse: 0.189 vs 0.220 ms on 24x24x64 -> 12x12x128, 0.175 vs 0.218 ms on 32x32x42 -> 16x16x48)
     bool prof_on = false;
@@ -330,8 +336,16 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                         input_ready = true;
                     }
                     const bool pw = op.kh == 1 && op.kw == 1 && op.sh == 1 && op.sw == 1 && op.pt == 0 && op.pl == 0;
-                    prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : pw ? "conv_gemm<pw>" : "conv_gemm<gather>", bytes, flops,
-                                [&] { launch_conv(p, pw ? CONV_PW : CONV_GATHER, s); });
+                    // tcgen05 GEMM for 1x1 / dense / non-overlapping-window convs (3xTF32); the thin SIMT kernel keeps the
+                    // few-channel 1x1 convs on large maps it was measured on
+                    bool done = false;
+                    if (ctx->tc_mode > 0 && ctx->tcb_gemm_mode > 0 && op.wtc_hi_off >= 0 && p.M >= ctx->tcb_gemm_min_m &&
+                        tcb_gemm_supported(p, op.NP) && !(pw && pw_thin_supported(p)))
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : pw ? "tcb_gemm<pw>" : "tcb_gemm<gather>", bytes, flops,
+                                    [&] { done = launch_tcb_gemm(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, op.Kpad, s); });
+                    if (!done)
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : pw ? "conv_gemm<pw>" : "conv_gemm<gather>", bytes, flops,
+                                    [&] { launch_conv(p, pw ? CONV_PW : CONV_GATHER, s); });
                 } else if (op.kind == OP_DW) {
                     p.w = W + op.w_off;
                     prof_launch(ctx, s, "dw", bytes, flops, [&] { launch_dw(p, s); });
@@ -348,7 +362,16 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                                         p.K >= ctx->tc_min_k && p.M >= (p.sh == 2 ? ctx->tc_min_ctas_s2 : ctx->tc_min_ctas) * 128 &&
                                         !(p.sh == 2 && dwpw_thin_supported(p));
                     const bool use_ttc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_ttc_supported(p, op.NP);
-                    if (use_ttc) {
+                    // tile-block kernel: every fused block with K >= 32 that the large-map specialists do not cover
+                    const bool use_tcb = ctx->tc_mode > 0 && ctx->tcb_mode > 0 && op.wtc_hi_off >= 0 && p.K >= ctx->tcb_min_k &&
+                                         tcb_dwpw_supported(p, op.NP) && (!use_ttc || ctx->tcb_over_ttc) &&
+                                         (!dwpw_thin_supported(p) || ctx->tcb_over_thin);
+                    bool done = false;
+                    if (use_tcb)
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "tcb<tcgen05+tma>", bytes, flops,
+                                    [&] { done = launch_tcb_dwpw(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
+                    if (done) {
+                    } else if (use_ttc) {
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dwpw_ttc<tcgen05>", bytes, flops,
                                     [&] { launch_dwpw_ttc(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
                     } else if (use_tc) {
@@ -503,6 +526,12 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         if (const char *c = getenv("ZB_TC_MIN_K")) ctx->tc_min_k = atoi(c);
         if (const char *c = getenv("ZB_TC_MIN_CTAS")) ctx->tc_min_ctas = atoi(c);
         if (const char *c = getenv("ZB_TC_MIN_CTAS_S2")) ctx->tc_min_ctas_s2 = atoi(c);
+        if (const char *c = getenv("ZB_TCB")) ctx->tcb_mode = atoi(c);
+        if (const char *c = getenv("ZB_TCB_MIN_K")) ctx->tcb_min_k = atoi(c);
+        if (const char *c = getenv("ZB_TCB_OVER_THIN")) ctx->tcb_over_thin = atoi(c);
+        if (const char *c = getenv("ZB_TCB_GEMM")) ctx->tcb_gemm_mode = atoi(c);
+        if (const char *c = getenv("ZB_TCB_GEMM_MIN_M")) ctx->tcb_gemm_min_m = atoi(c);
+        if (const char *c = getenv("ZB_TCB_OVER_TTC")) ctx->tcb_over_ttc = atoi(c);
         if (const char *c = getenv("ZB_CHUNK")) {
             int v = atoi(c);
             if (v > 0) ctx->default_chunk = v;

@@ -87,6 +87,7 @@ void launch_nchw_to_nhwc4(const float *in_nchw, int n, int H, int W, float *out,
 void launch_round_f16(float *data, long long count, cudaStream_t s);
 
 bool launch_pw_thin(const ConvDev &p, cudaStream_t s);   // kernels_thin.cu: thin 1x1 convs (few channels, large maps); false = not taken
+bool pw_thin_supported(const ConvDev &p);
 bool dwpw_thin_supported(const ConvDev &p);   // kernels_thin.cu: would launch_conv(CONV_DWPW) take the thin kernel?
 
 // ---- tensor-core path: kernels_tc.cu ------------------------------------------------------------
@@ -94,6 +95,12 @@ bool dwpw_tc_supported(const ConvDev &p, int NP);
 bool launch_dwpw_tc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
 bool dwpw_ttc_supported(const ConvDev &p, int NP);   // thin blocks: smem tile + sliding-window dw + tcgen05 pw
 bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
+// kernels_tcb.cu: fused dw 3x3 / 5x5 (stride 1 / 2) -> pw blocks of any map size: TMA tensor-map halo staging + tcgen05
+bool tcb_dwpw_supported(const ConvDev &p, int NP);
+bool launch_tcb_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
+// plain convs as tcgen05 GEMMs: 1x1, dense / Gemm, non-overlapping windows; weights [N tile of 256][kpad / 4][NT][4] hi / lo
+bool tcb_gemm_supported(const ConvDev &p, int NP);
+bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, int kpad, cudaStream_t s);
 bool launch_tc_mma_rate(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps, int ctas, long long *cycles_dev, cudaStream_t s);
 bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s);
 

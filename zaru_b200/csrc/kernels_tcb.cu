@@ -1,0 +1,550 @@
+// sm_100a "tile block" kernels: fused depthwise KSxKS (3x3 / 5x5, stride 1 / 2) -> pointwise blocks of ANY map size and
+// channel count (K = Cs_in up to 1024, N up to 256) with
+//   * the input halo staged in shared memory by TMA TENSOR copies (cp.async.bulk.tensor.4d through a CUtensorMap over
+//     the NHWC activation: box = 32 channels x tile width + halo x 1 row, out-of-image rows / columns / channels are
+//     zero-filled by the hardware, completion counted on an mbarrier; SASS: UTMALDG) - every input element is read from
+//     L2 / HBM once per CTA instead of up to KS*KS times by per-thread window loads, and the next 32-channel chunk
+//     streams in while the current one is being convolved;
+//   * the depthwise stage on the CUDA cores as a sliding window (4 horizontally adjacent outputs x one channel quad per
+//     thread, weights of the chunk in shared memory), written straight into the UMMA K-major operand tile as TF32
+//     hi / lo parts;
+//   * the pointwise contraction on tcgen05.mma kind::tf32 (3xTF32, FP32 accumulation in TMEM), pre-split weights
+//     streamed per K chunk by TMA bulk copy;
+//   * the fused epilogue (bias -> act -> residual [channel-pad, 2x2 max-pool] -> act) from TMEM.
+//
+// One CTA = one tile of 128 output pixels = TH "virtual rows" x TW columns, where the virtual rows run over
+// (image, output row) in order: on small maps (12x12, 6x6, 3x3 ...) a tile spans several images, so the M = 128 MMA
+// rows stay full whatever the map size.  Replaces both the global-window tcgen05 kernel (dwpw_tc_kernel) and the FFMA
+// implicit-GEMM tile (conv_gemm_kernel<.., CONV_DWPW, ..>) for these blocks.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+
+#include "conv_common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
+
+namespace zb {
+namespace {
+
+using namespace tc;
+
+constexpr int TCB_M = 128;            // UMMA M
+constexpr int TCB_CK = 32;            // channels per K chunk
+constexpr int TCB_KQC = TCB_CK / 4;   // channel quads per chunk
+constexpr int TCB_AROWS = TCB_M + 1;  // padded chunk stride of the A tile: conflict-free 128-bit stores
+
+struct TcbGeom {
+    int TW, TH;            // tile = TH virtual rows x TW columns, TW * TH = 128
+    int tiles_x, tiles_y;
+    int vrows;             // images * Ho
+    int WBOX;              // staged input columns per row = (TW - 1) * S + KS
+    int rows_max;          // worst-case staged input rows of one tile
+    int nin;               // input staging buffers (1 or 2)
+};
+
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int KS, int S>
+__global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant__ CUtensorMap tmap, const ConvDev p,
+                                                          const float *__restrict__ w_hi, const float *__restrict__ w_lo, int NP,
+                                                          int nchunks, const TcbGeom g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int TAPS = KS * KS, SPAN = 3 * S + KS;
+    const int in_floats = g.rows_max * g.WBOX * TCB_CK;                      // one staging buffer (multiple of 32 floats = 128 B)
+    float *s_in0 = reinterpret_cast<float *>(smem_raw);                      // nin x [rows][WBOX][32]   (TMA destination)
+    float *sA_hi = s_in0 + (size_t)g.nin * in_floats;                        // [8][129][4]
+    float *sA_lo = sA_hi + TCB_KQC * TCB_AROWS * 4;
+    float *sB_hi = sA_lo + TCB_KQC * TCB_AROWS * 4;                          // [8][NP][4]               (bulk-copy destination)
+    float *sB_lo = sB_hi + TCB_KQC * NP * 4;
+    float *s_w0 = sB_lo + TCB_KQC * NP * 4;                                  // 2 x [(TAPS + 1)][32]: dw weights + bias of a chunk
+    __shared__ __align__(8) uint64_t mbar_in[2], mbar_b, mbar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
+    const int vr0 = tile_y * g.TH, ox0 = tile_x * g.TW;
+    const int n_vr = min(g.TH, g.vrows - vr0);                               // valid virtual rows of this tile (>= 1)
+    const int img0 = vr0 / p.Ho, oy0 = vr0 - img0 * p.Ho;
+    // staged row of virtual row r: srow(r) = S * r + (img(r) - img0) * (KS - S)   (pieces of consecutive images back to back)
+    const int last_img = (vr0 + n_vr - 1) / p.Ho;
+    const int rows_total = S * (n_vr - 1) + (last_img - img0) * (KS - S) + KS;
+    const int len0 = (min(p.Ho - oy0, n_vr) - 1) * S + KS;                   // staged rows of the first image piece
+    const int len_full = (p.Ho - 1) * S + KS;                                // ... of a whole image
+    const uint32_t ncols = tmem_cols_for(NP);
+    const uint32_t b_bytes = (uint32_t)TCB_KQC * NP * 16;
+    const uint32_t in_bytes = (uint32_t)rows_total * g.WBOX * TCB_CK * 4;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) {
+        mbar_init(&mbar_in[0], 1);
+        mbar_init(&mbar_in[1], 1);
+        mbar_init(&mbar_b, 1);
+        mbar_init(&mbar_mma, 1);
+        mbar_expect_tx(&mbar_b, 2 * b_bytes);
+        bulk_copy_g2s(sB_hi, w_hi, b_bytes, &mbar_b);
+        bulk_copy_g2s(sB_lo, w_lo, b_bytes, &mbar_b);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    // stage the input rows of K chunk c into buffer `buf`: one TMA per staged row (box = 32 channels x WBOX columns)
+    auto issue_in = [&](int c, int buf) {
+        if (lane == 0) mbar_expect_tx(&mbar_in[buf], in_bytes);
+        __syncwarp();
+        float *dst = s_in0 + (size_t)buf * in_floats;
+        for (int j = lane; j < rows_total; j += 32) {
+            int pimg, jj, oy_first;
+            if (j < len0) {
+                pimg = 0, jj = j, oy_first = oy0;
+            } else {
+                pimg = 1 + (j - len0) / len_full;
+                jj = (j - len0) - (pimg - 1) * len_full;
+                oy_first = 0;
+            }
+            const int iy = oy_first * S - p.pt + jj;
+            tma_load_4d(dst + (size_t)j * g.WBOX * TCB_CK, &tmap, c * TCB_CK, ox0 * S - p.pl, iy, img0 + pimg, &mbar_in[buf]);
+        }
+    };
+    if (warp == 0) issue_in(0, 0);
+
+    // this thread's producer item: strip of 4 horizontally adjacent outputs x channel quad
+    const int quad = tid & 7, strip = tid >> 3;
+    const int strips_x = g.TW >> 2;
+    const int pr = strip / strips_x, pcol = (strip - pr * strips_x) << 2;      // virtual row offset, first column of the strip
+    const int pm = pr * g.TW + pcol;                                          // tile row (MMA row) of the strip's first pixel
+    const bool p_valid = pr < n_vr && ox0 + pcol < p.Wo;
+    const int p_img = (vr0 + pr) / p.Ho;
+    const int origin = (S * pr + (p_img - img0) * (KS - S)) * g.WBOX + pcol * S;   // staged pixel index of the window's corner
+
+    const uint32_t idesc = make_idesc_tf32(TCB_M, NP);
+    const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), TCB_AROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), TCB_AROWS * 16, 128);
+    const uint64_t bd_hi = make_smem_desc(smem_u32(sB_hi), (uint32_t)NP * 16, 128), bd_lo = make_smem_desc(smem_u32(sB_lo), (uint32_t)NP * 16, 128);
+    uint32_t acc_flag = 0;
+
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = g.nin == 2 ? (c & 1) : 0;
+        // depthwise weights + bias of this chunk (zero beyond the true channel count: padded channels contribute nothing)
+        float *s_w = s_w0 + (c & 1) * ((TAPS + 1) * TCB_CK);
+        if (tid < (TAPS + 1) * TCB_KQC) {
+            const int t = tid >> 3, q = tid & 7;
+            const int k = c * TCB_CK + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < p.K) v = ldg4((t < TAPS ? p.dw_w + (size_t)t * p.Cs_in : p.dw_b) + k);
+            *reinterpret_cast<float4 *>(s_w + t * TCB_CK + q * 4) = v;
+        }
+        mbar_wait(&mbar_in[buf], g.nin == 2 ? ((c >> 1) & 1) : (c & 1));       // the chunk's input rows have landed
+        __syncthreads();                                                      // ... and its depthwise weights are in place
+        if (g.nin == 2 && warp == 0 && c + 1 < nchunks) issue_in(c + 1, buf ^ 1);   // next chunk streams in behind this one
+
+        if (p_valid) {
+            const float *s_in = s_in0 + (size_t)buf * in_floats + (size_t)origin * TCB_CK + quad * 4;
+            const float4 bias = *reinterpret_cast<const float4 *>(s_w + TAPS * TCB_CK + quad * 4);
+            float4 v[4] = {bias, bias, bias, bias};
+#pragma unroll
+            for (int ky = 0; ky < KS; ky++) {
+                float4 x[SPAN];
+                const float *rowp = s_in + (size_t)ky * g.WBOX * TCB_CK;
+#pragma unroll
+                for (int j = 0; j < SPAN; j++) x[j] = *reinterpret_cast<const float4 *>(rowp + j * TCB_CK);
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(s_w + (ky * KS + kx) * TCB_CK + quad * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v[i].x = fmaf(x[i * S + kx].x, wv.x, v[i].x);
+                        v[i].y = fmaf(x[i * S + kx].y, wv.y, v[i].y);
+                        v[i].z = fmaf(x[i * S + kx].z, wv.z, v[i].z);
+                        v[i].w = fmaf(x[i * S + kx].w, wv.w, v[i].w);
+                    }
+                }
+            }
+            const int k = c * TCB_CK + quad * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (k < p.K) act4(v[i], p.act_mid, k);
+                float4 hi, lo;
+                split_tf32_fast(v[i].x, hi.x, lo.x);
+                split_tf32_fast(v[i].y, hi.y, lo.y);
+                split_tf32_fast(v[i].z, hi.z, lo.z);
+                split_tf32_fast(v[i].w, hi.w, lo.w);
+                *reinterpret_cast<float4 *>(sA_hi + ((size_t)quad * TCB_AROWS + pm + i) * 4) = hi;
+                *reinterpret_cast<float4 *>(sA_lo + ((size_t)quad * TCB_AROWS + pm + i) * 4) = lo;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (g.nin == 1 && warp == 0 && c + 1 < nchunks) issue_in(c + 1, 0);    // single buffer: refill behind the MMAs
+        if (tid == 0) {
+            mbar_wait(&mbar_b, c & 1);                                        // this chunk's pointwise weights have landed
+#pragma unroll 1
+            for (int pass = 0; pass < 3; pass++) {                            // lo*hi, hi*lo, hi*hi (small terms first)
+                uint64_t ad = pass == 0 ? ad_lo : ad_hi;
+                uint64_t bd = pass == 1 ? bd_lo : bd_hi;
+#pragma unroll
+                for (int j = 0; j < TCB_CK / 8; j++) {
+                    umma_tf32(tmem, ad, bd, idesc, acc_flag);
+                    acc_flag = 1;
+                    ad += (uint64_t)(2 * TCB_AROWS);
+                    bd += (uint64_t)(2 * NP);
+                }
+            }
+            umma_commit(&mbar_mma);
+            mbar_wait(&mbar_mma, c & 1);                                      // one poller; everybody else parks at the barrier
+            if (c + 1 < nchunks) {                                            // A and B are free again: next weight chunk
+                mbar_expect_tx(&mbar_b, 2 * b_bytes);
+                bulk_copy_g2s(sB_hi, w_hi + (size_t)(c + 1) * TCB_KQC * NP * 4, b_bytes, &mbar_b);
+                bulk_copy_g2s(sB_lo, w_lo + (size_t)(c + 1) * TCB_KQC * NP * 4, b_bytes, &mbar_b);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    // --- epilogue: warp w owns TMEM lanes 32 * (w % 4) .., columns [half * NP / 2, (half + 1) * NP / 2) ----------------
+    const int row = (warp & 3) * 32 + lane;
+    const int er = row / g.TW, ecol = row - er * g.TW;
+    const int evr = vr0 + er;
+    const int ox = ox0 + ecol;
+    const bool rowok = er < n_vr && ox < p.Wo;
+    int img = 0, oy = 0;
+    if (rowok) {
+        img = evr / p.Ho;
+        oy = evr - img * p.Ho;
+    }
+    float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+    const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0);
+    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int half = warp >> 2;
+    // column split in multiples of 16 so both halves can use the wide TMEM loads (NP is a multiple of 16)
+    const int csplit = ((NP / 16 + 1) / 2) * 16;
+    const int cbeg = half ? csplit : 0, cend = half ? NP : csplit;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        ResidualPrefetch<16> pre;
+        if (rowok) tc_prefetch_residual<16>(p, c0, img, oy, ox, pre);
+        tmem_ld16(tbase + (uint32_t)c0, v);
+        if (rowok) tc_epilogue_cols<16>(p, v, c0, img, oy, ox, orow, vec_ok, pre);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain convolutions as tcgen05 GEMMs ("direct" operand: no depthwise stage): 1x1 convs, Gemm / dense heads, and
+// non-overlapping-window convs (2x2 stride 2, 3x3 stride 3 ...) whose im2col row is a concatenation of whole pixels
+// (Cs_in % 32 == 0, so a 32-wide K chunk never straddles two taps).  One CTA = 128 consecutive output pixels x one
+// tile of up to 256 output channels (blockIdx.y); the A chunk is gathered with coalesced 128-bit loads, TF32-split and
+// stored in the UMMA K-major layout; the loads of chunk c + 1 are in flight while the MMAs of chunk c run.
+// Weights: [N tile][Kpad / 4][NT][4], TF32 hi / lo, one TMA bulk copy per chunk and half.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const float *__restrict__ w_hi, const float *__restrict__ w_lo,
+                                                          int NP, int nchunks, int kpad) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int n0 = blockIdx.y * 256;
+    const int NT = min(256, NP - n0);                                        // output channels of this CTA (multiple of 16)
+    float *sA_hi = reinterpret_cast<float *>(smem_raw);                      // [8][129][4]
+    float *sA_lo = sA_hi + TCB_KQC * TCB_AROWS * 4;
+    float *sB_hi = sA_lo + TCB_KQC * TCB_AROWS * 4;                          // 2 x [8][NT][4]: double-buffered weight chunks
+    float *sB_lo = sB_hi + 2 * TCB_KQC * NT * 4;
+    __shared__ __align__(8) uint64_t mbar_b[2], mbar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TCB_M;
+    const int HoWo = p.Ho * p.Wo;
+    const uint32_t ncols = tmem_cols_for(NT);
+    const uint32_t b_bytes = (uint32_t)TCB_KQC * NT * 16;
+    // this N tile's weights: tiles of 256 columns precede it
+    const float *wt_hi = w_hi + (size_t)blockIdx.y * kpad * 256, *wt_lo = w_lo + (size_t)blockIdx.y * kpad * 256;
+    auto load_b = [&](int c) {
+        const int b = c & 1;
+        mbar_expect_tx(&mbar_b[b], 2 * b_bytes);
+        bulk_copy_g2s(sB_hi + (size_t)b * TCB_KQC * NT * 4, wt_hi + (size_t)c * TCB_KQC * NT * 4, b_bytes, &mbar_b[b]);
+        bulk_copy_g2s(sB_lo + (size_t)b * TCB_KQC * NT * 4, wt_lo + (size_t)c * TCB_KQC * NT * 4, b_bytes, &mbar_b[b]);
+    };
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) {
+        mbar_init(&mbar_b[0], 1);
+        mbar_init(&mbar_b[1], 1);
+        mbar_init(&mbar_mma, 1);
+        load_b(0);
+        if (nchunks > 1) load_b(1);
+    }
+    // this thread's 4 operand rows (row = (tid >> 3) + 32 i) and channel quad
+    const int quad = tid & 7;
+    long long roff[4];
+    int riy[4], rix[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int gm = m0 + (tid >> 3) + 32 * i;
+        roff[i] = -1;
+        riy[i] = rix[i] = 0;
+        if (gm < p.M) {
+            const int img = gm / HoWo;
+            const int r = gm - img * HoWo;
+            const int oy = r / p.Wo, ox = r - oy * p.Wo;
+            roff[i] = (long long)img * p.in_img_stride;
+            riy[i] = oy * p.sh - p.pt;
+            rix[i] = ox * p.sw - p.pl;
+        }
+    }
+    const bool multi_tap = p.kh * p.kw > 1;
+    auto fetch = [&](int c, float4 (&x)[4]) {
+        int k = c * TCB_CK + quad * 4, ky = 0, kx = 0;
+        if (multi_tap) {
+            const int tap = (c * TCB_CK) / p.Cs_in;
+            k -= tap * p.Cs_in;
+            ky = tap / p.kw, kx = tap - ky * p.kw;
+        }
+        const bool kok = multi_tap ? true : k < p.K;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int iy = riy[i] + ky, ix = rix[i] + kx;
+            x[i] = (roff[i] >= 0 && kok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                       ? ldg4(p.in + roff[i] + ((long long)iy * p.W + ix) * p.Cs_in + k)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float4 x[4];
+    fetch(0, x);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = make_idesc_tf32(TCB_M, NT);
+    const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), TCB_AROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), TCB_AROWS * 16, 128);
+    uint32_t acc_flag = 0;
+
+    for (int c = 0; c < nchunks; c++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int m = (tid >> 3) + 32 * i;
+            float4 hi, lo;
+            split_tf32_fast(x[i].x, hi.x, lo.x);
+            split_tf32_fast(x[i].y, hi.y, lo.y);
+            split_tf32_fast(x[i].z, hi.z, lo.z);
+            split_tf32_fast(x[i].w, hi.w, lo.w);
+            *reinterpret_cast<float4 *>(sA_hi + ((size_t)quad * TCB_AROWS + m) * 4) = hi;
+            *reinterpret_cast<float4 *>(sA_lo + ((size_t)quad * TCB_AROWS + m) * 4) = lo;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (c + 1 < nchunks) fetch(c + 1, x);                                 // next chunk's loads fly behind the MMAs
+        if (tid == 0) {
+            const int b = c & 1;
+            mbar_wait(&mbar_b[b], (c >> 1) & 1);
+            const uint64_t bd_hi = make_smem_desc(smem_u32(sB_hi + (size_t)b * TCB_KQC * NT * 4), (uint32_t)NT * 16, 128);
+            const uint64_t bd_lo = make_smem_desc(smem_u32(sB_lo + (size_t)b * TCB_KQC * NT * 4), (uint32_t)NT * 16, 128);
+#pragma unroll 1
+            for (int pass = 0; pass < 3; pass++) {
+                uint64_t ad = pass == 0 ? ad_lo : ad_hi;
+                uint64_t bd = pass == 1 ? bd_lo : bd_hi;
+#pragma unroll
+                for (int j = 0; j < TCB_CK / 8; j++) {
+                    umma_tf32(tmem, ad, bd, idesc, acc_flag);
+                    acc_flag = 1;
+                    ad += (uint64_t)(2 * TCB_AROWS);
+                    bd += (uint64_t)(2 * NT);
+                }
+            }
+            umma_commit(&mbar_mma);
+            mbar_wait(&mbar_mma, c & 1);
+            if (c + 2 < nchunks) load_b(c + 2);                               // this weight buffer is free again
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    // --- epilogue -------------------------------------------------------------------------------------------------
+    const int row = (warp & 3) * 32 + lane;
+    const int m = m0 + row;
+    const bool rowok = m < p.M;
+    int img = 0, oy = 0, ox = 0, r = 0;
+    if (rowok) {
+        img = m / HoWo;
+        r = m - img * HoWo;
+        oy = r / p.Wo;
+        ox = r - oy * p.Wo;
+    }
+    float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
+    const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int half = warp >> 2;
+    const int csplit = ((NT / 16 + 1) / 2) * 16;
+    const int cbeg = half ? csplit : 0, cend = half ? NT : csplit;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        ResidualPrefetch<16> pre;
+        if (rowok) tc_prefetch_residual<16>(p, n0 + c0, img, oy, ox, pre);
+        tmem_ld16(tbase + (uint32_t)c0, v);
+        if (rowok) tc_epilogue_cols<16>(p, v, n0 + c0, img, oy, ox, orow, vec_ok, pre);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (EncodeTiledFn) nullptr;
+        }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// NHWC activation as a 4-D tensor (channel, x, y, image); box = 32 channels x WBOX columns x 1 row x 1 image; OOB -> 0.
+bool make_input_map(const ConvDev &p, int images, int WBOX, CUtensorMap *out) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Cs_in, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)images};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.Cs_in * 4, (cuuint64_t)p.W * p.Cs_in * 4, (cuuint64_t)p.in_img_stride * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)TCB_CK, (cuuint32_t)WBOX, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(p.in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+TcbGeom choose_geom(const ConvDev &p, int KS, int S) {
+    const int images = p.M / (p.Ho * p.Wo);
+    TcbGeom best{};
+    double best_cost = 1e30;
+    static const int force_tw = getenv("ZB_TCB_TW") ? atoi(getenv("ZB_TCB_TW")) : 0;
+    for (int TW = 4; TW <= (S == 2 ? 64 : 128); TW *= 2) {
+        if (force_tw && TW != force_tw) continue;
+        const int TH = TCB_M / TW;
+        const int tiles_x = (p.Wo + TW - 1) / TW;
+        const int WBOX = (TW - 1) * S + KS;
+        if (WBOX > 256) continue;
+        const double pieces = std::min<double>(TH, (double)TH / p.Ho + 1.0);
+        const double rows = (TH - pieces) * S + pieces * KS;
+        const double valid = (double)TH * p.Wo / tiles_x;
+        const double cost = rows * WBOX / valid + 0.5 * TCB_M / valid;   // staged pixels per output + half-weighted MMA / producer waste
+        if (cost < best_cost) {
+            best_cost = cost;
+            best.TW = TW, best.TH = TH, best.tiles_x = tiles_x, best.WBOX = WBOX;
+        }
+    }
+    best.vrows = images * p.Ho;
+    best.tiles_y = (best.vrows + best.TH - 1) / best.TH;
+    const int pmax = std::min(best.TH, (best.TH + p.Ho - 1) / p.Ho + 1);
+    best.rows_max = (best.TH - pmax) * S + pmax * KS;
+    return best;
+}
+
+size_t tcb_smem(const TcbGeom &g, int KS, int NP, int nin) {
+    return (size_t)nin * g.rows_max * g.WBOX * TCB_CK * 4 + 2 * (size_t)TCB_KQC * TCB_AROWS * 16 + 2 * (size_t)TCB_KQC * NP * 16 +
+           2 * (size_t)(KS * KS + 1) * TCB_CK * 4 + 1024;
+}
+
+template <int KS, int S>
+bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    TcbGeom g = choose_geom(p, KS, S);
+    if (g.TW == 0) return false;
+    // two staging buffers when two CTAs still fit on an SM with them (the next chunk streams in behind the convolution of
+    // this one); otherwise one buffer, refilled behind the MMAs
+    static const int force_nin = getenv("ZB_TCB_NIN") ? atoi(getenv("ZB_TCB_NIN")) : 0;
+    int nin = tcb_smem(g, KS, NP, 2) <= 110 * 1024 ? 2 : 1;
+    if (force_nin == 1 || force_nin == 2) nin = force_nin;
+    if (tcb_smem(g, KS, NP, nin) > 220 * 1024) nin = 1;
+    const size_t smem = tcb_smem(g, KS, NP, nin);
+    if (smem > 220 * 1024) return false;
+    g.nin = nin;
+    const int images = p.M / (p.Ho * p.Wo);
+    CUtensorMap tmap;
+    if (!make_input_map(p, images, g.WBOX, &tmap)) return false;
+    auto kern = tcb_dwpw_kernel<KS, S>;
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, smem)) return false;
+    const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
+    ZB_KNAME("tcb_dwpw_kernel", KS, S);
+    kern<<<(unsigned)(g.tiles_x * g.tiles_y), 256, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
+    return true;
+}
+
+}  // namespace
+
+bool tcb_dwpw_supported(const ConvDev &p, int NP) {
+    static const bool disabled = getenv("ZB_NO_TCB") && atoi(getenv("ZB_NO_TCB")) != 0;
+    if (disabled) return false;
+    if (!((p.kh == 3 && p.kw == 3) || (p.kh == 5 && p.kw == 5))) return false;
+    if (!((p.sh == 1 && p.sw == 1) || (p.sh == 2 && p.sw == 2))) return false;
+    if (p.K != p.Cs_in || p.K % 8 || p.K < 8 || p.K > 1024 || NP % 16 || NP < 16 || NP > 256) return false;
+    if (p.M % (p.Ho * p.Wo) || p.pt < 0 || p.pl < 0) return false;
+    if (((uintptr_t)p.in) % 16 || (p.in_img_stride % 4)) return false;
+    return encode_fn() != nullptr;
+}
+
+bool tcb_gemm_supported(const ConvDev &p, int NP) {
+    static const bool disabled = getenv("ZB_NO_TCB_GEMM") && atoi(getenv("ZB_NO_TCB_GEMM")) != 0;
+    if (disabled) return false;
+    if (p.Cs_in % 8 || p.Cs_in < 8 || NP % 16 || NP < 16) return false;
+    if (p.kh * p.kw > 1 && p.Cs_in % TCB_CK) return false;                   // a K chunk must not straddle two taps
+    if (p.K != p.kh * p.kw * p.Cs_in || p.K > 8192) return false;
+    if (p.M % (p.Ho * p.Wo) || ((uintptr_t)p.in) % 16 || (p.in_img_stride % 4)) return false;
+    return true;
+}
+
+bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, int kpad, cudaStream_t s) {
+    if (!tcb_gemm_supported(p, NP)) return false;
+    const int ntiles = (NP + 255) / 256;
+    const int nt_max = std::min(NP, 256);
+    const size_t smem = 2 * (size_t)TCB_KQC * TCB_AROWS * 16 + 4 * (size_t)TCB_KQC * nt_max * 16 + 1024;
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(tcb_gemm_kernel, smem)) return false;
+    g_launch_count++;
+    const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
+    ZB_KNAME("tcb_gemm_kernel");
+    tcb_gemm_kernel<<<dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), 256, smem, s>>>(p, w_hi, w_lo, NP, nchunks, kpad);
+    return true;
+}
+
+bool launch_tcb_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
+    if (!tcb_dwpw_supported(p, NP)) return false;
+    g_launch_count++;
+    bool ok;
+    if (p.kh == 3) ok = p.sh == 1 ? launch_tcb_cfg<3, 1>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<3, 2>(p, w_hi, w_lo, NP, s);
+    else ok = p.sh == 1 ? launch_tcb_cfg<5, 1>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<5, 2>(p, w_hi, w_lo, NP, s);
+    if (!ok) g_launch_count--;
+    return ok;
+}
+
+}  // namespace zb

@@ -572,13 +572,18 @@ bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s) {
 
 // Pointwise convs the thin kernel takes from the GEMM tile: 1x1 stride 1, Cs_in 16 or 32, N <= 32, maps >= 32x32,
 // 4-aligned stores, residual (if any) vectorisable.
-bool launch_pw_thin(const ConvDev &p, cudaStream_t s) {
+bool pw_thin_supported(const ConvDev &p) {
     static const bool disabled = getenv("ZB_NO_PW_THIN") && atoi(getenv("ZB_NO_PW_THIN")) != 0;
     if (disabled) return false;
     if (p.kh != 1 || p.kw != 1 || p.sh != 1 || p.sw != 1 || p.pt != 0 || p.pl != 0) return false;
     if (p.K != p.Cs_in || (p.Cs_in != 16 && p.Cs_in != 32) || p.Ns > 32 || p.Ns % 4 || p.Nstore % 4 || p.out_pix_stride % 4) return false;
     if (p.Ho * p.Wo < 1024 || p.M % (p.Ho * p.Wo)) return false;
     if (p.epi.res && (p.epi.res_Cs % 4)) return false;
+    return true;
+}
+
+bool launch_pw_thin(const ConvDev &p, cudaStream_t s) {
+    if (!pw_thin_supported(p)) return false;
     const int np = p.Ns <= 8 ? 8 : p.Ns <= 16 ? 16 : 32;
     if (p.Cs_in == 16) {
         if (np == 8) return launch_pw_thin_cfg<16, 8, 4>(p, s);

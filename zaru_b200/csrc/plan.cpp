@@ -700,6 +700,27 @@ struct Lowerer {
                             }
                 op.w_off = push_weights(w);
                 op.b_off = pack_vec(s.b, op.N, op.Ns, "bias");
+                // tensor-core copy for the GEMM kernel (1x1 / dense / non-overlapping windows; not the 3-channel stem):
+                // TF32 hi + lo, K-major UMMA layout, one block per tile of 256 output channels
+                if (ti.Cs % 8 == 0 && (op.kh * op.kw == 1 || ti.Cs % 32 == 0) && op.K <= 8192) {
+                    op.NP = round_up(op.Ns, 16);
+                    op.Kpad = round_up(op.K, 32);
+                    const int ntiles = (op.NP + 255) / 256;
+                    std::vector<float> whi((size_t)op.Kpad * op.NP, 0.f), wlo((size_t)op.Kpad * op.NP, 0.f);
+                    for (int k = 0; k < op.K; k++)
+                        for (int co = 0; co < op.N; co++) {
+                            const float v = w[(size_t)k * op.Ns + co];
+                            const int tile = co / 256, cn = co % 256;
+                            const int nt = std::min(256, op.NP - 256 * tile);
+                            const size_t idx = (size_t)tile * op.Kpad * 256 + ((size_t)(k / 4) * nt + cn) * 4 + (k & 3);
+                            const float hi = rna_tf32(v);
+                            whi[idx] = hi;
+                            wlo[idx] = rna_tf32(v - hi);
+                        }
+                    (void)ntiles;
+                    op.wtc_hi_off = push_weights(whi);
+                    op.wtc_lo_off = push_weights(wlo);
+                }
             } else if (op.kind == OP_DW || op.kind == OP_DWPW) {
                 int C = ti.C, Cs = ti.Cs;
                 if (s.w->f.size() != (size_t)C * op.kh * op.kw) throw std::runtime_error("onnx: depthwise weight holds the wrong number of elements");
@@ -726,6 +747,7 @@ struct Lowerer {
                     op.NP = round_up(op.Ns, 16);
                     // rows padded (with zeros) to a multiple of the 64-deep K chunk the kernel keeps in smem
                     const int kpad = round_up(op.K, 64);   // any chunk size in {16, 32, 64} divides it
+                    op.Kpad = kpad;
                     std::vector<float> whi((size_t)kpad * op.NP, 0.f), wlo((size_t)kpad * op.NP, 0.f);
                     for (int co = 0; co < op.N; co++)
                         for (int ci = 0; ci < C; ci++) {
@@ -846,7 +868,7 @@ std::string Plan::to_json() const {
            << ",\"kh\":" << o.kh << ",\"kw\":" << o.kw << ",\"sh\":" << o.sh << ",\"sw\":" << o.sw << ",\"pt\":" << o.pt
            << ",\"pl\":" << o.pl << ",\"K\":" << o.K << ",\"N\":" << o.N << ",\"Ns\":" << o.Ns
            << ",\"Nstore\":" << o.Nstore << ",\"w_off\":" << o.w_off << ",\"b_off\":" << o.b_off
-           << ",\"wtc_hi_off\":" << o.wtc_hi_off << ",\"wtc_lo_off\":" << o.wtc_lo_off << ",\"NP\":" << o.NP
+           << ",\"wtc_hi_off\":" << o.wtc_hi_off << ",\"wtc_lo_off\":" << o.wtc_lo_off << ",\"NP\":" << o.NP << ",\"Kpad\":" << o.Kpad
            << ",\"w2_off\":" << o.w2_off << ",\"b2_off\":" << o.b2_off << ",\"res\":" << o.res
            << ",\"res_pool\":" << o.res_pool << ",";
         json_act(os, "act_mid", o.act_mid);
