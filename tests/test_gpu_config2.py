@@ -142,7 +142,7 @@ def test_detector_and_estimator_timers(zb, sad_linus_full, sad_linus_cropped):
         s = str(t)
         names.append(s.split(":")[0])
         assert s.split(": ")[1].startswith("3x")
-        vals.append(float(s.split("x")[1][:-2]))
+        vals.append(float(s.split(": ")[1].split("x")[1][:-2]))
     assert names == ["infer", "extract", "nms"]
     assert vals[0] > 0.0 and vals[0] > vals[1] and vals[0] > vals[2]
     assert [str(t).split(": ")[1] for t in det.timers()] == ["0x0.0ms"] * 3

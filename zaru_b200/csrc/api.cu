@@ -131,6 +131,7 @@ struct zb_ctx {
     int tc_min_ctas = 500;               // ZB_TC_MIN_CTAS: stride-1 blocks (8x8x96 at batch 1024 = 512 CTAs: 0.23 vs 0.42 ms on the GEMM tile)
     int tcb_mode = 1;                    // ZB_TCB: 1 = tile-block kernel (TMA halo staging + tcgen05) for fused blocks with K >= tcb_min_k
     int tcb_min_k = 32;                  // ZB_TCB_MIN_K
+    int tcp_mode = 1;                    // ZB_TCP: persistent warp-specialised variant of the tile-block kernel
     int tcb_gemm_mode = 1;               // ZB_TCB_GEMM: tcgen05 GEMM kernel for plain convs (1x1, dense, 2x2 stride 2 ...)
     int tcb_gemm_min_m = 1;              // ZB_TCB_GEMM_MIN_M: smaller launches stay on the FFMA tile
     int tcb_over_thin = 0;               // ZB_TCB_OVER_THIN: also take the stride-2 blocks the SIMT thin kernel covers
@@ -354,6 +355,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     p.epi.bias = W + op.b2_off;
                     p.dw_w = W + op.w_off;
                     p.dw_b = W + op.b_off;
+                    p.dw_c = op.dwc_off >= 0 ? W + op.dwc_off : nullptr;
                     p.act_mid = act_dev(op.act_mid, W);
                     // kernel choice for fused blocks: tcgen05 (3xTF32) for the wide ones, SIMT thin/tile otherwise
                     // (measured: the tcgen05 kernel has the higher per-CTA latency, so it needs >= ~2 waves of CTAs)
@@ -367,7 +369,11 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                                          tcb_dwpw_supported(p, op.NP) && (!use_ttc || ctx->tcb_over_ttc) &&
                                          (!dwpw_thin_supported(p) || ctx->tcb_over_thin);
                     bool done = false;
-                    if (use_tcb)
+                    // persistent warp-specialised pipeline first; the one-tile-per-CTA kernel is its fallback
+                    if (use_tcb && ctx->tcp_mode > 0 && tcp_dwpw_supported(p, op.NP))
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "tcp<tcgen05+tma,persistent>", bytes, flops,
+                                    [&] { done = launch_tcp_dwpw(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
+                    if (!done && use_tcb)
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "tcb<tcgen05+tma>", bytes, flops,
                                     [&] { done = launch_tcb_dwpw(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, s); });
                     if (done) {
@@ -529,6 +535,7 @@ zb_status zb_ctx_create(int32_t device, zb_ctx **out) {
         if (const char *c = getenv("ZB_TCB")) ctx->tcb_mode = atoi(c);
         if (const char *c = getenv("ZB_TCB_MIN_K")) ctx->tcb_min_k = atoi(c);
         if (const char *c = getenv("ZB_TCB_OVER_THIN")) ctx->tcb_over_thin = atoi(c);
+        if (const char *c = getenv("ZB_TCP")) ctx->tcp_mode = atoi(c);
         if (const char *c = getenv("ZB_TCB_GEMM")) ctx->tcb_gemm_mode = atoi(c);
         if (const char *c = getenv("ZB_TCB_GEMM_MIN_M")) ctx->tcb_gemm_min_m = atoi(c);
         if (const char *c = getenv("ZB_TCB_OVER_TTC")) ctx->tcb_over_ttc = atoi(c);

@@ -63,6 +63,7 @@ struct ConvDev {
     // fused depthwise producer (OP_DWPW): `w`/K describe the pointwise stage
     const float *dw_w;         // [kh*kw][Cs_in]
     const float *dw_b;         // [Cs_in]
+    const float *dw_c;         // per 32-channel chunk: [chunks][kh*kw + 1][32] (weights, then bias), zero-padded; may be nullptr
     ActDev act_mid;
 };
 
@@ -101,6 +102,10 @@ bool launch_tcb_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int
 // plain convs as tcgen05 GEMMs: 1x1, dense / Gemm, non-overlapping windows; weights [N tile of 256][kpad / 4][NT][4] hi / lo
 bool tcb_gemm_supported(const ConvDev &p, int NP);
 bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, int kpad, cudaStream_t s);
+// kernels_tcp.cu: the same fused blocks as a PERSISTENT, WARP-SPECIALISED pipeline (TMA warp / depthwise warps / MMA thread /
+// epilogue warps, double-buffered TMEM accumulators)
+bool tcp_dwpw_supported(const ConvDev &p, int NP);
+bool launch_tcp_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
 bool launch_tc_mma_rate(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps, int ctas, long long *cycles_dev, cudaStream_t s);
 bool launch_tc_gemm_test(const float *A, const float *B, float *D, int N, int K, int nsplit, cudaStream_t s);
 

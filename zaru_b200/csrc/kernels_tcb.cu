@@ -38,6 +38,8 @@ constexpr int TCB_M = 128;            // UMMA M
 constexpr int TCB_CK = 32;            // channels per K chunk
 constexpr int TCB_KQC = TCB_CK / 4;   // channel quads per chunk
 constexpr int TCB_AROWS = TCB_M + 1;  // padded chunk stride of the A tile: conflict-free 128-bit stores
+// floats reserved for the A tile (hi + lo); the epilogue's staging tile (128 x TCE_STRIDE) aliases it once the MMAs are done
+constexpr int TCB_A_FLOATS = 2 * TCB_KQC * TCB_AROWS * 4 > TCB_M * TCE_STRIDE ? 2 * TCB_KQC * TCB_AROWS * 4 : TCB_M * TCE_STRIDE;
 
 struct TcbGeom {
     int TW, TH;            // tile = TH virtual rows x TW columns, TW * TH = 128
@@ -48,44 +50,41 @@ struct TcbGeom {
     int nin;               // input staging buffers (1 or 2)
 };
 
-__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
             smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int KS, int S>
-__global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant__ CUtensorMap tmap, const ConvDev p,
+// PPT = horizontally adjacent outputs per producer thread: 4 (256 threads, 2 CTAs per SM at <= 128 registers) or 2 (512 lighter
+// threads, 2 CTAs per SM at <= 64 registers: twice the warps to hide shared-memory and barrier latency behind)
+template <int KS, int S, int PPT>
+__global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_constant__ CUtensorMap tmap, const ConvDev p,
                                                           const float *__restrict__ w_hi, const float *__restrict__ w_lo, int NP,
                                                           int nchunks, const TcbGeom g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    constexpr int TAPS = KS * KS, SPAN = 3 * S + KS;
+    constexpr int TAPS = KS * KS, SPAN = (PPT - 1) * S + KS, NT = 1024 / PPT;
     const int in_floats = g.rows_max * g.WBOX * TCB_CK;                      // one staging buffer (multiple of 32 floats = 128 B)
     float *s_in0 = reinterpret_cast<float *>(smem_raw);                      // nin x [rows][WBOX][32]   (TMA destination)
     float *sA_hi = s_in0 + (size_t)g.nin * in_floats;                        // [8][129][4]
     float *sA_lo = sA_hi + TCB_KQC * TCB_AROWS * 4;
-    float *sB_hi = sA_lo + TCB_KQC * TCB_AROWS * 4;                          // [8][NP][4]               (bulk-copy destination)
+    float *sB_hi = sA_hi + TCB_A_FLOATS;                                     // [8][NP][4]               (bulk-copy destination)
     float *sB_lo = sB_hi + TCB_KQC * NP * 4;
     float *s_w0 = sB_lo + TCB_KQC * NP * 4;                                  // 2 x [(TAPS + 1)][32]: dw weights + bias of a chunk
     __shared__ __align__(8) uint64_t mbar_in[2], mbar_b, mbar_mma;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) int4 s_rowinfo[TCB_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
     const int vr0 = tile_y * g.TH, ox0 = tile_x * g.TW;
     const int n_vr = min(g.TH, g.vrows - vr0);                               // valid virtual rows of this tile (>= 1)
-    const int img0 = vr0 / p.Ho, oy0 = vr0 - img0 * p.Ho;
-    // staged row of virtual row r: srow(r) = S * r + (img(r) - img0) * (KS - S)   (pieces of consecutive images back to back)
-    const int last_img = (vr0 + n_vr - 1) / p.Ho;
-    const int rows_total = S * (n_vr - 1) + (last_img - img0) * (KS - S) + KS;
-    const int len0 = (min(p.Ho - oy0, n_vr) - 1) * S + KS;                   // staged rows of the first image piece
-    const int len_full = (p.Ho - 1) * S + KS;                                // ... of a whole image
     const uint32_t ncols = tmem_cols_for(NP);
     const uint32_t b_bytes = (uint32_t)TCB_KQC * NP * 16;
-    const uint32_t in_bytes = (uint32_t)rows_total * g.WBOX * TCB_CK * 4;
+    const uint32_t in_bytes = (uint32_t)in_floats * 4;
 
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) {
@@ -102,34 +101,30 @@ __global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    // stage the input rows of K chunk c into buffer `buf`: one TMA per staged row (box = 32 channels x WBOX columns)
+    // stage the halo of K chunk c into buffer `buf` with ONE tensor copy: the (image, row) dimensions of the activation are
+    // merged (images are contiguous, H == Ho * S), so a tile's input rows are one contiguous range even when it spans
+    // several images; rows that belong to a neighbouring image are masked in the window loop below.  (One copy per staged
+    // row - the first version - was bound by the TMA unit's per-instruction cost: ~20 small copies per chunk.)
     auto issue_in = [&](int c, int buf) {
-        if (lane == 0) mbar_expect_tx(&mbar_in[buf], in_bytes);
-        __syncwarp();
-        float *dst = s_in0 + (size_t)buf * in_floats;
-        for (int j = lane; j < rows_total; j += 32) {
-            int pimg, jj, oy_first;
-            if (j < len0) {
-                pimg = 0, jj = j, oy_first = oy0;
-            } else {
-                pimg = 1 + (j - len0) / len_full;
-                jj = (j - len0) - (pimg - 1) * len_full;
-                oy_first = 0;
-            }
-            const int iy = oy_first * S - p.pt + jj;
-            tma_load_4d(dst + (size_t)j * g.WBOX * TCB_CK, &tmap, c * TCB_CK, ox0 * S - p.pl, iy, img0 + pimg, &mbar_in[buf]);
+        if (lane == 0) {
+            mbar_expect_tx(&mbar_in[buf], in_bytes);
+            tma_load_3d(s_in0 + (size_t)buf * in_floats, &tmap, c * TCB_CK, ox0 * S - p.pl, vr0 * S - p.pt, &mbar_in[buf]);
         }
     };
     if (warp == 0) issue_in(0, 0);
 
-    // this thread's producer item: strip of 4 horizontally adjacent outputs x channel quad
+    // this thread's producer item: strip of PPT horizontally adjacent outputs x channel quad
     const int quad = tid & 7, strip = tid >> 3;
-    const int strips_x = g.TW >> 2;
-    const int pr = strip / strips_x, pcol = (strip - pr * strips_x) << 2;      // virtual row offset, first column of the strip
+    const int strips_x = g.TW / PPT;
+    const int pr = strip / strips_x, pcol = (strip - pr * strips_x) * PPT;     // virtual row offset, first column of the strip
     const int pm = pr * g.TW + pcol;                                          // tile row (MMA row) of the strip's first pixel
     const bool p_valid = pr < n_vr && ox0 + pcol < p.Wo;
-    const int p_img = (vr0 + pr) / p.Ho;
-    const int origin = (S * pr + (p_img - img0) * (KS - S)) * g.WBOX + pcol * S;   // staged pixel index of the window's corner
+    const int origin = S * pr * g.WBOX + pcol * S;                            // staged pixel index of the window's corner
+    const int p_vr = vr0 + pr;
+    const int p_iy0 = (p_vr - (p_vr / p.Ho) * p.Ho) * S - p.pt;              // input row of the window's first tap row
+    unsigned kymask = 0;                                                      // bit ky: that tap row lies inside the image
+#pragma unroll
+    for (int ky = 0; ky < KS; ky++) kymask |= (p_iy0 + ky >= 0 && p_iy0 + ky < p.H) ? (1u << ky) : 0u;
 
     const uint32_t idesc = make_idesc_tf32(TCB_M, NP);
     const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), TCB_AROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), TCB_AROWS * 16, 128);
@@ -154,9 +149,12 @@ __global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant_
         if (p_valid) {
             const float *s_in = s_in0 + (size_t)buf * in_floats + (size_t)origin * TCB_CK + quad * 4;
             const float4 bias = *reinterpret_cast<const float4 *>(s_w + TAPS * TCB_CK + quad * 4);
-            float4 v[4] = {bias, bias, bias, bias};
+            float4 v[PPT];
+#pragma unroll
+            for (int i = 0; i < PPT; i++) v[i] = bias;
 #pragma unroll
             for (int ky = 0; ky < KS; ky++) {
+                if (!((kymask >> ky) & 1u)) continue;
                 float4 x[SPAN];
                 const float *rowp = s_in + (size_t)ky * g.WBOX * TCB_CK;
 #pragma unroll
@@ -165,7 +163,7 @@ __global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant_
                 for (int kx = 0; kx < KS; kx++) {
                     const float4 wv = *reinterpret_cast<const float4 *>(s_w + (ky * KS + kx) * TCB_CK + quad * 4);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < PPT; i++) {
                         v[i].x = fmaf(x[i * S + kx].x, wv.x, v[i].x);
                         v[i].y = fmaf(x[i * S + kx].y, wv.y, v[i].y);
                         v[i].z = fmaf(x[i * S + kx].z, wv.z, v[i].z);
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant_
             }
             const int k = c * TCB_CK + quad * 4;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < PPT; i++) {
                 if (k < p.K) act4(v[i], p.act_mid, k);
                 float4 hi, lo;
                 split_tf32_fast(v[i].x, hi.x, lo.x);
@@ -218,32 +216,19 @@ __global__ void __launch_bounds__(256, 2) tcb_dwpw_kernel(const __grid_constant_
         tc_fence_after();
     }
 
-    // --- epilogue: warp w owns TMEM lanes 32 * (w % 4) .., columns [half * NP / 2, (half + 1) * NP / 2) ----------------
-    const int row = (warp & 3) * 32 + lane;
-    const int er = row / g.TW, ecol = row - er * g.TW;
-    const int evr = vr0 + er;
-    const int ox = ox0 + ecol;
-    const bool rowok = er < n_vr && ox < p.Wo;
-    int img = 0, oy = 0;
-    if (rowok) {
-        img = evr / p.Ho;
-        oy = evr - img * p.Ho;
+    // --- epilogue through shared memory (coalesced residual reads / stores); the staging tile aliases the input buffers ---
+    if (tid < TCB_M) {
+        const int er = tid / g.TW, ecol = tid - er * g.TW;
+        const int evr = vr0 + er, ox = ox0 + ecol;
+        int4 ri = make_int4(0, 0, 0, 0);
+        if (er < n_vr && ox < p.Wo) {
+            const int img = evr / p.Ho;
+            ri = make_int4(img, evr - img * p.Ho, ox, 1);
+        }
+        s_rowinfo[tid] = ri;
     }
-    float *orow = p.out + (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
-    const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0);
-    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int half = warp >> 2;
-    // column split in multiples of 16 so both halves can use the wide TMEM loads (NP is a multiple of 16)
-    const int csplit = ((NP / 16 + 1) / 2) * 16;
-    const int cbeg = half ? csplit : 0, cend = half ? NP : csplit;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float v[16];
-        ResidualPrefetch<16> pre;
-        if (rowok) tc_prefetch_residual<16>(p, c0, img, oy, ox, pre);
-        tmem_ld16(tbase + (uint32_t)c0, v);
-        if (rowok) tc_epilogue_cols<16>(p, v, c0, img, oy, ox, orow, vec_ok, pre);
-    }
+    __syncthreads();
+    tc_epilogue_tile<NT>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, ncols);
@@ -264,10 +249,11 @@ __global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const
     const int NT = min(256, NP - n0);                                        // output channels of this CTA (multiple of 16)
     float *sA_hi = reinterpret_cast<float *>(smem_raw);                      // [8][129][4]
     float *sA_lo = sA_hi + TCB_KQC * TCB_AROWS * 4;
-    float *sB_hi = sA_lo + TCB_KQC * TCB_AROWS * 4;                          // 2 x [8][NT][4]: double-buffered weight chunks
+    float *sB_hi = sA_hi + TCB_A_FLOATS;                                     // 2 x [8][NT][4]: double-buffered weight chunks
     float *sB_lo = sB_hi + 2 * TCB_KQC * NT * 4;
     __shared__ __align__(8) uint64_t mbar_b[2], mbar_mma;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) int4 s_rowinfo[TCB_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TCB_M;
@@ -378,32 +364,20 @@ __global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const
         tc_fence_after();
     }
 
-    // --- epilogue -------------------------------------------------------------------------------------------------
-    const int row = (warp & 3) * 32 + lane;
-    const int m = m0 + row;
-    const bool rowok = m < p.M;
-    int img = 0, oy = 0, ox = 0, r = 0;
-    if (rowok) {
-        img = m / HoWo;
-        r = m - img * HoWo;
-        oy = r / p.Wo;
-        ox = r - oy * p.Wo;
+    // --- epilogue through shared memory (the staging tile aliases the A tile) -----------------------------------------
+    if (tid < TCB_M) {
+        const int m = m0 + tid;
+        int4 ri = make_int4(0, 0, 0, 0);
+        if (m < p.M) {
+            const int img = m / HoWo;
+            const int r = m - img * HoWo;
+            const int oy = r / p.Wo;
+            ri = make_int4(img, oy, r - oy * p.Wo, 1);
+        }
+        s_rowinfo[tid] = ri;
     }
-    float *orow = p.out + (long long)img * p.out_img_stride + (long long)r * p.out_pix_stride;
-    const bool vec_ok = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int half = warp >> 2;
-    const int csplit = ((NT / 16 + 1) / 2) * 16;
-    const int cbeg = half ? csplit : 0, cend = half ? NT : csplit;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float v[16];
-        ResidualPrefetch<16> pre;
-        if (rowok) tc_prefetch_residual<16>(p, n0 + c0, img, oy, ox, pre);
-        tmem_ld16(tbase + (uint32_t)c0, v);
-        if (rowok) tc_epilogue_cols<16>(p, v, n0 + c0, img, oy, ox, orow, vec_ok, pre);
-    }
+    __syncthreads();
+    tc_epilogue_tile(p, tmem, n0, NT, s_rowinfo, sA_hi, tid);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, ncols);
@@ -429,15 +403,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// NHWC activation as a 4-D tensor (channel, x, y, image); box = 32 channels x WBOX columns x 1 row x 1 image; OOB -> 0.
-bool make_input_map(const ConvDev &p, int images, int WBOX, CUtensorMap *out) {
+// NHWC activation as a 3-D tensor (channel, x, image * H + y); box = 32 channels x WBOX columns x BR rows; OOB -> 0.
+bool make_input_map(const ConvDev &p, int images, int WBOX, int BR, CUtensorMap *out) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)p.Cs_in, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)images};
-    const cuuint64_t strides[3] = {(cuuint64_t)p.Cs_in * 4, (cuuint64_t)p.W * p.Cs_in * 4, (cuuint64_t)p.in_img_stride * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)TCB_CK, (cuuint32_t)WBOX, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(p.in), dims, strides, box, estr,
+    const cuuint64_t dims[3] = {(cuuint64_t)p.Cs_in, (cuuint64_t)p.W, (cuuint64_t)p.H * images};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.Cs_in * 4, (cuuint64_t)p.W * p.Cs_in * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)TCB_CK, (cuuint32_t)WBOX, (cuuint32_t)BR};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p.in), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -454,8 +428,7 @@ TcbGeom choose_geom(const ConvDev &p, int KS, int S) {
         const int tiles_x = (p.Wo + TW - 1) / TW;
         const int WBOX = (TW - 1) * S + KS;
         if (WBOX > 256) continue;
-        const double pieces = std::min<double>(TH, (double)TH / p.Ho + 1.0);
-        const double rows = (TH - pieces) * S + pieces * KS;
+        const double rows = (TH - 1) * S + KS;
         const double valid = (double)TH * p.Wo / tiles_x;
         const double cost = rows * WBOX / valid + 0.5 * TCB_M / valid;   // staged pixels per output + half-weighted MMA / producer waste
         if (cost < best_cost) {
@@ -465,17 +438,16 @@ TcbGeom choose_geom(const ConvDev &p, int KS, int S) {
     }
     best.vrows = images * p.Ho;
     best.tiles_y = (best.vrows + best.TH - 1) / best.TH;
-    const int pmax = std::min(best.TH, (best.TH + p.Ho - 1) / p.Ho + 1);
-    best.rows_max = (best.TH - pmax) * S + pmax * KS;
+    best.rows_max = (best.TH - 1) * S + KS;    // one contiguous row range per tile (merged image / row dimension)
     return best;
 }
 
 size_t tcb_smem(const TcbGeom &g, int KS, int NP, int nin) {
-    return (size_t)nin * g.rows_max * g.WBOX * TCB_CK * 4 + 2 * (size_t)TCB_KQC * TCB_AROWS * 16 + 2 * (size_t)TCB_KQC * NP * 16 +
+    return (size_t)nin * g.rows_max * g.WBOX * TCB_CK * 4 + (size_t)TCB_A_FLOATS * 4 + 2 * (size_t)TCB_KQC * NP * 16 +
            2 * (size_t)(KS * KS + 1) * TCB_CK * 4 + 1024;
 }
 
-template <int KS, int S>
+template <int KS, int S, int PPT>
 bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s) {
     TcbGeom g = choose_geom(p, KS, S);
     if (g.TW == 0) return false;
@@ -490,13 +462,13 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     g.nin = nin;
     const int images = p.M / (p.Ho * p.Wo);
     CUtensorMap tmap;
-    if (!make_input_map(p, images, g.WBOX, &tmap)) return false;
-    auto kern = tcb_dwpw_kernel<KS, S>;
+    if (!make_input_map(p, images, g.WBOX, g.rows_max, &tmap)) return false;
+    auto kern = tcb_dwpw_kernel<KS, S, PPT>;
     static SmemOptIn opt_in;
     if (!opt_in.ensure(kern, smem)) return false;
     const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
-    ZB_KNAME("tcb_dwpw_kernel", KS, S);
-    kern<<<(unsigned)(g.tiles_x * g.tiles_y), 256, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
+    ZB_KNAME("tcb_dwpw_kernel", KS, S, PPT);
+    kern<<<(unsigned)(g.tiles_x * g.tiles_y), 1024 / PPT, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
     return true;
 }
 
@@ -510,6 +482,7 @@ bool tcb_dwpw_supported(const ConvDev &p, int NP) {
     if (p.K != p.Cs_in || p.K % 8 || p.K < 8 || p.K > 1024 || NP % 16 || NP < 16 || NP > 256) return false;
     if (p.M % (p.Ho * p.Wo) || p.pt < 0 || p.pl < 0) return false;
     if (((uintptr_t)p.in) % 16 || (p.in_img_stride % 4)) return false;
+    if (p.in_img_stride != (long long)p.H * p.W * p.Cs_in || p.H != p.Ho * p.sh) return false;   // merged (image, row) staging
     return encode_fn() != nullptr;
 }
 
@@ -527,7 +500,7 @@ bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int
     if (!tcb_gemm_supported(p, NP)) return false;
     const int ntiles = (NP + 255) / 256;
     const int nt_max = std::min(NP, 256);
-    const size_t smem = 2 * (size_t)TCB_KQC * TCB_AROWS * 16 + 4 * (size_t)TCB_KQC * nt_max * 16 + 1024;
+    const size_t smem = (size_t)TCB_A_FLOATS * 4 + 4 * (size_t)TCB_KQC * nt_max * 16 + 1024;
     static SmemOptIn opt_in;
     if (!opt_in.ensure(tcb_gemm_kernel, smem)) return false;
     g_launch_count++;
@@ -541,8 +514,14 @@ bool launch_tcb_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int
     if (!tcb_dwpw_supported(p, NP)) return false;
     g_launch_count++;
     bool ok;
-    if (p.kh == 3) ok = p.sh == 1 ? launch_tcb_cfg<3, 1>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<3, 2>(p, w_hi, w_lo, NP, s);
-    else ok = p.sh == 1 ? launch_tcb_cfg<5, 1>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<5, 2>(p, w_hi, w_lo, NP, s);
+    static const int ppt = getenv("ZB_TCB_PPT") ? atoi(getenv("ZB_TCB_PPT")) : 4;
+    if (ppt == 2) {
+        if (p.kh == 3) ok = p.sh == 1 ? launch_tcb_cfg<3, 1, 2>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<3, 2, 2>(p, w_hi, w_lo, NP, s);
+        else ok = p.sh == 1 ? launch_tcb_cfg<5, 1, 2>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<5, 2, 2>(p, w_hi, w_lo, NP, s);
+    } else {
+        if (p.kh == 3) ok = p.sh == 1 ? launch_tcb_cfg<3, 1, 4>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<3, 2, 4>(p, w_hi, w_lo, NP, s);
+        else ok = p.sh == 1 ? launch_tcb_cfg<5, 1, 4>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<5, 2, 4>(p, w_hi, w_lo, NP, s);
+    }
     if (!ok) g_launch_count--;
     return ok;
 }

@@ -759,6 +759,16 @@ struct Lowerer {
                         }
                     op.wtc_hi_off = push_weights(whi);
                     op.wtc_lo_off = push_weights(wlo);
+                    {   // per-chunk depthwise weights for the persistent tile kernel: one TMA bulk copy per K chunk
+                        const int taps = op.kh * op.kw, nch = (Cs + 31) / 32;
+                        std::vector<float> dwc((size_t)nch * (taps + 1) * 32, 0.f);
+                        for (int c = 0; c < C; c++) {
+                            float *base = dwc.data() + (size_t)(c / 32) * (taps + 1) * 32 + (c % 32);
+                            for (int t = 0; t < taps; t++) base[(size_t)t * 32] = s.w->f[(size_t)c * taps + t];
+                            if (s.b) base[(size_t)taps * 32] = s.b->f[c];
+                        }
+                        op.dwc_off = push_weights(dwc);
+                    }
                     op.b2_off = pack_vec(s.b2, op.N, op.Ns, "bias");
                     if (op.act_mid.kind == ACT_PRELU) op.act_mid.slope_off = pack_vec(s.slope_mid, C, Cs, "slope");
                 }

@@ -57,6 +57,7 @@ struct Op {
     int64_t w_off = -1, b_off = -1;      // CONV / DW weights, bias
     int64_t w2_off = -1, b2_off = -1;    // DWPW: pointwise weights, bias
     int64_t wtc_hi_off = -1, wtc_lo_off = -1;   // DWPW: pointwise weights, TF32 hi/lo split, UMMA layout [K/4][NP][4]
+    int64_t dwc_off = -1;         // DWPW: depthwise weights + bias per 32-channel chunk: [Kpad32 / 32][kh * kw + 1][32], zero-padded
     int NP = 0;                   // DWPW / CONV: Cout padded to a multiple of 16 (UMMA N)
     int Kpad = 0;                 // rows of the tensor-core weight copy (K zero-padded); CONV: [N tile of 256][Kpad / 4][NT][4]
     ActSpec act_mid;              // DWPW: activation between dw and pw

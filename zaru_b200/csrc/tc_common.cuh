@@ -72,6 +72,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Make generic-proxy shared-memory writes visible to the async proxy (the tensor core reads smem through it).
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
