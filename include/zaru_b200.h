@@ -142,6 +142,15 @@ zb_status zb_view_to_image(zb_ctx *ctx, const zb_frames *frames, const zb_view *
  * memory belongs to the caller and is rejected).  rgba = {r, g, b, a}.                              */
 zb_status zb_frames_clear(zb_frames *frames, int32_t first, int32_t count, const uint8_t rgba[4]);
 
+/* `zaru_image::blend(&mut dest_view, &src_view)` (crates/zaru-image/src/blend.rs:13-32, :44-93) for n pairs of views: the
+ * source view is drawn over the destination view with LINEAR filtering (gpu.rs:191-205; sRGB texels filtered in linear
+ * light, ClampToEdge), source UVs outside [0,1] write Color::NONE (blend.wgsl:27-38), pixels are replaced.  As in the
+ * reference only the transformed top-left and bottom-right corners of each view are used (view.rs:81-104), so quad and UV
+ * rectangle are axis-aligned.  dst must be an UPLOADED batch.  What wgpu leaves to the GPU (fill rule at exact edges,
+ * weight precision) is fixed as the APIs specify it; the reference pins one result (`blend_to_partial_target`).      */
+zb_status zb_blend(zb_ctx *ctx, zb_frames *dst, const zb_view *dst_views, const zb_frames *src, const zb_view *src_views,
+                   int32_t n);
+
 /* ---- Cnn image->tensor (crates/zaru/src/nn/mod.rs:46-126, :146-167) ------------------------ */
 /* The `image_map` closure + `sample` + `ColorMapper::linear(lo..=hi)` for n views:
  * out = f32 [n,3,out_h,out_w] (ZB_NCHW) or [n,out_h,out_w,3] (ZB_NHWC); host_or_device.

@@ -499,3 +499,46 @@ def test_empty_and_degenerate_inputs(zb, sad_linus_full):
     # frame index out of range
     bad = (_ffi.zb_view * 1)(_ffi.zb_view(3, 10.0, 10.0, 5.0, 5.0, 0.0))
     assert lib.zb_preprocess(context(), batch._h, bad, 1, 8, 8, 0.0, 1.0, _ffi.ZB_NCHW, out.ctypes.data) == _ffi.ZB_ERR_INVALID_ARGUMENT
+
+
+# ------------------------------------------------------------------------------------------------
+# zaru_image::blend with linear filtering
+# ------------------------------------------------------------------------------------------------
+def test_blend_matches_oracle_and_reference_kat(zb, sad_linus_cropped):
+    """`zaru_image::blend` (zaru-image/src/blend.rs): the reference's own test (`blend_to_partial_target`, :157-178) on the
+    device, then scaling blits (up, down, fractional views, views reaching beyond the source, a 180-degree view = flipped
+    corners) against the oracle's restatement: equal up to one 8-bit step (f32 weights on both sides; the sRGB encode is
+    evaluated with the device's and the host's `pow`)."""
+    from oracle.blend import blend as oblend
+    from oracle.geometry import Rect as ORect, RotatedRect as ORR
+    from zaru_b200.image import Image, ImageBatch, blend
+    from zaru_b200.rect import Rect, RotatedRect, Resolution
+    source = np.empty((3, 3, 4), np.uint8)
+    source[:] = (0xAA, 0xBB, 0xCC, 0xDD)
+    tb = ImageBatch.from_rgba8(Resolution(2, 1), np.zeros((1, 1, 2, 4), np.uint8))
+    target = tb.frame(0)
+    blend(target.view(Rect.from_top_left(1.0, 0.0, 1.0, 1.0)), Image(source).view(Rect.from_top_left(1.0, 1.0, 1.0, 1.0)))
+    assert target.as_view().to_image()._pixels.reshape(-1).tolist() == [0, 0, 0, 0, 0xAA, 0xBB, 0xCC, 0xDD]
+    src = sad_linus_cropped
+    simg = Image(src)
+    cases = [  # (dest size, dest view (cx, cy, w, h, rad), source view)
+        ((90, 60), (45, 30, 90, 60, 0.0), (267.5, 267.5, 535, 535, 0.0)),                 # downscale of the whole image
+        ((128, 96), (64, 48, 100.5, 66.25, 0.0), (260, 250, 24, 16, 0.0)),                # upscale of a crop, fractional dest view
+        ((64, 64), (32, 32, 64, 64, 0.0), (500, 500, 200, 200, 0.0)),                     # source view reaches beyond the image
+        ((100, 50), (50, 25, 80, 40, np.pi), (267, 267, 300, 150, 0.0)),                  # 180-degree dest view: flipped corners
+        ((64, 64), (40, 20, 100, 90, 0.0), (100.25, 99.75, 64, 64, 0.0)),                 # dest view larger than the dest image
+    ]
+    worst = 0
+    for (dw, dh), dv, sv in cases:
+        base = np.full((dh, dw, 4), 77, np.uint8)
+        db = ImageBatch.from_rgba8(Resolution(dw, dh), base[None])
+        dimg = db.frame(0)
+        blend(dimg.view(RotatedRect(Rect.from_center(*dv[:4]), dv[4])), simg.view(RotatedRect(Rect.from_center(*sv[:4]), sv[4])))
+        got = dimg.as_view().to_image()._pixels
+        want = base.copy()
+        oblend(want, ORR(ORect.from_center(*dv[:4]), dv[4]), src, ORR(ORect.from_center(*sv[:4]), sv[4]))
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert (got != 77).any()
+        assert diff.max() <= 1, (dv, sv, int(diff.max()))
+        assert (diff > 0).mean() < 1e-3
+        worst = max(worst, int(diff.max()))

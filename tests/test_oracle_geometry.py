@@ -243,3 +243,31 @@ def test_sigmoid_threshold_edge():
     assert sigmoid(0.0) == f32(0.5)
     assert not (sigmoid(f32(-1e-8)) < f32(0.5))
     assert sigmoid(f32(-1e-3)) < f32(0.5)
+
+
+def test_blend_reference_kat_and_properties():
+    """Port of `blend_to_partial_target` (zaru-image/src/blend.rs:157-178) for the oracle's restatement of blend, plus the
+    properties any linear-filter blit has: an identity blit copies, a constant source stays constant under scaling, and
+    source UVs outside the image write Color::NONE."""
+    from oracle.blend import blend, srgb_decode_lut, srgb_encode
+    from oracle.geometry import Rect, RotatedRect
+    assert np.array_equal(srgb_encode(srgb_decode_lut()), np.arange(256, dtype=np.uint8))      # decode/encode round trip
+    source = np.empty((3, 3, 4), np.uint8)
+    source[:] = (0xAA, 0xBB, 0xCC, 0xDD)
+    target = np.zeros((1, 2, 4), np.uint8)
+    blend(target, RotatedRect(Rect.from_top_left(1.0, 0.0, 1.0, 1.0), 0.0), source, RotatedRect(Rect.from_top_left(1.0, 1.0, 1.0, 1.0), 0.0))
+    assert target.reshape(-1).tolist() == [0x00, 0x00, 0x00, 0x00, 0xAA, 0xBB, 0xCC, 0xDD]
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, 256, (6, 7, 4), dtype=np.uint8)
+    dst = np.zeros((6, 7, 4), np.uint8)
+    full = RotatedRect(Rect.from_top_left(0.0, 0.0, 7.0, 6.0), 0.0)
+    blend(dst, full, src, full)
+    assert np.array_equal(dst, src)                                                           # texel centres hit exactly
+    big = np.zeros((12, 14, 4), np.uint8)
+    const = np.empty((6, 7, 4), np.uint8)
+    const[:] = (10, 200, 33, 128)
+    blend(big, RotatedRect(Rect.from_top_left(0.0, 0.0, 14.0, 12.0), 0.0), const, full)
+    assert (big == np.array([10, 200, 33, 128], np.uint8)).all()
+    out = np.full((4, 4, 4), 9, np.uint8)
+    blend(out, RotatedRect(Rect.from_top_left(0.0, 0.0, 4.0, 4.0), 0.0), src, RotatedRect(Rect.from_top_left(5.0, 0.0, 4.0, 4.0), 0.0))
+    assert (out[:, 2:] == 0).all() and (out[:, :2] != 9).any()       # right half samples beyond the 7-wide source: NONE

@@ -87,6 +87,7 @@ SIGNATURES = {
     "zb_estimator_set_filter": (i32, [P, i32, f32, f32, f32, f32]),
     "zb_tracker_set_filter": (i32, [P, i32, f32, f32, f32, f32]),
     "zb_filter_apply": (i32, [P, i32, f32, f32, f32, f32, P, P, i64]),
+    "zb_blend": (i32, [P, P, P, P, P, i32]),
     "zb_view_to_image": (i32, [P, P, P, i32, i32, i32, P]),
     "zb_frames_clear": (i32, [P, i32, i32, P]),
     "zb_hand_pipeline_create": (i32, [P, P, P, PP]),

@@ -131,7 +131,8 @@ struct zb_ctx {
     int tc_min_ctas = 500;               // ZB_TC_MIN_CTAS: stride-1 blocks (8x8x96 at batch 1024 = 512 CTAs: 0.23 vs 0.42 ms on the GEMM tile)
     int tcb_mode = 1;                    // ZB_TCB: 1 = tile-block kernel (TMA halo staging + tcgen05) for fused blocks with K >= tcb_min_k
     int tcb_min_k = 32;                  // ZB_TCB_MIN_K
-    int tcp_mode = 1;                    // ZB_TCP: persistent warp-specialised variant of the tile-block kernel
+    int tcp_mode = 0;                    // ZB_TCP=1: warp-specialised variant of the tile-block kernel (measured slower: 8 depthwise warps per SM
+                                         // against 16-32 in the default kernel; kept for the A/B, profiles/README.md)
     int tcb_gemm_mode = 1;               // ZB_TCB_GEMM: tcgen05 GEMM kernel for plain convs (1x1, dense, 2x2 stride 2 ...)
     int tcb_gemm_min_m = 1;              // ZB_TCB_GEMM_MIN_M: smaller launches stay on the FFMA tile
     int tcb_over_thin = 0;               // ZB_TCB_OVER_THIN: also take the stride-2 blocks the SIMT thin kernel covers
@@ -959,6 +960,55 @@ zb_status zb_frames_clear(zb_frames *frames, int32_t first, int32_t count, const
                             frames->f.height, first, count, c, ctx->stream);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(ctx->stream));
+        return ZB_OK;
+    });
+}
+
+// `zaru_image::blend(&mut dest_view, &src_view)` for n (destination view, source view) pairs.
+zb_status zb_blend(zb_ctx *ctx, zb_frames *dst, const zb_view *dst_views, const zb_frames *src, const zb_view *src_views, int32_t n) {
+    return guarded([&]() -> zb_status {
+        if (!ctx || !dst || !src || (!dst_views && n) || (!src_views && n)) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx/frames/views is NULL");
+        if (!dst->owned) return fail(ZB_ERR_INVALID_ARGUMENT, "aliased frames belong to the caller and cannot be blended onto");
+        check_frames(dst, dst_views, n);
+        check_frames(src, src_views, n);
+        if (n == 0) return ZB_OK;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        static float lut[256];
+        static std::once_flag lut_once;
+        std::call_once(lut_once, [] {
+            for (int i = 0; i < 256; i++) {
+                const double c = i / 255.0;
+                lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+            }
+        });
+        std::vector<BlendJobHost> jobs(n);
+        int max_w = 1, max_h = 1;
+        for (int i = 0; i < n; i++) {
+            const RRectF d = rrect_from_view(dst_views[i]), sv = rrect_from_view(src_views[i]);
+            BlendJobHost &j = jobs[i];
+            j.dframe = dst_views[i].frame, j.sframe = src_views[i].frame;
+            transform_out(d, 0.0f, 0.0f, j.dx0, j.dy0);          // view.rs:94-104: only these two corners are used
+            transform_out(d, d.r.w, d.r.h, j.dx1, j.dy1);
+            transform_out(sv, 0.0f, 0.0f, j.sx0, j.sy0);
+            transform_out(sv, sv.r.w, sv.r.h, j.sx1, j.sy1);
+            const float xlo = std::min(j.dx0, j.dx1), xhi = std::max(j.dx0, j.dx1), ylo = std::min(j.dy0, j.dy1), yhi = std::max(j.dy0, j.dy1);
+            if (!(xhi > xlo) || !(yhi > ylo)) {                   // degenerate quad (or NaN): nothing is rasterised
+                j.bx = j.by = 0, j.bw = j.bh = 0;
+                continue;
+            }
+            const long long bx0 = std::max<long long>(0, (long long)floorf(xlo) - 1), by0 = std::max<long long>(0, (long long)floorf(ylo) - 1);
+            const long long bx1 = std::min<long long>(dst->f.width, (long long)ceilf(xhi) + 1), by1 = std::min<long long>(dst->f.height, (long long)ceilf(yhi) + 1);
+            j.bx = (int)bx0, j.by = (int)by0;
+            j.bw = (int)std::max<long long>(0, bx1 - bx0), j.bh = (int)std::max<long long>(0, by1 - by0);
+            max_w = std::max(max_w, j.bw), max_h = std::max(max_h, j.bh);
+        }
+        DevBuf dj;
+        dj.reserve(sizeof(BlendJobHost) * n);
+        CU(cudaMemcpyAsync(dj.p, jobs.data(), sizeof(BlendJobHost) * n, cudaMemcpyHostToDevice, s));
+        launch_blend(dst->f, src->f, dj.p, n, max_w, max_h, lut, s);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
         return ZB_OK;
     });
 }

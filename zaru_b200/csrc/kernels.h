@@ -144,6 +144,15 @@ void launch_gather_texels(const FramesDev &f, const ViewDev *views, int n, int o
 
 // ImageView::to_image (image/mod.rs:314-325): view pixel (x, y) -> RGBA8 [n][out_h][out_w][4]; Color::NONE outside.
 void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint8_t *out, cudaStream_t s);
+// zaru_image::blend (zaru-image/src/blend.rs): n jobs {dframe, sframe, dest corners, source corners, dest pixel box} (BlendJobHost
+// layout), linear filtering in linear light; see blend_kernel
+struct BlendJobHost {
+    int dframe, sframe;
+    float dx0, dy0, dx1, dy1, sx0, sy0, sx1, sy1;
+    int bx, by, bw, bh;
+};
+void launch_blend(const FramesDev &dst, const FramesDev &src, const void *jobs_dev, int n, int max_w, int max_h, const float *lut_host,
+                  cudaStream_t s);
 // Image::clear (image/mod.rs:171-173) for frames [first, first + count)
 void launch_frames_clear(uint8_t *base, long long frame_stride, long long row_stride, int width, int height, int first,
                          int count, unsigned rgba, cudaStream_t s);

@@ -1097,6 +1097,71 @@ __global__ void tracker_set_roi_kernel(TrackState *__restrict__ state, const int
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// zaru_image::blend(&mut dest_view, &src_view)  (zaru-image/src/blend.rs:13-32, :44-93; view.rs:81-119; blend.wgsl:27-38;
+// gpu.rs:191-205): the destination quad and the source UV rectangle are axis-aligned between the transformed top-left and
+// bottom-right corners of the two views; linear filtering (ClampToEdge) in linear light on sRGB texels, UV outside [0,1]
+// -> Color::NONE, replace (no real blending).  One thread per destination pixel of the quad's bounding box.
+// Rules the wgpu backend leaves to the GPU are fixed as the APIs specify them (oracle/blend.py): pixel centres at +0.5,
+// top-left fill rule, exact f32 weights, sRGB transfer in f64.
+// ------------------------------------------------------------------------------------------------
+struct BlendJob {
+    int dframe, sframe;
+    float dx0, dy0, dx1, dy1;      // destination: transformed (0,0) and (w,h) of the destination view
+    float sx0, sy0, sx1, sy1;      // source: the same for the source view
+    int bx, by, bw, bh;            // destination pixel box to visit
+};
+
+__constant__ float c_srgb_lut[256];
+
+__device__ __forceinline__ unsigned char srgb_encode_ref(float lin) {
+    double x = fmin(fmax((double)lin, 0.0), 1.0);
+    const double sv = x <= 0.0031308 ? x * 12.92 : 1.055 * pow(x, 1.0 / 2.4) - 0.055;
+    return (unsigned char)floor(sv * 255.0 + 0.5);
+}
+
+__global__ void __launch_bounds__(256) blend_kernel(const FramesDev dst, const FramesDev src, const BlendJob *__restrict__ jobs) {
+    const BlendJob j = jobs[blockIdx.z];
+    const int x = j.bx + blockIdx.x * 32 + (threadIdx.x & 31), y = j.by + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= j.bx + j.bw || y >= j.by + j.bh || x < 0 || y < 0 || x >= dst.width || y >= dst.height) return;
+    const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
+    const float xlo = fminf(j.dx0, j.dx1), xhi = fmaxf(j.dx0, j.dx1), ylo = fminf(j.dy0, j.dy1), yhi = fmaxf(j.dy0, j.dy1);
+    if (!(xlo <= cx && cx < xhi && ylo <= cy && cy < yhi)) return;
+    const float tx = (cx - j.dx0) / (j.dx1 - j.dx0), ty = (cy - j.dy0) / (j.dy1 - j.dy0);
+    const float px = j.sx0 + tx * (j.sx1 - j.sx0), py = j.sy0 + ty * (j.sy1 - j.sy0);
+    const float u = px / (float)src.width, v = py / (float)src.height;
+    unsigned char *out = const_cast<unsigned char *>(dst.base) + (long long)j.dframe * dst.frame_stride + (long long)y * dst.row_stride + 4ll * x;
+    if (u > 1.0f || v > 1.0f || u < 0.0f || v < 0.0f) {
+        *reinterpret_cast<unsigned *>(out) = 0u;
+        return;
+    }
+    const float fx = px - 0.5f, fy = py - 0.5f;
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    const float wx = fx - x0f, wy = fy - y0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int xa = min(max(x0, 0), src.width - 1), xb = min(max(x0 + 1, 0), src.width - 1);
+    const int ya = min(max(y0, 0), src.height - 1), yb = min(max(y0 + 1, 0), src.height - 1);
+    const unsigned char *sb = src.base + (long long)j.sframe * src.frame_stride;
+    const unsigned t00 = *reinterpret_cast<const unsigned *>(sb + (long long)ya * src.row_stride + 4ll * xa);
+    const unsigned t01 = *reinterpret_cast<const unsigned *>(sb + (long long)ya * src.row_stride + 4ll * xb);
+    const unsigned t10 = *reinterpret_cast<const unsigned *>(sb + (long long)yb * src.row_stride + 4ll * xa);
+    const unsigned t11 = *reinterpret_cast<const unsigned *>(sb + (long long)yb * src.row_stride + 4ll * xb);
+    unsigned res = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned a = (t00 >> (8 * c)) & 255u, b = (t01 >> (8 * c)) & 255u, d = (t10 >> (8 * c)) & 255u, e = (t11 >> (8 * c)) & 255u;
+        const float fa = c < 3 ? c_srgb_lut[a] : (float)a / 255.0f, fb = c < 3 ? c_srgb_lut[b] : (float)b / 255.0f;
+        const float fd = c < 3 ? c_srgb_lut[d] : (float)d / 255.0f, fe = c < 3 ? c_srgb_lut[e] : (float)e / 255.0f;
+        const float top = fa + wx * (fb - fa), bot = fd + wx * (fe - fd);
+        const float val = top + wy * (bot - top);
+        unsigned q;
+        if (c < 3) q = srgb_encode_ref(val);
+        else q = (unsigned)floor(fmin(fmax((double)val, 0.0), 1.0) * 255.0 + 0.5);
+        res |= q << (8 * c);
+    }
+    *reinterpret_cast<unsigned *>(out) = res;
+}
+
 void launch_gather_texels(const FramesDev &f, const ViewDev *views, int n, int out_w, int out_h, uint32_t *out, int max_ctas,
                           cudaStream_t s) {
     g_launch_count++;
@@ -1111,6 +1176,20 @@ void launch_view_to_image(const FramesDev &f, const ViewDev *views, int n, int o
     g_launch_count++;
     ZB_KNAME("view_to_image_kernel");
     view_to_image_kernel<<<dim3((out_w + 127) / 128, out_h, n), 128, 0, s>>>(f, views, out_w, out_h, reinterpret_cast<unsigned *>(out));
+}
+
+void launch_blend(const FramesDev &dst, const FramesDev &src, const void *jobs_dev, int n, int max_w, int max_h, const float *lut_host,
+                  cudaStream_t s) {
+    g_launch_count++;
+    static std::atomic<bool> lut_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!lut_set[dev & 63].load()) {       // sRGB decode table (computed once on the host in f64, like the oracle)
+        cudaMemcpyToSymbol(c_srgb_lut, lut_host, 256 * sizeof(float));
+        lut_set[dev & 63].store(true);
+    }
+    ZB_KNAME("blend_kernel");
+    blend_kernel<<<dim3((max_w + 31) / 32, (max_h + 7) / 8, n), 256, 0, s>>>(dst, src, reinterpret_cast<const BlendJob *>(jobs_dev));
 }
 
 void launch_frames_clear(uint8_t *base, long long frame_stride, long long row_stride, int width, int height, int first,

@@ -1,10 +1,11 @@
 // sm_100a "tile block" kernels: fused depthwise KSxKS (3x3 / 5x5, stride 1 / 2) -> pointwise blocks of ANY map size and
 // channel count (K = Cs_in up to 1024, N up to 256) with
-//   * the input halo staged in shared memory by TMA TENSOR copies (cp.async.bulk.tensor.4d through a CUtensorMap over
-//     the NHWC activation: box = 32 channels x tile width + halo x 1 row, out-of-image rows / columns / channels are
-//     zero-filled by the hardware, completion counted on an mbarrier; SASS: UTMALDG) - every input element is read from
-//     L2 / HBM once per CTA instead of up to KS*KS times by per-thread window loads, and the next 32-channel chunk
-//     streams in while the current one is being convolved;
+//   * the input halo staged in shared memory by ONE TMA TENSOR copy per 32-channel chunk (cp.async.bulk.tensor.3d through
+//     a CUtensorMap over the NHWC activation with the image and row dimensions merged: box = 32 channels x tile width +
+//     halo x tile rows + halo; columns / channels outside the tensor are zero-filled by the hardware, completion counted on
+//     an mbarrier together with the chunk's depthwise weights; SASS: UTMALDG) - every input element is read from L2 / HBM
+//     once per CTA instead of up to KS*KS times by per-thread window loads, and the next chunk (of this tile or of the
+//     CTA's next tile) streams in while the current one is being convolved;
 //   * the depthwise stage on the CUDA cores as a sliding window (4 horizontally adjacent outputs x one channel quad per
 //     thread, weights of the chunk in shared memory), written straight into the UMMA K-major operand tile as TF32
 //     hi / lo parts;
@@ -12,9 +13,10 @@
 //     streamed per K chunk by TMA bulk copy;
 //   * the fused epilogue (bias -> act -> residual [channel-pad, 2x2 max-pool] -> act) from TMEM.
 //
-// One CTA = one tile of 128 output pixels = TH "virtual rows" x TW columns, where the virtual rows run over
-// (image, output row) in order: on small maps (12x12, 6x6, 3x3 ...) a tile spans several images, so the M = 128 MMA
-// rows stay full whatever the map size.  Replaces both the global-window tcgen05 kernel (dwpw_tc_kernel) and the FFMA
+// A tile = 128 output pixels = TH "virtual rows" x TW columns, where the virtual rows run over (image, output row) in
+// order: on small maps (12x12, 6x6, 3x3 ...) a tile spans several images, so the M = 128 MMA rows stay full whatever the
+// map size.  CTAs are PERSISTENT (two per SM, striding over the tiles): TMEM, barriers and - when they fit - the pointwise
+// weights are set up once per CTA.  Replaces both the global-window tcgen05 kernel (dwpw_tc_kernel) and the FFMA
 // implicit-GEMM tile (conv_gemm_kernel<.., CONV_DWPW, ..>) for these blocks.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -48,6 +50,7 @@ struct TcbGeom {
     int WBOX;              // staged input columns per row = (TW - 1) * S + KS
     int rows_max;          // worst-case staged input rows of one tile
     int nin;               // input staging buffers (1 or 2)
+    int nbw;               // pointwise-weight buffers (1 or 2)
 };
 
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar) {
@@ -67,168 +70,185 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
                                                           int nchunks, const TcbGeom g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int TAPS = KS * KS, SPAN = (PPT - 1) * S + KS, NT = 1024 / PPT;
-    const int in_floats = g.rows_max * g.WBOX * TCB_CK;                      // one staging buffer (multiple of 32 floats = 128 B)
-    float *s_in0 = reinterpret_cast<float *>(smem_raw);                      // nin x [rows][WBOX][32]   (TMA destination)
+    const int halo_floats = g.rows_max * g.WBOX * TCB_CK;                    // staged halo of one chunk (multiple of 32 floats = 128 B)
+    const int in_floats = halo_floats + (TAPS + 1) * TCB_CK;                 // ... followed by the chunk's depthwise weights + bias
+    float *s_in0 = reinterpret_cast<float *>(smem_raw);                      // nin x {[rows][WBOX][32], [TAPS + 1][32]}   (TMA destinations)
     float *sA_hi = s_in0 + (size_t)g.nin * in_floats;                        // [8][129][4]
     float *sA_lo = sA_hi + TCB_KQC * TCB_AROWS * 4;
-    float *sB_hi = sA_hi + TCB_A_FLOATS;                                     // [8][NP][4]               (bulk-copy destination)
-    float *sB_lo = sB_hi + TCB_KQC * NP * 4;
-    float *s_w0 = sB_lo + TCB_KQC * NP * 4;                                  // 2 x [(TAPS + 1)][32]: dw weights + bias of a chunk
-    __shared__ __align__(8) uint64_t mbar_in[2], mbar_b, mbar_mma;
+    float *sB0 = sA_hi + TCB_A_FLOATS;                                       // nbw x {hi [8][NP][4], lo [8][NP][4]}   (bulk-copy destinations)
+    const int b_floats = 2 * TCB_KQC * NP * 4;
+    __shared__ __align__(8) uint64_t mbar_in[2], mbar_b[2], mbar_mma;
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) int4 s_rowinfo[TCB_M];
+    __shared__ __align__(16) TceRow s_rowinfo[TCB_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile_x = blockIdx.x % g.tiles_x, tile_y = blockIdx.x / g.tiles_x;
-    const int vr0 = tile_y * g.TH, ox0 = tile_x * g.TW;
-    const int n_vr = min(g.TH, g.vrows - vr0);                               // valid virtual rows of this tile (>= 1)
     const uint32_t ncols = tmem_cols_for(NP);
     const uint32_t b_bytes = (uint32_t)TCB_KQC * NP * 16;
-    const uint32_t in_bytes = (uint32_t)in_floats * 4;
+    const uint32_t in_bytes = (uint32_t)in_floats * 4;                        // halo box + depthwise weights: one mbarrier phase
+    // PERSISTENT: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a "step" is one (tile, K chunk) pair and the
+    // input / weight rings run across tile boundaries, so the next tile's first halo is in flight during this tile's
+    // epilogue, TMEM and the barriers are set up once, and layers whose weight chunks all fit in the weight buffers
+    // (K <= 32 * nbw) fetch them once per CTA instead of once per tile.
+    const int total_tiles = g.tiles_x * g.tiles_y;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_steps = my_tiles * nchunks;
+    const bool b_resident = nchunks <= g.nbw;
 
+    // pointwise weights of step s (chunk s % nchunks) -> weight buffer s % nbw
+    auto load_b = [&](int s) {
+        const int b = s % g.nbw, c = s % nchunks;
+        float *dst = sB0 + (size_t)b * b_floats;
+        mbar_expect_tx(&mbar_b[b], 2 * b_bytes);
+        bulk_copy_g2s(dst, w_hi + (size_t)c * TCB_KQC * NP * 4, b_bytes, &mbar_b[b]);
+        bulk_copy_g2s(dst + TCB_KQC * NP * 4, w_lo + (size_t)c * TCB_KQC * NP * 4, b_bytes, &mbar_b[b]);
+    };
+    // stage the halo of step s into input buffer s % nin with ONE tensor copy: the (image, row) dimensions of the activation
+    // are merged (images are contiguous, H == Ho * S), so a tile's input rows are one contiguous range even when it spans
+    // several images; rows that belong to a neighbouring image are masked in the window loop below.  (One copy per staged
+    // row - the first version - paid the TMA unit's per-instruction cost ~20 times per chunk.)
+    auto issue_in = [&](int s) {
+        if (lane == 0 && s < total_steps) {
+            const int tile = (int)blockIdx.x + (s / nchunks) * (int)gridDim.x, c = s % nchunks;
+            const int tx = tile % g.tiles_x, ty = tile / g.tiles_x;
+            float *dst = s_in0 + (size_t)(s % g.nin) * in_floats;
+            uint64_t *bar = &mbar_in[s % g.nin];
+            mbar_expect_tx(bar, in_bytes);
+            tma_load_3d(dst, &tmap, c * TCB_CK, tx * g.TW * S - p.pl, ty * g.TH * S - p.pt, bar);
+            // the chunk's depthwise weights + bias, pre-packed per chunk (zero beyond the true channel count), ride along
+            bulk_copy_g2s(dst + halo_floats, p.dw_c + (size_t)c * (TAPS + 1) * TCB_CK, (uint32_t)(TAPS + 1) * TCB_CK * 4, bar);
+        }
+    };
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) {
         mbar_init(&mbar_in[0], 1);
         mbar_init(&mbar_in[1], 1);
-        mbar_init(&mbar_b, 1);
+        mbar_init(&mbar_b[0], 1);
+        mbar_init(&mbar_b[1], 1);
         mbar_init(&mbar_mma, 1);
-        mbar_expect_tx(&mbar_b, 2 * b_bytes);
-        bulk_copy_g2s(sB_hi, w_hi, b_bytes, &mbar_b);
-        bulk_copy_g2s(sB_lo, w_lo, b_bytes, &mbar_b);
+        for (int s0 = 0; s0 < g.nbw && s0 < total_steps; s0++) load_b(s0);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-
-    // stage the halo of K chunk c into buffer `buf` with ONE tensor copy: the (image, row) dimensions of the activation are
-    // merged (images are contiguous, H == Ho * S), so a tile's input rows are one contiguous range even when it spans
-    // several images; rows that belong to a neighbouring image are masked in the window loop below.  (One copy per staged
-    // row - the first version - was bound by the TMA unit's per-instruction cost: ~20 small copies per chunk.)
-    auto issue_in = [&](int c, int buf) {
-        if (lane == 0) {
-            mbar_expect_tx(&mbar_in[buf], in_bytes);
-            tma_load_3d(s_in0 + (size_t)buf * in_floats, &tmap, c * TCB_CK, ox0 * S - p.pl, vr0 * S - p.pt, &mbar_in[buf]);
-        }
-    };
-    if (warp == 0) issue_in(0, 0);
+    if (warp == 0) issue_in(0);
 
     // this thread's producer item: strip of PPT horizontally adjacent outputs x channel quad
     const int quad = tid & 7, strip = tid >> 3;
     const int strips_x = g.TW / PPT;
     const int pr = strip / strips_x, pcol = (strip - pr * strips_x) * PPT;     // virtual row offset, first column of the strip
     const int pm = pr * g.TW + pcol;                                          // tile row (MMA row) of the strip's first pixel
-    const bool p_valid = pr < n_vr && ox0 + pcol < p.Wo;
     const int origin = S * pr * g.WBOX + pcol * S;                            // staged pixel index of the window's corner
-    const int p_vr = vr0 + pr;
-    const int p_iy0 = (p_vr - (p_vr / p.Ho) * p.Ho) * S - p.pt;              // input row of the window's first tap row
-    unsigned kymask = 0;                                                      // bit ky: that tap row lies inside the image
-#pragma unroll
-    for (int ky = 0; ky < KS; ky++) kymask |= (p_iy0 + ky >= 0 && p_iy0 + ky < p.H) ? (1u << ky) : 0u;
-
     const uint32_t idesc = make_idesc_tf32(TCB_M, NP);
     const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), TCB_AROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), TCB_AROWS * 16, 128);
-    const uint64_t bd_hi = make_smem_desc(smem_u32(sB_hi), (uint32_t)NP * 16, 128), bd_lo = make_smem_desc(smem_u32(sB_lo), (uint32_t)NP * 16, 128);
-    uint32_t acc_flag = 0;
 
-    for (int c = 0; c < nchunks; c++) {
-        const int buf = g.nin == 2 ? (c & 1) : 0;
-        // depthwise weights + bias of this chunk (zero beyond the true channel count: padded channels contribute nothing)
-        float *s_w = s_w0 + (c & 1) * ((TAPS + 1) * TCB_CK);
-        if (tid < (TAPS + 1) * TCB_KQC) {
-            const int t = tid >> 3, q = tid & 7;
-            const int k = c * TCB_CK + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < p.K) v = ldg4((t < TAPS ? p.dw_w + (size_t)t * p.Cs_in : p.dw_b) + k);
-            *reinterpret_cast<float4 *>(s_w + t * TCB_CK + q * 4) = v;
-        }
-        mbar_wait(&mbar_in[buf], g.nin == 2 ? ((c >> 1) & 1) : (c & 1));       // the chunk's input rows have landed
-        __syncthreads();                                                      // ... and its depthwise weights are in place
-        if (g.nin == 2 && warp == 0 && c + 1 < nchunks) issue_in(c + 1, buf ^ 1);   // next chunk streams in behind this one
+    int step = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tile_x = tile % g.tiles_x, tile_y = tile / g.tiles_x;
+        const int vr0 = tile_y * g.TH, ox0 = tile_x * g.TW;
+        const int n_vr = min(g.TH, g.vrows - vr0);                           // valid virtual rows of this tile (>= 1)
+        const bool p_valid = pr < n_vr && ox0 + pcol < p.Wo;
+        const int p_vr = vr0 + pr;
+        const int p_iy0 = (p_vr - (p_vr / p.Ho) * p.Ho) * S - p.pt;          // input row of the window's first tap row
+        unsigned kymask = 0;                                                  // bit ky: that tap row lies inside the image
+#pragma unroll
+        for (int ky = 0; ky < KS; ky++) kymask |= (p_iy0 + ky >= 0 && p_iy0 + ky < p.H) ? (1u << ky) : 0u;
+        uint32_t acc_flag = 0;
 
-        if (p_valid) {
-            const float *s_in = s_in0 + (size_t)buf * in_floats + (size_t)origin * TCB_CK + quad * 4;
-            const float4 bias = *reinterpret_cast<const float4 *>(s_w + TAPS * TCB_CK + quad * 4);
-            float4 v[PPT];
+        for (int c = 0; c < nchunks; c++, step++) {
+            const int buf = step % g.nin;
+            mbar_wait(&mbar_in[buf], (step / g.nin) & 1);                     // this step's halo + depthwise weights have landed
+            __syncthreads();                                                  // (everybody is past the previous step's MMAs / epilogue)
+            if (g.nin == 2 && warp == 0) issue_in(step + 1);                  // next step streams in behind this one
+
+            if (p_valid) {
+                const float *s_w = s_in0 + (size_t)buf * in_floats + halo_floats;
+                const float *s_in = s_in0 + (size_t)buf * in_floats + (size_t)origin * TCB_CK + quad * 4;
+                const float4 bias = *reinterpret_cast<const float4 *>(s_w + TAPS * TCB_CK + quad * 4);
+                float4 v[PPT];
 #pragma unroll
-            for (int i = 0; i < PPT; i++) v[i] = bias;
+                for (int i = 0; i < PPT; i++) v[i] = bias;
 #pragma unroll
-            for (int ky = 0; ky < KS; ky++) {
-                if (!((kymask >> ky) & 1u)) continue;
-                float4 x[SPAN];
-                const float *rowp = s_in + (size_t)ky * g.WBOX * TCB_CK;
+                for (int ky = 0; ky < KS; ky++) {
+                    if (!((kymask >> ky) & 1u)) continue;
+                    float4 x[SPAN];
+                    const float *rowp = s_in + (size_t)ky * g.WBOX * TCB_CK;
 #pragma unroll
-                for (int j = 0; j < SPAN; j++) x[j] = *reinterpret_cast<const float4 *>(rowp + j * TCB_CK);
+                    for (int j = 0; j < SPAN; j++) x[j] = *reinterpret_cast<const float4 *>(rowp + j * TCB_CK);
 #pragma unroll
-                for (int kx = 0; kx < KS; kx++) {
-                    const float4 wv = *reinterpret_cast<const float4 *>(s_w + (ky * KS + kx) * TCB_CK + quad * 4);
+                    for (int kx = 0; kx < KS; kx++) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(s_w + (ky * KS + kx) * TCB_CK + quad * 4);
 #pragma unroll
-                    for (int i = 0; i < PPT; i++) {
-                        v[i].x = fmaf(x[i * S + kx].x, wv.x, v[i].x);
-                        v[i].y = fmaf(x[i * S + kx].y, wv.y, v[i].y);
-                        v[i].z = fmaf(x[i * S + kx].z, wv.z, v[i].z);
-                        v[i].w = fmaf(x[i * S + kx].w, wv.w, v[i].w);
+                        for (int i = 0; i < PPT; i++) {
+                            v[i].x = fmaf(x[i * S + kx].x, wv.x, v[i].x);
+                            v[i].y = fmaf(x[i * S + kx].y, wv.y, v[i].y);
+                            v[i].z = fmaf(x[i * S + kx].z, wv.z, v[i].z);
+                            v[i].w = fmaf(x[i * S + kx].w, wv.w, v[i].w);
+                        }
                     }
                 }
-            }
-            const int k = c * TCB_CK + quad * 4;
+                const int k = c * TCB_CK + quad * 4;
 #pragma unroll
-            for (int i = 0; i < PPT; i++) {
-                if (k < p.K) act4(v[i], p.act_mid, k);
-                float4 hi, lo;
-                split_tf32_fast(v[i].x, hi.x, lo.x);
-                split_tf32_fast(v[i].y, hi.y, lo.y);
-                split_tf32_fast(v[i].z, hi.z, lo.z);
-                split_tf32_fast(v[i].w, hi.w, lo.w);
-                *reinterpret_cast<float4 *>(sA_hi + ((size_t)quad * TCB_AROWS + pm + i) * 4) = hi;
-                *reinterpret_cast<float4 *>(sA_lo + ((size_t)quad * TCB_AROWS + pm + i) * 4) = lo;
-            }
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (g.nin == 1 && warp == 0 && c + 1 < nchunks) issue_in(c + 1, 0);    // single buffer: refill behind the MMAs
-        if (tid == 0) {
-            mbar_wait(&mbar_b, c & 1);                                        // this chunk's pointwise weights have landed
-#pragma unroll 1
-            for (int pass = 0; pass < 3; pass++) {                            // lo*hi, hi*lo, hi*hi (small terms first)
-                uint64_t ad = pass == 0 ? ad_lo : ad_hi;
-                uint64_t bd = pass == 1 ? bd_lo : bd_hi;
-#pragma unroll
-                for (int j = 0; j < TCB_CK / 8; j++) {
-                    umma_tf32(tmem, ad, bd, idesc, acc_flag);
-                    acc_flag = 1;
-                    ad += (uint64_t)(2 * TCB_AROWS);
-                    bd += (uint64_t)(2 * NP);
+                for (int i = 0; i < PPT; i++) {
+                    if (k < p.K) act4(v[i], p.act_mid, k);
+                    float4 hi, lo;
+                    split_tf32_fast(v[i].x, hi.x, lo.x);
+                    split_tf32_fast(v[i].y, hi.y, lo.y);
+                    split_tf32_fast(v[i].z, hi.z, lo.z);
+                    split_tf32_fast(v[i].w, hi.w, lo.w);
+                    *reinterpret_cast<float4 *>(sA_hi + ((size_t)quad * TCB_AROWS + pm + i) * 4) = hi;
+                    *reinterpret_cast<float4 *>(sA_lo + ((size_t)quad * TCB_AROWS + pm + i) * 4) = lo;
                 }
             }
-            umma_commit(&mbar_mma);
-            mbar_wait(&mbar_mma, c & 1);                                      // one poller; everybody else parks at the barrier
-            if (c + 1 < nchunks) {                                            // A and B are free again: next weight chunk
-                mbar_expect_tx(&mbar_b, 2 * b_bytes);
-                bulk_copy_g2s(sB_hi, w_hi + (size_t)(c + 1) * TCB_KQC * NP * 4, b_bytes, &mbar_b);
-                bulk_copy_g2s(sB_lo, w_lo + (size_t)(c + 1) * TCB_KQC * NP * 4, b_bytes, &mbar_b);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            if (g.nin == 1 && warp == 0) issue_in(step + 1);                  // single buffer: refill behind the MMAs
+            if (tid == 0) {
+                const int bb = b_resident ? c : step % g.nbw;
+                mbar_wait(&mbar_b[bb], b_resident ? 0 : ((step / g.nbw) & 1)); // this chunk's pointwise weights have landed
+                const float *sB = sB0 + (size_t)bb * b_floats;
+                const uint64_t bd_hi = make_smem_desc(smem_u32(sB), (uint32_t)NP * 16, 128);
+                const uint64_t bd_lo = make_smem_desc(smem_u32(sB + TCB_KQC * NP * 4), (uint32_t)NP * 16, 128);
+#pragma unroll 1
+                for (int pass = 0; pass < 3; pass++) {                        // lo*hi, hi*lo, hi*hi (small terms first)
+                    uint64_t ad = pass == 0 ? ad_lo : ad_hi;
+                    uint64_t bd = pass == 1 ? bd_lo : bd_hi;
+#pragma unroll
+                    for (int j = 0; j < TCB_CK / 8; j++) {
+                        umma_tf32(tmem, ad, bd, idesc, acc_flag);
+                        acc_flag = 1;
+                        ad += (uint64_t)(2 * TCB_AROWS);
+                        bd += (uint64_t)(2 * NP);
+                    }
+                }
+                umma_commit(&mbar_mma);
+                mbar_wait(&mbar_mma, step & 1);                               // one poller; everybody else parks at the barrier
+                if (!b_resident && step + g.nbw < total_steps) load_b(step + g.nbw);   // this weight buffer is free again
             }
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-    }
 
-    // --- epilogue through shared memory (coalesced residual reads / stores); the staging tile aliases the input buffers ---
-    if (tid < TCB_M) {
-        const int er = tid / g.TW, ecol = tid - er * g.TW;
-        const int evr = vr0 + er, ox = ox0 + ecol;
-        int4 ri = make_int4(0, 0, 0, 0);
-        if (er < n_vr && ox < p.Wo) {
-            const int img = evr / p.Ho;
-            ri = make_int4(img, evr - img * p.Ho, ox, 1);
+        // --- epilogue through shared memory (coalesced residual reads / stores); the staging tile aliases the A tile, the
+        // next tile's first halo is already on its way ---
+        if (tid < TCB_M) {
+            const int er = tid / g.TW, ecol = tid - er * g.TW;
+            const int evr = vr0 + er, ox = ox0 + ecol;
+            TceRow ri;
+            ri.out_off = -1, ri.res_off = 0;
+            if (er < n_vr && ox < p.Wo) {
+                const int img = evr / p.Ho;
+                ri = tce_row(p, img, evr - img * p.Ho, ox);
+            }
+            s_rowinfo[tid] = ri;
         }
-        s_rowinfo[tid] = ri;
+        __syncthreads();
+        tc_epilogue_tile<NT, 0>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid);
+        tc_fence_before();                                                    // accumulator read before the next tile's MMAs overwrite it
     }
-    __syncthreads();
-    tc_epilogue_tile<NT>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, ncols);
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const
     float *sB_lo = sB_hi + 2 * TCB_KQC * NT * 4;
     __shared__ __align__(8) uint64_t mbar_b[2], mbar_mma;
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) int4 s_rowinfo[TCB_M];
+    __shared__ __align__(16) TceRow s_rowinfo[TCB_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TCB_M;
@@ -367,17 +387,18 @@ __global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const
     // --- epilogue through shared memory (the staging tile aliases the A tile) -----------------------------------------
     if (tid < TCB_M) {
         const int m = m0 + tid;
-        int4 ri = make_int4(0, 0, 0, 0);
+        TceRow ri;
+        ri.out_off = -1, ri.res_off = 0;
         if (m < p.M) {
             const int img = m / HoWo;
             const int r = m - img * HoWo;
             const int oy = r / p.Wo;
-            ri = make_int4(img, oy, r - oy * p.Wo, 1);
+            ri = tce_row(p, img, oy, r - oy * p.Wo);
         }
         s_rowinfo[tid] = ri;
     }
     __syncthreads();
-    tc_epilogue_tile(p, tmem, n0, NT, s_rowinfo, sA_hi, tid);
+    tc_epilogue_tile<256, 0>(p, tmem, n0, NT, s_rowinfo, sA_hi, tid);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, ncols);
@@ -442,9 +463,9 @@ TcbGeom choose_geom(const ConvDev &p, int KS, int S) {
     return best;
 }
 
-size_t tcb_smem(const TcbGeom &g, int KS, int NP, int nin) {
-    return (size_t)nin * g.rows_max * g.WBOX * TCB_CK * 4 + (size_t)TCB_A_FLOATS * 4 + 2 * (size_t)TCB_KQC * NP * 16 +
-           2 * (size_t)(KS * KS + 1) * TCB_CK * 4 + 1024;
+size_t tcb_smem(const TcbGeom &g, int KS, int NP, int nin, int nbw = 1) {
+    return (size_t)nin * ((size_t)g.rows_max * g.WBOX * TCB_CK + (size_t)(KS * KS + 1) * TCB_CK) * 4 + (size_t)TCB_A_FLOATS * 4 +
+           (size_t)nbw * 2 * TCB_KQC * NP * 16 + 1024;
 }
 
 template <int KS, int S, int PPT>
@@ -457,9 +478,14 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     int nin = tcb_smem(g, KS, NP, 2) <= 110 * 1024 ? 2 : 1;
     if (force_nin == 1 || force_nin == 2) nin = force_nin;
     if (tcb_smem(g, KS, NP, nin) > 220 * 1024) nin = 1;
-    const size_t smem = tcb_smem(g, KS, NP, nin);
+    static const int force_nbw = getenv("ZB_TCB_NBW") ? atoi(getenv("ZB_TCB_NBW")) : 0;
+    int nbw = tcb_smem(g, KS, NP, nin, 2) <= 110 * 1024 ? 2 : 1;           // second weight buffer only while two CTAs still fit per SM
+    if (force_nbw == 1 || force_nbw == 2) nbw = force_nbw;
+    if (tcb_smem(g, KS, NP, nin, nbw) > 220 * 1024) nbw = 1;
+    const size_t smem = tcb_smem(g, KS, NP, nin, nbw);
     if (smem > 220 * 1024) return false;
     g.nin = nin;
+    g.nbw = nbw;
     const int images = p.M / (p.Ho * p.Wo);
     CUtensorMap tmap;
     if (!make_input_map(p, images, g.WBOX, g.rows_max, &tmap)) return false;
@@ -467,8 +493,17 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     static SmemOptIn opt_in;
     if (!opt_in.ensure(kern, smem)) return false;
     const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
+    // persistent CTAs: two per SM (what registers and shared memory allow), each striding over the tiles
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    static const int ctas_per_sm = getenv("ZB_TCB_CTAS_PER_SM") ? atoi(getenv("ZB_TCB_CTAS_PER_SM")) : 2;
+    const int grid = ctas_per_sm > 0 ? std::min(g.tiles_x * g.tiles_y, ctas_per_sm * num_sms) : g.tiles_x * g.tiles_y;
     ZB_KNAME("tcb_dwpw_kernel", KS, S, PPT);
-    kern<<<(unsigned)(g.tiles_x * g.tiles_y), 1024 / PPT, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
+    kern<<<(unsigned)grid, 1024 / PPT, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
     return true;
 }
 
@@ -479,7 +514,7 @@ bool tcb_dwpw_supported(const ConvDev &p, int NP) {
     if (disabled) return false;
     if (!((p.kh == 3 && p.kw == 3) || (p.kh == 5 && p.kw == 5))) return false;
     if (!((p.sh == 1 && p.sw == 1) || (p.sh == 2 && p.sw == 2))) return false;
-    if (p.K != p.Cs_in || p.K % 8 || p.K < 8 || p.K > 1024 || NP % 16 || NP < 16 || NP > 256) return false;
+    if (p.K != p.Cs_in || p.K % 8 || p.K < 8 || p.K > 1024 || NP % 16 || NP < 16 || NP > 256 || !p.dw_c) return false;
     if (p.M % (p.Ho * p.Wo) || p.pt < 0 || p.pl < 0) return false;
     if (((uintptr_t)p.in) % 16 || (p.in_img_stride % 4)) return false;
     if (p.in_img_stride != (long long)p.H * p.W * p.Cs_in || p.H != p.Ho * p.sh) return false;   // merged (image, row) staging
@@ -514,7 +549,9 @@ bool launch_tcb_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int
     if (!tcb_dwpw_supported(p, NP)) return false;
     g_launch_count++;
     bool ok;
-    static const int ppt = getenv("ZB_TCB_PPT") ? atoi(getenv("ZB_TCB_PPT")) : 4;
+    // measured per layer (profiles/): 512 lighter threads win on the 3x3 stride-2 blocks, 256 threads of 4 outputs elsewhere
+    static const int ppt_env = getenv("ZB_TCB_PPT") ? atoi(getenv("ZB_TCB_PPT")) : 0;
+    const int ppt = ppt_env ? ppt_env : (p.kh == 3 && p.sh == 2) ? 2 : 4;
     if (ppt == 2) {
         if (p.kh == 3) ok = p.sh == 1 ? launch_tcb_cfg<3, 1, 2>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<3, 2, 2>(p, w_hi, w_lo, NP, s);
         else ok = p.sh == 1 ? launch_tcb_cfg<5, 1, 2>(p, w_hi, w_lo, NP, s) : launch_tcb_cfg<5, 2, 2>(p, w_hi, w_lo, NP, s);

@@ -2,8 +2,8 @@
 // blocks, the same operation and the same tile geometry as tcb_dwpw_kernel (kernels_tcb.cu), restructured so that nothing
 // in a CTA waits for anything else:
 //
-//   warp 12 (TMA)      streams, for every (tile, 32-channel chunk) step, the input halo rows (cp.async.bulk.tensor.4d, one per
-//                      staged row, zero-filled outside the image) and the chunk's depthwise weights (one bulk copy) into a
+//   warp 12 (TMA)      streams, for every (tile, 32-channel chunk) step, the input halo (one cp.async.bulk.tensor.3d, image and
+//                      row dimensions merged) and the chunk's depthwise weights (one bulk copy) into a
 //                      ring of input slots, and the pointwise weight chunks into a ring of weight slots (or once, if the
 //                      whole layer's weights fit in shared memory);
 //   warps 0-7 (dw)     convolve a landed chunk (sliding window: 4 adjacent outputs x one channel quad per thread) and write
@@ -14,8 +14,12 @@
 //                      in shared memory and run the coalesced epilogue (bias, activation, residual, stores).
 //
 // One CTA per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...  All hand-offs are mbarriers (full / empty per
-// ring slot); the only CTA-wide barriers are at start-up and tear-down.  Per-tile prologue costs of the one-tile-per-CTA
-// kernel (TMEM allocation, first weight fetch, first TMA round trip) are paid once per SM.
+// ring slot); the only CTA-wide barriers are at start-up and tear-down.
+//
+// STATUS: parity-green, OFF by default (ZB_TCP=1 turns it on).  Measured on the face-mesh layers at batch 1024
+// (profiles/README.md): 1.3-2x SLOWER than tcb_dwpw_kernel.  With one CTA per SM only 8 warps do the depthwise stage, and
+// that stage - shared-memory loads and FMAs with little instruction-level parallelism - needs 16 to 32 warps per SM to
+// hide its latencies; the hand-offs this design removes were not the bound.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -53,7 +57,6 @@ __device__ __forceinline__ void tcp_tma_load_3d(void *smem_dst, const CUtensorMa
         : "memory");
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // geometry of one tile (see kernels_tcb.cu): TH virtual rows (image, output row) x TW columns
 struct TileGeo {
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tcp_dwpw_kernel(const __grid_c
     __shared__ __align__(8) uint64_t in_full[TCP_MAX_IN], in_empty[TCP_MAX_IN], a_full[TCP_MAX_A], a_empty[TCP_MAX_A];
     __shared__ __align__(8) uint64_t b_full[32], b_empty[TCP_MAX_B], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) int4 s_rowinfo[TCP_M];
+    __shared__ __align__(16) TceRow s_rowinfo[TCP_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ncols = tmem_cols_for(2 * NP);
@@ -249,101 +252,28 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tcp_dwpw_kernel(const __grid_c
         }
     } else if (warp < 12) {
         // ================================ epilogue warps ================================
-        const int etid = tid - 256, ewarp = etid >> 5;
-        const EpiDev &e = p.epi;
-        const bool vec_store = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0) &&
-                               ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-        const bool vec_res = e.res && (e.res_Cs % 4) == 0;
-        const uint32_t lane_base = ((uint32_t)(ewarp * 32) << 16);
+        const int etid = tid - 256;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, it++) {
             const int acc = it & 1;
             const TileGeo t = tile_geo(tile, g);
-            {   // row -> (image, oy, ox) of this tile
+            {   // row table of this tile
                 const int er = etid / g.TW, ecol = etid - er * g.TW;
                 const int evr = t.vr0 + er, ox = t.ox0 + ecol;
-                int4 ri = make_int4(0, 0, 0, 0);
+                TceRow ri;
+                ri.out_off = -1, ri.res_off = 0;
                 if (er < t.n_vr && ox < p.Wo) {
                     const int img = evr / p.Ho;
-                    ri = make_int4(img, evr - img * p.Ho, ox, 1);
+                    ri = tce_row(p, img, evr - img * p.Ho, ox);
                 }
                 s_rowinfo[etid] = ri;
             }
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t tbase = tmem + lane_base + (uint32_t)acc * NP;
-            for (int cb = 0; cb < NP; cb += TCE_NB) {
-                const int nb = min(TCE_NB, NP - cb);
-                for (int j = 0; j < nb / 16; j++) {
-                    float v[16];
-                    tmem_ld16(tbase + (uint32_t)(cb + 16 * j), v);
-                    float *dst = s_stage + etid * TCE_STRIDE + 16 * j;
-#pragma unroll
-                    for (int h = 0; h < 4; h++) *reinterpret_cast<float4 *>(dst + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-                }
-                if (cb + TCE_NB >= NP) {                                    // accumulator fully read: hand it back to the MMA thread
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                }
-                epi_bar_sync();
-                const int qb = nb >> 2, total = TCP_M * qb;
-#pragma unroll 1
-                for (int base = 0; base < total; base += TCP_EPI * 8) {
-                    int rows[8], ns[8];
-                    int4 ri[8];
-                    float4 rr[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int item = base + etid + i * TCP_EPI;
-                        rows[i] = -1;
-                        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (item < total) {
-                            const int r = item / qb, q = item - r * qb;
-                            const int n = cb + 4 * q;
-                            ri[i] = s_rowinfo[r];
-                            if (ri[i].w && n < p.Nstore) {
-                                rows[i] = r, ns[i] = n;
-                                if (vec_res) rr[i] = residual4_at(e, ri[i].x, ri[i].y, ri[i].z, n);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        if (rows[i] < 0) continue;
-                        const int n = ns[i];
-                        const float4 a = *reinterpret_cast<const float4 *>(s_stage + rows[i] * TCE_STRIDE + (n - cb));
-                        float v[4] = {a.x, a.y, a.z, a.w};
-                        if (n + 3 < p.Ns) {
-                            const float4 b = ldg4(e.bias + n);
-                            v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                if (n + q < p.Ns) v[q] += __ldg(e.bias + n + q);
-                        }
-                        act4(v, e.act1, n);
-                        if (e.res) {
-                            if (vec_res) {
-                                v[0] += rr[i].x, v[1] += rr[i].y, v[2] += rr[i].z, v[3] += rr[i].w;
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 4; q++) v[q] += residual_at(e, ri[i].x, ri[i].y, ri[i].z, n + q);
-                            }
-                        }
-                        act4(v, e.act2, n);
-                        float *orow = p.out + (long long)ri[i].x * p.out_img_stride + ((long long)ri[i].y * p.Wo + ri[i].z) * p.out_pix_stride;
-                        if (vec_store) {
-                            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                if (n + q < p.Nstore) orow[n + q] = v[q];
-                        }
-                    }
-                }
-                epi_bar_sync();                                             // staging tile (and row table) reused next
-            }
+            tc_epilogue_tile<TCP_EPI, 1>(p, tmem + (uint32_t)acc * NP, 0, NP, s_rowinfo, s_stage, etid);
+            tc_fence_before();                                              // accumulator read: hand it back to the MMA thread
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
     }
     tc_fence_before();

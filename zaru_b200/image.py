@@ -183,3 +183,18 @@ class ImageView:
 
     def __repr__(self):
         return f"ImageView @ {self._data!r}"
+
+
+def blend(dest, src):
+    """`zaru_image::blend(&mut dest, &src)` (crates/zaru-image/src/blend.rs:13-32): draws the source view over the destination
+    view with linear filtering; scaled up or down as the view sizes demand; source UVs outside the image write Color::NONE.
+    `dest` / `src`: Image or ImageView whose images live in uploaded ImageBatches (the destination is modified on the
+    device; read it back with `.to_image()`).  The reference performs the operation when the returned `BlendOp` is dropped;
+    here it happens at once."""
+    from . import context
+    dv, sv = dest.as_view(), src.as_view()
+    dbatch, didx = dv._image.device()
+    sbatch, sidx = sv._image.device()
+    d = (_ffi.zb_view * 1)(dv.to_zb_view(didx))
+    s = (_ffi.zb_view * 1)(sv.to_zb_view(sidx))
+    _ffi.check(_ffi.lib().zb_blend(context(), dbatch._h, d, sbatch._h, s, 1))
