@@ -132,6 +132,25 @@ zb_status zb_frames_alias(zb_ctx *ctx, const uint8_t *rgba_device, int32_t width
 zb_status zb_frames_update(zb_frames *frames, const uint8_t *rgba_host, int32_t first, int32_t count);
 void zb_frames_destroy(zb_frames *frames);
 
+/* ---- JPEG / MJPG ingest (crates/zaru-image/src/jpeg.rs:107-222; video/webcam.rs:287, httpcam.rs:76) -----------------
+ * `decode_jpeg(bytes)` for n baseline JPEG streams, decoded INTO frames [first, first + n) of an uploaded batch whose
+ * size they must have.  The reference picks one of five decoder libraries (ZARU_JPEG_BACKEND) whose pixels differ in the
+ * last bits; this one is bit-exact with libjpeg-turbo's default pipeline (`turbojpeg` / `mozjpeg` backends; also what
+ * OpenCV and Pillow use): islow inverse DCT, "fancy" chroma upsampling, 16-bit fixed-point YCbCr -> RGB; alpha = 255.
+ * Entropy (Huffman) decoding runs on the host - images in parallel - and only the sparse quantised coefficients cross
+ * PCIe; inverse DCT, upsampling and colour conversion run on the device.  Baseline sequential DCT, 8 bit, 4:4:4 / 4:2:2 /
+ * 4:2:0 or grey, restart intervals, missing DHT (MJPG) = the standard tables.  Progressive / arithmetic / 12-bit / CMYK:
+ * ZB_ERR_UNSUPPORTED_OP.  Malformed data: ZB_ERR_BAD_MODEL.  Wrong size: ZB_ERR_BAD_SHAPE.                              */
+zb_status zb_frames_decode_jpeg(zb_frames *frames, int32_t first, const uint8_t *const *jpegs, const size_t *sizes, int32_t n);
+/* Header only (no device): size, component count, luma sampling factors.                                              */
+zb_status zb_jpeg_info(const uint8_t *jpeg, size_t len, int32_t *width, int32_t *height, int32_t *components,
+                       int32_t *h_samp, int32_t *v_samp);
+/* Introspection (no device): the quantised DCT coefficients the host front end produces, densely: [block][64] int16 in
+ * natural order, blocks component-major (Y, Cb, Cr) and row-major inside a component (planes padded to whole MCUs);
+ * blocks_w / blocks_h per component, qtables[64 * c ..] = that component's quantisation table (natural order).    */
+zb_status zb_jpeg_coefficients(const uint8_t *jpeg, size_t len, int16_t *out, size_t cap_values, size_t *needed_values,
+                               int32_t blocks_w[3], int32_t blocks_h[3], uint16_t *qtables);
+
 /* `ImageView::to_image` (image/mod.rs:314-325) for n views of one size: out_rgba = RGBA8 [n][out_h][out_w][4] with
  * out_w = ceil(view width), out_h = ceil(view height) (the caller rounds, like the reference); view pixel (x, y) is
  * `ImageView::get(x, y)`: nearest texel through the rotated view, Color::NONE (0,0,0,0) outside the image.
@@ -349,6 +368,8 @@ zb_status zb_debug_mma_rate(zb_ctx *ctx, int32_t N, int32_t lbo_a, int32_t sbo_a
 /* Device time (ms, CUDA events on the handle's own stream) of the last *_run/_detect/_estimate
  * call, excluding host<->device result copies.                                                */
 float zb_last_device_ms(zb_ctx *ctx);
+/* Bytes the last zb_frames_decode_jpeg call on this context sent to the device (sparse coefficients). */
+int64_t zb_last_h2d_bytes(zb_ctx *ctx);
 /* CUDA-event stopwatch on the context's stream: start, (any number of calls), stop -> ms.      */
 zb_status zb_timer_start(zb_ctx *ctx);
 zb_status zb_timer_stop(zb_ctx *ctx, float *ms);

@@ -87,6 +87,10 @@ SIGNATURES = {
     "zb_estimator_set_filter": (i32, [P, i32, f32, f32, f32, f32]),
     "zb_tracker_set_filter": (i32, [P, i32, f32, f32, f32, f32]),
     "zb_filter_apply": (i32, [P, i32, f32, f32, f32, f32, P, P, i64]),
+    "zb_frames_decode_jpeg": (i32, [P, i32, P, P, i32]),
+    "zb_jpeg_info": (i32, [P, sz, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "zb_jpeg_coefficients": (i32, [P, sz, P, sz, C.POINTER(sz), C.POINTER(i32), C.POINTER(i32), P]),
+    "zb_last_h2d_bytes": (i64, [P]),
     "zb_blend": (i32, [P, P, P, P, P, i32]),
     "zb_view_to_image": (i32, [P, P, P, i32, i32, i32, P]),
     "zb_frames_clear": (i32, [P, i32, i32, P]),

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 // exported C ABI: everything else in the library has hidden visibility
@@ -16,6 +17,7 @@
 #include "../../include/zaru_b200.h"
 #pragma GCC visibility pop
 #include "geom.h"
+#include "jpeg_host.h"
 #include "kernels.h"
 #include "onnx_reader.h"
 #include "plan.h"
@@ -56,6 +58,7 @@ zb_status guarded(F &&f) {
         std::string m = e.what();
         if (m.rfind("unsupported op", 0) == 0) return fail(ZB_ERR_UNSUPPORTED_OP, m);
         if (m.rfind("onnx:", 0) == 0) return fail(ZB_ERR_BAD_MODEL, m);
+        if (m.rfind("jpeg:", 0) == 0) return fail(ZB_ERR_BAD_MODEL, m);
         return fail(ZB_ERR_INVALID_ARGUMENT, m);
     } catch (const std::exception &e) {
         return fail(ZB_ERR_INVALID_ARGUMENT, e.what());
@@ -124,6 +127,7 @@ struct zb_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float last_ms = 0.f;
+    size_t last_h2d_bytes = 0;           // bytes the last zb_frames_decode_jpeg call sent to the device
     int default_chunk = 1024;
     // per-launch CUDA-event profiler (off in timed runs; bench.py uses it for the roofline block)
     int tc_mode = 1;                     // ZB_TC: 0 = SIMT only, 1 = tcgen05 3xTF32 for fused blocks with K >= tc_min_k
@@ -214,6 +218,22 @@ struct zb_frames {
     FramesDev f{};
     uint8_t *owned = nullptr;
     bool host_mapped = false;            // pixels live in pinned host memory (zero-copy sampling across PCIe)
+    // JPEG ingest (zb_frames_decode_jpeg): sparse coefficient staging (pinned host -> device) and decoded component planes
+    struct JpegScratch *jpeg = nullptr;
+};
+
+struct JpegScratch {
+    void *h_pin = nullptr;               // pinned host staging of one call's coefficient streams
+    size_t h_cap = 0;
+    void *d_coef = nullptr;
+    size_t d_cap = 0;
+    void *d_planes = nullptr;
+    size_t p_cap = 0;
+    ~JpegScratch() {
+        if (h_pin) cudaFreeHost(h_pin);
+        if (d_coef) cudaFree(d_coef);
+        if (d_planes) cudaFree(d_planes);
+    }
 };
 
 namespace {
@@ -573,6 +593,7 @@ zb_status zb_sync(zb_ctx *ctx) {
 int64_t zb_launch_count(zb_ctx *) { return g_launch_count; }
 
 float zb_last_device_ms(zb_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+int64_t zb_last_h2d_bytes(zb_ctx *ctx) { return ctx ? (int64_t)ctx->last_h2d_bytes : 0; }
 
 zb_status zb_timer_start(zb_ctx *ctx) {
     return guarded([&]() -> zb_status {
@@ -913,7 +934,148 @@ void zb_frames_destroy(zb_frames *fr) {
     if (!fr) return;
     cudaSetDevice(fr->ctx->device);
     if (fr->owned) cudaFree(fr->owned);
+    delete fr->jpeg;
     delete fr;
+}
+
+// ---- JPEG ingest (crates/zaru-image/src/jpeg.rs:107-222; MJPG webcams, video/webcam.rs:287, httpcam.rs:76) ----------------
+zb_status zb_jpeg_info(const uint8_t *jpeg, size_t len, int32_t *width, int32_t *height, int32_t *components, int32_t *h_samp, int32_t *v_samp) {
+    return guarded([&]() -> zb_status {
+        if (!jpeg) return fail(ZB_ERR_INVALID_ARGUMENT, "jpeg is NULL");
+        const JpegHeader h = jpeg_parse_header(jpeg, len);
+        if (width) *width = h.width;
+        if (height) *height = h.height;
+        if (components) *components = h.ncomp;
+        if (h_samp) *h_samp = h.hmax;
+        if (v_samp) *v_samp = h.vmax;
+        return ZB_OK;
+    });
+}
+
+// Introspection (no device): the quantised DCT coefficients the host front end hands to the device, densely, as
+// [block][64] int16 in natural order, blocks component-major (Y, Cb, Cr), row-major inside a component (padded to whole MCUs).
+zb_status zb_jpeg_coefficients(const uint8_t *jpeg, size_t len, int16_t *out, size_t cap_values, size_t *needed_values,
+                               int32_t blocks_w[3], int32_t blocks_h[3], uint16_t *qtables) {
+    return guarded([&]() -> zb_status {
+        if (!jpeg) return fail(ZB_ERR_INVALID_ARGUMENT, "jpeg is NULL");
+        const JpegHeader h = jpeg_parse_header(jpeg, len);
+        const int nb = jpeg_total_blocks(h);
+        if (needed_values) *needed_values = (size_t)nb * 64;
+        for (int c = 0; c < 3; c++) {
+            if (blocks_w) blocks_w[c] = c < h.ncomp ? h.blocks_w[c] : 0;
+            if (blocks_h) blocks_h[c] = c < h.ncomp ? h.blocks_h[c] : 0;
+            if (qtables && c < h.ncomp) memcpy(qtables + 64 * c, h.qt[h.tq[c]], 64 * sizeof(uint16_t));
+        }
+        if (!out || cap_values < (size_t)nb * 64) return ZB_OK;
+        std::vector<uint32_t> start(nb);
+        std::vector<uint8_t> count(nb), stream;
+        jpeg_decode_sparse(jpeg, len, h, start.data(), count.data(), stream);
+        memset(out, 0, (size_t)nb * 64 * sizeof(int16_t));
+        for (int b = 0; b < nb; b++)
+            for (int k = 0; k < count[b]; k++) {
+                const uint8_t *t = stream.data() + start[b] + 3 * k;
+                out[(size_t)b * 64 + (t[0] & 63)] = (int16_t)(uint16_t)(t[1] | (t[2] << 8));
+            }
+        return ZB_OK;
+    });
+}
+
+// n baseline JPEG byte streams -> frames [first, first + n) of an UPLOADED batch of exactly their size.  Entropy decoding on
+// the host (one worker thread per image, up to the hardware concurrency), the sparse coefficients cross PCIe, inverse DCT +
+// chroma upsampling + colour conversion on the device.
+zb_status zb_frames_decode_jpeg(zb_frames *fr, int32_t first, const uint8_t *const *jpegs, const size_t *sizes, int32_t n) {
+    return guarded([&]() -> zb_status {
+        if (!fr || (!jpegs && n) || (!sizes && n)) return fail(ZB_ERR_INVALID_ARGUMENT, "frames/jpegs/sizes is NULL");
+        if (!fr->owned) return fail(ZB_ERR_INVALID_ARGUMENT, "aliased frames belong to the caller and cannot be decoded into");
+        if (first < 0 || n < 0 || first + n > fr->f.n) return fail(ZB_ERR_INVALID_ARGUMENT, "frame range out of bounds");
+        if (n == 0) return ZB_OK;
+        zb_ctx *ctx = fr->ctx;
+        CU(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        std::vector<JpegHeader> hdr(n);
+        for (int i = 0; i < n; i++) {
+            if (!jpegs[i]) return fail(ZB_ERR_INVALID_ARGUMENT, "jpegs[" + std::to_string(i) + "] is NULL");
+            hdr[i] = jpeg_parse_header(jpegs[i], sizes[i]);
+            if (hdr[i].width != fr->f.width || hdr[i].height != fr->f.height)
+                return fail(ZB_ERR_BAD_SHAPE, "JPEG " + std::to_string(i) + " is " + std::to_string(hdr[i].width) + "x" + std::to_string(hdr[i].height) +
+                                                  ", the frame batch is " + std::to_string(fr->f.width) + "x" + std::to_string(fr->f.height));
+        }
+        // host: entropy decoding, images in parallel
+        struct Img { std::vector<uint32_t> start; std::vector<uint8_t> count, stream; std::string err; };
+        std::vector<Img> img(n);
+        {
+            const int workers = std::max(1, std::min<int>(n, (int)std::thread::hardware_concurrency()));
+            std::atomic<int> next{0};
+            auto work = [&] {
+                for (int i = next++; i < n; i = next++) {
+                    try {
+                        const int nb = jpeg_total_blocks(hdr[i]);
+                        img[i].start.resize(nb), img[i].count.resize(nb);
+                        jpeg_decode_sparse(jpegs[i], sizes[i], hdr[i], img[i].start.data(), img[i].count.data(), img[i].stream);
+                    } catch (const std::exception &e) {
+                        img[i].err = e.what();
+                    }
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int w = 1; w < workers; w++) pool.emplace_back(work);
+            work();
+            for (auto &t : pool) t.join();
+        }
+        for (int i = 0; i < n; i++)
+            if (!img[i].err.empty()) throw std::runtime_error(img[i].err);
+        // one staging block per call: per image {start[nb] u32, count[nb] u8 (padded to 4), stream (padded to 4)}
+        std::vector<size_t> off(n + 1, 0);
+        size_t plane_max = 0;
+        for (int i = 0; i < n; i++) {
+            const size_t nb = img[i].start.size();
+            off[i + 1] = off[i] + nb * 4 + ((nb + 3) & ~(size_t)3) + ((img[i].stream.size() + 3) & ~(size_t)3);
+            plane_max = std::max(plane_max, jpeg_plane_bytes(hdr[i]));
+        }
+        if (!fr->jpeg) fr->jpeg = new JpegScratch();
+        JpegScratch &js = *fr->jpeg;
+        if (js.h_cap < off[n]) {
+            if (js.h_pin) CU(cudaFreeHost(js.h_pin));
+            js.h_pin = nullptr, js.h_cap = 0;
+            CU(cudaMallocHost(&js.h_pin, off[n] * 3 / 2 + 4096));
+            js.h_cap = off[n] * 3 / 2 + 4096;
+        }
+        if (js.d_cap < off[n]) {
+            if (js.d_coef) CU(cudaFree(js.d_coef));
+            js.d_coef = nullptr, js.d_cap = 0;
+            CU(cudaMalloc(&js.d_coef, off[n] * 3 / 2 + 4096));
+            js.d_cap = off[n] * 3 / 2 + 4096;
+        }
+        if (js.p_cap < plane_max * n) {
+            if (js.d_planes) CU(cudaFree(js.d_planes));
+            js.d_planes = nullptr, js.p_cap = 0;
+            CU(cudaMalloc(&js.d_planes, plane_max * n));
+            js.p_cap = plane_max * n;
+        }
+        uint8_t *hp = static_cast<uint8_t *>(js.h_pin);
+        for (int i = 0; i < n; i++) {
+            const size_t nb = img[i].start.size();
+            uint8_t *base = hp + off[i];
+            memcpy(base, img[i].start.data(), nb * 4);
+            memcpy(base + nb * 4, img[i].count.data(), nb);
+            memcpy(base + nb * 4 + ((nb + 3) & ~(size_t)3), img[i].stream.data(), img[i].stream.size());
+        }
+        Timer tm(ctx, s);
+        CU(cudaMemcpyAsync(js.d_coef, js.h_pin, off[n], cudaMemcpyHostToDevice, s));
+        for (int i = 0; i < n; i++) {
+            const size_t nb = img[i].start.size();
+            const uint8_t *base = static_cast<const uint8_t *>(js.d_coef) + off[i];
+            launch_jpeg_decode(hdr[i], reinterpret_cast<const uint32_t *>(base), base + nb * 4, base + nb * 4 + ((nb + 3) & ~(size_t)3),
+                               static_cast<uint8_t *>(js.d_planes) + plane_max * i, fr->owned + (size_t)(first + i) * fr->f.frame_stride,
+                               fr->f.row_stride, s);
+        }
+        CU(cudaGetLastError());
+        tm.stop();
+        CU(cudaStreamSynchronize(s));     // the pinned staging block is reused by the next call
+        tm.finish();
+        ctx->last_h2d_bytes = off[n];
+        return ZB_OK;
+    });
 }
 
 // ---- preprocess --------------------------------------------------------------------------------------

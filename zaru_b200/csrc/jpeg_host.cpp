@@ -11,6 +11,7 @@
 
 #include <cstring>
 #include <stdexcept>
+#include <vector>
 
 namespace zb {
 namespace {
@@ -123,6 +124,39 @@ inline int extend(int v, int n) { return v < (1 << (n - 1)) ? v - (1 << n) + 1 :
 
 uint16_t be16(const uint8_t *p) { return (uint16_t)((p[0] << 8) | p[1]); }
 
+// ITU T.81 Annex K.3 - K.6 "typical" Huffman tables: MJPG frames from webcams routinely omit their DHT segments and mean
+// these (libjpeg-turbo installs the same defaults, jstdhuff.c).
+const uint8_t STD_DC_LUM_BITS[16] = {0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+const uint8_t STD_DC_CHR_BITS[16] = {0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0};
+const uint8_t STD_DC_VALS[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+const uint8_t STD_AC_LUM_BITS[16] = {0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d};
+const uint8_t STD_AC_LUM_VALS[162] = {
+    0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32, 0x81, 0x91,
+    0xa1, 0x08, 0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a,
+    0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53,
+    0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79,
+    0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5,
+    0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9,
+    0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2,
+    0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+const uint8_t STD_AC_CHR_BITS[16] = {0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77};
+const uint8_t STD_AC_CHR_VALS[162] = {
+    0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81, 0x08, 0x14,
+    0x42, 0x91, 0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17,
+    0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a,
+    0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78,
+    0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3,
+    0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7,
+    0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2,
+    0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+
+void set_std(JpegHeader::RawHuff &r, const uint8_t *bits, const uint8_t *vals, int n) {
+    memcpy(r.counts, bits, 16);
+    memcpy(r.symbols, vals, n);
+    r.nsym = n;
+    r.present = true;
+}
+
 }  // namespace
 
 JpegHeader jpeg_parse_header(const uint8_t *data, size_t len) {
@@ -203,6 +237,11 @@ JpegHeader jpeg_parse_header(const uint8_t *data, size_t len) {
         i += 2 + L;
     }
     if (!h.have_sof || h.scan_offset == 0) bad("no baseline frame / scan found");
+    // MJPG without DHT: the standard tables (luminance = table 0, chrominance = table 1)
+    if (!h.huff[0][0].present) set_std(h.huff[0][0], STD_DC_LUM_BITS, STD_DC_VALS, 12);
+    if (!h.huff[0][1].present) set_std(h.huff[0][1], STD_DC_CHR_BITS, STD_DC_VALS, 12);
+    if (!h.huff[1][0].present) set_std(h.huff[1][0], STD_AC_LUM_BITS, STD_AC_LUM_VALS, 162);
+    if (!h.huff[1][1].present) set_std(h.huff[1][1], STD_AC_CHR_BITS, STD_AC_CHR_VALS, 162);
     h.hmax = h.vmax = 1;
     for (int c = 0; c < h.ncomp; c++) h.hmax = std::max(h.hmax, h.hs[c]), h.vmax = std::max(h.vmax, h.vs[c]);
     if (h.ncomp == 1) h.hs[0] = h.vs[0] = h.hmax = h.vmax = 1;     // a single-component scan is never interleaved
@@ -222,22 +261,32 @@ JpegHeader jpeg_parse_header(const uint8_t *data, size_t len) {
     return h;
 }
 
-// coeffs[c]: blocks_h[c] * blocks_w[c] blocks of 64 int16 in natural order (caller-allocated).
-void jpeg_decode_coefficients(const uint8_t *data, size_t len, const JpegHeader &h, int16_t *const coeffs[3]) {
+// Entropy decoding into a SPARSE coefficient stream (most quantised coefficients are zero, and the stream is what crosses
+// PCIe): for flat block index b = block_base[component] + by * blocks_w + bx, `start[b]` / `count[b]` delimit its non-zero
+// coefficients in `stream`, 3 bytes each: natural-order index, value low byte, value high byte.
+void jpeg_decode_sparse(const uint8_t *data, size_t len, const JpegHeader &h, uint32_t *start, uint8_t *count, std::vector<uint8_t> &stream) {
     HuffTable dc[4], ac[4];
     for (int t = 0; t < 4; t++) {
         if (h.huff[0][t].present) dc[t].build(h.huff[0][t].counts, h.huff[0][t].symbols, h.huff[0][t].nsym);
         if (h.huff[1][t].present) ac[t].build(h.huff[1][t].counts, h.huff[1][t].symbols, h.huff[1][t].nsym);
     }
+    int block_base[3] = {0, 0, 0};
+    for (int c = 1; c < h.ncomp; c++) block_base[c] = block_base[c - 1] + h.blocks_w[c - 1] * h.blocks_h[c - 1];
+    stream.clear();
+    stream.reserve(len * 4);
     BitReader br(data + h.scan_offset, data + len);
     int pred[3] = {0, 0, 0};
     int restart_left = h.restart_interval;
     int next_rst = 0;
+    auto put = [&](int idx, int v) {
+        stream.push_back((uint8_t)idx);
+        stream.push_back((uint8_t)(v & 255));
+        stream.push_back((uint8_t)((v >> 8) & 255));
+    };
     for (int my = 0; my < h.mcus_y; my++) {
         for (int mx = 0; mx < h.mcus_x; mx++) {
             if (h.restart_interval && restart_left == 0) {
-                // byte-align, expect RSTn
-                const uint8_t *q = br.p;
+                const uint8_t *q = br.p;      // the reader never consumes a marker: the RSTn is at or after its position
                 while (q + 1 < data + len && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
                 if (q + 1 >= data + len) bad("missing restart marker");
                 if (q[1] != 0xD0 + next_rst) bad("restart marker out of sequence");
@@ -250,14 +299,13 @@ void jpeg_decode_coefficients(const uint8_t *data, size_t len, const JpegHeader 
                 const HuffTable &tdc = dc[h.td[c]], &tac = ac[h.ta[c]];
                 for (int by = 0; by < h.vs[c]; by++)
                     for (int bx = 0; bx < h.hs[c]; bx++) {
-                        int16_t *blk = coeffs[c] + ((size_t)(my * h.vs[c] + by) * h.blocks_w[c] + (mx * h.hs[c] + bx)) * 64;
-                        memset(blk, 0, 64 * sizeof(int16_t));
-                        const int s = decode_symbol(br, tdc);
-                        if (s > 15) bad("DC category");
-                        int diff = 0;
-                        if (s) diff = extend(br.get(s), s);
-                        pred[c] += diff;
-                        blk[0] = (int16_t)pred[c];
+                        const int b = block_base[c] + (my * h.vs[c] + by) * h.blocks_w[c] + (mx * h.hs[c] + bx);
+                        start[b] = (uint32_t)stream.size();
+                        int n = 0;
+                        const int sdc = decode_symbol(br, tdc);
+                        if (sdc > 15) bad("DC category");
+                        if (sdc) pred[c] += extend(br.get(sdc), sdc);
+                        if (pred[c]) put(0, pred[c]), n++;
                         for (int k = 1; k < 64;) {
                             const int rs = decode_symbol(br, tac);
                             const int r = rs >> 4, sz = rs & 15;
@@ -268,9 +316,11 @@ void jpeg_decode_coefficients(const uint8_t *data, size_t len, const JpegHeader 
                             }
                             k += r;
                             if (k > 63) bad("AC coefficient index");
-                            blk[ZIGZAG[k]] = (int16_t)extend(br.get(sz), sz);
+                            put(ZIGZAG[k], extend(br.get(sz), sz));
+                            n++;
                             k++;
                         }
+                        count[b] = (uint8_t)n;
                     }
             }
             if (h.restart_interval) restart_left--;

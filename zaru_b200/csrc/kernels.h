@@ -242,6 +242,12 @@ void launch_tracker_update(TrackState *state, const float *out0, int s0, const f
 // roi[ids[k]] = rois[k] (radians kept), or None when rois == nullptr
 void launch_tracker_set_roi(TrackState *state, const int *ids, const ViewHost *rois, int k, cudaStream_t s);
 
+// kernels_jpeg.cu: baseline-JPEG back end (inverse DCT, chroma upsampling, YCbCr -> RGBA8) on one image's sparse coefficients
+struct JpegHeader;
+size_t jpeg_plane_bytes(const JpegHeader &h);
+void launch_jpeg_decode(const JpegHeader &h, const uint32_t *start_dev, const uint8_t *count_dev, const uint8_t *stream_dev,
+                        uint8_t *plane_dev, uint8_t *rgba, long long row_stride, cudaStream_t s);
+
 extern std::atomic<long long> g_launch_count;   // total kernel launches issued by this library (process-wide)
 
 // Name of the kernel FUNCTION (with its template arguments) the last launch_* call on this thread actually launched:
