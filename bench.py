@@ -72,15 +72,41 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through NVML every ~5 ms from a
+    thread of this process (`nvidia-smi -lms` cannot sample faster than ~10 Hz, and the device-timed loop lasts ~0.1 s);
+    falls back to `nvidia-smi` when NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines, self.stamps, self.window = index, None, [], [], None
+    def __init__(self, index, bus_id=None):
+        self.index, self.proc, self.lines, self.stamps, self.window, self.bus_id = index, None, [], [], None, bus_id
+        self.samples, self.reason_bits, self.max_mhz, self.stop_flag, self.thread, self.nvml = [], 0, None, False, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES re-maps devices: prefer the PCI bus id
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(self.bus_id.encode()) if self.bus_id else pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+
+            def pump():
+                get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))))
+                        self.reason_bits |= int(get_reasons(h))
+                    except Exception:  # noqa: BLE001
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 - no NVML binding: nvidia-smi loop instead
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -99,6 +125,16 @@ class ClockSampler:
         self.window = (t0, t1)
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = [v for _, v in self.samples]
+            inside = [v for t, v in self.samples if self.window and self.window[0] <= t <= self.window[1]]
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            reasons = sorted(n for bit, n in names.items() if self.reason_bits & bit)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "samples_in_device_loop": len(inside), "sm_mhz_in_device_loop": statistics.median(inside) if inside else None,
+                    "reasons": reasons, "sampled_over": "the device-timed loop and the e2e legs (NVML, every ~5 ms)"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -266,6 +302,40 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def cuda_bus_id(torch, local):
+    """PCI bus id ("0000:1b:00.0") of CUDA device `local`, or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        return f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and, by first touch, its pinned frame buffers) to the NUMA node its GPU hangs off: with
+    8 ranks on one node every rank otherwise inherits the same CPU set and its zero-copy texel reads cross the socket
+    interconnect (round-1 e2e scaling: 0.58 at N = 8).  Returns a description for the JSON line; never fails the run."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.startswith("0000"):
+            bdf = bdf[4:]                       # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA affinity for this GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"numa_node": node, "note": "no CPU of that node is in this process's affinity mask; left as is"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed), "pci": bdf}
+    except Exception as ex:  # noqa: BLE001
+        return {"numa_node": None, "note": f"not bound: {ex}"}
+
+
 def pinned_frames(torch, n):
     """[n,1080,1920,4] uint8 host tensor, page-locked by cudaHostRegister at its exact size.  (torch's pinned-memory
     allocator rounds every block up to a power of two: the 8.49 GB of a 1024-frame batch would pin 16 GB per buffer,
@@ -391,7 +461,7 @@ def run_gpu_stage(args):
         pipe = HandPipeline(capacity=args.cap)
         pipe.set_threshold(0.1, 0.3)     # no hand fixture exists in the reference: lowered until the frames yield palms
         pipe.set_dense(True)             # SURVEY 8d's unit: 1 palm pass + 1 hand-landmark pass per frame
-        run = lambda bt: pipe.run(bt, n)
+        run = lambda bt: pipe.run_raw(bt, n)
         d2h = n * (args.cap * 88 + 4 + 21 * 12 + 8 + 24)
         extra = {"palm_threshold": 0.1, "hand_stage": "every frame (dense): SURVEY 8d's unit is 1 palm pass + 1 hand pass"}
 
@@ -404,7 +474,7 @@ def run_gpu_stage(args):
     for _ in range(args.warmup):
         out = run(batch)
     barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, cuda_bus_id(torch, local))
     if rank == 0:
         clocks.start()
     launches0 = zaru_b200.launch_count()
@@ -418,7 +488,7 @@ def run_gpu_stage(args):
     launches = zaru_b200.launch_count() - launches0
     barrier()
     if cfg == 3:
-        extra["frames_with_palm"] = int(sum(len(x) > 0 for x in out.detections))
+        extra["frames_with_palm"] = int(sum(1 for c in out[1] if c > 0))
     (dev_ms_max,) = shard.max_over_ranks([dev_ms], dist, "cuda")
 
     def e2e_step():
@@ -499,6 +569,8 @@ def run_gpu(args):
     from zaru_b200.pipeline import FacePipeline
     from zaru_b200.rect import Resolution
 
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa else {"numa_node": None, "note": "--no-numa"}
+    log(f"[rank {rank}] NUMA binding: {numa}")
     zaru_b200.load_library()
     zaru_b200.context(local)
     res = Resolution(FRAME_W, FRAME_H)
@@ -540,7 +612,7 @@ def run_gpu(args):
     for _ in range(args.warmup):
         pipe.run_raw(batch, batch_n)
     barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, cuda_bus_id(torch, local))
     if rank == 0:
         clocks.start()
     launches0 = zaru_b200.launch_count()
@@ -682,6 +754,46 @@ def run_gpu(args):
             for hb in bufs[1:]:
                 unpin_frames(torch, hb)
         bufs = None
+    # --- e2e, MJPG ingest: the frames arrive as baseline JPEG byte streams; Huffman decoding on the host
+    # cores (inside zb_frames_decode_jpeg, one worker per image), sparse coefficients H2D, inverse DCT + upsampling + colour
+    # conversion + the whole pipeline on the device, results D2H.  Rank 0 only (every rank would use the same host cores).
+    jpeg_leg = None
+    if rank == 0 and not args.no_jpeg:
+        try:
+            import io
+
+            from PIL import Image as PILImage
+
+            from zaru_b200.jpeg import decode_jpegs_into
+            jn = min(args.jpeg_batch, e2e_n)
+            streams = []
+            for k in range(min(args.unique, jn)):
+                buf = io.BytesIO()
+                PILImage.fromarray(uniq[k][..., :3]).save(buf, format="JPEG", quality=80, subsampling=2)
+                streams.append(buf.getvalue())
+            jpegs = [streams[k % len(streams)] for k in range(jn)]
+            jbatch = ImageBatch.from_rgba8(res, np.zeros((jn, FRAME_H, FRAME_W, 4), np.uint8))
+            for _ in range(2):
+                decode_jpegs_into(jbatch, jpegs)
+                pipe.run_raw(jbatch, jn)
+            zaru_b200.sync()
+            j0 = time.perf_counter()
+            jsteps = max(2, args.steps // 4)
+            for _ in range(jsteps):
+                decode_jpegs_into(jbatch, jpegs)
+                jr = pipe.run_raw(jbatch, jn)
+            zaru_b200.sync()
+            j_ms = 1000.0 * (time.perf_counter() - j0)
+            jpeg_leg = {"value": jn * jsteps / (j_ms / 1000.0), "unit": UNIT, "batch": jn, "steps": jsteps, "ms_per_step": j_ms / jsteps,
+                        "h2d_bytes_per_step": int(zaru_b200.last_h2d_bytes()), "jpeg_bytes_per_step": int(sum(len(j) for j in jpegs)),
+                        "d2h_bytes_per_step": jn * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24), "host_threads": os.cpu_count(),
+                        "frames_with_face": int((jr[3] >= 0).sum()),
+                        "note": "baseline 4:2:0 JPEG (quality 80) of the same frames -> zb_frames_decode_jpeg (host Huffman decoding "
+                                "on all host cores, sparse coefficients H2D, device IDCT / upsampling / colour) -> zb_face_pipeline_run "
+                                "-> results D2H; bound by the host entropy decoding"}
+            del jbatch
+        except Exception as ex:  # noqa: BLE001
+            log(f"[rank 0] JPEG ingest leg skipped: {ex}")
     clock_info = clocks.stop() if rank == 0 else None
     d2h = e2e_n * (args.cap * 88 + 4 + 468 * 3 * 4 + 4 + 24)
 
@@ -765,6 +877,8 @@ def run_gpu(args):
                 e2e_best = dict(e2e_mt, single_thread=single, **nested)
             else:
                 e2e_best = dict(e2e_best, multi_thread=e2e_mt)
+    if jpeg_leg is not None:
+        e2e_best = dict(e2e_best, jpeg_ingest=jpeg_leg)
     peak, peak_src = peaks()
     roof, kernels = roofline_block(prof, peak, peak_src)
     face_frac = n_with_face / float(batch_n)
@@ -787,6 +901,7 @@ def run_gpu(args):
                                "without a detection, examples/facemesh.rs:49-55); `all_frames_landmarked` = SURVEY §8d's unit",
                    "landmark_policy": "face mesh runs on the frames in which BlazeFace found a face (device-side compaction), as "
                                       "the reference's loop and the CPU arm do; `all_frames_landmarked` = forced over every frame",
+                   "numa": numa,
                    "timing": "CUDA events on the library stream around the K steps, max over ranks"},
         "wall_ms_per_step": wall_ms_max / args.steps,
         "gpu_launches": int(launches),
@@ -831,6 +946,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-steady-state", action="store_true")
+    ap.add_argument("--no-jpeg", action="store_true", help="skip the MJPG ingest leg of e2e")
+    ap.add_argument("--jpeg-batch", type=int, default=256)
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank's host threads to its GPU's NUMA node")
     ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4],
                     help="BASELINE.json config: 4 = full face pipeline (default, the headline), 2 = face mesh + iris on "
                          "detector crops (batch 256), 3 = palm detection + hand landmarks (batch 256)")

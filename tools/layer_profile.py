@@ -42,7 +42,7 @@ elif args.config == 3:
     pipe = HandPipeline()
     pipe.set_threshold(0.1, 0.3)
     pipe.set_dense(True)
-    run = lambda: pipe.run(batch, n)
+    run = lambda: pipe.run_raw(batch, n)
 else:
     det = FacePipeline().run(batch, n)
     found = [i for i in range(n) if len(det.detections[i]) > 0]

@@ -94,6 +94,11 @@ def timer_stop_ms() -> float:
     return float(ms.value)
 
 
+def last_h2d_bytes() -> int:
+    """Bytes the last `zb_frames_decode_jpeg` call on this thread's context sent to the device."""
+    return int(_ffi.lib().zb_last_h2d_bytes(context()))
+
+
 def profile_begin(per_layer: bool = False):
     """Bracket every kernel launch on this thread's context with CUDA events; per_layer: one row per network layer."""
     _ffi.check(_ffi.lib().zb_profile_set_detail(context(), 1 if per_layer else 0))

@@ -272,16 +272,17 @@ void jpeg_decode_sparse(const uint8_t *data, size_t len, const JpegHeader &h, ui
     }
     int block_base[3] = {0, 0, 0};
     for (int c = 1; c < h.ncomp; c++) block_base[c] = block_base[c - 1] + h.blocks_w[c - 1] * h.blocks_h[c - 1];
-    stream.clear();
-    stream.reserve(len * 4);
+    // every non-zero coefficient costs at least 3 bits of entropy-coded data (a >= 2-bit code and >= 1 value bit), so
+    // 3 bytes per coefficient never exceed 8 x the compressed size (+ one triple per block for the DC terms)
+    stream.resize((len - h.scan_offset) * 8 + (size_t)3 * (h.mcus_x * h.mcus_y * 6) + 64);
+    uint8_t *wp = stream.data();
     BitReader br(data + h.scan_offset, data + len);
     int pred[3] = {0, 0, 0};
     int restart_left = h.restart_interval;
     int next_rst = 0;
     auto put = [&](int idx, int v) {
-        stream.push_back((uint8_t)idx);
-        stream.push_back((uint8_t)(v & 255));
-        stream.push_back((uint8_t)((v >> 8) & 255));
+        wp[0] = (uint8_t)idx, wp[1] = (uint8_t)(v & 255), wp[2] = (uint8_t)((v >> 8) & 255);
+        wp += 3;
     };
     for (int my = 0; my < h.mcus_y; my++) {
         for (int mx = 0; mx < h.mcus_x; mx++) {
@@ -300,7 +301,8 @@ void jpeg_decode_sparse(const uint8_t *data, size_t len, const JpegHeader &h, ui
                 for (int by = 0; by < h.vs[c]; by++)
                     for (int bx = 0; bx < h.hs[c]; bx++) {
                         const int b = block_base[c] + (my * h.vs[c] + by) * h.blocks_w[c] + (mx * h.hs[c] + bx);
-                        start[b] = (uint32_t)stream.size();
+                        start[b] = (uint32_t)(wp - stream.data());
+                        if ((size_t)(wp - stream.data()) + 3 * 64 > stream.size()) bad("coefficient stream overflow");
                         int n = 0;
                         const int sdc = decode_symbol(br, tdc);
                         if (sdc > 15) bad("DC category");
@@ -326,6 +328,7 @@ void jpeg_decode_sparse(const uint8_t *data, size_t len, const JpegHeader &h, ui
             if (h.restart_interval) restart_left--;
         }
     }
+    stream.resize((size_t)(wp - stream.data()));
 }
 
 }  // namespace zb

@@ -145,14 +145,20 @@ class HandPipeline:
         """dense=True: run the hand landmark network over every frame instead of only those with a palm (same results)."""
         _ffi.check(_ffi.lib().zb_hand_pipeline_set_dense(self._h, 1 if dense else 0))
 
+    def run_raw(self, batch, n=None):
+        """One pass over `n` frames; results land in reusable host buffers (no Python unpacking)."""
+        n = len(batch) if n is None else n
+        if getattr(self, "_bufs", None) is None or self._bufs[0] != n:
+            self._bufs = (n, (_ffi.zb_detection * (n * self._cap))(), (C.c_int32 * n)(), np.empty((n, 21, 3), np.float32),
+                          np.empty((n, 2), np.float32), (_ffi.zb_view * n)())
+        _, dets, counts, lm, sc, rois = self._bufs
+        _ffi.check(_ffi.lib().zb_hand_pipeline_run(self._h, batch._h, n, dets, counts, self._cap, lm.ctypes.data, sc.ctypes.data, rois))
+        return dets, counts, lm, sc, rois
+
     def run(self, batch, n=None) -> HandPipelineResult:
         n = len(batch) if n is None else n
-        dets = (_ffi.zb_detection * (n * self._cap))()
-        counts = (C.c_int32 * n)()
-        lm = np.empty((n, 21, 3), np.float32)
-        sc = np.empty((n, 2), np.float32)
-        rois = (_ffi.zb_view * n)()
-        _ffi.check(_ffi.lib().zb_hand_pipeline_run(self._h, batch._h, n, dets, counts, self._cap, lm.ctypes.data, sc.ctypes.data, rois))
+        dets, counts, lm, sc, rois = self.run_raw(batch, n)
+        lm, sc = lm.copy(), sc.copy()
         out = [Detections(Detection(dets[i * self._cap + k]) for k in range(min(counts[i], self._cap))) for i in range(n)]
         r = np.array([[v.cx, v.cy, v.w, v.h, v.radians] for v in rois], np.float32).reshape(n, 5)
         return HandPipelineResult(out, lm, sc[:, 0].copy(), sc[:, 1].copy(), r)
