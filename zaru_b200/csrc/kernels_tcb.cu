@@ -51,7 +51,13 @@ struct TcbGeom {
     int rows_max;          // worst-case staged input rows of one tile
     int nin;               // input staging buffers (1 or 2)
     int nbw;               // pointwise-weight buffers (1 or 2)
+    int tw_shift;          // log2(TW)
+    unsigned ho_magic, tx_magic;   // magic multipliers of the per-tile divisions by Ho and tiles_x (0: divisor is 1)
 };
+
+// n / d for 0 <= n, n * d < 2^32, with magic = floor(2^32 / d) + 1 (d >= 2) or 0 (d == 1)
+__device__ __forceinline__ int fast_div(int n, unsigned magic) { return magic ? (int)__umulhi((unsigned)n, magic) : n; }
+__host__ unsigned div_magic(int d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)d + 1ull); }
 
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile(
@@ -142,30 +148,56 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
     const uint32_t idesc = make_idesc_tf32(TCB_M, NP);
     const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), TCB_AROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), TCB_AROWS * 16, 128);
 
+    // The MMAs of step s are only WAITED FOR where their result or their operand buffer is needed: before the A tile is
+    // overwritten by step s + 1 (after that step's depthwise FMAs, which only touch registers) and before the epilogue.
+    // (ncu on the first version, which waited right after the commit: a third of all warp samples sat on that barrier.)
+    bool mma_pending = false;
     int step = 0;
+    auto mma_done = [&]() {                                                   // all threads; `step` = steps issued so far
+        if (!mma_pending) return;
+        mbar_wait(&mbar_mma, (step - 1) & 1);
+        tc_fence_after();
+        mma_pending = false;
+        if (tid == 0 && !b_resident && step - 1 + g.nbw < total_steps) load_b(step - 1 + g.nbw);   // that weight buffer is free again
+    };
+    const bool prelu_mid = p.act_mid.kind == ACT_PRELU;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tile_x = tile % g.tiles_x, tile_y = tile / g.tiles_x;
+        const int tile_y = fast_div(tile, g.tx_magic), tile_x = tile - tile_y * g.tiles_x;
         const int vr0 = tile_y * g.TH, ox0 = tile_x * g.TW;
         const int n_vr = min(g.TH, g.vrows - vr0);                           // valid virtual rows of this tile (>= 1)
         const bool p_valid = pr < n_vr && ox0 + pcol < p.Wo;
         const int p_vr = vr0 + pr;
-        const int p_iy0 = (p_vr - (p_vr / p.Ho) * p.Ho) * S - p.pt;          // input row of the window's first tap row
+        const int p_iy0 = (p_vr - fast_div(p_vr, g.ho_magic) * p.Ho) * S - p.pt;          // input row of the window's first tap row
         unsigned kymask = 0;                                                  // bit ky: that tap row lies inside the image
 #pragma unroll
         for (int ky = 0; ky < KS; ky++) kymask |= (p_iy0 + ky >= 0 && p_iy0 + ky < p.H) ? (1u << ky) : 0u;
         uint32_t acc_flag = 0;
+        // row table of this tile's epilogue (the previous tile's epilogue ended with a CTA barrier; the barriers of the steps
+        // below order these writes before the reads)
+        if (tid < TCB_M) {
+            const int er = tid >> g.tw_shift, ecol = tid - (er << g.tw_shift);
+            const int evr = vr0 + er, ox = ox0 + ecol;
+            TceRow ri;
+            ri.out_off = -1, ri.res_off = 0;
+            if (er < n_vr && ox < p.Wo) {
+                const int img = fast_div(evr, g.ho_magic);
+                ri = tce_row(p, img, evr - img * p.Ho, ox);
+            }
+            s_rowinfo[tid] = ri;
+        }
 
         for (int c = 0; c < nchunks; c++, step++) {
-            const int buf = step % g.nin;
-            mbar_wait(&mbar_in[buf], (step / g.nin) & 1);                     // this step's halo + depthwise weights have landed
-            __syncthreads();                                                  // (everybody is past the previous step's MMAs / epilogue)
+            const int buf = g.nin == 2 ? (step & 1) : 0;
+            mbar_wait(&mbar_in[buf], (g.nin == 2 ? (step >> 1) : step) & 1);  // this step's halo + depthwise weights have landed
+            // buffer (step + 1) % 2 was last read by step - 1, and everybody passed that step's barrier
             if (g.nin == 2 && warp == 0) issue_in(step + 1);                  // next step streams in behind this one
 
+            float4 v[PPT];
+            const int k = c * TCB_CK + quad * 4;
             if (p_valid) {
                 const float *s_w = s_in0 + (size_t)buf * in_floats + halo_floats;
                 const float *s_in = s_in0 + (size_t)buf * in_floats + (size_t)origin * TCB_CK + quad * 4;
                 const float4 bias = *reinterpret_cast<const float4 *>(s_w + TAPS * TCB_CK + quad * 4);
-                float4 v[PPT];
 #pragma unroll
                 for (int i = 0; i < PPT; i++) v[i] = bias;
 #pragma unroll
@@ -179,18 +211,29 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
                     for (int kx = 0; kx < KS; kx++) {
                         const float4 wv = *reinterpret_cast<const float4 *>(s_w + (ky * KS + kx) * TCB_CK + quad * 4);
 #pragma unroll
-                        for (int i = 0; i < PPT; i++) {
-                            v[i].x = fmaf(x[i * S + kx].x, wv.x, v[i].x);
-                            v[i].y = fmaf(x[i * S + kx].y, wv.y, v[i].y);
-                            v[i].z = fmaf(x[i * S + kx].z, wv.z, v[i].z);
-                            v[i].w = fmaf(x[i * S + kx].w, wv.w, v[i].w);
-                        }
+                        for (int i = 0; i < PPT; i++) fma4(v[i], x[i * S + kx], wv);   // packed FFMA2, rounds like fmaf
                     }
                 }
-                const int k = c * TCB_CK + quad * 4;
+                if (k < p.K && p.act_mid.kind != ACT_NONE) {
+                    if (prelu_mid) {
+                        const float4 sl = ldg4(p.act_mid.slope + k);
+#pragma unroll
+                        for (int i = 0; i < PPT; i++) {
+                            v[i].x = v[i].x < 0.0f ? v[i].x * sl.x : v[i].x;
+                            v[i].y = v[i].y < 0.0f ? v[i].y * sl.y : v[i].y;
+                            v[i].z = v[i].z < 0.0f ? v[i].z * sl.z : v[i].z;
+                            v[i].w = v[i].w < 0.0f ? v[i].w * sl.w : v[i].w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < PPT; i++) act4(v[i], p.act_mid, k);
+                    }
+                }
+            }
+            mma_done();                                                       // the previous step's MMAs have read the A tile
+            if (p_valid) {
 #pragma unroll
                 for (int i = 0; i < PPT; i++) {
-                    if (k < p.K) act4(v[i], p.act_mid, k);
                     float4 hi, lo;
                     split_tf32_fast(v[i].x, hi.x, lo.x);
                     split_tf32_fast(v[i].y, hi.y, lo.y);
@@ -203,9 +246,9 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            tc_fence_after();
             if (g.nin == 1 && warp == 0) issue_in(step + 1);                  // single buffer: refill behind the MMAs
             if (tid == 0) {
+                tc_fence_after();
                 const int bb = b_resident ? c : step % g.nbw;
                 mbar_wait(&mbar_b[bb], b_resident ? 0 : ((step / g.nbw) & 1)); // this chunk's pointwise weights have landed
                 const float *sB = sB0 + (size_t)bb * b_floats;
@@ -224,29 +267,13 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
                     }
                 }
                 umma_commit(&mbar_mma);
-                mbar_wait(&mbar_mma, step & 1);                               // one poller; everybody else parks at the barrier
-                if (!b_resident && step + g.nbw < total_steps) load_b(step + g.nbw);   // this weight buffer is free again
             }
-            tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
+            mma_pending = true;
         }
-
         // --- epilogue through shared memory (coalesced residual reads / stores); the staging tile aliases the A tile, the
-        // next tile's first halo is already on its way ---
-        if (tid < TCB_M) {
-            const int er = tid / g.TW, ecol = tid - er * g.TW;
-            const int evr = vr0 + er, ox = ox0 + ecol;
-            TceRow ri;
-            ri.out_off = -1, ri.res_off = 0;
-            if (er < n_vr && ox < p.Wo) {
-                const int img = evr / p.Ho;
-                ri = tce_row(p, img, evr - img * p.Ho, ox);
-            }
-            s_rowinfo[tid] = ri;
-        }
-        __syncthreads();
-        tc_epilogue_tile<NT, 0>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid);
+        // next tile's first halo is already on its way.  `step` now counts this tile's last step as issued. ---
+        // the wait for the last MMAs sits inside, behind the epilogue's residual / bias loads
+        tc_epilogue_tile<NT, 0>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid, [&]() { mma_done(); });      // ends with a CTA barrier
         tc_fence_before();                                                    // accumulator read before the next tile's MMAs overwrite it
     }
     tc_fence_before();
@@ -460,6 +487,13 @@ TcbGeom choose_geom(const ConvDev &p, int KS, int S) {
     best.vrows = images * p.Ho;
     best.tiles_y = (best.vrows + best.TH - 1) / best.TH;
     best.rows_max = (best.TH - 1) * S + KS;    // one contiguous row range per tile (merged image / row dimension)
+    best.tw_shift = 0;
+    while ((1 << best.tw_shift) < best.TW) best.tw_shift++;
+    // the magic divisions are exact while n * d < 2^32: n < vrows (resp. tiles), d = Ho (resp. tiles_x)
+    const bool ho_ok = (unsigned long long)best.vrows * (unsigned)p.Ho < (1ull << 32);
+    const bool tx_ok = (unsigned long long)best.tiles_x * best.tiles_y * (unsigned)best.tiles_x < (1ull << 32);
+    if (!ho_ok || !tx_ok) best.TW = 0;         // (never for the networks here: 65535 frames x 96 rows is 6e6 virtual rows)
+    best.ho_magic = div_magic(p.Ho), best.tx_magic = div_magic(best.tiles_x);
     return best;
 }
 

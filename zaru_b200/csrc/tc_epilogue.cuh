@@ -83,7 +83,7 @@ constexpr int TCE_NB = 64;                 // columns per staging block
 constexpr int TCE_STRIDE = TCE_NB + 4;     // padded row stride (floats): conflict-free 128-bit row-per-lane stores
 
 struct TceRow {
-    long long out_off, res_off;
+    long long out_off, res_off;            // BYTE offsets of the output pixel / its residual pixel; out_off < 0: no pixel
 };
 
 template <int NTHREADS, int BAR_ID>
@@ -96,35 +96,108 @@ __device__ __forceinline__ void tce_sync() {
 // its 2x2 pooling window
 __device__ __forceinline__ TceRow tce_row(const ConvDev &p, int img, int oy, int ox) {
     TceRow r;
-    r.out_off = (long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride;
+    r.out_off = 4 * ((long long)img * p.out_img_stride + ((long long)oy * p.Wo + ox) * p.out_pix_stride);
     const EpiDev &e = p.epi;
     r.res_off = 0;
-    if (e.res) r.res_off = (long long)img * e.res_img_stride + (e.res_pool ? ((long long)(2 * oy) * e.res_W + 2 * ox) : ((long long)oy * e.res_W + ox)) * e.res_Cs;
+    if (e.res)
+        r.res_off = 4 * ((long long)img * e.res_img_stride +
+                         (e.res_pool ? ((long long)(2 * oy) * e.res_W + 2 * ox) : ((long long)oy * e.res_W + ox)) * e.res_Cs);
     return r;
 }
 
-__device__ __forceinline__ void tce_act(float (&v)[4], int kind, float lo, float hi, const float4 &sl) {
-    if (kind == ACT_NONE) return;
-    if (kind == ACT_RELU) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], 0.0f);
-    } else if (kind == ACT_PRELU) {
-        v[0] = v[0] < 0.0f ? v[0] * sl.x : v[0];
-        v[1] = v[1] < 0.0f ? v[1] * sl.y : v[1];
-        v[2] = v[2] < 0.0f ? v[2] * sl.z : v[2];
-        v[3] = v[3] < 0.0f ? v[3] * sl.w : v[3];
-    } else if (kind == ACT_CLIP) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = fminf(fmaxf(v[q], lo), hi);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = 1.0f / (1.0f + expf(-v[q]));
+// activation of one channel quad.  The kinds arrive as flags the caller derived ONCE (an if-chain on the raw kind was
+// turned into a jump table - LDC + BRX per call - by the compiler)
+struct TceAct {
+    bool relu, prelu, other;
+    int kind;
+    float lo, hi;
+};
+__device__ __forceinline__ TceAct tce_act_of(const ActDev &a) {
+    TceAct t;
+    t.relu = a.kind == ACT_RELU, t.prelu = a.kind == ACT_PRELU;
+    t.other = a.kind != ACT_NONE && !t.relu && !t.prelu;
+    t.kind = a.kind, t.lo = a.lo, t.hi = a.hi;
+    return t;
+}
+__device__ __forceinline__ void tce_act(float4 &v, const TceAct &a, const float4 &sl) {
+    if (a.prelu) {
+        v.x = v.x < 0.0f ? v.x * sl.x : v.x;
+        v.y = v.y < 0.0f ? v.y * sl.y : v.y;
+        v.z = v.z < 0.0f ? v.z * sl.z : v.z;
+        v.w = v.w < 0.0f ? v.w * sl.w : v.w;
+    } else if (a.relu) {
+        v.x = fmaxf(v.x, 0.0f), v.y = fmaxf(v.y, 0.0f), v.z = fmaxf(v.z, 0.0f), v.w = fmaxf(v.w, 0.0f);
+    } else if (a.other) {
+        if (a.kind == ACT_CLIP) {
+            v.x = fminf(fmaxf(v.x, a.lo), a.hi), v.y = fminf(fmaxf(v.y, a.lo), a.hi);
+            v.z = fminf(fmaxf(v.z, a.lo), a.hi), v.w = fminf(fmaxf(v.w, a.lo), a.hi);
+        } else {
+            v.x = 1.0f / (1.0f + expf(-v.x)), v.y = 1.0f / (1.0f + expf(-v.y));
+            v.z = 1.0f / (1.0f + expf(-v.z)), v.w = 1.0f / (1.0f + expf(-v.w));
+        }
     }
 }
 
-template <int NTHREADS = 256, int BAR_ID = 0>
+// Fast path, split in two so that the global loads fly while the accumulator is still on its way:
+//   tce_fetch  - row table entries + residual loads of NI rows r0, r0 + rstep, ... of one channel quad (issued, not consumed)
+//   tce_finish - staged accumulator + bias -> act1 -> + residual -> act2 -> 128-bit store
+// Rows without a pixel (out_off < 0) run the arithmetic on zeros and skip the store: no divergent control flow in the loop.
+template <int NI>
+struct TceFetch {
+    float4 rr[NI];                 // residual quads in flight (the row offsets are re-read from the table: registers)
+};
+template <int NI, bool GUARD>
+__device__ __forceinline__ void tce_fetch(const EpiDev &e, const TceRow *rt, int r0, int rstep, const char *resb, bool has_res, TceFetch<NI> &f) {
+#pragma unroll
+    for (int i = 0; i < NI; i++) f.rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!has_res) return;
+    if (!e.res_pool) {
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            if (GUARD && r0 + i * rstep >= TCB_EPI_ROWS) continue;
+            const TceRow t = rt[i * rstep];
+            if (t.out_off >= 0) f.rr[i] = ldg4(reinterpret_cast<const float *>(resb + t.res_off));
+        }
+    } else {                                           // 2x2 max-pool of the residual (stride-2 blocks)
+        const long long pool_dx = 4ll * e.res_Cs, pool_dy = 4ll * e.res_W * e.res_Cs;
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            if (GUARD && r0 + i * rstep >= TCB_EPI_ROWS) continue;
+            const TceRow t = rt[i * rstep];
+            if (t.out_off < 0) continue;
+            const char *rp = resb + t.res_off;
+            const float4 a = ldg4(reinterpret_cast<const float *>(rp)), b = ldg4(reinterpret_cast<const float *>(rp + pool_dx));
+            const float4 c = ldg4(reinterpret_cast<const float *>(rp + pool_dy)), d = ldg4(reinterpret_cast<const float *>(rp + pool_dy + pool_dx));
+            f.rr[i] = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
+                                  fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
+        }
+    }
+}
+template <int NI, bool GUARD>
+__device__ __forceinline__ void tce_finish(const TceFetch<NI> &f, const TceRow *rt, const float *stg, int r0, int rstep, char *outb,
+                                           const float4 &bias, const TceAct &a1, const TceAct &a2, const float4 &sl1, const float4 &sl2) {
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        if (GUARD && r0 + i * rstep >= TCB_EPI_ROWS) continue;
+        const float4 a = *reinterpret_cast<const float4 *>(stg + i * rstep * TCE_STRIDE);
+        const long long oo = rt[i * rstep].out_off;
+        float4 v = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+        tce_act(v, a1, sl1);
+        v.x += f.rr[i].x, v.y += f.rr[i].y, v.z += f.rr[i].z, v.w += f.rr[i].w;
+        tce_act(v, a2, sl2);
+        if (oo >= 0) *reinterpret_cast<float4 *>(outb + oo) = v;
+    }
+}
+
+struct TceNoWait {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `ready()` is called once, after the first column block's global loads have been issued and before the accumulator is
+// read: callers park their wait for the tile's last MMAs there.
+template <int NTHREADS = 256, int BAR_ID = 0, class Ready = TceNoWait>
 __device__ __forceinline__ void tc_epilogue_tile(const ConvDev &p, uint32_t tmem, int n0, int NT, const TceRow *s_rowinfo,
-                                                 float *s_stage, int tid) {
+                                                 float *s_stage, int tid, Ready ready = Ready()) {
     const EpiDev &e = p.epi;
     const int warp = tid >> 5, lane = tid & 31;
     const int row_t = (warp & 3) * 32 + lane, grp = warp >> 2;      // grp: which 16-column chunks this warp moves
@@ -133,9 +206,33 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvDev &p, uint32_t tmem
     // guarded path)
     const bool fast = (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0) && (p.Ns % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (!e.res || (e.res_Cs % 4) == 0);
-    const long long pool_dx = e.res_Cs, pool_dy = (long long)e.res_W * e.res_Cs;
+    const TceAct a1 = tce_act_of(e.act1), a2 = tce_act_of(e.act2);
+    // rows in flight per thread: one batch covers the tile when a thread has <= 8 rows (512-thread CTAs run at 64 registers: 4)
+    constexpr int NI = NTHREADS >= 512 ? 4 : 8;
     for (int cb = 0; cb < NT; cb += TCE_NB) {
         const int nb = min(TCE_NB, NT - cb);             // multiple of 16
+        // one channel quad per thread, rows r0, r0 + rstep, ...
+        const int qb = nb >> 2;                          // 4, 8, 12 or 16 quads
+        int q, r0, rstep;
+        if (qb == 16) q = tid & 15, r0 = tid >> 4, rstep = NTHREADS / 16;
+        else if (qb == 8) q = tid & 7, r0 = tid >> 3, rstep = NTHREADS / 8;
+        else if (qb == 4) q = tid & 3, r0 = tid >> 2, rstep = NTHREADS / 4;
+        else q = tid % 12, r0 = tid / 12, rstep = NTHREADS / 12;
+        const int n = n0 + cb + 4 * q;
+        const bool active = r0 < rstep && n < p.Nstore;
+        // 0. (fast path) everything that comes from global memory for the first batch of rows
+        TceFetch<NI> f;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sl1 = bias, sl2 = bias;
+        const bool has_res = e.res && n < e.res_Cs;
+        const char *resb = reinterpret_cast<const char *>(e.res + n);
+        char *outb = reinterpret_cast<char *>(p.out + n);
+        if (fast && active) {
+            bias = ldg4(e.bias + n);
+            if (a1.prelu) sl1 = ldg4(e.act1.slope + n);
+            if (a2.prelu) sl2 = ldg4(e.act2.slope + n);
+            tce_fetch<NI, true>(e, s_rowinfo + r0, r0, rstep, resb, has_res, f);
+        }
+        if (cb == 0) ready();
         // 1. TMEM -> shared
         for (int j = grp; j < nb / 16; j += NTHREADS / 128) {
             float v[16];
@@ -145,56 +242,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvDev &p, uint32_t tmem
             for (int h = 0; h < 4; h++) *reinterpret_cast<float4 *>(dst + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
         }
         tce_sync<NTHREADS, BAR_ID>();
-        // 2. one channel quad per thread, rows r0, r0 + rstep, ...
-        const int qb = nb >> 2;
-        const int rstep = NTHREADS / qb;
-        const int q = tid % qb, r0 = tid / qb;
-        const int n = n0 + cb + 4 * q;
-        if (r0 < rstep && n < p.Nstore) {
+        // 2. finish
+        if (active) {
             if (fast) {
-                const float4 bias = ldg4(e.bias + n);
-                const float4 sl1 = e.act1.kind == ACT_PRELU ? ldg4(e.act1.slope + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 sl2 = e.act2.kind == ACT_PRELU ? ldg4(e.act2.slope + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const bool has_res = e.res && n < e.res_Cs;
-                const float *resn = e.res + n;
-                constexpr int MAXI = NTHREADS >= 512 ? 4 : 8;   // rows in flight per thread (512-thread CTAs run at 64 registers)
+                const float *stg = s_stage + r0 * TCE_STRIDE + 4 * q;
+                tce_finish<NI, true>(f, s_rowinfo + r0, stg, r0, rstep, outb, bias, a1, a2, sl1, sl2);
 #pragma unroll 1
-                for (int rb = r0; rb < TCB_EPI_ROWS; rb += MAXI * rstep) {
-                    TceRow ri[MAXI];
-                    float4 rr[MAXI];
-#pragma unroll
-                    for (int i = 0; i < MAXI; i++) {
-                        const int r = rb + i * rstep;
-                        ri[i].out_off = -1;
-                        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < TCB_EPI_ROWS) {
-                            ri[i] = s_rowinfo[r];
-                            if (ri[i].out_off >= 0 && has_res) {
-                                const float *rp = resn + ri[i].res_off;
-                                if (!e.res_pool) {
-                                    rr[i] = ldg4(rp);
-                                } else {
-                                    const float4 a = ldg4(rp), b = ldg4(rp + pool_dx), c = ldg4(rp + pool_dy), d = ldg4(rp + pool_dy + pool_dx);
-                                    rr[i] = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
-                                                        fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < MAXI; i++) {
-                        if (ri[i].out_off < 0) continue;
-                        const int r = rb + i * rstep;
-                        const float4 a = *reinterpret_cast<const float4 *>(s_stage + r * TCE_STRIDE + 4 * q);
-                        float v[4] = {a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w};
-                        tce_act(v, e.act1.kind, e.act1.lo, e.act1.hi, sl1);
-                        v[0] += rr[i].x, v[1] += rr[i].y, v[2] += rr[i].z, v[3] += rr[i].w;
-                        tce_act(v, e.act2.kind, e.act2.lo, e.act2.hi, sl2);
-                        *reinterpret_cast<float4 *>(p.out + ri[i].out_off + n) = make_float4(v[0], v[1], v[2], v[3]);
-                    }
+                for (int rb = r0 + NI * rstep; rb < TCB_EPI_ROWS; rb += NI * rstep) {     // further batches (small CTAs / few quads)
+                    tce_fetch<NI, true>(e, s_rowinfo + rb, rb, rstep, resb, has_res, f);
+                    tce_finish<NI, true>(f, s_rowinfo + rb, s_stage + rb * TCE_STRIDE + 4 * q, rb, rstep, outb, bias, a1, a2, sl1, sl2);
                 }
             } else {
                 // guarded path: scalar tails of bias / store, scalar residual
+                const long long pool_dx = e.res_Cs, pool_dy = (long long)e.res_W * e.res_Cs;
                 for (int r = r0; r < TCB_EPI_ROWS; r += rstep) {
                     const TceRow ri = s_rowinfo[r];
                     if (ri.out_off < 0) continue;
@@ -208,7 +268,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvDev &p, uint32_t tmem
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             if (n + k >= e.res_Cs) continue;
-                            const float *rp = e.res + ri.res_off + n + k;
+                            const float *rp = e.res + (ri.res_off >> 2) + n + k;
                             v[k] += e.res_pool ? fmaxf(fmaxf(__ldg(rp), __ldg(rp + pool_dx)), fmaxf(__ldg(rp + pool_dy), __ldg(rp + pool_dy + pool_dx)))
                                                : __ldg(rp);
                         }
@@ -216,7 +276,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvDev &p, uint32_t tmem
                     act4(v, e.act2, n);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        if (n + k < p.Nstore) p.out[ri.out_off + n + k] = v[k];
+                        if (n + k < p.Nstore) p.out[(ri.out_off >> 2) + n + k] = v[k];
                 }
             }
         }
