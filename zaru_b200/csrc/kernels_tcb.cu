@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
         unsigned kymask = 0;                                                  // bit ky: that tap row lies inside the image
 #pragma unroll
         for (int ky = 0; ky < KS; ky++) kymask |= (p_iy0 + ky >= 0 && p_iy0 + ky < p.H) ? (1u << ky) : 0u;
-        uint32_t acc_flag = 0;
         // row table of this tile's epilogue (the previous tile's epilogue ended with a CTA barrier; the barriers of the steps
         // below order these writes before the reads)
         if (tid < TCB_M) {
@@ -247,8 +246,11 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
             tc_fence_before();
             __syncthreads();
             if (g.nin == 1 && warp == 0) issue_in(step + 1);                  // single buffer: refill behind the MMAs
-            if (tid == 0) {
+            // the issuing thread rotates over the warps: the ~100 dependent instructions of descriptor arithmetic and MMA
+            // issue sit on a different warp's critical path every step (every warp does the same producer work)
+            if (tid == ((step & (NT / 32 - 1)) << 5)) {
                 tc_fence_after();
+                uint32_t acc_flag = c > 0;
                 const int bb = b_resident ? c : step % g.nbw;
                 mbar_wait(&mbar_b[bb], b_resident ? 0 : ((step / g.nbw) & 1)); // this chunk's pointwise weights have landed
                 const float *sB = sB0 + (size_t)bb * b_floats;
