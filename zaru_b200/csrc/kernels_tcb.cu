@@ -43,6 +43,8 @@ constexpr int TCB_AROWS = TCB_M + 1;  // padded chunk stride of the A tile: conf
 // floats reserved for the A tile (hi + lo); the epilogue's staging tile (128 x TCE_STRIDE) aliases it once the MMAs are done
 constexpr int TCB_A_FLOATS = 2 * TCB_KQC * TCB_AROWS * 4 > TCB_M * TCE_STRIDE ? 2 * TCB_KQC * TCB_AROWS * 4 : TCB_M * TCE_STRIDE;
 
+constexpr int TCB_ZERO_FLOATS = ((4 - 1) * 2 + 5) * TCB_CK;   // widest window row: SPAN = (PPT - 1) * S + KS channel-chunk pixels
+
 struct TcbGeom {
     int TW, TH;            // tile = TH virtual rows x TW columns, TW * TH = 128
     int tiles_x, tiles_y;
@@ -86,8 +88,13 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
     __shared__ __align__(8) uint64_t mbar_in[2], mbar_b[2], mbar_mma;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) TceRow s_rowinfo[TCB_M];
+    // a window row of zeros: tap rows outside the image read it instead of branching around the row, which keeps the whole
+    // window in one basic block (the per-row branch stopped the compiler from issuing row ky + 1's loads above row ky's FMAs)
+    // (it lives behind the weight buffers in dynamic shared memory: static shared memory is not part of the launch's budget)
+    float *s_zero = sB0 + (size_t)g.nbw * b_floats;                          // [TCB_ZERO_FLOATS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < TCB_ZERO_FLOATS; i += 1024 / PPT) s_zero[i] = 0.0f;
     const uint32_t ncols = tmem_cols_for(NP);
     const uint32_t b_bytes = (uint32_t)TCB_KQC * NP * 16;
     const uint32_t in_bytes = (uint32_t)in_floats * 4;                        // halo box + depthwise weights: one mbarrier phase
@@ -201,9 +208,8 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
                 for (int i = 0; i < PPT; i++) v[i] = bias;
 #pragma unroll
                 for (int ky = 0; ky < KS; ky++) {
-                    if (!((kymask >> ky) & 1u)) continue;
                     float4 x[SPAN];
-                    const float *rowp = s_in + (size_t)ky * g.WBOX * TCB_CK;
+                    const float *rowp = ((kymask >> ky) & 1u) ? s_in + (size_t)ky * g.WBOX * TCB_CK : s_zero + quad * 4;
 #pragma unroll
                     for (int j = 0; j < SPAN; j++) x[j] = *reinterpret_cast<const float4 *>(rowp + j * TCB_CK);
 #pragma unroll
@@ -501,7 +507,7 @@ TcbGeom choose_geom(const ConvDev &p, int KS, int S) {
 
 size_t tcb_smem(const TcbGeom &g, int KS, int NP, int nin, int nbw = 1) {
     return (size_t)nin * ((size_t)g.rows_max * g.WBOX * TCB_CK + (size_t)(KS * KS + 1) * TCB_CK) * 4 + (size_t)TCB_A_FLOATS * 4 +
-           (size_t)nbw * 2 * TCB_KQC * NP * 16 + 1024;
+           (size_t)nbw * 2 * TCB_KQC * NP * 16 + (size_t)TCB_ZERO_FLOATS * 4;   // (static smem is 3 KB: the 1024-byte alignment of the base costs nothing)
 }
 
 template <int KS, int S, int PPT>
