@@ -12,10 +12,13 @@
 //   zaru::landmark::{Estimator, LandmarkTracker, LandmarkFilter} . crates/zaru/src/landmark.rs
 //   zaru::filter::{Ema, OneEuroFilter, AlphaBetaFilter} .......... crates/zaru/src/filter/*.rs
 #pragma once
+#include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <fstream>
 #include <iterator>
+#include <limits>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -67,6 +70,16 @@ struct Rect {
     float width() const { return r.w; }
     float height() const { return r.h; }
     std::pair<float, float> center() const { return {r.cx, r.cy}; }
+    // `Rect::bounding` (rect.rs:49-68): smallest axis-aligned rectangle around the points; empty input -> nullopt
+    static std::optional<Rect> bounding(const std::vector<std::pair<float, float>> &pts) {
+        if (pts.empty()) return std::nullopt;
+        float minx = pts[0].first, miny = pts[0].second, maxx = minx, maxy = miny;
+        for (size_t i = 1; i < pts.size(); i++) {
+            minx = std::min(minx, pts[i].first), miny = std::min(miny, pts[i].second);
+            maxx = std::max(maxx, pts[i].first), maxy = std::max(maxy, pts[i].second);
+        }
+        return from_top_left(minx, miny, maxx - minx, maxy - miny);
+    }
     Rect grow_rel(float amount) const { return Rect{zb::grow_rel(r, amount)}; }                     // rect.rs:84-94
     Rect grow_to_fit_aspect(AspectRatio a) const { return Rect{zb::grow_to_fit_aspect(r, a.as_f32())}; }   // :104-117
 };
@@ -91,6 +104,22 @@ struct RotatedRect {
         zb::transform_out(with_trig(), px, py, ox, oy);
         return {ox, oy};
     }
+    // `RotatedRect::bounding(radians, points)` (rect.rs:287-325): rotate the points clockwise into the rectangle's frame,
+    // take the axis-aligned bounds there, rotate the centre back.  Same operation order as the reference (Mat2 * v is
+    // folded from 0: (0 + c*x) + (-s)*y), glibc cosf / sinf.
+    static std::optional<RotatedRect> bounding(float radians, const std::vector<std::pair<float, float>> &pts) {
+        if (pts.empty()) return std::nullopt;
+        auto rot = [](float c, float s, float x, float y) { return std::pair<float, float>{(0.0f + c * x) + (-s) * y, (0.0f + s * x) + c * y}; };
+        const float c = std::cos(-radians), s = std::sin(-radians);
+        float minx = std::numeric_limits<float>::max(), miny = minx, maxx = -minx, maxy = -minx;
+        for (auto &pt : pts) {
+            auto [px, py] = rot(c, s, pt.first, pt.second);
+            minx = std::min(minx, px), miny = std::min(miny, py), maxx = std::max(maxx, px), maxy = std::max(maxy, py);
+        }
+        const float ccx = (minx + maxx) * 0.5f, ccy = (miny + maxy) * 0.5f;
+        auto [cx, cy] = rot(std::cos(radians), std::sin(radians), ccx, ccy);
+        return RotatedRect(Rect::from_center(cx, cy, maxx - minx, maxy - miny), radians);
+    }
     zb_view to_zb_view(int32_t frame) const { return zb_view{frame, rect_.r.cx, rect_.r.cy, rect_.r.w, rect_.r.h, radians}; }
     static RotatedRect from_zb_view(const zb_view &v) { return RotatedRect(Rect::from_center(v.cx, v.cy, v.w, v.h), v.radians); }
 };
@@ -108,7 +137,16 @@ class ImageBatch {
     ImageBatch(const ImageBatch &) = delete;
     ImageBatch &operator=(const ImageBatch &) = delete;
     void update(const uint8_t *rgba, int32_t first, int32_t count) { check(zb_frames_update(h_, rgba, first, count)); }
+    // `decode_jpeg` (zaru-image/src/jpeg.rs:107-222) for `count` baseline JPEG / MJPG streams, straight into frames
+    // [first, first + count): Huffman decoding on the host, inverse DCT / upsampling / colour conversion on the device
+    void decode_jpegs(int32_t first, const std::vector<std::pair<const uint8_t *, size_t>> &jpegs) {
+        std::vector<const uint8_t *> ptrs;
+        std::vector<size_t> sizes;
+        for (auto &j : jpegs) ptrs.push_back(j.first), sizes.push_back(j.second);
+        check(zb_frames_decode_jpeg(h_, first, ptrs.data(), sizes.data(), (int32_t)jpegs.size()));
+    }
     int32_t len() const { return n_; }
+    zb_frames *mutable_handle() { return h_; }
     Resolution resolution() const { return res_; }
     const zb_frames *handle() const { return h_; }
 
@@ -118,9 +156,28 @@ class ImageBatch {
     int32_t n_;
 };
 
+// `JpegInfo`: what the header says (no device work)
+struct JpegInfo {
+    int32_t width = 0, height = 0, components = 0, h_samp = 0, v_samp = 0;
+};
+inline JpegInfo jpeg_info(const uint8_t *jpeg, size_t len) {
+    JpegInfo i;
+    check(zb_jpeg_info(jpeg, len, &i.width, &i.height, &i.components, &i.h_samp, &i.v_samp));
+    return i;
+}
+
 class Image {
    public:
     static Image from_rgba8(Resolution res, const uint8_t *rgba) { return Image(std::make_shared<ImageBatch>(res, rgba, 1), 0); }
+    // `decode_jpeg(data) -> Image` (zaru-image/src/jpeg.rs:107): size from the header, pixels decoded on the device
+    static Image decode_jpeg(const uint8_t *jpeg, size_t len) {
+        const JpegInfo i = jpeg_info(jpeg, len);
+        const Resolution res{(uint32_t)i.width, (uint32_t)i.height};
+        std::vector<uint8_t> blank((size_t)res.w * res.h * 4, 0);
+        auto batch = std::make_shared<ImageBatch>(res, blank.data(), 1);
+        batch->decode_jpegs(0, {{jpeg, len}});
+        return Image(batch, 0);
+    }
     Image(std::shared_ptr<ImageBatch> batch, int32_t frame) : batch_(std::move(batch)), frame_(frame) {}
     uint32_t width() const { return batch_->resolution().w; }
     uint32_t height() const { return batch_->resolution().h; }
@@ -166,6 +223,14 @@ class ImageView {
 };
 inline ImageView Image::view(const RotatedRect &r) const { return ImageView(*this, RotatedRect(rect(), 0.0f)).view(r); }
 inline ImageView Image::as_view() const { return view(RotatedRect(rect(), 0.0f)); }
+
+// `zaru_image::blend(&mut dest, &src)` (zaru-image/src/blend.rs:13-32): draws the source view over the destination view with
+// linear filtering; happens at once (the reference defers it to the drop of the returned BlendOp).  The destination image
+// is modified on the device.
+inline void blend(const ImageView &dest, const ImageView &src) {
+    zb_view d = dest.to_zb_view(), sv = src.to_zb_view();
+    check(zb_blend(context(), dest.image().batch()->mutable_handle(), &d, src.image().batch()->handle(), &sv, 1));
+}
 
 // ---- zaru::nn -----------------------------------------------------------------------------------------
 namespace nn {
@@ -328,6 +393,12 @@ class Detector {                                                           // de
     ~Detector() { zb_detector_destroy(h_); }
     Detector(const Detector &) = delete;
     Resolution input_resolution() const { return cnn_.input_resolution(); }
+    // `Detector::timers()` (detection.rs:272-275): device ms of the last detect call: {t_infer, t_extract, t_nms}
+    std::array<float, 3> timers() const {
+        std::array<float, 3> ms{};
+        check(zb_detector_timers(h_, ms.data()));
+        return ms;
+    }
     void set_threshold(float t) { check(zb_detector_set_threshold(h_, t)); }
     void set_nms(float iou_thresh, NmsMode mode) { check(zb_detector_set_nms(h_, iou_thresh, (zb_nms_mode)mode)); }
     // `Detector::detect(&image)`: detections in the coordinate system of `view`, descending seed confidence
@@ -371,6 +442,17 @@ struct Estimate {                                     // `Estimate` + `Confidenc
     std::vector<float> positions;
     float confidence = 0.0f, scalar1 = 0.0f;          // scalar1: hand raw handedness / FaceMeshV2 tongueOut
     size_t len() const { return positions.size() / 3; }
+    std::pair<float, float> xy(size_t i) const { return {positions[3 * i], positions[3 * i + 1]}; }
+    // face mesh results (mediapipe.rs:146-192, :315-344, :407-421): head roll from the outer eye corners, and the
+    // RotatedRects around the eyes that seed the iris network
+    float rotation_radians() const {                                                // (right - left).signed_angle_to(Vec2::X)
+        const auto le = xy(33), re = xy(263);
+        const float ax = re.first - le.first, ay = re.second - le.second;
+        const float perp = ax * 0.0f - ay * 1.0f, dot = (0.0f + ax * 1.0f) + ay * 0.0f;
+        return -std::atan2(perp, dot);
+    }
+    RotatedRect left_eye() const { return *RotatedRect::bounding(rotation_radians(), {xy(145), xy(33), xy(133), xy(159)}); }
+    RotatedRect right_eye() const { return *RotatedRect::bounding(rotation_radians(), {xy(374), xy(362), xy(263), xy(386)}); }
 };
 
 class Estimator {                                     // landmark.rs:256-349
@@ -384,6 +466,12 @@ class Estimator {                                     // landmark.rs:256-349
     Estimator(const Estimator &) = delete;
     Resolution input_resolution() const { return cnn_.input_resolution(); }
     void set_filter(const LandmarkFilter &f) { check(zb_estimator_set_filter(h_, f.kind, f.p0, f.p1, f.p2, f.elapsed)); }
+    // `Estimator::timers()` (landmark.rs:347-349): device ms of the last estimate call: {t_infer, t_extract, t_filter}
+    std::array<float, 3> timers() const {
+        std::array<float, 3> ms{};
+        check(zb_estimator_timers(h_, ms.data()));
+        return ms;
+    }
     Estimate estimate(const ImageView &view, bool flip_x = false) {
         zb_view v = view.to_zb_view();
         Estimate e;
@@ -509,6 +597,53 @@ class FacePipeline {
     std::shared_ptr<nn::NeuralNetwork> det_, lm_;
     int32_t cap_, L_ = 0;
     zb_face_pipeline *h_ = nullptr;
+};
+
+// Face mesh + iris landmarks on device (BASELINE config 2): face mesh on each face crop -> `left_eye()` / `right_eye()`
+// (mediapipe.rs:163-192) grown by the eye margin -> EyeNetwork on both eye crops, the right one mirrored
+// (face/eye.rs:24-28, :121-125).  The reference ships the pieces and no composition; include/zaru_b200.h states the rule.
+class FaceIrisPipeline {
+   public:
+    struct Result {
+        std::vector<float> face_landmarks;                            // [n][L][3], frame coordinates
+        std::vector<float> face_flags;                                // [n]
+        std::vector<RotatedRect> face_view_rects;                     // aspect-fitted view the mesh ran on
+        std::vector<RotatedRect> eye_rois;                            // [n][2]: left, right
+        std::vector<float> eye_landmarks;                             // [n][2][76][3]: 5 iris points, then 71 contour points
+        int32_t num_landmarks = 0;
+    };
+    FaceIrisPipeline(const landmark::Network &mesh, const std::string &model_dir, float eye_margin = 0.0f)
+        : mesh_(nn::NeuralNetwork::from_path(model_dir + "/" + mesh.onnx)),
+          iris_(nn::NeuralNetwork::from_path(model_dir + "/" + landmark::EyeNetwork().onnx)) {
+        check(zb_face_iris_pipeline_create(context(), mesh_->handle(), iris_->handle(), &h_));
+        L_ = zb_face_iris_pipeline_num_landmarks(h_);
+        if (eye_margin != 0.0f) set_eye_margin(eye_margin);
+    }
+    ~FaceIrisPipeline() { zb_face_iris_pipeline_destroy(h_); }
+    FaceIrisPipeline(const FaceIrisPipeline &) = delete;
+    void set_eye_margin(float grow_rel_amount) { check(zb_face_iris_pipeline_set_eye_margin(h_, grow_rel_amount)); }
+    // face_rois: one crop per face (frame index inside); empty: every whole frame of the batch
+    Result run(const ImageBatch &batch, const std::vector<std::pair<int32_t, RotatedRect>> &face_rois = {}) {
+        const int32_t n = face_rois.empty() ? batch.len() : (int32_t)face_rois.size();
+        std::vector<zb_view> rois;
+        for (auto &r : face_rois) rois.push_back(r.second.to_zb_view(r.first));
+        std::vector<zb_view> vr(n), er((size_t)2 * n);
+        Result r;
+        r.num_landmarks = L_;
+        r.face_landmarks.resize((size_t)n * L_ * 3);
+        r.face_flags.resize(n);
+        r.eye_landmarks.resize((size_t)n * 2 * 76 * 3);
+        check(zb_face_iris_pipeline_run(h_, batch.handle(), rois.empty() ? nullptr : rois.data(), n, r.face_landmarks.data(),
+                                        r.face_flags.data(), vr.data(), er.data(), r.eye_landmarks.data()));
+        for (auto &v : vr) r.face_view_rects.push_back(RotatedRect::from_zb_view(v));
+        for (auto &v : er) r.eye_rois.push_back(RotatedRect::from_zb_view(v));
+        return r;
+    }
+
+   private:
+    std::shared_ptr<nn::NeuralNetwork> mesh_, iris_;
+    int32_t L_ = 0;
+    zb_face_iris_pipeline *h_ = nullptr;
 };
 
 // Palm detection + hand landmarks on device (BASELINE config 3): per frame the best palm seeds

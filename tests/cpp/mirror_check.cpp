@@ -54,6 +54,21 @@ int main(int argc, char **argv) {
         hands.set_threshold(0.1f, 0.3f);
         auto hr = hands.run(*full.batch());
 
+        // round-2 surface: config 2 (face mesh -> eye crops -> iris network), timers, eye accessors, blend
+        FaceIrisPipeline iris(landmark::FaceMeshV1(), models);
+        auto ir = iris.run(*crop.batch());
+        const auto det_ms = det.timers();
+        const auto est_ms = est.timers();
+        const RotatedRect le = e.left_eye(), re = e.right_eye();
+        auto bb = Rect::bounding({{1.0f, 2.0f}, {5.0f, -1.0f}, {3.0f, 7.0f}});
+        // blend: draw the crop over the top-left quarter of a copy of the full image, read one pixel region back
+        Image canvas = Image::from_rgba8(full.resolution(), full_px.data());
+        blend(canvas.view(RotatedRect(Rect::from_top_left(0.0f, 0.0f, 200.0f, 200.0f))), crop.as_view());
+        Resolution bres{};
+        auto blended = canvas.view(RotatedRect(Rect::from_top_left(0.0f, 0.0f, 8.0f, 8.0f))).to_rgba8(&bres);
+        long blend_sum = 0;
+        for (uint8_t v : blended) blend_sum += v;
+
         bool threw = false;
         try {
             trk.set_roi_padding(-1.0f);
@@ -77,6 +92,15 @@ int main(int argc, char **argv) {
         std::printf(" \"hand_dets\": %zu, \"hand_presence\": %.9g, \"hand_lm0\": [%.9g, %.9g, %.9g], \"hand_roi\": [%.9g, %.9g, %.9g, %.9g, %.9g],\n",
                     hr.detections[0].size(), hr.presence[0], hr.landmarks[0], hr.landmarks[1], hr.landmarks[2], hr.rois[0].rect().r.cx,
                     hr.rois[0].rect().r.cy, hr.rois[0].rect().width(), hr.rois[0].rect().height(), hr.rois[0].radians);
+        std::printf(" \"iris_L\": %d, \"iris_flag\": %.9g, \"iris_lm0\": [%.9g, %.9g, %.9g], \"eye0\": [%.9g, %.9g, %.9g, %.9g, %.9g], \"eye_lm0\": [%.9g, %.9g, %.9g],\n",
+                    ir.num_landmarks, ir.face_flags[0], ir.face_landmarks[0], ir.face_landmarks[1], ir.face_landmarks[2], ir.eye_rois[0].rect().r.cx,
+                    ir.eye_rois[0].rect().r.cy, ir.eye_rois[0].rect().width(), ir.eye_rois[0].rect().height(), ir.eye_rois[0].radians,
+                    ir.eye_landmarks[0], ir.eye_landmarks[1], ir.eye_landmarks[2]);
+        std::printf(" \"det_ms\": [%.9g, %.9g, %.9g], \"est_ms\": [%.9g, %.9g, %.9g], \"left_eye\": [%.9g, %.9g, %.9g, %.9g, %.9g], \"right_eye\": [%.9g, %.9g, %.9g, %.9g, %.9g],\n",
+                    det_ms[0], det_ms[1], det_ms[2], est_ms[0], est_ms[1], est_ms[2], le.rect().r.cx, le.rect().r.cy, le.rect().width(),
+                    le.rect().height(), le.radians, re.rect().r.cx, re.rect().r.cy, re.rect().width(), re.rect().height(), re.radians);
+        std::printf(" \"bounding\": [%.9g, %.9g, %.9g, %.9g], \"blend_res\": [%u, %u], \"blend_sum\": %ld,\n", bb->x(), bb->y(), bb->width(),
+                    bb->height(), bres.w, bres.h, blend_sum);
         std::printf(" \"tensor_len\": %zu, \"tensor_sum\": %.9g, \"padding_rejected\": %s}\n", tensor.size(), tsum, threw ? "true" : "false");
         return 0;
     } catch (const std::exception &ex) {

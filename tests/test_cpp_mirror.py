@@ -86,3 +86,23 @@ def test_cpp_mirror_matches_python_mirror_and_reference_assertions(tmp_path, ass
     assert abs(got["hand_presence"] - float(hr.presence[0])) <= 1e-6
     assert np.allclose(got["hand_lm0"], hr.landmarks[0, 0], rtol=0, atol=1e-3)
     assert np.allclose(got["hand_roi"], hr.rois[0], rtol=0, atol=1e-3)
+    # round-2 surface: config 2, timers, eye accessors, Rect::bounding, blend - against the Python mirror
+    from zaru_b200.image import blend
+    from zaru_b200.pipeline import FaceIrisPipeline
+    cbatch, _ = cimg.device()
+    ir = FaceIrisPipeline().run(cbatch)
+    assert got["iris_L"] == 468 and abs(got["iris_flag"] - float(ir.face_flags[0])) <= 1e-6
+    assert np.allclose(got["iris_lm0"], ir.face_landmarks[0, 0], rtol=0, atol=1e-3)
+    assert np.allclose(got["eye0"], ir.eye_rois[0, 0], rtol=0, atol=1e-3)
+    assert np.allclose(got["eye_lm0"], ir.eye_landmarks[0, 0, 0], rtol=0, atol=1e-3)
+    assert all(v >= 0.0 for v in got["det_ms"] + got["est_ms"]) and got["det_ms"][0] > 0.0 and got["est_ms"][0] > 0.0
+    le, re = e.left_eye(), e.right_eye()
+    for name, rr in (("left_eye", le), ("right_eye", re)):
+        want = [*rr.rect().center(), rr.rect().width(), rr.rect().height(), rr.rotation_radians()]
+        assert np.allclose(got[name], want, rtol=0, atol=1e-4), name
+    assert got["bounding"] == [1.0, -1.0, 4.0, 8.0]
+    canvas = Image(sad_linus_full.copy())
+    blend(canvas.view(Rect.from_top_left(0, 0, 200, 200)), cimg)
+    px = canvas.view(Rect.from_top_left(0, 0, 8, 8)).to_image().data()
+    assert got["blend_res"] == [8, 8] and got["blend_sum"] == int(np.asarray(px, np.int64).sum())
+
