@@ -127,6 +127,31 @@ struct RotatedRect {
 // ---- images ---------------------------------------------------------------------------------------------
 class ImageView;
 
+// Page-locked host array (zb_host_alloc): result buffers that live across calls should be these - a device->host copy into
+// pageable memory (std::vector) is staged by the driver at a fraction of the PCIe rate.  Every entry point accepts either.
+template <class T>
+class PinnedArray {
+   public:
+    explicit PinnedArray(size_t n) : n_(n) {
+        void *p = nullptr;
+        check(zb_host_alloc((n ? n : 1) * sizeof(T), &p));
+        p_ = static_cast<T *>(p);
+        std::fill(p_, p_ + n, T{});
+    }
+    ~PinnedArray() { zb_host_free(p_); }
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    size_t size() const { return n_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+
+   private:
+    T *p_ = nullptr;
+    size_t n_;
+};
+
 // `Image::from_rgba8`: RGBA8 pixels resident in HBM (one frame; `ImageBatch` holds n frames of one size).
 class ImageBatch {
    public:

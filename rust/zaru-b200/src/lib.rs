@@ -29,6 +29,29 @@ impl Context {
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { sys::zb_ctx_destroy(self.0) } } }
 
+/// Page-locked host buffer (`zb_host_alloc`): result slices handed to the batched calls come back at the PCIe rate
+/// instead of through the driver's pageable bounce buffers (7.2 MB per 1024-frame step: 0.15 ms instead of 0.45 ms).
+/// Any `&mut [T]` works everywhere; long-lived per-stream result buffers should be these.
+pub struct PinnedBuf<T: Copy> { ptr: *mut T, len: usize }
+unsafe impl<T: Copy + Send> Send for PinnedBuf<T> {}
+impl<T: Copy> PinnedBuf<T> {
+    /// Zero-initialised (all-zero bytes are valid for the plain-data result types used here).
+    pub fn zeroed(len: usize) -> anyhow::Result<Self> {
+        let mut p: *mut std::ffi::c_void = ptr::null_mut();
+        sys::check(unsafe { sys::zb_host_alloc(len.max(1) * std::mem::size_of::<T>(), &mut p) })?;
+        unsafe { ptr::write_bytes(p as *mut u8, 0, len.max(1) * std::mem::size_of::<T>()) };
+        Ok(PinnedBuf { ptr: p as *mut T, len })
+    }
+}
+impl<T: Copy> std::ops::Deref for PinnedBuf<T> {
+    type Target = [T];
+    fn deref(&self) -> &[T] { unsafe { std::slice::from_raw_parts(self.ptr, self.len) } }
+}
+impl<T: Copy> std::ops::DerefMut for PinnedBuf<T> {
+    fn deref_mut(&mut self) -> &mut [T] { unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) } }
+}
+impl<T: Copy> Drop for PinnedBuf<T> { fn drop(&mut self) { unsafe { sys::zb_host_free(self.ptr as *mut std::ffi::c_void) } } }
+
 /// `NeuralNetwork` with `Session::Cuda` (nn/mod.rs:365-540): immutable after load, `Send + Sync`.
 pub struct NeuralNetwork { net: *mut sys::zb_net, ctx: Arc<Context> }
 unsafe impl Send for NeuralNetwork {}

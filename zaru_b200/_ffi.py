@@ -116,6 +116,8 @@ SIGNATURES = {
     "zb_debug_tc_gemm": (i32, [P, P, P, P, i32, i32, i32]),
     "zb_debug_mma_rate": (i32, [P, i32, i32, i32, i32, i32, i32, i32, P]),
     "zb_last_device_ms": (f32, [P]),
+    "zb_host_alloc": (i32, [C.c_size_t, PP]),
+    "zb_host_free": (None, [P]),
     "zb_timer_start": (i32, [P]),
     "zb_timer_stop": (i32, [P, C.POINTER(f32)]),
     "zb_profile_begin": (i32, [P]),

@@ -598,6 +598,22 @@ int64_t zb_launch_count(zb_ctx *) { return g_launch_count; }
 float zb_last_device_ms(zb_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
 int64_t zb_last_h2d_bytes(zb_ctx *ctx) { return ctx ? (int64_t)ctx->last_h2d_bytes : 0; }
 
+zb_status zb_host_alloc(size_t bytes, void **out) {
+    return guarded([&]() -> zb_status {
+        if (!out) throw std::invalid_argument("zb_host_alloc: out is NULL");
+        *out = nullptr;
+        if (bytes == 0) return ZB_OK;
+        void *p = nullptr;
+        CU(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
+        *out = p;
+        return ZB_OK;
+    });
+}
+
+void zb_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 zb_status zb_timer_start(zb_ctx *ctx) {
     return guarded([&]() -> zb_status {
         if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "ctx is NULL");

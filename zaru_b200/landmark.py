@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _ffi, context, context_key, model_path
+from . import _ffi, _pinned, context, context_key, model_path
 from .nn import Cnn, CnnInputShape, ColorMapper, NeuralNetwork
 from .rect import RotatedRect, signed_angle_to
 from .timer import Timer
@@ -263,8 +263,9 @@ class LandmarkTracker:
                                                 network.color_range[1], self._n, C.byref(h)))
         self._h = h
         self._L = network.result.NUM_LANDMARKS
-        self._bufs = (np.empty((self._n, self._L, 3), np.float32), np.empty(self._n, np.float32),
-                      (_ffi.zb_view * self._n)(), (_ffi.zb_view * self._n)(), np.empty(self._n, np.uint8))
+        self._bufs = (_pinned.empty((self._n, self._L, 3), np.float32), _pinned.empty(self._n, np.float32),    # page-locked results
+                      _pinned.ctypes_array(_ffi.zb_view, self._n), _pinned.ctypes_array(_ffi.zb_view, self._n),
+                      _pinned.empty(self._n, np.uint8))
 
     def streams(self):
         return self._n

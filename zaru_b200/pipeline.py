@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _ffi, context
+from . import _ffi, _pinned, context
 from .detection import Detection, Detections, Detector, ShortRangeNetwork
 from .landmark import EyeLandmarks, EyeNetwork, FaceMeshV1, LandmarkTracker
 
@@ -43,8 +43,9 @@ class FacePipeline:
 
     def _buffers(self, n):
         if self._bufs is None or self._bufs[0] != n:
-            self._bufs = (n, (_ffi.zb_detection * (n * self._cap))(), (C.c_int32 * n)(),
-                          np.empty((n, self._L, 3), np.float32), np.empty(n, np.float32), (_ffi.zb_view * n)())
+            # page-locked: the results of a step come back at the PCIe rate instead of through the driver's bounce buffers
+            self._bufs = (n, _pinned.ctypes_array(_ffi.zb_detection, n * self._cap), _pinned.ctypes_array(C.c_int32, n),
+                          _pinned.empty((n, self._L, 3), np.float32), _pinned.empty(n, np.float32), _pinned.ctypes_array(_ffi.zb_view, n))
         return self._bufs
 
     def run_raw(self, batch, n=None):
@@ -149,8 +150,8 @@ class HandPipeline:
         """One pass over `n` frames; results land in reusable host buffers (no Python unpacking)."""
         n = len(batch) if n is None else n
         if getattr(self, "_bufs", None) is None or self._bufs[0] != n:
-            self._bufs = (n, (_ffi.zb_detection * (n * self._cap))(), (C.c_int32 * n)(), np.empty((n, 21, 3), np.float32),
-                          np.empty((n, 2), np.float32), (_ffi.zb_view * n)())
+            self._bufs = (n, _pinned.ctypes_array(_ffi.zb_detection, n * self._cap), _pinned.ctypes_array(C.c_int32, n),
+                          _pinned.empty((n, 21, 3), np.float32), _pinned.empty((n, 2), np.float32), _pinned.ctypes_array(_ffi.zb_view, n))
         _, dets, counts, lm, sc, rois = self._bufs
         _ffi.check(_ffi.lib().zb_hand_pipeline_run(self._h, batch._h, n, dets, counts, self._cap, lm.ctypes.data, sc.ctypes.data, rois))
         return dets, counts, lm, sc, rois
@@ -207,8 +208,8 @@ class FaceIrisPipeline:
 
     def _buffers(self, n):
         if self._bufs is None or self._bufs[0] != n:
-            self._bufs = (n, np.empty((n, self._L, 3), np.float32), np.empty(n, np.float32), (_ffi.zb_view * n)(),
-                          (_ffi.zb_view * (2 * n))(), np.empty((n, 2, 76, 3), np.float32))
+            self._bufs = (n, _pinned.empty((n, self._L, 3), np.float32), _pinned.empty(n, np.float32), _pinned.ctypes_array(_ffi.zb_view, n),
+                          _pinned.ctypes_array(_ffi.zb_view, 2 * n), _pinned.empty((n, 2, 76, 3), np.float32))
         return self._bufs
 
     def run_raw(self, batch, rois=None, n=None):
