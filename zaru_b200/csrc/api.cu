@@ -141,7 +141,8 @@ struct zb_ctx {
     int tcb_gemm_min_m = 1;              // ZB_TCB_GEMM_MIN_M: smaller launches stay on the FFMA tile
     int tcb_over_thin = 1;               // ZB_TCB_OVER_THIN: also take the stride-2 blocks the SIMT thin kernel covers (measured: 291 vs 304 us)
     int tcb_over_ttc = 2;                // ZB_TCB_OVER_TTC: take the large-map thin blocks of the tile-tc kernel: 0 never, 1 always,
-                                         // 2 where measured faster (48x48x32: 573 vs 625 us, 32x32x36->42: 218 vs 260; 32x32x32->36: 156 vs 146)
+                                         // 2 where measured faster (48x48x32: 573 vs 625 us, 32x32x36->42: 218 vs 260, iris 32x32x32->64:
+                                         // 95 vs 188; the tile-tc kernel keeps 32x32x32->36: 146 vs 156)
     int tc_min_ctas_s2 = 1 << 20;        // ZB_TC_MIN_CTAS_S2: stride-2 blocks stay on the GEMM tile (their tcgen05 producer has no
                                          // window reuse: 0.189 vs 0.220 ms on 24x24x64 -> 12x12x128, 0.175 vs 0.218 ms on 32x32x42 -> 16x16x48)
     bool prof_on = false;
@@ -390,7 +391,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     const bool use_tcb = ctx->tc_mode > 0 && ctx->tcb_mode > 0 && op.wtc_hi_off >= 0 && p.K >= ctx->tcb_min_k &&
                                          tcb_dwpw_supported(p, op.NP) &&
                                          (!use_ttc || ctx->tcb_over_ttc == 1 ||
-                                          (ctx->tcb_over_ttc == 2 && (p.Cs_in > 32 || p.H * p.W >= 2048))) &&
+                                          (ctx->tcb_over_ttc == 2 && (p.Cs_in > 32 || p.H * p.W >= 2048 || op.NP > 48))) &&
                                          (!dwpw_thin_supported(p) || ctx->tcb_over_thin);
                     bool done = false;
                     // persistent warp-specialised pipeline first; the one-tile-per-CTA kernel is its fallback
