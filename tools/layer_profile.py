@@ -2,6 +2,7 @@
 layer went to, its time, algorithmic GB/s and fraction of the HBM roofline.
 
     python tools/layer_profile.py [--config 2|3|4] [--batch N] [--dense]         # env switches (ZB_NO_TCB=1 ...) apply
+    python tools/layer_profile.py --detector full --mesh v2 [--batch 512]        # config 4 with the widened networks
 """
 import argparse
 import json
@@ -23,6 +24,8 @@ ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--dense", action="store_true")
 ap.add_argument("--json", default="")
+ap.add_argument("--detector", choices=["short", "full"], default="short")
+ap.add_argument("--mesh", choices=["v1", "v2"], default="v1")
 args = ap.parse_args()
 n = args.batch or (1024 if args.config == 4 else 256)
 zaru_b200.load_library()
@@ -35,7 +38,10 @@ uniq = np.stack([synth.s_face_frame(1000 + i)[0] for i in range(32)])
 frames = np.concatenate([uniq] * ((n + 31) // 32))[:n]
 batch = ImageBatch.from_rgba8(Resolution(1920, 1080), frames)
 if args.config == 4:
-    pipe = FacePipeline()
+    from zaru_b200.detection import FullRangeNetwork, ShortRangeNetwork
+    from zaru_b200.landmark import FaceMeshV1, FaceMeshV2
+    pipe = FacePipeline(detector_network=(FullRangeNetwork if args.detector == "full" else ShortRangeNetwork)(),
+                        landmark_network=(FaceMeshV2 if args.mesh == "v2" else FaceMeshV1)())
     pipe.set_dense(args.dense)
     run = lambda: pipe.run_raw(batch, n)
 elif args.config == 3:
