@@ -45,6 +45,10 @@ constexpr int TCB_A_FLOATS = 2 * TCB_KQC * TCB_AROWS * 4 > TCB_M * TCE_STRIDE ? 
 
 constexpr int TCB_ZERO_FLOATS = ((4 - 1) * 2 + 5) * TCB_CK;   // widest window row: SPAN = (PPT - 1) * S + KS channel-chunk pixels
 
+#ifndef TCB_GEMM_CTAS
+#define TCB_GEMM_CTAS 3
+#endif
+
 struct TcbGeom {
     int TW, TH;            // tile = TH virtual rows x TW columns, TW * TH = 128
     int tiles_x, tiles_y;
@@ -60,6 +64,11 @@ struct TcbGeom {
 // n / d for 0 <= n, n * d < 2^32, with magic = floor(2^32 / d) + 1 (d >= 2) or 0 (d == 1)
 __device__ __forceinline__ int fast_div(int n, unsigned magic) { return magic ? (int)__umulhi((unsigned)n, magic) : n; }
 __host__ unsigned div_magic(int d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)d + 1ull); }
+// the same with an escape: magic == ~0u means "n * d may reach 2^32: divide for real" (div_magic_checked decides on the host)
+__device__ __forceinline__ int fast_div_or(int n, int d, unsigned magic) { return magic == 0xffffffffu ? n / d : fast_div(n, magic); }
+__host__ unsigned div_magic_checked(int d, unsigned long long n_max) {
+    return (n_max * (unsigned long long)d < (1ull << 32)) ? div_magic(d) : 0xffffffffu;
+}
 
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile(
@@ -297,8 +306,10 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
 // stored in the UMMA K-major layout; the loads of chunk c + 1 are in flight while the MMAs of chunk c run.
 // Weights: [N tile][Kpad / 4][NT][4], TF32 hi / lo, one TMA bulk copy per chunk and half.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const float *__restrict__ w_hi, const float *__restrict__ w_lo,
-                                                          int NP, int nchunks, int kpad) {
+// Three CTAs per SM (<= 85 registers): ncu had a third of this kernel's warp samples on the barrier behind the MMA wait at two.
+// The row -> (image, y, x) divisions use host-computed magic multipliers (17 % of the executed instructions were divisions).
+__global__ void __launch_bounds__(256, TCB_GEMM_CTAS) tcb_gemm_kernel(const ConvDev p, const float *__restrict__ w_hi, const float *__restrict__ w_lo,
+                                                          int NP, int nchunks, int kpad, unsigned howo_magic, unsigned wo_magic) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int n0 = blockIdx.y * 256;
     const int NT = min(256, NP - n0);                                        // output channels of this CTA (multiple of 16)
@@ -335,15 +346,20 @@ __global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const
     const int quad = tid & 7;
     long long roff[4];
     int riy[4], rix[4];
+    // one true division per CTA tile: (image, offset) of the tile's first row; the rows of a tile are consecutive, so row
+    // m0 + d sits at offset r_b + d < HoWo + 128 of image img_b, and the small quotients come from magic multipliers
+    const int img_b = m0 / HoWo, r_b = m0 - img_b * HoWo;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int gm = m0 + (tid >> 3) + 32 * i;
+        const int d = (tid >> 3) + 32 * i;
+        const int gm = m0 + d;
         roff[i] = -1;
         riy[i] = rix[i] = 0;
         if (gm < p.M) {
-            const int img = gm / HoWo;
-            const int r = gm - img * HoWo;
-            const int oy = r / p.Wo, ox = r - oy * p.Wo;
+            const int wrap = fast_div_or(r_b + d, HoWo, howo_magic);
+            const int img = img_b + wrap;
+            const int r = r_b + d - wrap * HoWo;
+            const int oy = fast_div_or(r, p.Wo, wo_magic), ox = r - oy * p.Wo;
             roff[i] = (long long)img * p.in_img_stride;
             riy[i] = oy * p.sh - p.pt;
             rix[i] = ox * p.sw - p.pl;
@@ -425,9 +441,10 @@ __global__ void __launch_bounds__(256, 2) tcb_gemm_kernel(const ConvDev p, const
         TceRow ri;
         ri.out_off = -1, ri.res_off = 0;
         if (m < p.M) {
-            const int img = m / HoWo;
-            const int r = m - img * HoWo;
-            const int oy = r / p.Wo;
+            const int wrap = fast_div_or(r_b + tid, HoWo, howo_magic);
+            const int img = img_b + wrap;
+            const int r = r_b + tid - wrap * HoWo;
+            const int oy = fast_div_or(r, p.Wo, wo_magic);
             ri = tce_row(p, img, oy, r - oy * p.Wo);
         }
         s_rowinfo[tid] = ri;
@@ -583,7 +600,9 @@ bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int
     g_launch_count++;
     const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
     ZB_KNAME("tcb_gemm_kernel");
-    tcb_gemm_kernel<<<dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), 256, smem, s>>>(p, w_hi, w_lo, NP, nchunks, kpad);
+    tcb_gemm_kernel<<<dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), 256, smem, s>>>(p, w_hi, w_lo, NP, nchunks, kpad,
+                                                                                                     div_magic_checked(p.Ho * p.Wo, (unsigned long long)p.Ho * p.Wo + TCB_M),
+                                                                                                     div_magic_checked(p.Wo, (unsigned long long)p.Ho * p.Wo));
     return true;
 }
 
