@@ -7,10 +7,11 @@
 //     once per CTA instead of up to KS*KS times by per-thread window loads, and the next chunk (of this tile or of the
 //     CTA's next tile) streams in while the current one is being convolved;
 //   * the depthwise stage on the CUDA cores as a sliding window (4 horizontally adjacent outputs x one channel quad per
-//     thread, weights of the chunk in shared memory), written straight into the UMMA K-major operand tile as TF32
-//     hi / lo parts;
+//     thread, packed FFMA2, weights of the chunk in shared memory), written straight into the UMMA K-major operand tile
+//     as TF32 hi / lo parts;
 //   * the pointwise contraction on tcgen05.mma kind::tf32 (3xTF32, FP32 accumulation in TMEM), pre-split weights
-//     streamed per K chunk by TMA bulk copy;
+//     streamed per K chunk by TMA bulk copy; the commit is waited for only where the operand tile is overwritten or the
+//     accumulator read, and the issuing thread rotates over the warps;
 //   * the fused epilogue (bias -> act -> residual [channel-pad, 2x2 max-pool] -> act) from TMEM.
 //
 // A tile = 128 output pixels = TH "virtual rows" x TW columns, where the virtual rows run over (image, output row) in
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
     };
     // stage the halo of step s into input buffer s % nin with ONE tensor copy: the (image, row) dimensions of the activation
     // are merged (images are contiguous, H == Ho * S), so a tile's input rows are one contiguous range even when it spans
-    // several images; rows that belong to a neighbouring image are masked in the window loop below.  (One copy per staged
+    // several images; tap rows that belong to a neighbouring image read the row of zeros instead (window loop below).  (One copy per staged
     // row - the first version - paid the TMA unit's per-instruction cost ~20 times per chunk.)
     auto issue_in = [&](int s) {
         if (lane == 0 && s < total_steps) {
