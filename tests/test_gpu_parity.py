@@ -4,6 +4,7 @@ Tolerances (BASELINE.json north_star / SURVEY §8d): preprocessing tensor bit-ex
 post-NMS detection sets; boxes / keypoints / landmarks within 1e-3 NORMALISED units (pixels of the
 network input / input size); scores and flags within 1e-3 absolute; angles within 1e-3 rad.
 """
+import ctypes as C
 import math
 import os
 
@@ -499,6 +500,40 @@ def test_empty_and_degenerate_inputs(zb, sad_linus_full):
     # frame index out of range
     bad = (_ffi.zb_view * 1)(_ffi.zb_view(3, 10.0, 10.0, 5.0, 5.0, 0.0))
     assert lib.zb_preprocess(context(), batch._h, bad, 1, 8, 8, 0.0, 1.0, _ffi.ZB_NCHW, out.ctypes.data) == _ffi.ZB_ERR_INVALID_ARGUMENT
+    # maximum size: one call takes at most 65535 views (one grid dimension); more is refused with a message, not a launch error
+    many = (_ffi.zb_view * 65536)()
+    big = np.empty((65536, 3, 2, 2), np.float32)
+    rc = lib.zb_preprocess(context(), batch._h, many, 65536, 2, 2, 0.0, 1.0, _ffi.ZB_NCHW, big.ctypes.data)
+    assert rc != 0 and b"65535" in lib.zb_last_error()
+    for j in range(65535):
+        many[j] = _ffi.zb_view(0, 10.0, 10.0, 4.0, 4.0, 0.0)
+    assert lib.zb_preprocess(context(), batch._h, many, 65535, 2, 2, 0.0, 1.0, _ffi.ZB_NCHW, big.ctypes.data) == 0
+    assert np.isfinite(big[:65535]).all() and (big[0] == big[65534]).all()
+
+
+@pytest.mark.gpu
+def test_page_locked_result_buffers(zb, sad_linus_full):
+    """zb_host_alloc / zb_host_free (the mirrors' reusable result arrays): page-locked memory is ordinary host memory to every
+    entry point - the same call writes the same bytes into a pinned and into a pageable destination - and it is released."""
+    from zaru_b200 import _ffi, _pinned, context
+    from zaru_b200.image import Image
+    lib = _ffi.lib()
+    batch, _ = Image(sad_linus_full).device()
+    pageable = np.empty((1, 3, 32, 32), np.float32)
+    pinned = _pinned.empty((1, 3, 32, 32), np.float32)
+    h, w = sad_linus_full.shape[:2]
+    whole = (_ffi.zb_view * 1)(_ffi.zb_view(0, w / 2.0, h / 2.0, float(w), float(h), 0.0))
+    for dst in (pageable, pinned):
+        assert lib.zb_preprocess(context(), batch._h, whole, 1, 32, 32, -1.0, 1.0, _ffi.ZB_NCHW, dst.ctypes.data) == 0
+    assert (pageable == pinned).all()
+    views = _pinned.ctypes_array(_ffi.zb_view, 3)
+    assert len(views) == 3 and views[2].cx == 0.0
+    p = C.c_void_p()
+    assert lib.zb_host_alloc(C.c_size_t(0), C.byref(p)) == 0 and not p.value          # zero bytes: no allocation, no error
+    assert lib.zb_host_alloc(C.c_size_t(4096), C.byref(p)) == 0 and p.value
+    lib.zb_host_free(p)
+    lib.zb_host_free(None)                                                            # NULL is a no-op
+    del pinned, views
 
 
 # ------------------------------------------------------------------------------------------------
