@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
     constexpr int HALVES = M / 128;
     constexpr int IN_TILE = IH * IW * PS;                            // floats per staged input tile
     constexpr uint32_t LBO_A = (M + 1) * 16;                         // padded chunk stride of the A tile (bytes)
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *sA_hi = reinterpret_cast<float *>(smem_raw);              // [CQ][(M+1)][4]
     float *sA_lo = sA_hi + CQ * (M + 1) * 4;
     float *sB_hi = sA_lo + CQ * (M + 1) * 4;                         // [CQ][NP][4]  (TMA destination, 16 B aligned)
@@ -640,7 +640,7 @@ bool launch_ttc_cs(const ConvDev &p, const float *w_hi, const float *w_lo, int N
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) tc_mma_rate_kernel(int N, int lbo_a, int sbo_a, int a_off, int iters, int ksteps,
                                                           long long *cycles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256, TCB_GEMM_CTAS) tcb_gemm_kernel(const Conv
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) TceRow s_rowinfo[TCB_M];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.x * TCB_M;
     const int HoWo = p.Ho * p.Wo;
     const uint32_t ncols = tmem_cols_for(NT);
