@@ -178,7 +178,10 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
         if (tid == 0 && !b_resident && step - 1 + g.nbw < total_steps) load_b(step - 1 + g.nbw);   // that weight buffer is free again
     };
     const bool prelu_mid = p.act_mid.kind == ACT_PRELU;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // The epilogue (quarter-local barriers, tc_epilogue.cuh; outputs on the all-128-bit path only: tcb_dwpw_supported) ends
+    // WITHOUT a CTA barrier, so the first step of the next tile places one before it overwrites the row table and the A tile.
+    int it = 0;                                                               // tiles done by this CTA
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
         const int tile_y = fast_div(tile, g.tx_magic), tile_x = tile - tile_y * g.tiles_x;
         const int vr0 = tile_y * g.TH, ox0 = tile_x * g.TW;
         const int n_vr = min(g.TH, g.vrows - vr0);                           // valid virtual rows of this tile (>= 1)
@@ -188,20 +191,6 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
         unsigned kymask = 0;                                                  // bit ky: that tap row lies inside the image
 #pragma unroll
         for (int ky = 0; ky < KS; ky++) kymask |= (p_iy0 + ky >= 0 && p_iy0 + ky < p.H) ? (1u << ky) : 0u;
-        // row table of this tile's epilogue (the previous tile's epilogue ended with a CTA barrier; the barriers of the steps
-        // below order these writes before the reads)
-        if (tid < TCB_M) {
-            const int er = tid >> g.tw_shift, ecol = tid - (er << g.tw_shift);
-            const int evr = vr0 + er, ox = ox0 + ecol;
-            TceRow ri;
-            ri.out_off = -1, ri.res_off = 0;
-            if (er < n_vr && ox < p.Wo) {
-                const int img = fast_div(evr, g.ho_magic);
-                ri = tce_row(p, img, evr - img * p.Ho, ox);
-            }
-            s_rowinfo[tid] = ri;
-        }
-
         for (int c = 0; c < nchunks; c++, step++) {
             const int buf = g.nin == 2 ? (step & 1) : 0;
             mbar_wait(&mbar_in[buf], (g.nin == 2 ? (step >> 1) : step) & 1);  // this step's halo + depthwise weights have landed
@@ -246,6 +235,20 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
                 }
             }
             mma_done();                                                       // the previous step's MMAs have read the A tile
+            if (c == 0) {
+                if (it > 0) __syncthreads();                                  // the previous tile's epilogue is over for everybody
+                if (tid < TCB_M) {                                            // row table of this tile's epilogue
+                    const int er = tid >> g.tw_shift, ecol = tid - (er << g.tw_shift);
+                    const int evr = vr0 + er, ox = ox0 + ecol;
+                    TceRow ri;
+                    ri.out_off = -1, ri.res_off = 0;
+                    if (er < n_vr && ox < p.Wo) {
+                        const int img = fast_div(evr, g.ho_magic);
+                        ri = tce_row(p, img, evr - img * p.Ho, ox);
+                    }
+                    s_rowinfo[tid] = ri;
+                }
+            }
             if (p_valid) {
 #pragma unroll
                 for (int i = 0; i < PPT; i++) {
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
         // --- epilogue through shared memory (coalesced residual reads / stores); the staging tile aliases the A tile, the
         // next tile's first halo is already on its way.  `step` now counts this tile's last step as issued. ---
         // the wait for the last MMAs sits inside, behind the epilogue's residual / bias loads
-        tc_epilogue_tile<NT, 0>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid, [&]() { mma_done(); });      // ends with a CTA barrier
+        tc_epilogue_tile_quarters<NT>(p, tmem, 0, NP, s_rowinfo, sA_hi, tid, [&]() { mma_done(); });
         tc_fence_before();                                                    // accumulator read before the next tile's MMAs overwrite it
     }
     tc_fence_before();
@@ -578,6 +581,10 @@ bool tcb_dwpw_supported(const ConvDev &p, int NP) {
     if (p.M % (p.Ho * p.Wo) || p.pt < 0 || p.pl < 0) return false;
     if (((uintptr_t)p.in) % 16 || (p.in_img_stride % 4)) return false;
     if (p.in_img_stride != (long long)p.H * p.W * p.Cs_in || p.H != p.Ho * p.sh) return false;   // merged (image, row) staging
+    // the epilogue is the all-128-bit one (every block-to-block tensor qualifies; odd-width graph outputs go elsewhere)
+    if (p.out_pix_stride % 4 || p.Nstore % 4 || p.out_img_stride % 4 || p.Ns % 4 || ((uintptr_t)p.out) % 16 ||
+        (p.epi.res && p.epi.res_Cs % 4))
+        return false;
     return encode_fn() != nullptr;
 }
 

@@ -147,14 +147,15 @@ struct TceFetch {
     float4 rr[NI];                 // residual quads in flight (the row offsets are re-read from the table: registers)
 };
 template <int NI, bool GUARD>
-__device__ __forceinline__ void tce_fetch(const EpiDev &e, const TceRow *rt, int r0, int rstep, const char *resb, bool has_res, TceFetch<NI> &f) {
+__device__ __forceinline__ void tce_fetch(const EpiDev &e, const TceRow *rt, int r0, int rstep, const char *resb, bool has_res, TceFetch<NI> &f,
+                                          int limit = TCB_EPI_ROWS) {
 #pragma unroll
     for (int i = 0; i < NI; i++) f.rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!has_res) return;
     if (!e.res_pool) {
 #pragma unroll
         for (int i = 0; i < NI; i++) {
-            if (GUARD && r0 + i * rstep >= TCB_EPI_ROWS) continue;
+            if (GUARD && r0 + i * rstep >= limit) continue;
             const TceRow t = rt[i * rstep];
             if (t.out_off >= 0) f.rr[i] = ldg4(reinterpret_cast<const float *>(resb + t.res_off));
         }
@@ -162,7 +163,7 @@ __device__ __forceinline__ void tce_fetch(const EpiDev &e, const TceRow *rt, int
         const long long pool_dx = 4ll * e.res_Cs, pool_dy = 4ll * e.res_W * e.res_Cs;
 #pragma unroll
         for (int i = 0; i < NI; i++) {
-            if (GUARD && r0 + i * rstep >= TCB_EPI_ROWS) continue;
+            if (GUARD && r0 + i * rstep >= limit) continue;
             const TceRow t = rt[i * rstep];
             if (t.out_off < 0) continue;
             const char *rp = resb + t.res_off;
@@ -175,10 +176,11 @@ __device__ __forceinline__ void tce_fetch(const EpiDev &e, const TceRow *rt, int
 }
 template <int NI, bool GUARD>
 __device__ __forceinline__ void tce_finish(const TceFetch<NI> &f, const TceRow *rt, const float *stg, int r0, int rstep, char *outb,
-                                           const float4 &bias, const TceAct &a1, const TceAct &a2, const float4 &sl1, const float4 &sl2) {
+                                           const float4 &bias, const TceAct &a1, const TceAct &a2, const float4 &sl1, const float4 &sl2,
+                                           int limit = TCB_EPI_ROWS) {
 #pragma unroll
     for (int i = 0; i < NI; i++) {
-        if (GUARD && r0 + i * rstep >= TCB_EPI_ROWS) continue;
+        if (GUARD && r0 + i * rstep >= limit) continue;
         const float4 a = *reinterpret_cast<const float4 *>(stg + i * rstep * TCE_STRIDE);
         const long long oo = rt[i * rstep].out_off;
         float4 v = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
@@ -281,6 +283,83 @@ __device__ __forceinline__ void tc_epilogue_tile(const ConvDev &p, uint32_t tmem
             }
         }
         tce_sync<NTHREADS, BAR_ID>();                   // the staging tile is overwritten by the next column block
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same epilogue with QUARTER-LOCAL barriers.  A warp can only read its own 32-lane quarter of the accumulator, so rows
+// 32 q .. 32 q + 31 of the staging tile are written by the NTHREADS / 128 warps with (warp & 3) == q - and if exactly those
+// warps also finish those rows, nobody needs the other quarters: the CTA-wide barrier between staging and finishing becomes
+// four independent barriers of NTHREADS / 4 threads (ids 1 .. 4), and a warp that arrives late (the one that issued the MMAs,
+// the one whose residual load was slow) holds up its quarter instead of the CTA.  ncu on the 5x5 palm blocks: 17 % of the warp
+// samples sat on the two CTA-wide epilogue barriers.  There is NO barrier at the end: the caller orders the reuse of the staging
+// tile (it aliases the A tile) and of the row table with its own CTA barrier before it overwrites them.
+// Fast path only (everything 128-bit); returns false without touching anything when the tensor needs the guarded path.
+// ------------------------------------------------------------------------------------------------
+template <int NTHREADS>
+__device__ __forceinline__ void tce_quarter_sync(int q4) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + q4), "n"(NTHREADS / 4) : "memory");
+}
+
+__device__ __forceinline__ bool tce_fast_ok(const ConvDev &p) {
+    const EpiDev &e = p.epi;
+    return (p.out_pix_stride % 4 == 0) && (p.Nstore % 4 == 0) && (p.out_img_stride % 4 == 0) && (p.Ns % 4 == 0) &&
+           ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (!e.res || (e.res_Cs % 4) == 0);
+}
+
+template <int NTHREADS, class Ready>
+__device__ __forceinline__ void tc_epilogue_tile_quarters(const ConvDev &p, uint32_t tmem, int n0, int NT, const TceRow *s_rowinfo,
+                                                          float *s_stage, int tid, Ready ready) {
+    const EpiDev &e = p.epi;
+    constexpr int GT = NTHREADS / 4;                    // threads per quarter group
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, grp = warp >> 2;           // lane quarter; which 16-column chunks this warp moves
+    const int row_t = q4 * 32 + lane;
+    const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16);
+    const TceAct a1 = tce_act_of(e.act1), a2 = tce_act_of(e.act2);
+    constexpr int NI = NTHREADS >= 512 ? 4 : 8;
+    const int t = grp * 32 + lane;                      // index inside the quarter group
+    const TceRow *rt_q = s_rowinfo + q4 * 32;
+    float *stage_q = s_stage + q4 * 32 * TCE_STRIDE;
+    for (int cb = 0; cb < NT; cb += TCE_NB) {
+        const int nb = min(TCE_NB, NT - cb);            // multiple of 16
+        const int qb = nb >> 2;                         // 4, 8, 12 or 16 quads per row
+        int q, rl, rstep;                               // this thread's quad, first local row, local row step
+        if (qb == 16) q = t & 15, rl = t >> 4, rstep = GT / 16;
+        else if (qb == 8) q = t & 7, rl = t >> 3, rstep = GT / 8;
+        else if (qb == 4) q = t & 3, rl = t >> 2, rstep = GT / 4;
+        else q = t % 12, rl = t / 12, rstep = GT / 12;
+        const int n = n0 + cb + 4 * q;
+        const bool active = rl < rstep && n < p.Nstore;
+        TceFetch<NI> f;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sl1 = bias, sl2 = bias;
+        const bool has_res = e.res && n < e.res_Cs;
+        const char *resb = reinterpret_cast<const char *>(e.res + n);
+        char *outb = reinterpret_cast<char *>(p.out + n);
+        if (active) {
+            bias = ldg4(e.bias + n);
+            if (a1.prelu) sl1 = ldg4(e.act1.slope + n);
+            if (a2.prelu) sl2 = ldg4(e.act2.slope + n);
+            tce_fetch<NI, true>(e, rt_q + rl, rl, rstep, resb, has_res, f, 32);
+        }
+        if (cb == 0) ready();
+        else tce_quarter_sync<NTHREADS>(q4);            // the previous column block's rows of this quarter have been finished
+        for (int j = grp; j < nb / 16; j += NTHREADS / 128) {
+            float v[16];
+            tmem_ld16(tbase + (uint32_t)(cb + 16 * j), v);
+            float *dst = s_stage + row_t * TCE_STRIDE + 16 * j;
+#pragma unroll
+            for (int h = 0; h < 4; h++) *reinterpret_cast<float4 *>(dst + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+        }
+        tce_quarter_sync<NTHREADS>(q4);
+        if (active) {
+            tce_finish<NI, true>(f, rt_q + rl, stage_q + rl * TCE_STRIDE + 4 * q, rl, rstep, outb, bias, a1, a2, sl1, sl2, 32);
+#pragma unroll 1
+            for (int rb = rl + NI * rstep; rb < 32; rb += NI * rstep) {
+                tce_fetch<NI, true>(e, rt_q + rb, rb, rstep, resb, has_res, f, 32);
+                tce_finish<NI, true>(f, rt_q + rb, stage_q + rb * TCE_STRIDE + 4 * q, rb, rstep, outb, bias, a1, a2, sl1, sl2, 32);
+            }
+        }
     }
 }
 
