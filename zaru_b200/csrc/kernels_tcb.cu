@@ -536,15 +536,28 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     TcbGeom g = choose_geom(p, KS, S);
     if (g.TW == 0) return false;
     // two staging buffers when two CTAs still fit on an SM with them (the next chunk streams in behind the convolution of
-    // this one); otherwise one buffer, refilled behind the MMAs
+    // this one); otherwise one buffer, refilled behind the MMAs.  A layer whose smallest footprint already excludes a second
+    // CTA (stride-2 halos, N = 256 weight chunks) has the rest of the SM's shared memory for free: it takes the second weight
+    // buffer first (a 64 KB chunk fetched only after the previous MMAs retire is a serial L2 round trip per step), then the
+    // second staging buffer.
     static const int force_nin = getenv("ZB_TCB_NIN") ? atoi(getenv("ZB_TCB_NIN")) : 0;
-    int nin = tcb_smem(g, KS, NP, 2) <= 110 * 1024 ? 2 : 1;
-    if (force_nin == 1 || force_nin == 2) nin = force_nin;
-    if (tcb_smem(g, KS, NP, nin) > 220 * 1024) nin = 1;
     static const int force_nbw = getenv("ZB_TCB_NBW") ? atoi(getenv("ZB_TCB_NBW")) : 0;
-    int nbw = tcb_smem(g, KS, NP, nin, 2) <= 110 * 1024 ? 2 : 1;           // second weight buffer only while two CTAs still fit per SM
+    static const bool fill_sm = !(getenv("ZB_TCB_FILL") && atoi(getenv("ZB_TCB_FILL")) == 0);
+    constexpr size_t TWO_CTAS = 110 * 1024, ONE_CTA = 220 * 1024;
+    const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
+    const bool alone = fill_sm && tcb_smem(g, KS, NP, 1, 1) > TWO_CTAS;     // one CTA per SM whatever the buffering
+    int nin, nbw;
+    if (alone) {
+        nbw = (nchunks > 1 && tcb_smem(g, KS, NP, 1, 2) <= ONE_CTA) ? 2 : 1;
+        nin = tcb_smem(g, KS, NP, 2, nbw) <= ONE_CTA ? 2 : 1;
+    } else {
+        nin = tcb_smem(g, KS, NP, 2) <= TWO_CTAS ? 2 : 1;
+        nbw = tcb_smem(g, KS, NP, nin, 2) <= TWO_CTAS ? 2 : 1;              // second weight buffer only while two CTAs still fit per SM
+    }
+    if (force_nin == 1 || force_nin == 2) nin = force_nin;
+    if (tcb_smem(g, KS, NP, nin) > ONE_CTA) nin = 1;
     if (force_nbw == 1 || force_nbw == 2) nbw = force_nbw;
-    if (tcb_smem(g, KS, NP, nin, nbw) > 220 * 1024) nbw = 1;
+    if (tcb_smem(g, KS, NP, nin, nbw) > ONE_CTA) nbw = 1;
     const size_t smem = tcb_smem(g, KS, NP, nin, nbw);
     if (smem > 220 * 1024) return false;
     g.nin = nin;
@@ -555,7 +568,6 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     auto kern = tcb_dwpw_kernel<KS, S, PPT>;
     static SmemOptIn opt_in;
     if (!opt_in.ensure(kern, smem)) return false;
-    const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
     // persistent CTAs: two per SM (what registers and shared memory allow), each striding over the tiles
     static int num_sms = 0;
     if (!num_sms) {
@@ -564,7 +576,9 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     static const int ctas_per_sm = getenv("ZB_TCB_CTAS_PER_SM") ? atoi(getenv("ZB_TCB_CTAS_PER_SM")) : 2;
-    const int grid = ctas_per_sm > 0 ? std::min(g.tiles_x * g.tiles_y, ctas_per_sm * num_sms) : g.tiles_x * g.tiles_y;
+    // (a footprint that leaves room for one CTA per SM gets one: a second "wave" of persistent CTAs would only queue up)
+    const int resident = (fill_sm && smem > TWO_CTAS) ? 1 : ctas_per_sm;
+    const int grid = ctas_per_sm > 0 ? std::min(g.tiles_x * g.tiles_y, resident * num_sms) : g.tiles_x * g.tiles_y;
     ZB_KNAME("tcb_dwpw_kernel", KS, S, PPT);
     kern<<<(unsigned)grid, 1024 / PPT, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
     return true;
