@@ -412,10 +412,14 @@ def test_pipeline_properties_at_batch(zb):
         assert np.array_equal(a.landmarks[i], a.landmarks[j])
 
 
-def test_fused_sampling_is_bit_identical_to_sample_then_forward(zb, sad_linus_full):
-    """The stem kernel samples frames on the fly (separable tables for unrotated views, per-texel math for
-    rotated ones).  Feeding the network the tensor produced by the bit-exact `zb_preprocess` must give exactly
-    the same head tensors as the fused path: same conv code, only the source of the input differs."""
+def test_fused_sampling_matches_sample_then_forward(zb, sad_linus_full):
+    """The fused stem samples frames on the fly (separable tables for unrotated views, per-texel math for rotated
+    ones, Color::NONE outside the image, zero padding outside the tensor) and convolves on the tensor core with the
+    ColorMapper folded into FP16 hi / lo weights (`stem_mma_kernel`).  Feeding the network the tensor produced by
+    the bit-exact `zb_preprocess` runs the SIMT f32 stem on the same values: the head tensors must agree to f32
+    rounding noise (a sampling or padding slip would move them by orders of magnitude more).  With
+    ZB_STEM_MMA=0 both paths run the same conv code and the tensors are bit-identical."""
+    import os
     from zaru_b200.detection import Detector, ShortRangeNetwork
     from zaru_b200.image import Image
     from zaru_b200.rect import AspectRatio, Rect, RotatedRect
@@ -426,12 +430,18 @@ def test_fused_sampling_is_bit_identical_to_sample_then_forward(zb, sad_linus_fu
     views = [img.as_view(), img.view(Rect.from_center(700, 400, 500, 333)),
              img.view(RotatedRect(Rect.from_center(640, 360, 900, 700), 0.3)),
              img.view(Rect.from_center(100, 100, 400, 400))]            # partly outside the image
+    simt = os.environ.get("ZB_STEM_MMA") == "0"
     for v in views:
         det.detect_views(batch, [v.to_zb_view(idx)], want_raw=True)
         raw_b, raw_s = det.last_raw
         fit = v.view(v.rect().grow_to_fit_aspect(AspectRatio.SQUARE))
         boxes, scores = cnn.nn.estimate(cnn.tensor(fit))
-        assert np.array_equal(raw_b, boxes) and np.array_equal(raw_s, scores)
+        if simt:
+            assert np.array_equal(raw_b, boxes) and np.array_equal(raw_s, scores)
+        else:
+            # head tensors reach |x| ~ 130; 2e-5 absolute on the logits is 5e-6 on a score
+            assert np.abs(raw_b - boxes).max() <= 2e-5 * (1.0 + np.abs(boxes).max()), np.abs(raw_b - boxes).max()
+            assert np.abs(raw_s - scores).max() <= 2e-5 * (1.0 + np.abs(scores).max()), np.abs(raw_s - scores).max()
 
 
 # ------------------------------------------------------------------------------------------------

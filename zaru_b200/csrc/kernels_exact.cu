@@ -20,6 +20,7 @@
 
 #include "geom.h"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace zb {
 namespace {
@@ -400,6 +401,297 @@ bool launch_stem_cfg(const FramesDev &f, const ViewDev *views, float lo, float h
     const int images = p.M / (p.Ho * p.Wo);
     ZB_KNAME("stem_kernel", KS, NP, PPT);
     kern<<<(unsigned)(tiles_x * tiles_y * images), 256, smem, s>>>(f, views, lo, hi, p, tiles_x, tiles_y, NSP, f16);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same stem on the tensor core ("stem_mma"): tcgen05.mma kind::f16 with the SAMPLED TEXEL TILE ITSELF as the A operand.
+//
+//   * An 8-bit texel value is exact in FP16, so the tile is stored once as (r, g, b, inside-the-tensor) FP16 quads - 8 bytes per
+//     texel, no hi / lo split of the activation side - and the affine ColorMapper is folded into the weights:
+//         sum_taps (a x + b) w  =  sum_taps x (a w)  +  sum_taps inside * (b (w_r + w_g + w_b))
+//     (a texel that reads Color::NONE is x = 0 WITH inside = 1: it maps to `b`; a tap outside the tensor is conv padding: all 0).
+//   * No im2col: in the K-major SWIZZLE_NONE layout the rows of a core matrix are 16 bytes apart = 2 texels = one output pixel of
+//     a stride-2 conv, so with a leading-dimension offset of 16 bytes a descriptor pointing at texel (2 oy + ky, 2 ox) reads, for
+//     the 8 x 16 output pixels of an MMA tile, the 4 consecutive taps (ky, 0..3) of every pixel as one K = 16 step - overlapping
+//     rows of the same tile, nothing is copied.  A tap row costs one (3x3) or two (5x5; slots 5..7 carry zero weights) MMAs.
+//   * Weights: f32 -> folded, scaled by a power of two into FP16's normal range, split into FP16 hi + lo (22 bits) by every CTA
+//     while its texel gather is in flight; two MMA passes (lo, hi) accumulate in FP32 in TMEM.
+//   * One CTA = 32 x 16 output pixels = four M = 128 accumulators; one barrier between the gather and the MMAs, one mbarrier
+//     wait, and an epilogue that needs no CTA barrier (each warp stages its own 32 pixels and writes them out coalesced).
+//     Three CTAs per SM overlap each other's gather / MMA / epilogue phases.
+// 5x5 -> 24 (BlazeFace): 1800 FMAs per output pixel on the FP32 pipe become 20 MMAs per 128 pixels.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // c_format = F32; a_format = b_format = 0 (F16), both K-major
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// (r, g, b, inside) as four FP16 values: bytes -> 0x6400 | byte = 1024 + byte, minus 1024 (exact)
+__device__ __forceinline__ uint2 texel_f16(unsigned rgba, bool inside) {
+    unsigned rg = __byte_perm(rgba, 0x64006400u, 0x5150);   // (0x6400 | r) | (0x6400 | g) << 16
+    unsigned bx = __byte_perm(rgba, 0x64006400u, 0x5452);   // (0x6400 | b) | 0x6400 << 16
+    const __half2 k = __floats2half2_rn(1024.0f, 1024.0f);
+    __half2 h0 = __hsub2(*reinterpret_cast<__half2 *>(&rg), k), h1 = __hsub2(*reinterpret_cast<__half2 *>(&bx), k);
+    uint2 o;
+    o.x = *reinterpret_cast<unsigned *>(&h0);
+    o.y = (*reinterpret_cast<unsigned *>(&h1) & 0xffffu) | (inside ? 0x3c000000u : 0u);
+    return inside ? o : make_uint2(0u, 0u);
+}
+
+template <int KS, int N>
+struct StemMma {
+    static constexpr int TW = 32, TH = 16, NT = 256;
+    static constexpr int KSTEPS = KS == 5 ? 2 : 1;            // K = 16 steps per tap row (4 taps each)
+    static constexpr int KX = 4 * KSTEPS;                     // tap slots per row (zero weights beyond KS)
+    static constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
+    static constexpr int P = ((TW - 1) * 2 + KX + 1) & ~1;    // texel pitch: the last pixel's padded tap slots stay inside the row
+    static constexpr int TILE_BYTES = IH * P * 8;
+    static constexpr int PART_BYTES = KS * (KX / 2) * N * 16; // [ky][k8][n][8 halves]
+    static constexpr int STAGE_STRIDE = N + 4;                // floats; conflict-free row-per-lane 128-bit stores
+    static constexpr int STAGE_BYTES = 8 * 32 * STAGE_STRIDE * 4;
+    static constexpr int MAIN_BYTES = (TILE_BYTES + 2 * PART_BYTES > STAGE_BYTES ? TILE_BYTES + 2 * PART_BYTES : STAGE_BYTES);
+    static constexpr int SMEM_BYTES = MAIN_BYTES + (2 * N + IW + IH) * 4;
+    static constexpr int TCOLS = 4 * N < 32 ? 32 : 4 * N;
+};
+
+template <int KS, int N, int MINB>
+__global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, const ViewDev *__restrict__ views, float lo, float hi,
+                                                          const ConvDev p, int tiles_x, int tiles_y) {
+    using G = StemMma<KS, N>;
+    constexpr int TW = G::TW, TH = G::TH, NT = G::NT, KX = G::KX, IW = G::IW, IH = G::IH, P = G::P;
+    extern __shared__ __align__(128) unsigned char stem_mma_smem[];
+    uint2 *s_tile = reinterpret_cast<uint2 *>(stem_mma_smem);                                  // [IH][P] FP16 quads
+    unsigned char *s_B = stem_mma_smem + G::TILE_BYTES;                                       // [part][ky][k8][N][8 halves]
+    float *s_stage = reinterpret_cast<float *>(stem_mma_smem);                                // epilogue: aliases tile + weights
+    float *s_bias = reinterpret_cast<float *>(stem_mma_smem + G::MAIN_BYTES);                 // [N]
+    float *s_sl = s_bias + N;                                                            // [N]
+    int *s_col = reinterpret_cast<int *>(s_sl + N);                                      // [IW]
+    int *s_row = s_col + IW;                                                             // [IH]
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_red[8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int b = blockIdx.x;
+    const int tile_x = b % tiles_x;
+    b /= tiles_x;
+    const int tile_y = b % tiles_y;
+    const int img = b / tiles_y;
+    const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+    const int iy_org = oy0 * 2 - p.pt, ix_org = ox0 * 2 - p.pl;
+    const ViewDev v = views[img];
+    const float adjust = (hi - lo) / 255.0f;
+    const bool separable = v.valid && v.cosr == 1.0f && v.sinr == 0.0f;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, G::TCOLS);
+    const int jmax = min(4, (p.Wo - ox0 + 7) >> 3);                  // MMA tiles (8 output columns each) inside the map
+    if (tid == 0) tc::mbar_init(&mbar, jmax);                         // one commit per issuing thread
+    if (separable) {
+        for (int e = tid; e < IW + IH; e += NT) {
+            if (e < IW) {
+                const int ix = ix_org + e;
+                s_col[e] = (ix >= 0 && ix < p.W) ? sample_axis(v.cx, v.w, ix, p.W, v.flip_x, f.width) : -2;
+            } else {
+                const int iy = iy_org + (e - IW);
+                s_row[e - IW] = (iy >= 0 && iy < p.H) ? sample_axis(v.cy, v.h, iy, p.H, 0, f.height) : -2;
+            }
+        }
+    }
+    for (int e = tid; e < N; e += NT) {
+        s_bias[e] = e < p.Ns ? __ldg(p.epi.bias + e) : 0.f;
+        s_sl[e] = (p.epi.act1.kind == ACT_PRELU && e < p.Ns) ? __ldg(p.epi.act1.slope + e) : 0.f;
+    }
+    // folded weights of this thread's (ky, tap slot, n) items: (a w_r, a w_g, a w_b, b (w_r + w_g + w_b)); zero beyond KS / Ns
+    constexpr int ITEMS = KS * KX * N, PER = (ITEMS + NT - 1) / NT;
+    float4 wv[PER];
+    float wmax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int e = tid + i * NT;
+        wv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < ITEMS) {
+            const int n = e % N, t = e / N, kx = t % KX, ky = t / KX;
+            if (kx < KS && n < p.Ns) {
+                const float *wp = p.w + (long long)((ky * KS + kx) * 4) * p.Ns + n;
+                const float wr = __ldg(wp), wg = __ldg(wp + p.Ns), wb = __ldg(wp + 2 * p.Ns);
+                wv[i] = make_float4(adjust * wr, adjust * wg, adjust * wb, lo * ((wr + wg) + wb));
+                wmax = fmaxf(wmax, fmaxf(fmaxf(fabsf(wv[i].x), fabsf(wv[i].y)), fmaxf(fabsf(wv[i].z), fabsf(wv[i].w))));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_red[warp] = wmax;
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    wmax = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) wmax = fmaxf(wmax, s_red[i]);
+    // ---- texel gather (the sampler of stem_kernel, unchanged), stored as FP16 quads; columns >= IW are padding for the
+    // zero-weight tap slots and must hold finite values.  All of a thread's texel loads are issued first; the weight split
+    // below runs while they are in flight ----
+    constexpr int TPT = (IH * P + NT - 1) / NT;                       // texels per thread
+    unsigned rgba[TPT];
+    unsigned inside_mask = 0;
+    if (separable) {
+        const uint8_t *fbase = f.base + (long long)v.frame * f.frame_stride;
+#pragma unroll
+        for (int u = 0; u < TPT; u++) {
+            const int e = tid + u * NT;
+            rgba[u] = 0u;
+            if (e < IH * P) {
+                const int ty = e / P, tx = e - ty * P;
+                const int sc = tx < IW ? s_col[tx] : -2, sr = s_row[ty];
+                if (sc != -2 && sr != -2) {
+                    inside_mask |= 1u << u;
+                    if (sc >= 0 && sr >= 0)
+                        rgba[u] = __ldg(reinterpret_cast<const unsigned *>(fbase + (long long)sr * f.row_stride + (long long)sc * 4));
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u0 = 0; u0 < TPT; u0 += 4) {
+            const unsigned *addr[4];
+#pragma unroll
+            for (int u = u0; u < u0 + 4 && u < TPT; u++) {
+                const int e = tid + u * NT;
+                const int ty = e / P, tx = e - ty * P;
+                const int iy = iy_org + ty, ix = ix_org + tx;
+                const bool in = e < IH * P && tx < IW && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                inside_mask |= in ? (1u << u) : 0u;
+                addr[u - u0] = in ? sample_address(f, v, ix, iy, p.W, p.H) : nullptr;
+            }
+#pragma unroll
+            for (int u = u0; u < u0 + 4 && u < TPT; u++) rgba[u] = addr[u - u0] ? __ldg(addr[u - u0]) : 0u;
+        }
+    }
+    // power-of-two scale that puts the largest folded weight into [2^14, 2^15): FP16 hi + lo then carry 22 bits of every
+    // weight that matters, and the products (x <= 255) stay far inside FP32
+    int sexp = 0;
+    if (wmax > 0.0f && wmax < 3.0e38f) sexp = 14 - ilogbf(wmax);
+    sexp = max(-60, min(60, sexp));
+    const float wscale = ldexpf(1.0f, sexp), inv_scale = ldexpf(1.0f, -sexp);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int e = tid + i * NT;
+        if (e < ITEMS) {
+            const int n = e % N, t = e / N, kx = t % KX, ky = t / KX;
+            const float x0 = wv[i].x * wscale, x1 = wv[i].y * wscale, x2 = wv[i].z * wscale, x3 = wv[i].w * wscale;
+            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1), h2 = __float2half_rn(x2), h3 = __float2half_rn(x3);
+            const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1)),
+                         l2 = __float2half_rn(x2 - __half2float(h2)), l3 = __float2half_rn(x3 - __half2float(h3));
+            const int off = ((ky * (KX / 2) + (kx >> 1)) * N + n) * 16 + (kx & 1) * 8;
+            __half2 a = __halves2half2(h0, h1), c = __halves2half2(h2, h3);
+            *reinterpret_cast<uint2 *>(s_B + G::PART_BYTES + off) = make_uint2(*reinterpret_cast<unsigned *>(&a), *reinterpret_cast<unsigned *>(&c));
+            a = __halves2half2(l0, l1), c = __halves2half2(l2, l3);
+            *reinterpret_cast<uint2 *>(s_B + off) = make_uint2(*reinterpret_cast<unsigned *>(&a), *reinterpret_cast<unsigned *>(&c));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < TPT; u++) {
+        const int e = tid + u * NT;
+        if (e < IH * P) s_tile[e] = texel_f16(rgba[u], (inside_mask >> u) & 1u);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    // one issuing thread per accumulator (lane 0 of warps 0 .. jmax - 1): 2 * KS * KSTEPS MMAs each, descriptors = base + constants
+    if (lane == 0 && warp < jmax) {
+        tc::tc_fence_after();
+        const int j = warp;
+        const uint32_t idesc = make_idesc_f16(128, N);
+        const uint64_t ad0 = tc::make_smem_desc(tc::smem_u32(s_tile) + (uint32_t)(j * 128), 16, 16 * P);
+        const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(s_B), N * 16, 128);
+        const uint32_t d = tmem + (uint32_t)(j * N);
+#pragma unroll
+        for (int part = 0; part < 2; part++) {                        // lo first, then hi
+#pragma unroll
+            for (int ky = 0; ky < KS; ky++) {
+#pragma unroll
+                for (int ks = 0; ks < G::KSTEPS; ks++) {
+                    const uint64_t ad = ad0 + (uint64_t)((ky * P * 8 + ks * 32) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)((part * G::PART_BYTES + (ky * (KX / 2) + 2 * ks) * N * 16) >> 4);
+                    umma_f16(d, ad, bd, idesc, (part | ky | ks) != 0);
+                }
+            }
+        }
+        tc::umma_commit(&mbar);
+    }
+    tc::mbar_wait(&mbar, 0);                                          // every MMA has read the tile and written TMEM
+    tc::tc_fence_after();
+    // ---- epilogue: warp (q, g) owns TMEM lanes 32 q .. 32 q + 31 of accumulators 2 g and 2 g + 1; it stages its 32 pixels
+    // in its own slice of shared memory (the tile and the weights are dead) and writes them out as contiguous float4 runs ----
+    {
+        const int q = warp & 3, g = warp >> 2;
+        float *stg = s_stage + warp * 32 * G::STAGE_STRIDE;
+        const int act = p.epi.act1.kind;
+        const int NQ = p.Ns >> 2;
+        float *obase = p.out + (long long)img * p.out_img_stride;
+        for (int jj = 0; jj < 2; jj++) {
+            const int j = 2 * g + jj;
+            if (j >= jmax) break;
+            float a[N];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * N);
+            if constexpr (N == 32) {
+                tc::tmem_ld32(taddr, a);
+            } else {
+                tc::tmem_ld16(taddr, a);
+            }
+#pragma unroll
+            for (int c = 0; c < N; c += 4) {
+                float r[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float x = a[c + k] * inv_scale + s_bias[c + k];
+                    if (act == ACT_RELU) x = fmaxf(x, 0.0f);
+                    else if (act == ACT_PRELU) x = x < 0.0f ? x * s_sl[c + k] : x;
+                    else if (act == ACT_CLIP) x = fminf(fmaxf(x, p.epi.act1.lo), p.epi.act1.hi);
+                    r[k] = x;
+                }
+                *reinterpret_cast<float4 *>(stg + lane * G::STAGE_STRIDE + c) = make_float4(r[0], r[1], r[2], r[3]);
+            }
+            __syncwarp();
+            for (int i = lane; i < 32 * NQ; i += 32) {
+                const int px = i / NQ, c4 = i - px * NQ;
+                const int oy = oy0 + 4 * q + (px >> 3), ox = ox0 + 8 * j + (px & 7);
+                if (oy < p.Ho && ox < p.Wo)
+                    *reinterpret_cast<float4 *>(obase + ((long long)oy * p.Wo + ox) * p.out_pix_stride + 4 * c4) =
+                        *reinterpret_cast<const float4 *>(stg + px * G::STAGE_STRIDE + 4 * c4);
+            }
+            __syncwarp();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, G::TCOLS);
+}
+
+template <int KS, int N, int MINB>
+bool launch_stem_mma_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
+    using G = StemMma<KS, N>;
+    auto kern = stem_mma_kernel<KS, N, MINB>;
+    static SmemOptIn opt_in;
+    if (!opt_in.ensure(kern, G::SMEM_BYTES)) return false;
+    const int tiles_x = (p.Wo + G::TW - 1) / G::TW, tiles_y = (p.Ho + G::TH - 1) / G::TH;
+    const int images = p.M / (p.Ho * p.Wo);
+    ZB_KNAME("stem_mma_kernel", KS, N, MINB);
+    kern<<<(unsigned)(tiles_x * tiles_y * images), 256, G::SMEM_BYTES, s>>>(f, views, lo, hi, p, tiles_x, tiles_y);
     return true;
 }
 
@@ -1262,6 +1554,21 @@ bool stem_supported(const ConvDev &p) {
 bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s, int round_f16) {
     if (!stem_supported(p)) return false;
     g_launch_count++;
+    // tensor-core stem: sampled views, f32 I/O, up to 32 output channels (everything but FaceMeshV2's FLOAT16 input, whose
+    // per-element rounding of the mapped value cannot be folded into the weights); ZB_STEM_MMA=0 keeps the SIMT stem for A/Bs
+    static const int mma_env = getenv("ZB_STEM_MMA") ? atoi(getenv("ZB_STEM_MMA")) : 3;   // bit 0: 5x5, bit 1: 3x3
+    if (views && !round_f16 && p.Ns <= 32 && (mma_env & (p.kh == 5 ? 1 : 2))) {
+        static const int minb = getenv("ZB_STEM_MMA_CTAS") ? atoi(getenv("ZB_STEM_MMA_CTAS")) : 5;   // measured: 5 (N = 16) / 4 (N = 32) CTAs per SM
+        bool ok;
+#define ZB_STEM_MMA_GO(KS_, N_, MAXB_) \
+    (minb >= 5 ? launch_stem_mma_cfg<KS_, N_, MAXB_>(f, views, lo, hi, p, s) : minb == 4 ? launch_stem_mma_cfg<KS_, N_, 4>(f, views, lo, hi, p, s) \
+                                                                                         : launch_stem_mma_cfg<KS_, N_, 3>(f, views, lo, hi, p, s))
+        // (a 32-column accumulator read needs > 48 registers: four CTAs per SM at most there)
+        if (p.kh == 5) ok = p.Ns <= 16 ? ZB_STEM_MMA_GO(5, 16, 5) : ZB_STEM_MMA_GO(5, 32, 4);
+        else ok = p.Ns <= 16 ? ZB_STEM_MMA_GO(3, 16, 5) : ZB_STEM_MMA_GO(3, 32, 4);
+#undef ZB_STEM_MMA_GO
+        if (ok) return true;
+    }
     // measured: 2 pixels per thread pays for the LDS-bound 5x5 stem (0.79 -> 0.63 ms), not for the 3x3 one
     static const int ppt = getenv("ZB_STEM_PPT") ? atoi(getenv("ZB_STEM_PPT")) : 0;
     if (p.kh == 3) {
