@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "geom.h"
 #include "kernels.h"
@@ -633,15 +634,16 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
         }
         tc::umma_commit(&mbar);
     }
-    tc::mbar_wait(&mbar, 0);                                          // every MMA has read the tile and written TMEM
+    if (lane == 0) tc::mbar_wait(&mbar, 0);                           // every MMA has read the tile and written TMEM
+    __syncwarp();                                                     // (one poller per warp instead of 256 spinning threads)
     tc::tc_fence_after();
     // ---- epilogue: warp (q, g) owns TMEM lanes 32 q .. 32 q + 31 of accumulators 2 g and 2 g + 1; it stages its 32 pixels
-    // in its own slice of shared memory (the tile and the weights are dead) and writes them out as contiguous float4 runs ----
+    // in its own slice of shared memory (the tile and the weights are dead) and writes them out as contiguous float4 runs:
+    // the 8 pixels of one output row of an MMA tile are 8 * Ns consecutive floats of the NHWC tensor (Wo % 8 == 0) ----
     {
         const int q = warp & 3, g = warp >> 2;
         float *stg = s_stage + warp * 32 * G::STAGE_STRIDE;
         const int act = p.epi.act1.kind;
-        const int NQ = p.Ns >> 2;
         float *obase = p.out + (long long)img * p.out_img_stride;
         for (int jj = 0; jj < 2; jj++) {
             const int j = 2 * g + jj;
@@ -654,26 +656,47 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
                 tc::tmem_ld16(taddr, a);
             }
 #pragma unroll
-            for (int c = 0; c < N; c += 4) {
-                float r[4];
+            for (int c = 0; c < N; c++) a[c] = a[c] * inv_scale + s_bias[c];
+            if (act == ACT_RELU) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float x = a[c + k] * inv_scale + s_bias[c + k];
-                    if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-                    else if (act == ACT_PRELU) x = x < 0.0f ? x * s_sl[c + k] : x;
-                    else if (act == ACT_CLIP) x = fminf(fmaxf(x, p.epi.act1.lo), p.epi.act1.hi);
-                    r[k] = x;
-                }
-                *reinterpret_cast<float4 *>(stg + lane * G::STAGE_STRIDE + c) = make_float4(r[0], r[1], r[2], r[3]);
+                for (int c = 0; c < N; c++) a[c] = fmaxf(a[c], 0.0f);
+            } else if (act == ACT_PRELU) {
+#pragma unroll
+                for (int c = 0; c < N; c++) a[c] = a[c] < 0.0f ? a[c] * s_sl[c] : a[c];
+            } else if (act == ACT_CLIP) {
+                const float clo = p.epi.act1.lo, chi = p.epi.act1.hi;
+#pragma unroll
+                for (int c = 0; c < N; c++) a[c] = fminf(fmaxf(a[c], clo), chi);
             }
+#pragma unroll
+            for (int c = 0; c < N; c += 4)
+                *reinterpret_cast<float4 *>(stg + lane * G::STAGE_STRIDE + c) = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
             __syncwarp();
-            for (int i = lane; i < 32 * NQ; i += 32) {
-                const int px = i / NQ, c4 = i - px * NQ;
-                const int oy = oy0 + 4 * q + (px >> 3), ox = ox0 + 8 * j + (px & 7);
-                if (oy < p.Ho && ox < p.Wo)
-                    *reinterpret_cast<float4 *>(obase + ((long long)oy * p.Wo + ox) * p.out_pix_stride + 4 * c4) =
-                        *reinterpret_cast<const float4 *>(stg + px * G::STAGE_STRIDE + 4 * c4);
-            }
+            auto write_out = [&](auto nq_tag) {
+                constexpr int NQ = decltype(nq_tag)::value;           // float4s per pixel
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int oy = oy0 + 4 * q + r;
+                    if (oy >= p.Ho) break;
+                    float4 *dst = reinterpret_cast<float4 *>(obase + ((long long)oy * p.Wo + ox0 + 8 * j) * (4 * NQ));
+#pragma unroll
+                    for (int i0 = 0; i0 < 8 * NQ; i0 += 32) {
+                        const int i = i0 + lane;
+                        if ((8 * NQ) % 32 == 0 || i < 8 * NQ) {
+                            const int px = i / NQ, c4 = i - px * NQ;
+                            dst[i] = *reinterpret_cast<const float4 *>(stg + (8 * r + px) * G::STAGE_STRIDE + 4 * c4);
+                        }
+                    }
+                }
+            };
+            const int nq = p.Ns >> 2;
+            if (nq == 4) write_out(std::integral_constant<int, 4>{});
+            else if (nq == 6) write_out(std::integral_constant<int, 6>{});
+            else if (nq == 8) write_out(std::integral_constant<int, 8>{});
+            else if (nq == 2) write_out(std::integral_constant<int, 2>{});
+            else if (nq == 3) write_out(std::integral_constant<int, 3>{});
+            else if (nq == 5) write_out(std::integral_constant<int, 5>{});
+            else write_out(std::integral_constant<int, 7>{});        // nq == 7 (1 is excluded by the launcher)
             __syncwarp();
         }
     }
@@ -1557,7 +1580,7 @@ bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, c
     // tensor-core stem: sampled views, f32 I/O, up to 32 output channels (everything but FaceMeshV2's FLOAT16 input, whose
     // per-element rounding of the mapped value cannot be folded into the weights); ZB_STEM_MMA=0 keeps the SIMT stem for A/Bs
     static const int mma_env = getenv("ZB_STEM_MMA") ? atoi(getenv("ZB_STEM_MMA")) : 3;   // bit 0: 5x5, bit 1: 3x3
-    if (views && !round_f16 && p.Ns <= 32 && (mma_env & (p.kh == 5 ? 1 : 2))) {
+    if (views && !round_f16 && p.Ns <= 32 && p.Ns >= 8 && p.Wo % 8 == 0 && (mma_env & (p.kh == 5 ? 1 : 2))) {
         static const int minb = getenv("ZB_STEM_MMA_CTAS") ? atoi(getenv("ZB_STEM_MMA_CTAS")) : 5;   // measured: 5 (N = 16) / 4 (N = 32) CTAs per SM
         bool ok;
 #define ZB_STEM_MMA_GO(KS_, N_, MAXB_) \
