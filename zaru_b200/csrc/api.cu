@@ -363,7 +363,10 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                     // tcgen05 GEMM for 1x1 / dense / non-overlapping-window convs (3xTF32); the thin SIMT kernel keeps the
                     // few-channel 1x1 convs on large maps it was measured on
                     bool done = false;
-                    if (ctx->tc_mode > 0 && ctx->tcb_gemm_mode > 0 && op.wtc_hi_off >= 0 && p.M >= ctx->tcb_gemm_min_m &&
+                    if (dense_head_supported(p))
+                        prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : "dense_head", bytes, flops,
+                                    [&] { done = launch_dense_head(p, s); });
+                    if (!done && ctx->tc_mode > 0 && ctx->tcb_gemm_mode > 0 && op.wtc_hi_off >= 0 && p.M >= ctx->tcb_gemm_min_m &&
                         tcb_gemm_supported(p, op.NP) && !(pw && pw_thin_supported(p)))
                         prof_launch(ctx, s, ctx->prof_detail ? op.label.c_str() : pw ? "tcb_gemm<pw>" : "tcb_gemm<gather>", bytes, flops,
                                     [&] { done = launch_tcb_gemm(p, W + op.wtc_hi_off, W + op.wtc_lo_off, op.NP, op.Kpad, s); });

@@ -89,6 +89,8 @@ void launch_round_f16(float *data, long long count, cudaStream_t s);
 
 bool launch_pw_thin(const ConvDev &p, cudaStream_t s);   // kernels_thin.cu: thin 1x1 convs (few channels, large maps); false = not taken
 bool pw_thin_supported(const ConvDev &p);
+bool dense_head_supported(const ConvDev &p);             // kernels_thin.cu: 1x1-output heads with little work (f32 FMA)
+bool launch_dense_head(const ConvDev &p, cudaStream_t s);
 bool dwpw_thin_supported(const ConvDev &p);   // kernels_thin.cu: would launch_conv(CONV_DWPW) take the thin kernel?
 
 // ---- tensor-core path: kernels_tc.cu ------------------------------------------------------------

@@ -545,7 +545,15 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     static const bool fill_sm = !(getenv("ZB_TCB_FILL") && atoi(getenv("ZB_TCB_FILL")) == 0);
     constexpr size_t TWO_CTAS = 110 * 1024, ONE_CTA = 220 * 1024;
     const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
-    const bool alone = fill_sm && tcb_smem(g, KS, NP, 1, 1) > TWO_CTAS;     // one CTA per SM whatever the buffering
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // one CTA per SM whatever the buffering - or fewer tiles than SMs (the deep layers of small batches: every CTA has its SM to
+    // itself and walks a long chain of K chunks, so the next chunk's halo and weights should already be on their way)
+    const bool alone = fill_sm && (tcb_smem(g, KS, NP, 1, 1) > TWO_CTAS || g.tiles_x * g.tiles_y <= num_sms);
     int nin, nbw;
     if (alone) {
         nbw = (nchunks > 1 && tcb_smem(g, KS, NP, 1, 2) <= ONE_CTA) ? 2 : 1;
@@ -569,12 +577,6 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     static SmemOptIn opt_in;
     if (!opt_in.ensure(kern, smem)) return false;
     // persistent CTAs: two per SM (what registers and shared memory allow), each striding over the tiles
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     static const int ctas_per_sm = getenv("ZB_TCB_CTAS_PER_SM") ? atoi(getenv("ZB_TCB_CTAS_PER_SM")) : 2;
     // (a footprint that leaves room for one CTA per SM gets one: a second "wave" of persistent CTAs would only queue up)
     const int resident = (fill_sm && smem > TWO_CTAS) ? 1 : ctas_per_sm;

@@ -532,6 +532,56 @@ __global__ void __launch_bounds__(128) pw_thin_kernel(const ConvDev p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dense heads: a convolution whose window IS the whole input map (Ho = Wo = 1: the Gemm / "conv kh x kw over a kh x kw map"
+// heads of the landmark networks, M = images rows of K = kh * kw * Cs_in contiguous inputs, N = 1 ... a few hundred).  The
+// tcgen05 GEMM runs such a layer as M / 128 CTAs walking K in 32-wide chunks - two CTAs and 21 serial chunks for the hand
+// network's 672 -> 63 head: 35 us for 11 MFLOP.  Here a CTA owns R rows and 32 output columns (lane = column: the weight row
+// is one coalesced 128-byte read shared by the R rows, the inputs are broadcast float4 reads), f32 FMA.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) dense_head_kernel(const ConvDev p) {
+    // a CTA = R rows x 32 output columns; its eight warps split K (the layer is a latency chain of L2 round trips otherwise:
+    // the first version, one warp per R rows walking all of K, took 140 us for the 672 -> 63 head) and reduce through shared memory
+    __shared__ float s_part[8][R][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 32 + lane;
+    const int m0 = blockIdx.y * R;
+    const float *w = p.w + (n < p.Ns ? n : 0);
+    const float *in[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) in[r] = p.in + (long long)min(m0 + r, p.M - 1) * p.in_img_stride;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.0f;
+    const int kc = ((p.K / 4 + 7) / 8) * 4;                          // K slice of a warp (multiple of 4)
+    const int k_end = min(p.K, (warp + 1) * kc);
+#pragma unroll 4
+    for (int k = warp * kc; k < k_end; k += 4) {
+        const float w0 = __ldg(w + (long long)k * p.Ns), w1 = __ldg(w + (long long)(k + 1) * p.Ns),
+                    w2 = __ldg(w + (long long)(k + 2) * p.Ns), w3 = __ldg(w + (long long)(k + 3) * p.Ns);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float4 x = ldg4(in[r] + k);
+            acc[r] = fmaf(x.x, w0, acc[r]);
+            acc[r] = fmaf(x.y, w1, acc[r]);
+            acc[r] = fmaf(x.z, w2, acc[r]);
+            acc[r] = fmaf(x.w, w3, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) s_part[warp][r][lane] = acc[r];
+    __syncthreads();
+    if (warp >= R || m0 + warp >= p.M || n >= p.Nstore) return;       // warp r finishes row r
+    float v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v += s_part[i][warp][lane];
+    v = n < p.Ns ? v + __ldg(p.epi.bias + n) : 0.0f;
+    v = apply_act(v, p.epi.act1, n);
+    v = apply_act(v, p.epi.act2, n);
+    p.out[(long long)(m0 + warp) * p.out_img_stride + n] = v;
+}
+
 template <int CIN, int NP, int PX>
 bool launch_pw_thin_cfg(const ConvDev &p, cudaStream_t s) {
     ZB_KNAME("pw_thin_kernel", CIN, NP, PX);
@@ -593,6 +643,24 @@ bool launch_pw_thin(const ConvDev &p, cudaStream_t s) {
     if (np == 8) return launch_pw_thin_cfg<32, 8, 2>(p, s);
     if (np == 16) return launch_pw_thin_cfg<32, 16, 2>(p, s);
     return launch_pw_thin_cfg<32, 32, 2>(p, s);
+}
+
+// Heads with a 1x1 output map and little work (see dense_head_kernel); large N x M stays on the tcgen05 GEMM.
+bool dense_head_supported(const ConvDev &p) {
+    static const bool disabled = getenv("ZB_NO_DENSE_HEAD") && atoi(getenv("ZB_NO_DENSE_HEAD")) != 0;
+    if (disabled) return false;
+    if (p.Ho != 1 || p.Wo != 1 || p.kh != p.H || p.kw != p.W || p.pt != 0 || p.pl != 0) return false;
+    if (p.K != p.kh * p.kw * p.Cs_in || p.K % 4 || p.in_img_stride % 4 || ((uintptr_t)p.in) % 16 || p.epi.res) return false;
+    return (long long)p.M * p.K * p.Ns <= (64ll << 20);
+}
+
+bool launch_dense_head(const ConvDev &p, cudaStream_t s) {
+    if (!dense_head_supported(p)) return false;
+    g_launch_count++;
+    constexpr int R = 4;
+    ZB_KNAME("dense_head_kernel", R);
+    dense_head_kernel<R><<<dim3((unsigned)((p.Ns + 31) / 32), (unsigned)((p.M + R - 1) / R)), 256, 0, s>>>(p);
+    return true;
 }
 
 }  // namespace zb
