@@ -2,6 +2,7 @@
 // kernels_exact.cu).  Plain structs, no CUDA types beyond cudaStream_t.
 #pragma once
 #include <cuda_runtime.h>
+#include <utility>
 
 #include <atomic>
 #include <initializer_list>
@@ -275,5 +276,34 @@ inline std::string make_kernel_name(const char *base, std::initializer_list<int>
         static const std::string _zb_kn = ::zb::make_kernel_name(base, {__VA_ARGS__}); \
         ::zb::t_kernel_name = _zb_kn.c_str();                                     \
     } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may become resident while the kernel in front
+// of it on the stream is still draining: its CTAs run their prologue (TMEM allocation, barrier init, weight copies - nothing
+// the predecessor produces) and then block in pdl_wait() until the predecessor has completed and its writes are visible.
+// Every kernel launched this way executes pdl_wait() before its first access to activations and pdl_trigger() once its own
+// TMEM is allocated (a dependent that grabbed TMEM first could starve a CTA of the predecessor that has not started yet).
+// ZB_PDL=0 launches everything fully serialised; stream capture always does (the graph path bakes plain edges).
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (pdl_enabled()) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusNone) cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
 
 }  // namespace zb

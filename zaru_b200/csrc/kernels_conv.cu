@@ -23,6 +23,10 @@
 namespace zb {
 
 std::atomic<long long> g_launch_count{0};
+bool pdl_enabled() {
+    static const bool on = !(getenv("ZB_PDL") && atoi(getenv("ZB_PDL")) == 0);
+    return on;
+}
 thread_local const char *t_kernel_name = nullptr;
 
 bool launch_dwpw_thin(const ConvDev &p, cudaStream_t s);   // kernels_thin.cu

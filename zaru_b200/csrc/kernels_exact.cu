@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
     const int img = b / tiles_y;
     const int oy0 = tile_y * TH, ox0 = tile_x * TW;
     const int iy_org = oy0 * 2 - p.pt, ix_org = ox0 * 2 - p.pl;
+    pdl_wait();                                                       // the views may come from the kernel in front (RoI / compaction)
     const ViewDev v = views[img];
     const float adjust = (hi - lo) / 255.0f;
     const bool separable = v.valid && v.cosr == 1.0f && v.sinr == 0.0f;
@@ -539,6 +540,7 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    pdl_trigger();                                                    // (TMEM is allocated)
     const uint32_t tmem = tmem_slot;
     wmax = s_red[0];
 #pragma unroll
@@ -714,7 +716,7 @@ bool launch_stem_mma_cfg(const FramesDev &f, const ViewDev *views, float lo, flo
     const int tiles_x = (p.Wo + G::TW - 1) / G::TW, tiles_y = (p.Ho + G::TH - 1) / G::TH;
     const int images = p.M / (p.Ho * p.Wo);
     ZB_KNAME("stem_mma_kernel", KS, N, MINB);
-    kern<<<(unsigned)(tiles_x * tiles_y * images), 256, G::SMEM_BYTES, s>>>(f, views, lo, hi, p, tiles_x, tiles_y);
+    launch_pdl(kern, dim3((unsigned)(tiles_x * tiles_y * images)), dim3(256), G::SMEM_BYTES, s, f, views, lo, hi, p, tiles_x, tiles_y);
     return true;
 }
 

@@ -429,10 +429,12 @@ __global__ void __launch_bounds__(256, 4) dwpw_ttc_kernel(const ConvDev p, const
     const int tile_step = NBUF == 1 ? total_tiles : (int)gridDim.x;
     int buf = 0;
     uint32_t phase = 0;
+    pdl_wait();                                // the previous kernel's activations are complete and visible
     if (tile < total_tiles) issue_fill(tile, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();                             // (after the TMEM allocation)
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = make_idesc_tf32(128, NP);
     const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), LBO_A, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), LBO_A, 128);
@@ -612,10 +614,10 @@ bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     static const int poll_all = getenv("ZB_TC_POLL_ALL") ? atoi(getenv("ZB_TC_POLL_ALL")) : 1;
     ZB_KNAME("dwpw_ttc_kernel", CS, TH, NBUF, TW);
     if (NBUF == 1) {
-        kern<<<dim3(tiles_x, tiles_y, images), 256, smem, s>>>(p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
+        launch_pdl(kern, dim3(tiles_x, tiles_y, images), dim3(256), smem, s, p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
     } else {
         const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
-        kern<<<(unsigned)grid, 256, smem, s>>>(p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
+        launch_pdl(kern, dim3((unsigned)grid), dim3(256), smem, s, p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
     }
     return true;
 }

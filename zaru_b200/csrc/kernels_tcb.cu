@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_trigger();                                                            // (TMEM is allocated: the next kernel's CTAs may move in)
+    pdl_wait();                                                               // the previous kernel's activations are complete and visible
     if (warp == 0) issue_in(0);
 
     // this thread's producer item: strip of PPT horizontally adjacent outputs x channel quad
@@ -387,10 +389,12 @@ __global__ void __launch_bounds__(256, TCB_GEMM_CTAS) tcb_gemm_kernel(const Conv
         }
     };
     float4 x[4];
+    pdl_wait();                                                               // the previous kernel's activations are complete and visible
     fetch(0, x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();                                                            // (after the TMEM allocation)
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = make_idesc_tf32(TCB_M, NT);
     const uint64_t ad_hi = make_smem_desc(smem_u32(sA_hi), TCB_AROWS * 16, 128), ad_lo = make_smem_desc(smem_u32(sA_lo), TCB_AROWS * 16, 128);
@@ -582,7 +586,7 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     const int resident = (fill_sm && smem > TWO_CTAS) ? 1 : ctas_per_sm;
     const int grid = ctas_per_sm > 0 ? std::min(g.tiles_x * g.tiles_y, resident * num_sms) : g.tiles_x * g.tiles_y;
     ZB_KNAME("tcb_dwpw_kernel", KS, S, PPT);
-    kern<<<(unsigned)grid, 1024 / PPT, smem, s>>>(tmap, p, w_hi, w_lo, NP, nchunks, g);
+    launch_pdl(kern, dim3((unsigned)grid), dim3(1024 / PPT), smem, s, tmap, p, w_hi, w_lo, NP, nchunks, g);
     return true;
 }
 
@@ -624,9 +628,8 @@ bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int
     g_launch_count++;
     const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
     ZB_KNAME("tcb_gemm_kernel");
-    tcb_gemm_kernel<<<dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), 256, smem, s>>>(p, w_hi, w_lo, NP, nchunks, kpad,
-                                                                                                     div_magic_checked(p.Ho * p.Wo, (unsigned long long)p.Ho * p.Wo + TCB_M),
-                                                                                                     div_magic_checked(p.Wo, (unsigned long long)p.Ho * p.Wo));
+    launch_pdl(tcb_gemm_kernel, dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), dim3(256), smem, s, p, w_hi, w_lo, NP, nchunks, kpad,
+               div_magic_checked(p.Ho * p.Wo, (unsigned long long)p.Ho * p.Wo + TCB_M), div_magic_checked(p.Wo, (unsigned long long)p.Ho * p.Wo));
     return true;
 }
 

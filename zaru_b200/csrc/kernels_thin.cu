@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(32 * WARPS) dwpw_strip_kernel(const ConvDev p,
     const int oy0 = tile_y * TH, ox0 = tile_x * TW;
     const int iy_org = oy0 * S - p.pt, ix_org = ox0 * S - p.pl;
     const float *in_img = p.in + (long long)img * p.in_img_stride;
+    pdl_trigger();
+    pdl_wait();                                        // the previous kernel's activations are complete and visible
 
     // Halo fill, row by row: a thread's (column, channel quad) pairs are fixed, so the index arithmetic (the
     // divisions cost a quarter of the kernel's instructions when done per 16-byte chunk) is hoisted out of the row loop.
@@ -387,7 +389,7 @@ bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     ZB_KNAME("dwpw_strip_kernel", CS, S, NP, PXV, TW, WARPS);
-    kern<<<dim3(tiles_x, tiles_y, images), 32 * WARPS, smem, s>>>(p, tiles_x, tiles_y);
+    launch_pdl(kern, dim3(tiles_x, tiles_y, images), dim3(32 * WARPS), smem, s, p, tiles_x, tiles_y);
     return true;
 }
 
@@ -548,6 +550,8 @@ __global__ void __launch_bounds__(256) dense_head_kernel(const ConvDev p) {
     const int n = blockIdx.x * 32 + lane;
     const int m0 = blockIdx.y * R;
     const float *w = p.w + (n < p.Ns ? n : 0);
+    pdl_trigger();
+    pdl_wait();                                                       // the previous kernel's activations are complete and visible
     const float *in[R];
 #pragma unroll
     for (int r = 0; r < R; r++) in[r] = p.in + (long long)min(m0 + r, p.M - 1) * p.in_img_stride;
@@ -659,7 +663,7 @@ bool launch_dense_head(const ConvDev &p, cudaStream_t s) {
     g_launch_count++;
     constexpr int R = 4;
     ZB_KNAME("dense_head_kernel", R);
-    dense_head_kernel<R><<<dim3((unsigned)((p.Ns + 31) / 32), (unsigned)((p.M + R - 1) / R)), 256, 0, s>>>(p);
+    launch_pdl(dense_head_kernel<R>, dim3((unsigned)((p.Ns + 31) / 32), (unsigned)((p.M + R - 1) / R)), dim3(256), 0, s, p);
     return true;
 }
 
