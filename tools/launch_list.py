@@ -13,7 +13,7 @@ hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 H = rows[hdr]
 ki, vi = H.index("Kernel Name"), H.index("Metric Value")
 body = [r for r in rows[hdr + 2:] if len(r) > vi]
-starts = [i for i, r in enumerate(body) if "stem_kernel<(int)5" in r[ki] or "stem_kernel<5" in r[ki]]
+starts = [i for i, r in enumerate(body) if re.search(r"stem(_mma)?_kernel<(\(int\))?5", r[ki])]
 last = body[starts[-1]:]
 with open(dst, "w", newline="") as f:
     w = csv.writer(f)
