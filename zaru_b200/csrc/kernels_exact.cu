@@ -452,25 +452,39 @@ __device__ __forceinline__ uint2 texel_f16(unsigned rgba, bool inside) {
     return inside ? o : make_uint2(0u, 0u);
 }
 
+// FLOAT16-input networks: NeuralNetwork::estimate rounds the mapped value to f16 (color_map, f16 = 1) - that value IS an FP16
+// number, so it goes into the tile as it is: (f16(a r + b), f16(a g + b), f16(a b + b), 0); conv padding stays all zero.
+__device__ __forceinline__ uint2 texel_f16_mapped(unsigned rgba, bool inside, float lo, float adjust) {
+    if (!inside) return make_uint2(0u, 0u);
+    const float4 c = color_map(rgba, lo, adjust, 1);
+    const __half2 h0 = __floats2half2_rn(c.x, c.y), h1 = __floats2half2_rn(c.z, 0.0f);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned *>(&h0);
+    o.y = *reinterpret_cast<const unsigned *>(&h1);
+    return o;
+}
+
 template <int KS, int N>
 struct StemMma {
-    static constexpr int TW = 32, TH = 16, NT = 256;
+    static constexpr int NACC = N <= 32 ? 4 : 2;              // M = 128 accumulators (8 x 16 output pixels each) per CTA: 128 TMEM columns
+    static constexpr int NLD = N <= 32 ? N : 32;              // accumulator columns a warp reads, finishes and stages at a time
+    static constexpr int TW = 8 * NACC, TH = 16, NT = 256;
     static constexpr int KSTEPS = KS == 5 ? 2 : 1;            // K = 16 steps per tap row (4 taps each)
     static constexpr int KX = 4 * KSTEPS;                     // tap slots per row (zero weights beyond KS)
     static constexpr int IW = (TW - 1) * 2 + KS, IH = (TH - 1) * 2 + KS;
     static constexpr int P = ((TW - 1) * 2 + KX + 1) & ~1;    // texel pitch: the last pixel's padded tap slots stay inside the row
     static constexpr int TILE_BYTES = IH * P * 8;
     static constexpr int PART_BYTES = KS * (KX / 2) * N * 16; // [ky][k8][n][8 halves]
-    static constexpr int STAGE_STRIDE = N + 4;                // floats; conflict-free row-per-lane 128-bit stores
+    static constexpr int STAGE_STRIDE = NLD + 4;              // floats; conflict-free row-per-lane 128-bit stores
     static constexpr int STAGE_BYTES = 8 * 32 * STAGE_STRIDE * 4;
     static constexpr int MAIN_BYTES = (TILE_BYTES + 2 * PART_BYTES > STAGE_BYTES ? TILE_BYTES + 2 * PART_BYTES : STAGE_BYTES);
     static constexpr int SMEM_BYTES = MAIN_BYTES + (2 * N + IW + IH) * 4;
-    static constexpr int TCOLS = 4 * N < 32 ? 32 : 4 * N;
+    static constexpr int TCOLS = NACC * N < 32 ? 32 : NACC * N;
 };
 
 template <int KS, int N, int MINB>
 __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, const ViewDev *__restrict__ views, float lo, float hi,
-                                                          const ConvDev p, int tiles_x, int tiles_y) {
+                                                          const ConvDev p, int tiles_x, int tiles_y, int f16) {
     using G = StemMma<KS, N>;
     constexpr int TW = G::TW, TH = G::TH, NT = G::NT, KX = G::KX, IW = G::IW, IH = G::IH, P = G::P;
     extern __shared__ __align__(128) unsigned char stem_mma_smem[];
@@ -499,7 +513,7 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
     const bool separable = v.valid && v.cosr == 1.0f && v.sinr == 0.0f;
 
     if (warp == 0) tc::tmem_alloc(&tmem_slot, G::TCOLS);
-    const int jmax = min(4, (p.Wo - ox0 + 7) >> 3);                  // MMA tiles (8 output columns each) inside the map
+    const int jmax = min(G::NACC, (p.Wo - ox0 + 7) >> 3);            // MMA tiles (8 output columns each) inside the map
     if (tid == 0) tc::mbar_init(&mbar, jmax);                         // one commit per issuing thread
     if (separable) {
         for (int e = tid; e < IW + IH; e += NT) {
@@ -529,7 +543,8 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
             if (kx < KS && n < p.Ns) {
                 const float *wp = p.w + (long long)((ky * KS + kx) * 4) * p.Ns + n;
                 const float wr = __ldg(wp), wg = __ldg(wp + p.Ns), wb = __ldg(wp + 2 * p.Ns);
-                wv[i] = make_float4(adjust * wr, adjust * wg, adjust * wb, lo * ((wr + wg) + wb));
+                // FLOAT16 input (FaceMeshV2): the tile holds f16(a x + b) itself, the weights stay as they are
+                wv[i] = f16 ? make_float4(wr, wg, wb, 0.0f) : make_float4(adjust * wr, adjust * wg, adjust * wb, lo * ((wr + wg) + wb));
                 wmax = fmaxf(wmax, fmaxf(fmaxf(fabsf(wv[i].x), fabsf(wv[i].y)), fmaxf(fabsf(wv[i].z), fabsf(wv[i].w))));
             }
         }
@@ -609,7 +624,7 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
 #pragma unroll
     for (int u = 0; u < TPT; u++) {
         const int e = tid + u * NT;
-        if (e < IH * P) s_tile[e] = texel_f16(rgba[u], (inside_mask >> u) & 1u);
+        if (e < IH * P) s_tile[e] = f16 ? texel_f16_mapped(rgba[u], (inside_mask >> u) & 1u, lo, adjust) : texel_f16(rgba[u], (inside_mask >> u) & 1u);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -639,66 +654,70 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
     if (lane == 0) tc::mbar_wait(&mbar, 0);                           // every MMA has read the tile and written TMEM
     __syncwarp();                                                     // (one poller per warp instead of 256 spinning threads)
     tc::tc_fence_after();
-    // ---- epilogue: warp (q, g) owns TMEM lanes 32 q .. 32 q + 31 of accumulators 2 g and 2 g + 1; it stages its 32 pixels
-    // in its own slice of shared memory (the tile and the weights are dead) and writes them out as contiguous float4 runs:
-    // the 8 pixels of one output row of an MMA tile are 8 * Ns consecutive floats of the NHWC tensor (Wo % 8 == 0) ----
+    // ---- epilogue: warp (q, g) owns TMEM lanes 32 q .. 32 q + 31 of two "units": accumulators 2 g and 2 g + 1 (N <= 32), or the
+    // two 32-column halves of accumulator g (N = 64).  It stages the unit's 32 pixels in its own slice of shared memory (the
+    // tile and the weights are dead) and writes them out as contiguous float4 runs: the 8 pixels of one output row of an MMA
+    // tile are 8 * Ns consecutive floats of the NHWC tensor (Wo % 8 == 0) ----
     {
+        constexpr int NLD = G::NLD;
         const int q = warp & 3, g = warp >> 2;
         float *stg = s_stage + warp * 32 * G::STAGE_STRIDE;
         const int act = p.epi.act1.kind;
         float *obase = p.out + (long long)img * p.out_img_stride;
-        for (int jj = 0; jj < 2; jj++) {
-            const int j = 2 * g + jj;
-            if (j >= jmax) break;
-            float a[N];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * N);
-            if constexpr (N == 32) {
+        const int nqt = p.Ns >> 2;                                    // float4s per pixel of the output tensor
+        for (int u = 0; u < 2; u++) {
+            const int j = N <= 32 ? 2 * g + u : g, c0 = N <= 32 ? 0 : 32 * u;   // accumulator, first column of the unit
+            if (j >= jmax || c0 >= p.Ns) break;
+            float a[NLD];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * N + c0);
+            if constexpr (NLD == 32) {
                 tc::tmem_ld32(taddr, a);
             } else {
                 tc::tmem_ld16(taddr, a);
             }
 #pragma unroll
-            for (int c = 0; c < N; c++) a[c] = a[c] * inv_scale + s_bias[c];
+            for (int c = 0; c < NLD; c++) a[c] = a[c] * inv_scale + s_bias[c0 + c];
             if (act == ACT_RELU) {
 #pragma unroll
-                for (int c = 0; c < N; c++) a[c] = fmaxf(a[c], 0.0f);
+                for (int c = 0; c < NLD; c++) a[c] = fmaxf(a[c], 0.0f);
             } else if (act == ACT_PRELU) {
 #pragma unroll
-                for (int c = 0; c < N; c++) a[c] = a[c] < 0.0f ? a[c] * s_sl[c] : a[c];
+                for (int c = 0; c < NLD; c++) a[c] = a[c] < 0.0f ? a[c] * s_sl[c0 + c] : a[c];
             } else if (act == ACT_CLIP) {
                 const float clo = p.epi.act1.lo, chi = p.epi.act1.hi;
 #pragma unroll
-                for (int c = 0; c < N; c++) a[c] = fminf(fmaxf(a[c], clo), chi);
+                for (int c = 0; c < NLD; c++) a[c] = fminf(fmaxf(a[c], clo), chi);
             }
 #pragma unroll
-            for (int c = 0; c < N; c += 4)
+            for (int c = 0; c < NLD; c += 4)
                 *reinterpret_cast<float4 *>(stg + lane * G::STAGE_STRIDE + c) = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
             __syncwarp();
             auto write_out = [&](auto nq_tag) {
-                constexpr int NQ = decltype(nq_tag)::value;           // float4s per pixel
+                constexpr int NQ = decltype(nq_tag)::value;           // float4s per pixel in this unit
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const int oy = oy0 + 4 * q + r;
                     if (oy >= p.Ho) break;
-                    float4 *dst = reinterpret_cast<float4 *>(obase + ((long long)oy * p.Wo + ox0 + 8 * j) * (4 * NQ));
+                    float4 *dst = reinterpret_cast<float4 *>(obase + ((long long)oy * p.Wo + ox0 + 8 * j) * p.Ns + c0);
 #pragma unroll
                     for (int i0 = 0; i0 < 8 * NQ; i0 += 32) {
                         const int i = i0 + lane;
                         if ((8 * NQ) % 32 == 0 || i < 8 * NQ) {
                             const int px = i / NQ, c4 = i - px * NQ;
-                            dst[i] = *reinterpret_cast<const float4 *>(stg + (8 * r + px) * G::STAGE_STRIDE + 4 * c4);
+                            dst[N <= 32 ? i : px * nqt + c4] = *reinterpret_cast<const float4 *>(stg + (8 * r + px) * G::STAGE_STRIDE + 4 * c4);
                         }
                     }
                 }
             };
-            const int nq = p.Ns >> 2;
+            const int nq = min(NLD / 4, nqt - (c0 >> 2));
             if (nq == 4) write_out(std::integral_constant<int, 4>{});
             else if (nq == 6) write_out(std::integral_constant<int, 6>{});
             else if (nq == 8) write_out(std::integral_constant<int, 8>{});
             else if (nq == 2) write_out(std::integral_constant<int, 2>{});
             else if (nq == 3) write_out(std::integral_constant<int, 3>{});
             else if (nq == 5) write_out(std::integral_constant<int, 5>{});
-            else write_out(std::integral_constant<int, 7>{});        // nq == 7 (1 is excluded by the launcher)
+            else if (nq == 7) write_out(std::integral_constant<int, 7>{});
+            else write_out(std::integral_constant<int, 1>{});
             __syncwarp();
         }
     }
@@ -708,7 +727,7 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
 }
 
 template <int KS, int N, int MINB>
-bool launch_stem_mma_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s) {
+bool launch_stem_mma_cfg(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, int f16, cudaStream_t s) {
     using G = StemMma<KS, N>;
     auto kern = stem_mma_kernel<KS, N, MINB>;
     static SmemOptIn opt_in;
@@ -716,7 +735,7 @@ bool launch_stem_mma_cfg(const FramesDev &f, const ViewDev *views, float lo, flo
     const int tiles_x = (p.Wo + G::TW - 1) / G::TW, tiles_y = (p.Ho + G::TH - 1) / G::TH;
     const int images = p.M / (p.Ho * p.Wo);
     ZB_KNAME("stem_mma_kernel", KS, N, MINB);
-    launch_pdl(kern, dim3((unsigned)(tiles_x * tiles_y * images)), dim3(256), G::SMEM_BYTES, s, f, views, lo, hi, p, tiles_x, tiles_y);
+    launch_pdl(kern, dim3((unsigned)(tiles_x * tiles_y * images)), dim3(256), G::SMEM_BYTES, s, f, views, lo, hi, p, tiles_x, tiles_y, f16);
     return true;
 }
 
@@ -1579,18 +1598,20 @@ bool stem_supported(const ConvDev &p) {
 bool launch_stem(const FramesDev &f, const ViewDev *views, float lo, float hi, const ConvDev &p, cudaStream_t s, int round_f16) {
     if (!stem_supported(p)) return false;
     g_launch_count++;
-    // tensor-core stem: sampled views, f32 I/O, up to 32 output channels (everything but FaceMeshV2's FLOAT16 input, whose
-    // per-element rounding of the mapped value cannot be folded into the weights); ZB_STEM_MMA=0 keeps the SIMT stem for A/Bs
-    static const int mma_env = getenv("ZB_STEM_MMA") ? atoi(getenv("ZB_STEM_MMA")) : 3;   // bit 0: 5x5, bit 1: 3x3
-    if (views && !round_f16 && p.Ns <= 32 && p.Ns >= 8 && p.Wo % 8 == 0 && (mma_env & (p.kh == 5 ? 1 : 2))) {
-        static const int minb = getenv("ZB_STEM_MMA_CTAS") ? atoi(getenv("ZB_STEM_MMA_CTAS")) : 5;   // measured: 5 (N = 16) / 4 (N = 32) CTAs per SM
+    // tensor-core stem: sampled views, up to 64 output channels, 8-aligned map width (every bundled network; FaceMeshV2's FLOAT16
+    // input included: the rounded mapped value is itself an FP16 number).  ZB_STEM_MMA=0 keeps the SIMT stem for A/Bs
+    static const int mma_env = getenv("ZB_STEM_MMA") ? atoi(getenv("ZB_STEM_MMA")) : 15;   // bit 0: 5x5, bit 1: 3x3, bit 2: N = 64, bit 3: FLOAT16 input
+    if (views && p.Ns <= 64 && p.Ns >= 8 && p.Wo % 8 == 0 && (mma_env & (p.kh == 5 ? 1 : 2)) && (p.Ns <= 32 || (mma_env & 4)) &&
+        (!round_f16 || (mma_env & 8))) {
+        static const int minb = getenv("ZB_STEM_MMA_CTAS") ? atoi(getenv("ZB_STEM_MMA_CTAS")) : 5;   // measured: 5 (N = 16) / 4 (N >= 32) CTAs per SM
         bool ok;
 #define ZB_STEM_MMA_GO(KS_, N_, MAXB_) \
-    (minb >= 5 ? launch_stem_mma_cfg<KS_, N_, MAXB_>(f, views, lo, hi, p, s) : minb == 4 ? launch_stem_mma_cfg<KS_, N_, 4>(f, views, lo, hi, p, s) \
-                                                                                         : launch_stem_mma_cfg<KS_, N_, 3>(f, views, lo, hi, p, s))
+    (minb >= 5 ? launch_stem_mma_cfg<KS_, N_, MAXB_>(f, views, lo, hi, p, round_f16, s) : minb == 4 ? launch_stem_mma_cfg<KS_, N_, 4>(f, views, lo, hi, p, round_f16, s) \
+                                                                                                   : launch_stem_mma_cfg<KS_, N_, 3>(f, views, lo, hi, p, round_f16, s))
         // (a 32-column accumulator read needs > 48 registers: four CTAs per SM at most there)
-        if (p.kh == 5) ok = p.Ns <= 16 ? ZB_STEM_MMA_GO(5, 16, 5) : ZB_STEM_MMA_GO(5, 32, 4);
-        else ok = p.Ns <= 16 ? ZB_STEM_MMA_GO(3, 16, 5) : ZB_STEM_MMA_GO(3, 32, 4);
+        if (p.kh == 5) ok = p.Ns <= 16 ? ZB_STEM_MMA_GO(5, 16, 5) : p.Ns <= 32 ? ZB_STEM_MMA_GO(5, 32, 4)
+                                                                     : launch_stem_mma_cfg<5, 64, 3>(f, views, lo, hi, p, round_f16, s);   // (40 weight registers: three CTAs)
+        else ok = p.Ns <= 16 ? ZB_STEM_MMA_GO(3, 16, 5) : p.Ns <= 32 ? ZB_STEM_MMA_GO(3, 32, 4) : ZB_STEM_MMA_GO(3, 64, 4);
 #undef ZB_STEM_MMA_GO
         if (ok) return true;
     }
