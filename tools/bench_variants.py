@@ -1,7 +1,7 @@
 """Device-resident throughput of the fused face pipeline for the widened networks, one JSON line
 per (detector, mesh) pair.  Same timing method as bench.py (CUDA events on the library stream, frames resident in HBM).
 
-    python tools/bench_variants.py [batch] > profiles/rX_pipeline_variants.jsonl
+    python tools/bench_variants.py [batch [detector:mesh]] > profiles/rX_pipeline_variants.jsonl
 """
 import json
 import os
@@ -19,12 +19,15 @@ from zaru_b200.pipeline import FacePipeline  # noqa: E402
 from zaru_b200.rect import Resolution  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+only = sys.argv[2] if len(sys.argv) > 2 else ""          # e.g. "full_range:face_mesh_v2": that pair only (A/Bs)
 zaru_b200.load_library()
 uniq = np.stack([synth.s_face_frame(1000 + s)[0] for s in range(32)])
 frames = np.concatenate([uniq] * ((n + 31) // 32))[:n]
 batch = ImageBatch.from_rgba8(Resolution(1920, 1080), frames)
 for dname, dnet in (("short_range", ShortRangeNetwork), ("full_range", FullRangeNetwork)):
     for lname, lnet in (("face_mesh_v1", FaceMeshV1), ("face_mesh_v2", FaceMeshV2)):
+        if only and only != f"{dname}:{lname}":
+            continue
         pipe = FacePipeline(detector_network=dnet(), landmark_network=lnet())
         for _ in range(3):
             pipe.run_raw(batch, n)
@@ -38,6 +41,8 @@ for dname, dnet in (("short_range", ShortRangeNetwork), ("full_range", FullRange
                           "ms_per_step": ms / steps, "frames_with_face": int((out[3] >= 0).sum())}), flush=True)
         del pipe
 
+if only:
+    sys.exit(0)
 # BASELINE config 3 as one fused call: palm detector + hand landmarks (threshold lowered: the frames hold no hands)
 from zaru_b200.pipeline import HandPipeline  # noqa: E402
 
