@@ -412,20 +412,23 @@ def test_pipeline_properties_at_batch(zb):
         assert np.array_equal(a.landmarks[i], a.landmarks[j])
 
 
-def test_fused_sampling_matches_sample_then_forward(zb, sad_linus_full):
+@pytest.mark.parametrize("netname", ["ShortRangeNetwork", "FullRangeNetwork", "PalmLiteNetwork"])
+def test_fused_sampling_matches_sample_then_forward(zb, sad_linus_full, netname):
     """The fused stem samples frames on the fly (separable tables for unrotated views, per-texel math for rotated
     ones, Color::NONE outside the image, zero padding outside the tensor) and convolves on the tensor core with the
     ColorMapper folded into FP16 hi / lo weights (`stem_mma_kernel`).  Feeding the network the tensor produced by
     the bit-exact `zb_preprocess` runs the SIMT f32 stem on the same values: the head tensors must agree to f32
     rounding noise (a sampling or padding slip would move them by orders of magnitude more).  With
     ZB_STEM_MMA=0 both paths run the same conv code and the tensors are bit-identical."""
-    import os
-    from zaru_b200.detection import Detector, ShortRangeNetwork
+    from zaru_b200 import detection
+    from zaru_b200.detection import Detector
     from zaru_b200.image import Image
     from zaru_b200.rect import AspectRatio, Rect, RotatedRect
     img = Image(sad_linus_full)
-    det = Detector(ShortRangeNetwork())
-    cnn = ShortRangeNetwork().cnn()
+    # 5x5 -> 24 with the -1..1 map, 3x3 -> 32 on a 192x192 input, 5x5 -> 32 with the 0..1 map (no validity term)
+    network = getattr(detection, netname)
+    det = Detector(network())
+    cnn = network().cnn()
     batch, idx = img.device()
     views = [img.as_view(), img.view(Rect.from_center(700, 400, 500, 333)),
              img.view(RotatedRect(Rect.from_center(640, 360, 900, 700), 0.3)),

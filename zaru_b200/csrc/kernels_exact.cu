@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(256, MINB) stem_mma_kernel(const FramesDev f, 
                 tc::tmem_ld16(taddr, a);
             }
 #pragma unroll
-            for (int c = 0; c < NLD; c++) a[c] = a[c] * inv_scale + s_bias[c0 + c];
+            for (int c = 0; c < NLD; c++) a[c] = fmaf(a[c], inv_scale, s_bias[c0 + c]);   // (explicit: this file is built with -fmad=false)
             if (act == ACT_RELU) {
 #pragma unroll
                 for (int c = 0; c < NLD; c++) a[c] = fmaxf(a[c], 0.0f);
