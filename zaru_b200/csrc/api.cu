@@ -391,7 +391,8 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                                         !(p.sh == 2 && dwpw_thin_supported(p));
                     const bool use_ttc = ctx->tc_mode > 0 && op.wtc_hi_off >= 0 && dwpw_ttc_supported(p, op.NP);
                     // tile-block kernel: every fused block with K >= 32 that the large-map specialists do not cover
-                    const bool use_tcb = ctx->tc_mode > 0 && ctx->tcb_mode > 0 && op.wtc_hi_off >= 0 && p.K >= ctx->tcb_min_k &&
+                    const bool use_tcb = ctx->tc_mode > 0 && ctx->tcb_mode > 0 && op.wtc_hi_off >= 0 &&
+                                         (p.K >= ctx->tcb_min_k || op.NP > 32) &&   // K < 32 only where the strip kernels (N <= 32) do not reach: 48x48x16 -> 64 294 -> 178 us
                                          tcb_dwpw_supported(p, op.NP) &&
                                          (!use_ttc || ctx->tcb_over_ttc == 1 ||
                                           (ctx->tcb_over_ttc == 2 && (p.Cs_in > 32 || p.H * p.W >= 2048 || op.NP > 48))) &&
@@ -2153,6 +2154,11 @@ zb_status zb_face_pipeline_run(zb_face_pipeline *p, const zb_frames *frames, int
         static const bool graph_env = !(getenv("ZB_NO_GRAPH") && atoi(getenv("ZB_NO_GRAPH")) != 0);
         static const int graph_max_n = getenv("ZB_GRAPH_MAX_N") ? atoi(getenv("ZB_GRAPH_MAX_N")) : 512;
         const bool use_graph = graph_env && !gather && !two_streams && !ctx->prof_on && n <= graph_max_n;
+        struct PdlSuppress {             // graph mode: no programmatic dependent launches in this call (kernels.h)
+            bool prev;
+            explicit PdlSuppress(bool on) : prev(t_pdl_suppress) { t_pdl_suppress = prev || on; }
+            ~PdlSuppress() { t_pdl_suppress = prev; }
+        } pdl_suppress(use_graph);
         uint64_t key = 0;
         bool capturing = false, replayed = false;
         struct CaptureGuard {            // an exception while capturing must not leave the stream in capture mode

@@ -283,14 +283,16 @@ inline std::string make_kernel_name(const char *base, std::initializer_list<int>
 // the predecessor produces) and then block in pdl_wait() until the predecessor has completed and its writes are visible.
 // Every kernel launched this way executes pdl_wait() before its first access to activations and pdl_trigger() once its own
 // TMEM is allocated (a dependent that grabbed TMEM first could starve a CTA of the predecessor that has not started yet).
-// ZB_PDL=0 launches everything fully serialised; stream capture always does (the graph path bakes plain edges).
+// ZB_PDL=0 launches everything fully serialised, and so do pipeline calls in CUDA-graph mode (batches <= 512: the capture bakes plain
+// edges, and the one or two eager calls in front of it launch the same way so that what is replayed is what was warmed up).
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();
+extern thread_local bool t_pdl_suppress;   // set while a pipeline call runs in CUDA-graph mode (small batches): plain launches only
+bool pdl_enabled(int family);   // ZB_PDL: bit mask over kernel families (1 tile-block, 2 GEMM, 4 strip, 8 tile-tc, 16 stem, 32 dense head)
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+inline cudaError_t launch_pdl(int family, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -298,7 +300,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 0;
-    if (pdl_enabled()) {
+    if (!t_pdl_suppress && pdl_enabled(family)) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusNone) cfg.numAttrs = 1;
     }

@@ -23,9 +23,10 @@
 namespace zb {
 
 std::atomic<long long> g_launch_count{0};
-bool pdl_enabled() {
-    static const bool on = !(getenv("ZB_PDL") && atoi(getenv("ZB_PDL")) == 0);
-    return on;
+thread_local bool t_pdl_suppress = false;
+bool pdl_enabled(int family) {
+    static const int mask = getenv("ZB_PDL") ? atoi(getenv("ZB_PDL")) : 63;
+    return (mask & family) != 0;
 }
 thread_local const char *t_kernel_name = nullptr;
 

@@ -735,7 +735,7 @@ bool launch_stem_mma_cfg(const FramesDev &f, const ViewDev *views, float lo, flo
     const int tiles_x = (p.Wo + G::TW - 1) / G::TW, tiles_y = (p.Ho + G::TH - 1) / G::TH;
     const int images = p.M / (p.Ho * p.Wo);
     ZB_KNAME("stem_mma_kernel", KS, N, MINB);
-    launch_pdl(kern, dim3((unsigned)(tiles_x * tiles_y * images)), dim3(256), G::SMEM_BYTES, s, f, views, lo, hi, p, tiles_x, tiles_y, f16);
+    launch_pdl(16, kern, dim3((unsigned)(tiles_x * tiles_y * images)), dim3(256), G::SMEM_BYTES, s, f, views, lo, hi, p, tiles_x, tiles_y, f16);
     return true;
 }
 

@@ -614,10 +614,10 @@ bool launch_ttc_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     static const int poll_all = getenv("ZB_TC_POLL_ALL") ? atoi(getenv("ZB_TC_POLL_ALL")) : 1;
     ZB_KNAME("dwpw_ttc_kernel", CS, TH, NBUF, TW);
     if (NBUF == 1) {
-        launch_pdl(kern, dim3(tiles_x, tiles_y, images), dim3(256), smem, s, p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
+        launch_pdl(8, kern, dim3(tiles_x, tiles_y, images), dim3(256), smem, s, p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
     } else {
         const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
-        launch_pdl(kern, dim3((unsigned)grid), dim3(256), smem, s, p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
+        launch_pdl(8, kern, dim3((unsigned)grid), dim3(256), smem, s, p, w_hi, w_lo, NP, tiles_x, tiles_y, total, poll_all);
     }
     return true;
 }

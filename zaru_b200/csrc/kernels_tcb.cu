@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(1024 / PPT, 2) tcb_dwpw_kernel(const __grid_co
 
 // ------------------------------------------------------------------------------------------------
 // Plain convolutions as tcgen05 GEMMs ("direct" operand: no depthwise stage): 1x1 convs, Gemm / dense heads, and
-// non-overlapping-window convs (2x2 stride 2, 3x3 stride 3 ...) whose im2col row is a concatenation of whole pixels
-// (Cs_in % 32 == 0, so a 32-wide K chunk never straddles two taps).  One CTA = 128 consecutive output pixels x one
+// windowed convs (2x2 stride 2, 3x3 stride 3 ...) whose im2col row is a concatenation of whole pixels (the tap of a
+// channel quad is worked out per thread, so a 32-wide K chunk may span several taps when Cs_in < 32).  One CTA = 128 consecutive output pixels x one
 // tile of up to 256 output channels (blockIdx.y); the A chunk is gathered with coalesced 128-bit loads, TF32-split and
 // stored in the UMMA K-major layout; the loads of chunk c + 1 are in flight while the MMAs of chunk c run.
 // Weights: [N tile][Kpad / 4][NT][4], TF32 hi / lo, one TMA bulk copy per chunk and half.
@@ -374,12 +374,13 @@ __global__ void __launch_bounds__(256, TCB_GEMM_CTAS) tcb_gemm_kernel(const Conv
     const bool multi_tap = p.kh * p.kw > 1;
     auto fetch = [&](int c, float4 (&x)[4]) {
         int k = c * TCB_CK + quad * 4, ky = 0, kx = 0;
+        const bool kok = k < p.K;                                             // (K is padded to the chunk width with zero weights)
         if (multi_tap) {
-            const int tap = (c * TCB_CK) / p.Cs_in;
+            // per thread: with Cs_in < 32 a chunk spans several taps (a quad never does: Cs_in % 4 == 0)
+            const int tap = k / p.Cs_in;
             k -= tap * p.Cs_in;
             ky = tap / p.kw, kx = tap - ky * p.kw;
         }
-        const bool kok = multi_tap ? true : k < p.K;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int iy = riy[i] + ky, ix = rix[i] + kx;
@@ -586,7 +587,7 @@ bool launch_tcb_cfg(const ConvDev &p, const float *w_hi, const float *w_lo, int 
     const int resident = (fill_sm && smem > TWO_CTAS) ? 1 : ctas_per_sm;
     const int grid = ctas_per_sm > 0 ? std::min(g.tiles_x * g.tiles_y, resident * num_sms) : g.tiles_x * g.tiles_y;
     ZB_KNAME("tcb_dwpw_kernel", KS, S, PPT);
-    launch_pdl(kern, dim3((unsigned)grid), dim3(1024 / PPT), smem, s, tmap, p, w_hi, w_lo, NP, nchunks, g);
+    launch_pdl(1, kern, dim3((unsigned)grid), dim3(1024 / PPT), smem, s, tmap, p, w_hi, w_lo, NP, nchunks, g);
     return true;
 }
 
@@ -612,7 +613,6 @@ bool tcb_gemm_supported(const ConvDev &p, int NP) {
     static const bool disabled = getenv("ZB_NO_TCB_GEMM") && atoi(getenv("ZB_NO_TCB_GEMM")) != 0;
     if (disabled) return false;
     if (p.Cs_in % 8 || p.Cs_in < 8 || NP % 16 || NP < 16) return false;
-    if (p.kh * p.kw > 1 && p.Cs_in % TCB_CK) return false;                   // a K chunk must not straddle two taps
     if (p.K != p.kh * p.kw * p.Cs_in || p.K > 8192) return false;
     if (p.M % (p.Ho * p.Wo) || ((uintptr_t)p.in) % 16 || (p.in_img_stride % 4)) return false;
     return true;
@@ -628,7 +628,7 @@ bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int
     g_launch_count++;
     const int nchunks = (p.K + TCB_CK - 1) / TCB_CK;
     ZB_KNAME("tcb_gemm_kernel");
-    launch_pdl(tcb_gemm_kernel, dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), dim3(256), smem, s, p, w_hi, w_lo, NP, nchunks, kpad,
+    launch_pdl(2, tcb_gemm_kernel, dim3((unsigned)((p.M + TCB_M - 1) / TCB_M), (unsigned)ntiles), dim3(256), smem, s, p, w_hi, w_lo, NP, nchunks, kpad,
                div_magic_checked(p.Ho * p.Wo, (unsigned long long)p.Ho * p.Wo + TCB_M), div_magic_checked(p.Wo, (unsigned long long)p.Ho * p.Wo));
     return true;
 }

@@ -389,7 +389,7 @@ bool launch_strip_cfg(const ConvDev &p, cudaStream_t s) {
     const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     const int images = p.M / (p.Ho * p.Wo);
     ZB_KNAME("dwpw_strip_kernel", CS, S, NP, PXV, TW, WARPS);
-    launch_pdl(kern, dim3(tiles_x, tiles_y, images), dim3(32 * WARPS), smem, s, p, tiles_x, tiles_y);
+    launch_pdl(4, kern, dim3(tiles_x, tiles_y, images), dim3(32 * WARPS), smem, s, p, tiles_x, tiles_y);
     return true;
 }
 
@@ -663,7 +663,7 @@ bool launch_dense_head(const ConvDev &p, cudaStream_t s) {
     g_launch_count++;
     constexpr int R = 4;
     ZB_KNAME("dense_head_kernel", R);
-    launch_pdl(dense_head_kernel<R>, dim3((unsigned)((p.Ns + 31) / 32), (unsigned)((p.M + R - 1) / R)), dim3(256), 0, s, p);
+    launch_pdl(32, dense_head_kernel<R>, dim3((unsigned)((p.Ns + 31) / 32), (unsigned)((p.M + R - 1) / R)), dim3(256), 0, s, p);
     return true;
 }
 

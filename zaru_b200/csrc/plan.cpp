@@ -702,7 +702,7 @@ struct Lowerer {
                 op.b_off = pack_vec(s.b, op.N, op.Ns, "bias");
                 // tensor-core copy for the GEMM kernel (1x1 / dense / non-overlapping windows; not the 3-channel stem):
                 // TF32 hi + lo, K-major UMMA layout, one block per tile of 256 output channels
-                if (ti.Cs % 8 == 0 && (op.kh * op.kw == 1 || ti.Cs % 32 == 0) && op.K <= 8192) {
+                if (ti.Cs % 8 == 0 && op.K <= 8192) {
                     op.NP = round_up(op.Ns, 16);
                     op.Kpad = round_up(op.K, 32);
                     const int ntiles = (op.NP + 255) / 256;
