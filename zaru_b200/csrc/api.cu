@@ -360,7 +360,7 @@ void run_ops(const zb_net *net, Workspace &ws, int c0, int nc, int stage, cudaSt
                         input_ready = true;
                     }
                     const bool pw = op.kh == 1 && op.kw == 1 && op.sh == 1 && op.sw == 1 && op.pt == 0 && op.pl == 0;
-                    // tcgen05 GEMM for 1x1 / dense / non-overlapping-window convs (3xTF32); the thin SIMT kernel keeps the
+                    // tcgen05 GEMM for 1x1 / dense / windowed convs (3xTF32; small 1x1-output heads go to dense_head_kernel); the thin SIMT kernel keeps the
                     // few-channel 1x1 convs on large maps it was measured on
                     bool done = false;
                     if (dense_head_supported(p))

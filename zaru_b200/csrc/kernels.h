@@ -102,7 +102,7 @@ bool launch_dwpw_ttc(const ConvDev &p, const float *w_hi, const float *w_lo, int
 // kernels_tcb.cu: fused dw 3x3 / 5x5 (stride 1 / 2) -> pw blocks of any map size: TMA tensor-map halo staging + tcgen05
 bool tcb_dwpw_supported(const ConvDev &p, int NP);
 bool launch_tcb_dwpw(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, cudaStream_t s);
-// plain convs as tcgen05 GEMMs: 1x1, dense / Gemm, non-overlapping windows; weights [N tile of 256][kpad / 4][NT][4] hi / lo
+// plain convs as tcgen05 GEMMs: 1x1, dense / Gemm, windowed convs (any Cs_in % 8 == 0); weights [N tile of 256][kpad / 4][NT][4] hi / lo
 bool tcb_gemm_supported(const ConvDev &p, int NP);
 bool launch_tcb_gemm(const ConvDev &p, const float *w_hi, const float *w_lo, int NP, int kpad, cudaStream_t s);
 // kernels_tcp.cu: the same fused blocks as a PERSISTENT, WARP-SPECIALISED pipeline (TMA warp / depthwise warps / MMA thread /

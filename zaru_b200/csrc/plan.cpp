@@ -700,7 +700,7 @@ struct Lowerer {
                             }
                 op.w_off = push_weights(w);
                 op.b_off = pack_vec(s.b, op.N, op.Ns, "bias");
-                // tensor-core copy for the GEMM kernel (1x1 / dense / non-overlapping windows; not the 3-channel stem):
+                // tensor-core copy for the GEMM kernel (1x1 / dense / windowed convs; not the 3-channel stem):
                 // TF32 hi + lo, K-major UMMA layout, one block per tile of 256 output channels
                 if (ti.Cs % 8 == 0 && op.K <= 8192) {
                     op.NP = round_up(op.Ns, 16);
