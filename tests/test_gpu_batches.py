@@ -402,8 +402,9 @@ def test_every_network_large_batch_equals_small_batch(assets_dir, name, lo, size
 
 def test_small_batch_cuda_graph_replay_is_invisible():
     """Small batches are launch-bound (49 launches per pass), so the pipeline replays a captured CUDA graph from the
-    third identical call on (first call: plain launches, second: capture).  Results must be bit-identical across the
-    three modes, a changed threshold or another batch must not replay a stale graph, and the frames' CURRENT content
+    third identical call on (first call: plain launches, second: capture) while (nearly) every frame of the previous
+    call had a detection - otherwise it runs the eager, detection-gated path.  Results must be bit-identical across
+    the modes, a changed threshold or another batch must not replay a stale graph, and the frames' CURRENT content
     is what gets processed (the graph bakes in addresses, not pixels)."""
     from zaru_b200 import synth
     from zaru_b200.image import ImageBatch
@@ -421,7 +422,9 @@ def test_small_batch_cuda_graph_replay_is_invisible():
         c0 = zaru_b200.launch_count()
         runs.append(pipe.run(batch))
         counts.append(zaru_b200.launch_count() - c0)
-    assert counts[0] > 40 and len(set(counts)) == 1, counts   # replayed launches are counted like issued ones
+    # replayed launches are counted like issued ones; a call that follows one in which fewer than 90 % of the frames had a
+    # detection runs the eager, detection-gated path instead of the graph (one more launch: the compaction)
+    assert counts[0] > 40 and max(counts) - min(counts) <= 1, counts
     for r in runs[1:]:
         assert np.array_equal(r.landmarks, runs[0].landmarks) and np.array_equal(r.face_flags, runs[0].face_flags)
         assert [len(d) for d in r.detections] == [len(d) for d in runs[0].detections]
